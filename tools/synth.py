@@ -1,0 +1,121 @@
+"""Deterministic synthetic FT8 inputs (BASELINE.json configs #1-#5).
+
+Host-side numpy only; used by tests/, bench.py and tools/make_golden.py to feed the CPU oracle and
+the CUDA path the SAME bytes.  Nothing here is on the product path.
+
+  slot_f32(...)      one 15 s slot of complex baseband at 3200 sps (what ft8_subsystem() consumes),
+                     8-FSK, 512 samples/symbol, 6.25 Hz tone spacing, complex AWGN, SNR in 2500 Hz.
+  raw_u8(...)        one 15 s slot of raw RTL-SDR uint8 IQ at 2.4 Msps (what rtlsdr_callback() consumes):
+                     the same tone sequence placed at (f - 600 kHz) so that the daemon's fs/4 mixer
+                     lands it at f after decimation; offset-128 unsigned bytes with saturation.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FS_AUDIO = 3200
+SYM_LEN = 512           # samples per symbol at 3200 sps
+N_SLOT = 48000
+FS_RAW = 2_400_000
+RAW_PER_SYM = 384_000   # 0.16 s at 2.4 Msps
+RAW_SLOT_SAMPLES = 36_000_000
+TONE_HZ = 6.25
+
+_CALL_A = "ABCDEFGHIJKLMNOPQRSTUVWXYZ"
+
+
+def random_call(rng: np.random.Generator) -> str:
+    """A standard callsign the type-1 packer accepts (letter, letter|digit, digit, 1-3 letters)."""
+    c = _CALL_A[rng.integers(26)] + (_CALL_A[rng.integers(26)] if rng.random() < 0.6 else "") + str(rng.integers(10))
+    c += "".join(_CALL_A[rng.integers(26)] for _ in range(int(rng.integers(1, 4))))
+    if len(c) >= 3 and not c[2].isdigit() and not c[1].isdigit():
+        c = c[0] + str(rng.integers(10)) + c[2:]
+    return c
+
+
+def random_grid(rng: np.random.Generator) -> str:
+    return "ABCDEFGHIJKLMNOPQR"[rng.integers(18)] + "ABCDEFGHIJKLMNOPQR"[rng.integers(18)] + str(rng.integers(10)) + str(rng.integers(10))
+
+
+def random_message(rng: np.random.Generator):
+    """(call_to, call_de, extra) triples covering CQ / grid / report / RR73 forms."""
+    kind = rng.integers(5)
+    de = random_call(rng)
+    if kind <= 1:
+        return ("CQ", de, random_grid(rng))
+    to = random_call(rng)
+    if kind == 2:
+        return (to, de, random_grid(rng))
+    if kind == 3:
+        return (to, de, "%+03d" % int(rng.integers(-24, 10)))
+    return (to, de, ["RRR", "RR73", "73"][rng.integers(3)])
+
+
+def slot_f32(signals, seed: int, noise_sigma: float = 1.0):
+    """signals: iterable of (tones[79], f0_hz, t0_sec, snr_db).  Returns (I, Q) float32[48000], NOT yet conditioned.
+
+    SNR is referred to a 2500 Hz bandwidth: amp^2 = 2 sigma^2 (2500/3200) 10^(snr/10), sigma per rail.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    z = (rng.standard_normal(N_SLOT) + 1j * rng.standard_normal(N_SLOT)) * noise_sigma
+    t = np.arange(SYM_LEN, dtype=np.float64) / FS_AUDIO
+    for tones, f0, t0, snr_db in signals:
+        amp = np.sqrt(2.0 * noise_sigma ** 2 * (2500.0 / FS_AUDIO) * 10.0 ** (snr_db / 10.0))
+        start = int(round(t0 * FS_AUDIO))
+        phase = 0.0
+        for k, tone in enumerate(np.asarray(tones, dtype=np.int64)):
+            f = f0 + float(tone) * TONE_HZ
+            lo = start + k * SYM_LEN
+            ph = phase + 2.0 * np.pi * f * t
+            phase = (phase + 2.0 * np.pi * f * SYM_LEN / FS_AUDIO) % (2.0 * np.pi)
+            a, b = max(lo, 0), min(lo + SYM_LEN, N_SLOT)
+            if a < b:
+                z[a:b] += amp * np.exp(1j * ph[a - lo:b - lo])
+    return z.real.astype(np.float32), z.imag.astype(np.float32)
+
+
+def raw_u8(signals, seed: int, noise_lsb: float = 30.0, n_samples: int = RAW_SLOT_SAMPLES, dc=(127.5, 127.5)):
+    """signals: iterable of (tones[79], f_hz, t0_sec, amp_lsb).  Returns uint8[2*n_samples] interleaved I,Q.
+
+    The signal is synthesised at complex baseband frequency (f - 600 kHz): rtlsdr_callback() multiplies
+    sample n by j^n (+fs/4), which moves it to +f in the 3200 sps output.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = np.empty(2 * n_samples, dtype=np.uint8)
+    sig_i = np.zeros(n_samples, dtype=np.float32)
+    sig_q = np.zeros(n_samples, dtype=np.float32)
+    n = np.arange(RAW_PER_SYM, dtype=np.float64)
+    for tones, f_hz, t0, amp in signals:
+        start = int(round(t0 * FS_RAW))
+        phase = 0.0
+        for k, tone in enumerate(np.asarray(tones, dtype=np.int64)):
+            f = f_hz + float(tone) * TONE_HZ - 600_000.0
+            w = 2.0 * np.pi * f / FS_RAW
+            lo = start + k * RAW_PER_SYM
+            a, b = max(lo, 0), min(lo + RAW_PER_SYM, n_samples)
+            if a < b:
+                ph = phase + w * n[a - lo:b - lo]
+                sig_i[a:b] += (amp * np.cos(ph)).astype(np.float32)
+                sig_q[a:b] += (amp * np.sin(ph)).astype(np.float32)
+            phase = (phase + w * RAW_PER_SYM) % (2.0 * np.pi)
+    step = 4_000_000
+    for o in range(0, n_samples, step):
+        e = min(o + step, n_samples)
+        ni = rng.standard_normal(e - o, dtype=np.float32) * np.float32(noise_lsb)
+        nq = rng.standard_normal(e - o, dtype=np.float32) * np.float32(noise_lsb)
+        out[2 * o:2 * e:2] = np.clip(np.rint(sig_i[o:e] + ni + np.float32(dc[0])), 0, 255).astype(np.uint8)
+        out[2 * o + 1:2 * e:2] = np.clip(np.rint(sig_q[o:e] + nq + np.float32(dc[1])), 0, 255).astype(np.uint8)
+    return out
+
+
+def crowded_band(oracle, n_signals: int, seed: int, f_lo=50.0, f_hi=1500.0, snr_lo=-24.0, snr_hi=5.0, dt=1.0):
+    """BASELINE.json config #3 on the daemon's 0..1600 Hz band: n overlapping messages, random f0/DT/SNR."""
+    rng = np.random.Generator(np.random.PCG64(seed ^ 0x5EED))
+    sigs, texts = [], []
+    for _ in range(n_signals):
+        to, de, ex = random_message(rng)
+        payload = oracle.pack_std(to, de, ex)
+        sigs.append((oracle.tones(payload), float(rng.uniform(f_lo, f_hi)), float(0.5 + rng.uniform(-dt, dt)), float(rng.uniform(snr_lo, snr_hi))))
+        texts.append(f"{to} {de} {ex}")
+    i_s, q_s = slot_f32(sigs, seed)
+    return i_s, q_s, texts
