@@ -1,0 +1,259 @@
+/* ft8b200.h -- C ABI of libft8b200.so, the B200-native (sm_100a) implementation of the
+ * rtlsdr-ft8d receive-and-decode hot path.
+ *
+ * Two layers, both `extern "C"`, plain pointers and sizes only:
+ *
+ *  (1) DROP-IN entry points carrying the reference's own names, signatures and struct
+ *      layouts, taking HOST pointers exactly as the reference's callers pass them.  Each one
+ *      cites the reference interface it replaces.  A daemon built from the reference's
+ *      rtlsdr_ft8d.c links against this library instead of compiling ft8_lib/ft8/decode.c etc.
+ *      (see INTEGRATION.md for the exact binding).
+ *
+ *  (2) BATCHED entry points (`ft8b200_*`) taking DEVICE pointers, used by the benchmarks, the
+ *      multi-GPU driver and the parity tests: many independent 15 s slots / receiver streams per
+ *      launch.  Layer (1) is implemented on top of layer (2).
+ *
+ * There is no CPU fallback: every entry point runs CUDA kernels and reports failure when no
+ * sm_100 device is usable (ft8b200_last_error()).
+ */
+#ifndef FT8B200_H
+#define FT8B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * ABI types, byte-for-byte those of the reference
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces: ft8_lib/ft8/constants.h:6-10 */
+typedef enum { PROTO_FT4, PROTO_FT8 } ftx_protocol_t;
+
+/* replaces: ft8_lib/ft8/decode.h:15-25 (40 bytes; mag @24, block_stride @32, protocol @36) */
+typedef struct {
+    int max_blocks;
+    int num_blocks;
+    int num_bins;
+    int time_osr;
+    int freq_osr;
+    uint8_t *mag; /* uint8_t[blocks][time_osr][freq_osr][num_bins], HOST memory */
+    int block_stride;
+    ftx_protocol_t protocol;
+} waterfall_t;
+
+/* replaces: ft8_lib/ft8/decode.h:29-36 (8 bytes) */
+typedef struct {
+    int16_t score;
+    int16_t time_offset;
+    int16_t freq_offset;
+    uint8_t time_sub;
+    uint8_t freq_sub;
+} candidate_t;
+
+/* replaces: ft8_lib/ft8/decode.h:39-44 (28 bytes; hash @26) */
+typedef struct {
+    char text[25];
+    uint16_t hash;
+} message_t;
+
+/* replaces: ft8_lib/ft8/decode.h:47-53 (12 bytes) */
+typedef struct {
+    int ldpc_errors;
+    uint16_t crc_extracted;
+    uint16_t crc_calculated;
+    int unpack_status;
+} decode_status_t;
+
+/* replaces: rtlsdr_ft8d.h:136-141 (28 bytes) */
+struct decoder_results {
+    char call[13];
+    char loc[7];
+    int32_t freq;
+    int32_t snr;
+};
+
+/* replaces: ft8_lib/decode_ft8.c:82-90 (defined inside the .c in the reference) */
+typedef struct {
+    float f_min;
+    float f_max;
+    int sample_rate;
+    int time_osr;
+    int freq_osr;
+    ftx_protocol_t protocol;
+} monitor_config_t;
+
+/* replaces: ft8_lib/decode_ft8.c:94-109.  Same leading fields as the reference so code that
+ * reads me->wf / block_size keeps working; the two kiss_fft housekeeping pointers of the
+ * reference are replaced by one opaque device-side handle of the same total size. */
+typedef struct {
+    float symbol_period;
+    int block_size;
+    int subblock_size;
+    int nfft;
+    float fft_norm;
+    float *window;     /* host copy of the Hann window (nfft floats) */
+    float *last_frame; /* host copy of the sliding analysis frame (nfft floats) */
+    waterfall_t wf;    /* wf.mag is HOST memory, refreshed after every monitor_process() */
+    float max_mag;
+    void *fft_work; /* opaque: device state of this monitor */
+    void *fft_cfg;  /* unused, kept for layout compatibility */
+} monitor_t;
+
+/* ------------------------------------------------------------------------------------------
+ * (1) drop-in entry points (host pointers)
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces: static rtlsdr_callback(), rtlsdr_ft8d.c:76-202 (type rtlsdr_read_async_cb_t).
+ * `samples_count` bytes of interleaved uint8 I/Q, a multiple of 8.  The bytes are consumed
+ * before returning.  ctx == NULL selects the process-wide default stream (the reference keeps
+ * its state in function statics); otherwise ctx is a ft8b200_stream_t* from
+ * ft8b200_stream_create(), which is how many receivers share one process.  Unlike the
+ * reference the caller's buffer is NOT modified. */
+void rtlsdr_callback(unsigned char *samples, uint32_t samples_count, void *ctx);
+
+/* replaces: initFFTW()/freeFFTW(), rtlsdr_ft8d.c:314-347: creates / destroys the default
+ * context (device tables, workspaces).  Every other entry point creates it on demand. */
+void initFFTW(void);
+void freeFFTW(void);
+
+/* replaces: ft8_subsystem(), rtlsdr_ft8d.c:1387-1524.  48000 conditioned samples per rail;
+ * samples_len is ignored exactly like the reference ignores it (:1393); decodes[] must hold
+ * K_MAX_MESSAGES (50) records; *n_results counts ALL unique messages, CQ or not. */
+void ft8_subsystem(float *iSamples, float *qSamples, uint32_t samples_len, struct decoder_results *decodes, int32_t *n_results);
+
+/* replaces: ft8_find_sync(), ft8_lib/ft8/decode.h:63 / decode.c:173-234 */
+int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap[], int min_score);
+
+/* replaces: ft8_decode(), ft8_lib/ft8/decode.h:72 / decode.c:316-376.  On early failure the
+ * later fields of *status are left unwritten, as in the reference. */
+bool ft8_decode(const waterfall_t *power, const candidate_t *cand, message_t *message, int max_iterations, decode_status_t *status);
+
+/* replaces: waterfall_init()/waterfall_free(), ft8_lib/decode_ft8.c:63-79 */
+void waterfall_init(waterfall_t *me, int max_blocks, int num_bins, int time_osr, int freq_osr);
+void waterfall_free(waterfall_t *me);
+
+/* replaces: monitor_init/process/reset/free, ft8_lib/decode_ft8.c:111-224 */
+void monitor_init(monitor_t *me, const monitor_config_t *cfg);
+void monitor_process(monitor_t *me, const float *frame);
+void monitor_reset(monitor_t *me);
+void monitor_free(monitor_t *me);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) batched entry points (device pointers unless the name says _host)
+ * All return 0 on success, a negative FT8B200_E* code otherwise; ft8b200_last_error() has text.
+ * `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).
+ * ---------------------------------------------------------------------------------------- */
+#define FT8B200_OK 0
+#define FT8B200_ENODEV (-1)   /* no usable sm_100 device / CUDA runtime error at init */
+#define FT8B200_EINVAL (-2)   /* bad argument */
+#define FT8B200_ECUDA (-3)    /* a CUDA call or kernel failed */
+#define FT8B200_ENOMEM (-4)
+
+#define FT8B200_SLOT_SAMPLES 48000  /* 15 s at 3200 sps per rail (rtlsdr_ft8d.h:34-35) */
+#define FT8B200_DECIM 751           /* input samples per output sample (rtlsdr_ft8d.c:156-160) */
+#define FT8B200_WF_BYTES 94208      /* daemon waterfall bytes per slot (rtlsdr_ft8d.h:54) */
+#define FT8B200_RAW_SLOT_BYTES 72000000
+
+typedef struct ft8b200_ctx ft8b200_ctx_t;
+typedef struct ft8b200_stream ft8b200_stream_t;
+
+typedef struct {
+    int device;          /* CUDA device ordinal */
+    int max_slots;       /* largest batch the workspaces are sized for */
+    int max_candidates;  /* K_MAX_CANDIDATES: 120 (daemon), 500 (crowded band) */
+    int max_messages;    /* K_MAX_MESSAGES: 50 (daemon), 200 (crowded band) */
+    int min_score;       /* K_MIN_SCORE: 10 */
+    int ldpc_iterations; /* K_LDPC_ITERS: 20 */
+} ft8b200_config_t;
+
+const char *ft8b200_last_error(void);
+const char *ft8b200_version(void);
+void ft8b200_default_config(ft8b200_config_t *cfg);
+ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg);
+void ft8b200_destroy(ft8b200_ctx_t *ctx);
+void *ft8b200_cuda_stream(ft8b200_ctx_t *ctx);
+int ft8b200_sync(ft8b200_ctx_t *ctx);
+/* number of kernels this library has launched since the context was created */
+uint64_t ft8b200_kernel_launches(ft8b200_ctx_t *ctx);
+
+/* a1-a3: n_streams independent receiver streams, each `bytes_per_stream` bytes of uint8 IQ
+ * (multiple of 16, 16-byte aligned, streams `stream_stride_bytes` apart), decimated from zero
+ * filter state.  Writes, per stream, floor(bytes/2/751) outputs (<= 48000) into
+ * d_i/d_q[stream*48000 ...], zero-fills the rest of the 48000, stores the output count in
+ * d_count[stream] and max(|I|,|Q|) in d_peak[stream] (the input of decoder()'s normalisation,
+ * rtlsdr_ft8d.c:248-258).  d_y2 (optional, int32[n_streams][48000][2]) receives the integer
+ * CIC output before the FIR. */
+int ft8b200_decimate(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams,
+                     float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, void *stream);
+
+/* a4: in-place decoder() conditioning of n_slots x 48000 samples using d_peak (rtlsdr_ft8d.c:242-263) */
+int ft8b200_condition(ft8b200_ctx_t *ctx, float *d_i, float *d_q, const float *d_peak, int n_slots, void *stream);
+
+/* a5: daemon waterfall.  d_peak may be NULL (samples already conditioned); otherwise the
+ * conditioning scale (float)(0.5/max(peak,1e-24)) is applied on load. d_mag: n_slots x 94208. */
+int ft8b200_waterfall(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, const float *d_peak, int n_slots, uint8_t *d_mag, void *stream);
+
+/* a7-a8: per slot, candidate list sorted exactly like ft8_find_sync(). d_cand: n_slots x max_candidates,
+ * d_ncand: n_slots.  Waterfall geometry as in waterfall_t (all slots share it). */
+int ft8b200_find_sync(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins,
+                      int time_osr, int freq_osr, candidate_t *d_cand, int *d_ncand, void *stream);
+
+/* a9-a14: decode every candidate of every slot.  Outputs are n_slots x max_candidates arrays:
+ * d_ok (uint8: 1 = message decoded), d_stage (uint8: 1 = stopped at LDPC, 2 = at CRC, 3 = at unpack, 4 = done:
+ * which decode_status_t fields the reference would have written), d_status, d_msg; optional d_plain
+ * (uint8[...][174]) and d_llr (float[...][174], the normalised LLRs fed to the BP decoder). */
+int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins,
+                   int time_osr, int freq_osr, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage,
+                   decode_status_t *d_status, message_t *d_msg, uint8_t *d_plain, float *d_llr, void *stream);
+
+/* a15: the daemon's duplicate table + CQ filter, one slot per thread.  d_results: n_slots x max_messages
+ * (zeroed here first), d_nresults: n_slots; optional first-seen unique message log: d_umsg (n_slots x
+ * max_messages message_t), d_ufreq (float), d_uscore (int32). */
+int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate_t *d_cand, const int *d_ncand, const uint8_t *d_ok,
+                  const message_t *d_msg, struct decoder_results *d_results, int32_t *d_nresults, message_t *d_umsg, float *d_ufreq,
+                  int32_t *d_uscore, void *stream);
+
+/* Whole path on device buffers owned by the context: raw uint8 IQ (d_iq != NULL) or conditioned
+ * 3200 sps samples (d_i/d_q) -> decoder_results.  Results stay on the device (ft8b200_results_device)
+ * until fetched. */
+int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots, void *stream);
+int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, int n_slots, void *stream);
+/* device pointers to the last batch's outputs: results (n_slots x max_messages), counts (n_slots) */
+int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults);
+int ft8b200_fetch_results(ft8b200_ctx_t *ctx, int n_slots, struct decoder_results *h_results, int32_t *h_nresults, void *stream);
+/* intermediate device buffers of the last batch (for tests / profiling): any pointer may be NULL */
+int ft8b200_workspace(ft8b200_ctx_t *ctx, float **d_i, float **d_q, float **d_peak, uint8_t **d_mag, candidate_t **d_cand, int **d_ncand,
+                      uint8_t **d_ok, decode_status_t **d_status, message_t **d_msg);
+
+/* Same, host buffers in / host results out (H2D + kernels + D2H): the end-to-end call. */
+int ft8b200_process_raw_host(ft8b200_ctx_t *ctx, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots,
+                             struct decoder_results *h_results, int32_t *h_nresults);
+int ft8b200_process_slots_host(ft8b200_ctx_t *ctx, const float *h_i, const float *h_q, int n_slots,
+                               struct decoder_results *h_results, int32_t *h_nresults);
+
+/* Receiver streams for rtlsdr_callback(): persistent decimator state, double-buffered 15 s slots. */
+ft8b200_stream_t *ft8b200_stream_create(ft8b200_ctx_t *ctx);
+void ft8b200_stream_destroy(ft8b200_stream_t *s);
+/* what main() does every 15 s (rtlsdr_ft8d.c:1339-1354): close the current slot buffer, start the next */
+int ft8b200_stream_flip(ft8b200_stream_t *s);
+/* samples collected so far in the slot being filled (rx_state.iqIndex[bufferIndex]) */
+uint32_t ft8b200_stream_count(ft8b200_stream_t *s);
+/* the slot closed by the last flip: copy its (unconditioned) samples to the host, return their number */
+int ft8b200_stream_fetch(ft8b200_stream_t *s, float *h_i, float *h_q, uint32_t *n_valid);
+/* decoder() (rtlsdr_ft8d.c:221-285) for the slot closed by the last flip: skip if < 12 s, condition, decode */
+int ft8b200_stream_decode(ft8b200_stream_t *s, struct decoder_results *h_results, int32_t *h_nresults);
+
+/* 12 kHz monitor waterfall, batched: n_slots x n_samples real audio -> u8[n_slots][blocks][time_osr][freq_osr][bins] */
+int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t slot_stride_samples, int n_samples, int n_slots,
+                              int sample_rate, int time_osr, int freq_osr, int protocol, uint8_t *d_mag, size_t mag_slot_stride,
+                              int *num_blocks_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FT8B200_H */

@@ -1,0 +1,271 @@
+"""rtlsdr-ft8d_b200 -- Python harness binding for libft8b200.so (the sm_100a implementation of the
+rtlsdr-ft8d receive-and-decode hot path).
+
+The product is the C-ABI shared library built from ``csrc/`` (see ``include/ft8b200.h``); this module
+only loads it with ctypes and moves torch device tensors in and out, for the tests and benchmarks.
+PyTorch is plumbing here (device memory, streams, torch.distributed), not the compute path.
+There is no fallback: if the library is missing or no B200 is visible, calls raise.
+
+The directory name contains a hyphen (it mirrors the reference's name), so import it through
+``ft8b200_loader.load()`` at the repository root, which registers it as ``rtlsdr_ft8d_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libft8b200.so")
+
+N_SLOT = 48000
+WF_BYTES = 94208
+RAW_SLOT_BYTES = 72_000_000
+
+cand_dtype = np.dtype([("score", "<i2"), ("time_offset", "<i2"), ("freq_offset", "<i2"), ("time_sub", "u1"), ("freq_sub", "u1")])
+msg_dtype = np.dtype([("text", "S25"), ("_pad", "u1"), ("hash", "<u2")])
+status_dtype = np.dtype([("ldpc_errors", "<i4"), ("crc_extracted", "<u2"), ("crc_calculated", "<u2"), ("unpack_status", "<i4")])
+result_dtype = np.dtype([("call", "S13"), ("loc", "S7"), ("freq", "<i4"), ("snr", "<i4")])
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("max_slots", C.c_int), ("max_candidates", C.c_int), ("max_messages", C.c_int),
+                ("min_score", C.c_int), ("ldpc_iterations", C.c_int)]
+
+
+class WaterfallT(C.Structure):
+    _fields_ = [("max_blocks", C.c_int), ("num_blocks", C.c_int), ("num_bins", C.c_int), ("time_osr", C.c_int),
+                ("freq_osr", C.c_int), ("mag", C.c_void_p), ("block_stride", C.c_int), ("protocol", C.c_int)]
+
+
+class MonitorConfig(C.Structure):
+    _fields_ = [("f_min", C.c_float), ("f_max", C.c_float), ("sample_rate", C.c_int), ("time_osr", C.c_int), ("freq_osr", C.c_int),
+                ("protocol", C.c_int)]
+
+
+class MonitorT(C.Structure):
+    _fields_ = [("symbol_period", C.c_float), ("block_size", C.c_int), ("subblock_size", C.c_int), ("nfft", C.c_int), ("fft_norm", C.c_float),
+                ("window", C.c_void_p), ("last_frame", C.c_void_p), ("wf", WaterfallT), ("max_mag", C.c_float), ("fft_work", C.c_void_p),
+                ("fft_cfg", C.c_void_p)]
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/*.cu into libft8b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", PKG_DIR, "-j8"]
+    if force:
+        subprocess.check_call(["make", "-C", PKG_DIR, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libft8b200.so (building it if the .so is absent). Raises if it cannot be loaded."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.ft8b200_last_error.restype = C.c_char_p
+        L.ft8b200_version.restype = C.c_char_p
+        L.ft8b200_create.restype = C.c_void_p
+        L.ft8b200_create.argtypes = [C.c_void_p]
+        L.ft8b200_cuda_stream.restype = C.c_void_p
+        L.ft8b200_kernel_launches.restype = C.c_uint64
+        if hasattr(L, "ft8b200_stream_create"):
+            L.ft8b200_stream_create.restype = C.c_void_p
+            L.ft8b200_stream_count.restype = C.c_uint32
+        L.ft8_decode.restype = C.c_bool
+        for name in ("ft8b200_destroy", "ft8b200_cuda_stream", "ft8b200_sync", "ft8b200_kernel_launches", "ft8b200_stream_create",
+                     "ft8b200_stream_destroy", "ft8b200_stream_flip", "ft8b200_stream_count"):
+            if hasattr(L, name):
+                getattr(L, name).argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class Ft8Error(RuntimeError):
+    pass
+
+
+def _p(t):
+    """Device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One ft8b200_ctx_t on one device. All tensors passed in must live on that device and be contiguous."""
+
+    def __init__(self, device: int = 0, max_candidates: int = 120, max_messages: int = 50, min_score: int = 10, ldpc_iterations: int = 20):
+        self.L = lib()
+        self.cfg = Config(device, 1, max_candidates, max_messages, min_score, ldpc_iterations)
+        self.h = self.L.ft8b200_create(C.byref(self.cfg))
+        if not self.h:
+            raise Ft8Error(self.L.ft8b200_last_error().decode())
+        self.device = device
+        self.K = max_candidates
+        self.M = max_messages
+
+    def close(self):
+        if self.h:
+            self.L.ft8b200_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise Ft8Error(f"ft8b200 error {rc}: {self.L.ft8b200_last_error().decode()}")
+
+    def sync(self):
+        self._chk(self.L.ft8b200_sync(C.c_void_p(self.h)))
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self.L.ft8b200_cuda_stream(C.c_void_p(self.h)) or 0)
+
+    def launches(self) -> int:
+        return int(self.L.ft8b200_kernel_launches(C.c_void_p(self.h)))
+
+    # ---- stage-wise (device tensors) -------------------------------------------------------------
+    def decimate(self, iq, n_streams: int, bytes_per_stream: int, stride: int | None = None, want_y2: bool = False, stream: int = 0):
+        import torch
+        dev = iq.device
+        stride = bytes_per_stream if stride is None else stride
+        d_i = torch.empty((n_streams, N_SLOT), dtype=torch.float32, device=dev)
+        d_q = torch.empty_like(d_i)
+        cnt = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+        peak = torch.zeros(n_streams, dtype=torch.float32, device=dev)
+        y2 = torch.zeros((n_streams, N_SLOT, 2), dtype=torch.int32, device=dev) if want_y2 else None
+        self._chk(self.L.ft8b200_decimate(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_streams, _p(d_i), _p(d_q),
+                                          _p(cnt), _p(peak), _p(y2), C.c_void_p(stream)))
+        return d_i, d_q, cnt, peak, y2
+
+    def condition(self, d_i, d_q, peak, stream: int = 0):
+        self._chk(self.L.ft8b200_condition(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), d_i.shape[0], C.c_void_p(stream)))
+
+    def waterfall(self, d_i, d_q, peak=None, stream: int = 0):
+        import torch
+        n = d_i.shape[0]
+        mag = torch.empty((n, WF_BYTES), dtype=torch.uint8, device=d_i.device)
+        self._chk(self.L.ft8b200_waterfall(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), n, _p(mag), C.c_void_p(stream)))
+        return mag
+
+    def find_sync(self, mag, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, stream: int = 0):
+        import torch
+        n = mag.shape[0]
+        cand = torch.zeros((n, self.K, 8), dtype=torch.uint8, device=mag.device)
+        ncand = torch.zeros(n, dtype=torch.int32, device=mag.device)
+        self._chk(self.L.ft8b200_find_sync(C.c_void_p(self.h), _p(mag), C.c_size_t(mag.stride(0)), n, num_blocks, num_bins, time_osr, freq_osr,
+                                           _p(cand), _p(ncand), C.c_void_p(stream)))
+        return cand, ncand
+
+    def decode(self, mag, cand, ncand, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, want_plain=False, want_llr=False, stream: int = 0):
+        import torch
+        n = mag.shape[0]
+        dev = mag.device
+        ok = torch.zeros((n, self.K), dtype=torch.uint8, device=dev)
+        stage = torch.zeros((n, self.K), dtype=torch.uint8, device=dev)
+        status = torch.zeros((n, self.K, 12), dtype=torch.uint8, device=dev)
+        msg = torch.zeros((n, self.K, 28), dtype=torch.uint8, device=dev)
+        plain = torch.zeros((n, self.K, 174), dtype=torch.uint8, device=dev) if want_plain else None
+        llr = torch.zeros((n, self.K, 174), dtype=torch.float32, device=dev) if want_llr else None
+        self._chk(self.L.ft8b200_decode(C.c_void_p(self.h), _p(mag), C.c_size_t(mag.stride(0)), n, num_blocks, num_bins, time_osr, freq_osr,
+                                        _p(cand), _p(ncand), _p(ok), _p(stage), _p(status), _p(msg), _p(plain), _p(llr), C.c_void_p(stream)))
+        return ok, stage, status, msg, plain, llr
+
+    def spots(self, cand, ncand, ok, msg, freq_osr=2, want_log=True, stream: int = 0):
+        import torch
+        n = cand.shape[0]
+        dev = cand.device
+        res = torch.zeros((n, self.M, 28), dtype=torch.uint8, device=dev)
+        nres = torch.zeros(n, dtype=torch.int32, device=dev)
+        umsg = torch.zeros((n, self.M, 28), dtype=torch.uint8, device=dev) if want_log else None
+        ufreq = torch.zeros((n, self.M), dtype=torch.float32, device=dev) if want_log else None
+        uscore = torch.zeros((n, self.M), dtype=torch.int32, device=dev) if want_log else None
+        self._chk(self.L.ft8b200_spots(C.c_void_p(self.h), n, freq_osr, _p(cand), _p(ncand), _p(ok), _p(msg), _p(res), _p(nres), _p(umsg), _p(ufreq),
+                                       _p(uscore), C.c_void_p(stream)))
+        return res, nres, umsg, ufreq, uscore
+
+    # ---- whole path ----------------------------------------------------------------------------------
+    def process_raw(self, iq, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None, stream: int = 0):
+        stride = bytes_per_stream if stride is None else stride
+        self._chk(self.L.ft8b200_process_raw(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_slots, C.c_void_p(stream)))
+
+    def process_slots(self, d_i, d_q, stream: int = 0):
+        self._chk(self.L.ft8b200_process_slots(C.c_void_p(self.h), _p(d_i), _p(d_q), d_i.shape[0], C.c_void_p(stream)))
+
+    def fetch_results(self, n_slots: int, stream: int = 0):
+        res = np.zeros((n_slots, self.M), result_dtype)
+        nres = np.zeros(n_slots, np.int32)
+        self._chk(self.L.ft8b200_fetch_results(C.c_void_p(self.h), n_slots, _p(res), _p(nres), C.c_void_p(stream)))
+        return res, nres
+
+    def results_device_ptrs(self):
+        a, b = C.c_void_p(0), C.c_void_p(0)
+        self._chk(self.L.ft8b200_results_device(C.c_void_p(self.h), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def workspace_ptrs(self):
+        ptrs = [C.c_void_p(0) for _ in range(9)]
+        self._chk(self.L.ft8b200_workspace(C.c_void_p(self.h), *[C.byref(p) for p in ptrs]))
+        names = ("i", "q", "peak", "mag", "cand", "ncand", "ok", "status", "msg")
+        return {k: p.value for k, p in zip(names, ptrs)}
+
+    def process_raw_host(self, iq_host: np.ndarray, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES):
+        res = np.zeros((n_slots, self.M), result_dtype)
+        nres = np.zeros(n_slots, np.int32)
+        self._chk(self.L.ft8b200_process_raw_host(C.c_void_p(self.h), _p(iq_host), C.c_size_t(bytes_per_stream), n_slots, _p(res), _p(nres)))
+        return res, nres
+
+    def process_slots_host(self, i_host: np.ndarray, q_host: np.ndarray):
+        n = i_host.shape[0]
+        res = np.zeros((n, self.M), result_dtype)
+        nres = np.zeros(n, np.int32)
+        self._chk(self.L.ft8b200_process_slots_host(C.c_void_p(self.h), _p(i_host), _p(q_host), n, _p(res), _p(nres)))
+        return res, nres
+
+
+# ---- the reference-named drop-in entry points (host pointers) ---------------------------------------
+def ft8_subsystem(i_samples: np.ndarray, q_samples: np.ndarray, decodes: np.ndarray | None = None):
+    """ft8_subsystem(float*, float*, uint32_t, struct decoder_results*, int32_t*) on host arrays."""
+    L = lib()
+    i_s = np.ascontiguousarray(i_samples, np.float32)
+    q_s = np.ascontiguousarray(q_samples, np.float32)
+    if decodes is None:
+        decodes = np.zeros(50, result_dtype)
+    n = C.c_int32(0)
+    L.ft8_subsystem(_p(i_s), _p(q_s), C.c_uint32(N_SLOT), _p(decodes), C.byref(n))
+    return decodes, n.value
+
+
+def ft8_find_sync(mag: np.ndarray, num_candidates=120, min_score=10, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, protocol=1):
+    L = lib()
+    mag = np.ascontiguousarray(mag, np.uint8)
+    wf = WaterfallT(num_blocks, num_blocks, num_bins, time_osr, freq_osr, mag.ctypes.data, time_osr * freq_osr * num_bins, protocol)
+    heap = np.zeros(num_candidates, cand_dtype)
+    n = L.ft8_find_sync(C.byref(wf), num_candidates, _p(heap), min_score)
+    return heap[:n]
+
+
+def ft8_decode(mag: np.ndarray, cand, max_iterations=20, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, protocol=1):
+    L = lib()
+    mag = np.ascontiguousarray(mag, np.uint8)
+    wf = WaterfallT(num_blocks, num_blocks, num_bins, time_osr, freq_osr, mag.ctypes.data, time_osr * freq_osr * num_bins, protocol)
+    c = np.array([cand], cand_dtype)
+    msg = np.zeros(1, msg_dtype)
+    st = np.frombuffer(bytes([0xA5]) * 12, status_dtype).copy()
+    ok = L.ft8_decode(C.byref(wf), _p(c), _p(msg), max_iterations, _p(st))
+    return bool(ok), msg[0], st[0]

@@ -1,0 +1,418 @@
+// api.cu -- the C ABI of libft8b200.so (include/ft8b200.h): contexts, workspaces, the batched device
+// entry points and the whole-path pipelines.  Host-side C++ only; every numeric step is a CUDA kernel
+// launched from here (decimator.cu, waterfall.cu, sync.cu, decode.cu).  No CPU fallback exists.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace ft8b200;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return FT8B200_ECUDA;
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        bytes = need;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+}  // namespace
+
+struct ft8b200_ctx {
+    ft8b200_config_t cfg;
+    cudaStream_t stream = nullptr;
+    DeviceTables tb = {};
+    int launches = 0;
+    uint64_t launches_total = 0;
+    int sm_count = 0;
+    // workspaces (grown on demand)
+    DevBuf raw, sums, si, sq, peak, count, mag, cand, ncand, ok, stage, status, msg, results, nresults, table, scratch;
+    int scratch_slots = 0;
+    int scratch_npos = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+int ctx_enter(ft8b200_ctx_t *ctx) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    cudaError_t e = cudaSetDevice(ctx->cfg.device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return 0;
+}
+cudaStream_t pick(ft8b200_ctx_t *ctx, void *stream) { return stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream; }
+void tally(ft8b200_ctx_t *ctx) {
+    ctx->launches_total += (uint64_t)ctx->launches;
+    ctx->launches = 0;
+}
+
+int ensure_slot_buffers(ft8b200_ctx_t *ctx, int n_slots) {
+    const size_t K = (size_t)ctx->cfg.max_candidates, M = (size_t)ctx->cfg.max_messages, S = (size_t)n_slots;
+    int rc;
+    if ((rc = ctx->mag.ensure(S * kWfBytes))) return rc;
+    if ((rc = ctx->cand.ensure(S * K * sizeof(candidate_t)))) return rc;
+    if ((rc = ctx->ncand.ensure(S * sizeof(int)))) return rc;
+    if ((rc = ctx->ok.ensure(S * K))) return rc;
+    if ((rc = ctx->stage.ensure(S * K))) return rc;
+    if ((rc = ctx->status.ensure(S * K * sizeof(decode_status_t)))) return rc;
+    if ((rc = ctx->msg.ensure(S * K * sizeof(message_t)))) return rc;
+    if ((rc = ctx->results.ensure(S * M * sizeof(struct decoder_results)))) return rc;
+    if ((rc = ctx->nresults.ensure(S * sizeof(int32_t)))) return rc;
+    if ((rc = ctx->table.ensure(S * M * sizeof(int16_t)))) return rc;
+    return 0;
+}
+
+int ensure_scratch(ft8b200_ctx_t *ctx, int npos, int n_slots) {
+    // one compaction list per resident CTA of the sync kernel (it loops over slots)
+    int want = ctx->sm_count * 2;
+    if (want > n_slots) want = n_slots;
+    if (want < 1) want = 1;
+    if (npos > ctx->scratch_npos || want > ctx->scratch_slots) {
+        const int slots = want > ctx->scratch_slots ? want : ctx->scratch_slots;
+        const int np = npos > ctx->scratch_npos ? npos : ctx->scratch_npos;
+        int rc = ctx->scratch.ensure((size_t)slots * np * sizeof(uint32_t));
+        if (rc) return rc;
+        ctx->scratch_slots = slots;
+        ctx->scratch_npos = np;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ft8b200_last_error(void) { return g_err.c_str(); }
+const char *ft8b200_version(void) { return "ft8b200 0.1 (sm_100a)"; }
+
+void ft8b200_default_config(ft8b200_config_t *cfg) {
+    if (!cfg) return;
+    cfg->device = 0;
+    cfg->max_slots = 1;
+    cfg->max_candidates = 120;  // K_MAX_CANDIDATES, rtlsdr_ft8d.h:46
+    cfg->max_messages = 50;     // K_MAX_MESSAGES,   rtlsdr_ft8d.h:48
+    cfg->min_score = 10;        // K_MIN_SCORE,      rtlsdr_ft8d.h:45
+    cfg->ldpc_iterations = 20;  // K_LDPC_ITERS,     rtlsdr_ft8d.h:47
+}
+
+ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg_in) {
+    ft8b200_config_t cfg;
+    ft8b200_default_config(&cfg);
+    if (cfg_in) cfg = *cfg_in;
+    if (cfg.max_candidates < 1 || cfg.max_candidates > 30000 || cfg.max_messages < 1 || cfg.max_messages > 30000 || cfg.ldpc_iterations < 0) {
+        fail(FT8B200_EINVAL, "bad configuration");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                " (libft8b200 has no CPU fallback)";
+        return nullptr;
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) {
+        fail(FT8B200_EINVAL, "device ordinal out of range");
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg.device)) != cudaSuccess) { cuda_fail(e, "cudaGetDeviceProperties"); return nullptr; }
+    if (prop.major != 10) {
+        g_err = "device " + std::to_string(cfg.device) + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                "; libft8b200 is built for sm_100a only and has no fallback";
+        return nullptr;
+    }
+    if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) { cuda_fail(e, "cudaSetDevice"); return nullptr; }
+    ft8b200_ctx_t *ctx = new ft8b200_ctx();
+    ctx->cfg = cfg;
+    ctx->sm_count = prop.multiProcessorCount;
+    bool okc = true;
+    okc = okc && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    // tables, built with the host libm exactly as the reference builds them
+    std::vector<float> win(kNfft), thr(257), fir(kFirTaps);
+    std::vector<float2> tw(kNfft);
+    build_window1024(win.data());
+    build_twiddles(kNfft, tw.data());
+    build_db_thresholds(thr.data());
+    build_fir(fir.data());
+    okc = okc && cudaMalloc(&ctx->tb.window1024, kNfft * sizeof(float)) == cudaSuccess;
+    okc = okc && cudaMalloc(&ctx->tb.twiddle1024, kNfft * sizeof(float2)) == cudaSuccess;
+    okc = okc && cudaMalloc(&ctx->tb.db_thresholds, 257 * sizeof(float)) == cudaSuccess;
+    okc = okc && cudaMalloc(&ctx->tb.fir, kFirTaps * sizeof(float)) == cudaSuccess;
+    okc = okc && cudaMemcpy(ctx->tb.window1024, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    okc = okc && cudaMemcpy(ctx->tb.twiddle1024, tw.data(), kNfft * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+    okc = okc && cudaMemcpy(ctx->tb.db_thresholds, thr.data(), 257 * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    okc = okc && cudaMemcpy(ctx->tb.fir, fir.data(), kFirTaps * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    okc = okc && upload_ldpc_tables() == cudaSuccess;
+    if (!okc) {
+        cuda_fail(cudaGetLastError(), "context initialisation");
+        ft8b200_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+void ft8b200_destroy(ft8b200_ctx_t *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.fir);
+    cudaFree(ctx->tb.mon_window); cudaFree(ctx->tb.mon_twiddle); cudaFree(ctx->tb.mon_super);
+    DevBuf *bufs[] = {&ctx->raw, &ctx->sums, &ctx->si, &ctx->sq, &ctx->peak, &ctx->count, &ctx->mag, &ctx->cand, &ctx->ncand, &ctx->ok,
+                      &ctx->stage, &ctx->status, &ctx->msg, &ctx->results, &ctx->nresults, &ctx->table, &ctx->scratch};
+    for (DevBuf *b : bufs) b->release();
+    delete ctx;
+}
+
+void *ft8b200_cuda_stream(ft8b200_ctx_t *ctx) { return ctx ? ctx->stream : nullptr; }
+int ft8b200_sync(ft8b200_ctx_t *ctx) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+uint64_t ft8b200_kernel_launches(ft8b200_ctx_t *ctx) { return ctx ? ctx->launches_total : 0; }
+
+int ft8b200_decimate(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams, float *d_i,
+                     float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!d_iq || !d_i || !d_q || n_streams < 1) return fail(FT8B200_EINVAL, "ft8b200_decimate: null buffer or n_streams < 1");
+    if ((bytes_per_stream & 7) || (stream_stride_bytes & 15) || (((size_t)d_iq) & 15))
+        return fail(FT8B200_EINVAL, "ft8b200_decimate: byte counts must be multiples of 8, stream stride and base 16-byte aligned");
+    const int blocks = (int)((bytes_per_stream / 2) / kDecim);
+    // the 128-bit loads of the last super-block may read up to 14 bytes past the last complete block
+    if ((size_t)(blocks / 8) * 12016 > bytes_per_stream) return fail(FT8B200_EINVAL, "internal: super-block overrun");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = pick(ctx, stream);
+    if ((rc = ctx->sums.ensure((size_t)n_streams * (blocks > 0 ? blocks : 1) * sizeof(BlockSums)))) return rc;
+    if (d_peak) CU(cudaMemsetAsync(d_peak, 0, sizeof(float) * n_streams, st));
+    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_streams, blocks, ctx->sums.as<BlockSums>(), st, &ctx->launches));
+    CU(launch_cic_comb_fir(ctx->sums.as<BlockSums>(), blocks, n_streams, ctx->tb.fir, d_i, d_q, d_count, d_peak, d_y2, st, &ctx->launches));
+    tally(ctx);
+    return 0;
+}
+
+int ft8b200_condition(ft8b200_ctx_t *ctx, float *d_i, float *d_q, const float *d_peak, int n_slots, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!d_i || !d_q || !d_peak || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_condition: bad argument");
+    CU(launch_condition(d_i, d_q, d_peak, n_slots, pick(ctx, stream), &ctx->launches));
+    tally(ctx);
+    return 0;
+}
+
+int ft8b200_waterfall(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, const float *d_peak, int n_slots, uint8_t *d_mag, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!d_i || !d_q || !d_mag || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_waterfall: bad argument");
+    if (((size_t)d_mag) & 15) return fail(FT8B200_EINVAL, "ft8b200_waterfall: d_mag must be 16-byte aligned");
+    CU(launch_waterfall(ctx->tb, d_i, d_q, d_peak, n_slots, d_mag, pick(ctx, stream), &ctx->launches));
+    tally(ctx);
+    return 0;
+}
+
+int ft8b200_find_sync(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins, int time_osr,
+                      int freq_osr, candidate_t *d_cand, int *d_ncand, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!d_mag || !d_cand || !d_ncand || n_slots < 1 || num_blocks < 1 || num_bins < 8 || time_osr < 1 || freq_osr < 1)
+        return fail(FT8B200_EINVAL, "ft8b200_find_sync: bad argument");
+    const long npos = (long)time_osr * freq_osr * 36 * (num_bins - 7);
+    if (npos >= (1l << 20)) return fail(FT8B200_EINVAL, "ft8b200_find_sync: waterfall too large (position index exceeds 20 bits)");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = ensure_scratch(ctx, (int)npos, n_slots))) return rc;
+    CU(launch_find_sync(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->cfg.max_candidates, ctx->cfg.min_score,
+                        d_cand, d_ncand, ctx->scratch.as<uint32_t>(), ctx->scratch_slots, pick(ctx, stream), &ctx->launches));
+    tally(ctx);
+    return 0;
+}
+
+int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins, int time_osr,
+                   int freq_osr, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage, decode_status_t *d_status,
+                   message_t *d_msg, uint8_t *d_plain, float *d_llr, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!d_mag || !d_cand || !d_ncand || !d_ok || !d_stage || !d_status || !d_msg || n_slots < 1)
+        return fail(FT8B200_EINVAL, "ft8b200_decode: bad argument");
+    CU(launch_decode(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
+                     d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, pick(ctx, stream), &ctx->launches));
+    tally(ctx);
+    return 0;
+}
+
+int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate_t *d_cand, const int *d_ncand, const uint8_t *d_ok,
+                  const message_t *d_msg, struct decoder_results *d_results, int32_t *d_nresults, message_t *d_umsg, float *d_ufreq,
+                  int32_t *d_uscore, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!d_cand || !d_ncand || !d_ok || !d_msg || !d_results || !d_nresults || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_spots: bad argument");
+    if (d_umsg && (!d_ufreq || !d_uscore)) return fail(FT8B200_EINVAL, "ft8b200_spots: d_umsg needs d_ufreq and d_uscore");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = ctx->table.ensure((size_t)n_slots * ctx->cfg.max_messages * sizeof(int16_t)))) return rc;
+    CU(launch_spots(n_slots, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, freq_osr, d_cand, d_ncand, d_ok, d_msg, d_results,
+                    d_nresults, d_umsg, d_ufreq, d_uscore, ctx->table.as<int16_t>(), pick(ctx, stream), &ctx->launches));
+    tally(ctx);
+    return 0;
+}
+
+// waterfall (already in ctx->mag or produced here) -> sync -> decode -> spots, all on `st`
+static int run_back_end(ft8b200_ctx_t *ctx, int n_slots, cudaStream_t st) {
+    int rc;
+    const int npos = 2 * 2 * 36 * (256 - 7);
+    if ((rc = ensure_scratch(ctx, npos, n_slots))) return rc;
+    CU(launch_find_sync(ctx->mag.as<uint8_t>(), kWfBytes, n_slots, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.min_score,
+                        ctx->cand.as<candidate_t>(), ctx->ncand.as<int>(), ctx->scratch.as<uint32_t>(), ctx->scratch_slots, st, &ctx->launches));
+    CU(launch_decode(ctx->mag.as<uint8_t>(), kWfBytes, n_slots, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
+                     ctx->cand.as<candidate_t>(), ctx->ncand.as<int>(), ctx->ok.as<uint8_t>(), ctx->stage.as<uint8_t>(),
+                     ctx->status.as<decode_status_t>(), ctx->msg.as<message_t>(), nullptr, nullptr, st, &ctx->launches));
+    CU(launch_spots(n_slots, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, 2, ctx->cand.as<candidate_t>(),
+                    ctx->ncand.as<int>(), ctx->ok.as<uint8_t>(), ctx->msg.as<message_t>(), ctx->results.as<struct decoder_results>(),
+                    ctx->nresults.as<int32_t>(), nullptr, nullptr, nullptr, ctx->table.as<int16_t>(), st, &ctx->launches));
+    return 0;
+}
+
+int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!d_iq || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_process_raw: bad argument");
+    if ((bytes_per_stream & 7) || (stream_stride_bytes & 15) || (((size_t)d_iq) & 15))
+        return fail(FT8B200_EINVAL, "ft8b200_process_raw: byte counts must be multiples of 8, stream stride and base 16-byte aligned");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = pick(ctx, stream);
+    const int blocks = (int)((bytes_per_stream / 2) / kDecim);
+    if ((rc = ensure_slot_buffers(ctx, n_slots))) return rc;
+    if ((rc = ctx->sums.ensure((size_t)n_slots * (blocks > 0 ? blocks : 1) * sizeof(BlockSums)))) return rc;
+    if ((rc = ctx->si.ensure((size_t)n_slots * kSlot * sizeof(float)))) return rc;
+    if ((rc = ctx->sq.ensure((size_t)n_slots * kSlot * sizeof(float)))) return rc;
+    if ((rc = ctx->peak.ensure((size_t)n_slots * sizeof(float)))) return rc;
+    if ((rc = ctx->count.ensure((size_t)n_slots * sizeof(uint32_t)))) return rc;
+    CU(cudaMemsetAsync(ctx->peak.p, 0, sizeof(float) * n_slots, st));
+    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_slots, blocks, ctx->sums.as<BlockSums>(), st, &ctx->launches));
+    CU(launch_cic_comb_fir(ctx->sums.as<BlockSums>(), blocks, n_slots, ctx->tb.fir, ctx->si.as<float>(), ctx->sq.as<float>(),
+                           ctx->count.as<uint32_t>(), ctx->peak.as<float>(), nullptr, st, &ctx->launches));
+    // decoder()'s normalisation is applied on load inside the waterfall kernel (scale from the slot peak)
+    CU(launch_waterfall(ctx->tb, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), n_slots, ctx->mag.as<uint8_t>(), st, &ctx->launches));
+    rc = run_back_end(ctx, n_slots, st);
+    tally(ctx);
+    return rc;
+}
+
+int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, int n_slots, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!d_i || !d_q || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_process_slots: bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = pick(ctx, stream);
+    if ((rc = ensure_slot_buffers(ctx, n_slots))) return rc;
+    CU(launch_waterfall(ctx->tb, d_i, d_q, nullptr, n_slots, ctx->mag.as<uint8_t>(), st, &ctx->launches));
+    rc = run_back_end(ctx, n_slots, st);
+    tally(ctx);
+    return rc;
+}
+
+int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    if (d_results) *d_results = ctx->results.as<struct decoder_results>();
+    if (d_nresults) *d_nresults = ctx->nresults.as<int32_t>();
+    return 0;
+}
+
+int ft8b200_fetch_results(ft8b200_ctx_t *ctx, int n_slots, struct decoder_results *h_results, int32_t *h_nresults, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!h_results || !h_nresults || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_fetch_results: bad argument");
+    cudaStream_t st = pick(ctx, stream);
+    const size_t M = (size_t)ctx->cfg.max_messages;
+    if (ctx->results.bytes < (size_t)n_slots * M * sizeof(struct decoder_results)) return fail(FT8B200_EINVAL, "ft8b200_fetch_results: no such batch");
+    CU(cudaMemcpyAsync(h_results, ctx->results.p, (size_t)n_slots * M * sizeof(struct decoder_results), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_nresults, ctx->nresults.p, (size_t)n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ft8b200_workspace(ft8b200_ctx_t *ctx, float **d_i, float **d_q, float **d_peak, uint8_t **d_mag, candidate_t **d_cand, int **d_ncand,
+                      uint8_t **d_ok, decode_status_t **d_status, message_t **d_msg) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    if (d_i) *d_i = ctx->si.as<float>();
+    if (d_q) *d_q = ctx->sq.as<float>();
+    if (d_peak) *d_peak = ctx->peak.as<float>();
+    if (d_mag) *d_mag = ctx->mag.as<uint8_t>();
+    if (d_cand) *d_cand = ctx->cand.as<candidate_t>();
+    if (d_ncand) *d_ncand = ctx->ncand.as<int>();
+    if (d_ok) *d_ok = ctx->ok.as<uint8_t>();
+    if (d_status) *d_status = ctx->status.as<decode_status_t>();
+    if (d_msg) *d_msg = ctx->msg.as<message_t>();
+    return 0;
+}
+
+int ft8b200_process_raw_host(ft8b200_ctx_t *ctx, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots, struct decoder_results *h_results,
+                             int32_t *h_nresults) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!h_iq || n_slots < 1 || (bytes_per_stream & 7)) return fail(FT8B200_EINVAL, "ft8b200_process_raw_host: bad argument");
+    const size_t stride = (bytes_per_stream + 15) & ~(size_t)15;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if ((rc = ctx->raw.ensure(stride * n_slots + 16))) return rc;
+    }
+    if (stride == bytes_per_stream) {
+        CU(cudaMemcpyAsync(ctx->raw.p, h_iq, bytes_per_stream * n_slots, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CU(cudaMemcpy2DAsync(ctx->raw.p, stride, h_iq, bytes_per_stream, bytes_per_stream, n_slots, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = ft8b200_process_raw(ctx, ctx->raw.as<uint8_t>(), bytes_per_stream, stride, n_slots, nullptr))) return rc;
+    return ft8b200_fetch_results(ctx, n_slots, h_results, h_nresults, nullptr);
+}
+
+int ft8b200_process_slots_host(ft8b200_ctx_t *ctx, const float *h_i, const float *h_q, int n_slots, struct decoder_results *h_results,
+                               int32_t *h_nresults) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!h_i || !h_q || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_process_slots_host: bad argument");
+    const size_t bytes = (size_t)n_slots * kSlot * sizeof(float);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if ((rc = ctx->si.ensure(bytes))) return rc;
+        if ((rc = ctx->sq.ensure(bytes))) return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->si.p, h_i, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->sq.p, h_q, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ft8b200_process_slots(ctx, ctx->si.as<float>(), ctx->sq.as<float>(), n_slots, nullptr))) return rc;
+    return ft8b200_fetch_results(ctx, n_slots, h_results, h_nresults, nullptr);
+}
+
+}  // extern "C"

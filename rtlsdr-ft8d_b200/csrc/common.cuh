@@ -1,0 +1,63 @@
+// common.cuh -- internal declarations shared by the kernels and the C-ABI layer of libft8b200.so.
+// Nothing in csrc/ includes, links or calls anything under oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/ft8b200.h"
+
+namespace ft8b200 {
+
+constexpr int kSlot = FT8B200_SLOT_SAMPLES;  // 48000
+constexpr int kDecim = FT8B200_DECIM;        // 751
+constexpr int kWfBytes = FT8B200_WF_BYTES;   // 94208
+constexpr int kNfft = 1024;
+constexpr int kFrames = 184;                 // 92 blocks x 2 time subdivisions
+constexpr int kFirTaps = 57;
+constexpr int kLdpcN = 174, kLdpcK = 91, kLdpcM = 83, kLdpcEdges = 522;
+
+// per 751-sample block: sum s, sum i*s for the I and Q rails after the fs/4 mixer (int32, wrapping)
+struct __align__(16) BlockSums { int32_t s0i, s1i, s0q, s1q; };
+
+// ---- tables uploaded once per context (built on the host with the host libm, see tables.cu) ----
+struct DeviceTables {
+    float *window1024;     // sinf((float)((M_PI/1024)*i))               rtlsdr_ft8d.c:331-334
+    float2 *twiddle1024;   // ((float)cos, (float)sin)(-2*pi*k/1024)      kiss_fft.c:351-357
+    float *db_thresholds;  // [257] smallest x with quantise(x) >= k       rtlsdr_ft8d.c:1416,1425-1427
+    float *fir;            // [57]                                          rtlsdr_ft8d.c:93-110
+    // monitor (12 kHz) tables, built lazily per nfft
+    float *mon_window;     // fft_norm-free Hann, nfft floats
+    float2 *mon_twiddle;   // nfft/2 complex twiddles
+    float2 *mon_super;     // nfft/4 "super twiddles" of kiss_fftr
+    int mon_nfft;
+};
+
+// ---- launchers (each returns cudaGetLastError()) ----
+cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int blocks_per_stream,
+                                  BlockSums *d_sums, cudaStream_t st, int *launches);
+cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int first_block, int n_blocks,
+                                          int blocks_per_stream, BlockSums *d_sums, cudaStream_t st, int *launches);
+cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, int blocks_per_stream, int n_streams, const float *d_fir, float *d_i, float *d_q,
+                                uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st, int *launches);
+cudaError_t launch_condition(float *d_i, float *d_q, const float *d_peak, int n_slots, cudaStream_t st, int *launches);
+cudaError_t launch_waterfall(const DeviceTables &t, const float *d_i, const float *d_q, const float *d_peak, int n_slots, uint8_t *d_mag,
+                             cudaStream_t st, int *launches);
+cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
+                             int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, uint32_t *d_scratch, int scratch_slots,
+                             cudaStream_t st, int *launches);
+cudaError_t launch_decode(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
+                          int max_cand, int max_iters, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage,
+                          decode_status_t *d_status, message_t *d_msg, uint8_t *d_plain, float *d_llr, cudaStream_t st, int *launches);
+cudaError_t launch_spots(int n_slots, int max_cand, int max_msgs, int min_score, int freq_osr, const candidate_t *d_cand, const int *d_ncand,
+                         const uint8_t *d_ok, const message_t *d_msg, struct decoder_results *d_results, int32_t *d_nresults,
+                         message_t *d_umsg, float *d_ufreq, int32_t *d_uscore, int16_t *d_table, cudaStream_t st, int *launches);
+cudaError_t upload_ldpc_tables();
+
+// host-side table builders (tables.cu)
+void build_window1024(float *w);
+void build_twiddles(int n, float2 *tw);
+void build_db_thresholds(float *t257);
+void build_fir(float *z57);
+
+}  // namespace ft8b200

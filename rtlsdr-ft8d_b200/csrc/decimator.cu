@@ -1,0 +1,380 @@
+// decimator.cu -- uint8 IQ @ 2.4 Msps -> float I/Q @ 3200 sps (fs/4 mixer, CIC N=2 R=751 M=2, 57-tap FIR).
+// Replaces rtlsdr_callback(), /root/reference/rtlsdr_ft8d.c:76-202, for whole batches of streams.
+//
+// Design (B200-first, not a translation of the sample-by-sample loop):
+//   The two integrators + two combs of the reference are, exactly and in wrapping int32 arithmetic,
+//   a 3003-tap triangular FIR sampled every 751 inputs.  Splitting the input
+//   into 751-sample blocks b with S0_b = sum s, S1_b = sum i*s (i = index inside the block):
+//       y2[k] = (751*S0_k - S1_k) + (1502*S0_{k-1} - S1_{k-1}) + (751*S0_{k-2} + S1_{k-2}) + S1_{k-3}
+//   so the only pass over the 72 MB/slot input is a streaming reduction (kernel 1, HBM-bound:
+//   2 B/sample in, 16 B/751 samples out), and everything order-sensitive (the float FIR, the
+//   double-precision scale) happens on the 751x smaller block-sum array (kernel 2).
+//
+//   Kernel 1 maps one warp to one "super-block" of 8 blocks = 6008 samples = 12016 B = exactly 751
+//   16-byte chunks, so every lane issues aligned, fully coalesced 128-bit loads and the block layout
+//   inside a super-block is a compile-time constant (the 24 warp-iterations are fully unrolled).
+//   The mixer (multiply sample n by j^n, with the reference's wrapping int8 negate: -(-128) == -128)
+//   is done four bytes at a time: bytes are regrouped by PRMT into {I-rail plain, I-rail negated,
+//   Q-rail plain, Q-rail negated} words, the negated words get a carry-free per-byte two's-complement
+//   (3 ALU ops), and S0/S1 partial sums are DP4A dot products with constant weight words.  Values are
+//   kept as unsigned bytes v+128; the -128 offsets are constants per block.  Block totals are warp
+//   reductions (REDUX), one per finished block.  The 7 chunks per super-block that straddle a block
+//   boundary are first attributed whole to the earlier block and corrected afterwards by 7 lanes.
+#include "common.cuh"
+
+namespace ft8b200 {
+
+namespace {
+
+constexpr int kChunksPerSuper = 751;          // 16-byte chunks per super-block
+constexpr int kSuperBytes = 12016;            // 8 * 751 * 2
+constexpr int kIters = 24;                    // ceil(751 / 32)
+constexpr uint32_t kOnes = 0x01010101u;
+// sample index (0..7 inside the chunk) of each byte of the regrouped words
+constexpr uint32_t kW_IP = 0x07040300u;  // I rail, plain   : samples 0,3,4,7  (bytes I0,Q3,I4,Q7)
+constexpr uint32_t kW_IN = 0x06050201u;  // I rail, negated : samples 1,2,5,6  (bytes Q1,I2,Q5,I6)
+constexpr uint32_t kW_QP = 0x05040100u;  // Q rail, plain   : samples 0,1,4,5  (bytes Q0,I1,Q4,I5)
+constexpr uint32_t kW_QN = 0x07060302u;  // Q rail, negated : samples 2,3,6,7  (bytes Q2,I3,Q6,I7)
+constexpr uint32_t kOff0 = 128u * 751u;                 // sum of the +128 offsets over a block
+constexpr uint32_t kOff1 = 128u * (750u * 751u / 2u);   // sum of i*128
+
+struct Acc { uint32_t s0i, s1i, s0q, s1q; };
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// per-byte two's complement (mod 256) of all four bytes, no carries between bytes
+__device__ __forceinline__ uint32_t neg4(uint32_t u) { return (0x80808080u - (u & 0x7f7f7f7fu)) ^ (~u & 0x80808080u); }
+
+// regroup one 16-byte chunk (samples 0..7 as I0 Q0 I1 Q1 ...) into the four rail words
+__device__ __forceinline__ void regroup(const uint4 w, uint32_t &ip, uint32_t &in, uint32_t &qp, uint32_t &qn) {
+    qp = __byte_perm(w.x, w.z, 0x6521);                 // Q0 I1 Q4 I5
+    qn = neg4(__byte_perm(w.y, w.w, 0x6521));           // -(Q2 I3 Q6 I7)
+    const uint32_t t01 = __byte_perm(w.x, w.y, 0x4370); // I0 Q3 Q1 I2
+    const uint32_t t23 = __byte_perm(w.z, w.w, 0x4370); // I4 Q7 Q5 I6
+    ip = __byte_perm(t01, t23, 0x5410);                 // I0 Q3 I4 Q7
+    in = neg4(__byte_perm(t01, t23, 0x7632));           // -(Q1 I2 Q5 I6)
+}
+
+template <int K>
+struct IterInfo {
+    static constexpr int c0 = 32 * K;
+    static constexpr int nvalid = (kChunksPerSuper - c0) < 32 ? (kChunksPerSuper - c0) : 32;
+    static constexpr int bF = (8 * c0) / kDecim;                      // block of lane 0's chunk
+    static constexpr int bL = (8 * (c0 + nvalid - 1)) / kDecim;       // block of the last valid lane's chunk
+    static constexpr bool trans = (bL != bF);
+    static constexpr int Lk = trans ? ((kDecim * (bF + 1) - 1) / 8 - c0) : 31;  // last lane still in block bF
+    static constexpr int bN = (c0 + 32 < kChunksPerSuper) ? (8 * (c0 + 32)) / kDecim : 8;
+    static constexpr bool flush = (bN > bF);                          // block bF is complete after this iteration
+    static constexpr int ibase = 8 * c0 - kDecim * bF;                // in-block index of lane 0's first sample
+};
+
+template <int K>
+__device__ __forceinline__ uint4 load_chunk(const uint4 *base, int lane) {
+    using I = IterInfo<K>;
+    if (I::nvalid == 32 || lane < I::nvalid) return ldg_stream(base + I::c0 + lane);
+    return make_uint4(0u, 0u, 0u, 0u);  // contributes nothing to the unsigned sums
+}
+
+template <int K>
+__device__ __forceinline__ void process_chunk(const uint4 w, int lane, uint32_t lane8, Acc &A, Acc &B, uint4 *wsums) {
+    using I = IterInfo<K>;
+    uint32_t ip, in, qp, qn;
+    regroup(w, ip, in, qp, qn);
+    const uint32_t u0i = __dp4a(ip, kOnes, __dp4a(in, kOnes, 0u));
+    const uint32_t u0q = __dp4a(qp, kOnes, __dp4a(qn, kOnes, 0u));
+    if (!I::trans) {
+        const uint32_t i0 = lane8 + (uint32_t)I::ibase;
+        A.s0i += u0i;
+        A.s0q += u0q;
+        A.s1i = __dp4a(ip, kW_IP, __dp4a(in, kW_IN, A.s1i + i0 * u0i));
+        A.s1q = __dp4a(qp, kW_QP, __dp4a(qn, kW_QN, A.s1q + i0 * u0q));
+    } else {
+        const bool later = lane > I::Lk;  // this lane's chunk starts in block bF+1
+        const uint32_t i0 = lane8 + (uint32_t)I::ibase - (later ? (uint32_t)kDecim : 0u);
+        const uint32_t u1i = __dp4a(ip, kW_IP, __dp4a(in, kW_IN, i0 * u0i));
+        const uint32_t u1q = __dp4a(qp, kW_QP, __dp4a(qn, kW_QN, i0 * u0q));
+        if (later) { B.s0i += u0i; B.s0q += u0q; B.s1i += u1i; B.s1q += u1q; }
+        else       { A.s0i += u0i; A.s0q += u0q; A.s1i += u1i; A.s1q += u1q; }
+    }
+    if (I::flush) {
+        uint4 t;
+        t.x = __reduce_add_sync(0xffffffffu, A.s0i);
+        t.y = __reduce_add_sync(0xffffffffu, A.s1i);
+        t.z = __reduce_add_sync(0xffffffffu, A.s0q);
+        t.w = __reduce_add_sync(0xffffffffu, A.s1q);
+        if (lane == 0) wsums[I::bF] = t;
+        A = B;
+        B.s0i = B.s1i = B.s0q = B.s1q = 0u;
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void load_group(uint4 (&buf)[4], const uint4 *base, int lane) {
+    buf[0] = load_chunk<4 * G + 0>(base, lane);
+    buf[1] = load_chunk<4 * G + 1>(base, lane);
+    buf[2] = load_chunk<4 * G + 2>(base, lane);
+    buf[3] = load_chunk<4 * G + 3>(base, lane);
+}
+template <int G>
+__device__ __forceinline__ void process_group(const uint4 (&buf)[4], int lane, uint32_t lane8, Acc &A, Acc &B, uint4 *wsums) {
+    process_chunk<4 * G + 0>(buf[0], lane, lane8, A, B, wsums);
+    process_chunk<4 * G + 1>(buf[1], lane, lane8, A, B, wsums);
+    process_chunk<4 * G + 2>(buf[2], lane, lane8, A, B, wsums);
+    process_chunk<4 * G + 3>(buf[3], lane, lane8, A, B, wsums);
+}
+
+// byte masks (0xFF where the sample of that byte is >= t) for the four rail words, t = 1..7
+__device__ __forceinline__ uint32_t tail_mask(uint32_t sample_idx_word, uint32_t t) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if (((sample_idx_word >> (8 * b)) & 0xffu) >= t) m |= 0xffu << (8 * b);
+    return m;
+}
+
+constexpr int kWarpsPerCta = 8;
+
+// Kernel 1: block sums of full, 16-byte aligned super-blocks.  One warp per super-block.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+cic_block_sums_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int supers_per_stream, int blocks_per_stream,
+                      BlockSums *__restrict__ sums) {
+    __shared__ uint4 s_sums[kWarpsPerCta][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sb = blockIdx.x * kWarpsPerCta + warp;
+    if (sb >= supers_per_stream) return;  // whole warp leaves together
+    const int stream = blockIdx.y;
+    const uint4 *base = reinterpret_cast<const uint4 *>(iq + (size_t)stream * stream_stride_bytes + (size_t)sb * kSuperBytes);
+    uint4 *wsums = s_sums[warp];
+    const uint32_t lane8 = 8u * (uint32_t)lane;
+
+    Acc A = {0u, 0u, 0u, 0u}, B = {0u, 0u, 0u, 0u};
+    uint4 b0[4], b1[4];
+    load_group<0>(b0, base, lane);
+    load_group<1>(b1, base, lane);
+    process_group<0>(b0, lane, lane8, A, B, wsums);
+    load_group<2>(b0, base, lane);
+    process_group<1>(b1, lane, lane8, A, B, wsums);
+    load_group<3>(b1, base, lane);
+    process_group<2>(b0, lane, lane8, A, B, wsums);
+    load_group<4>(b0, base, lane);
+    process_group<3>(b1, lane, lane8, A, B, wsums);
+    load_group<5>(b1, base, lane);
+    process_group<4>(b0, lane, lane8, A, B, wsums);
+    process_group<5>(b1, lane, lane8, A, B, wsums);
+    __syncwarp();
+
+    // Boundary fix-up: the chunk holding sample 751*beta (beta = 1..7) was summed whole into block
+    // beta-1 with in-block indices >= 751; move its tail (samples t >= t*) into block beta.
+    uint32_t t0i = 0, t1i = 0, t0q = 0, t1q = 0, tstar = 0;
+    if (lane < 7) {
+        const uint32_t beta = (uint32_t)lane + 1u;
+        const uint32_t cstar = (kDecim * beta) >> 3;
+        tstar = kDecim * beta - 8u * cstar;  // = 8 - beta, never 0 for beta < 8
+        const uint4 w = ldg_stream(base + cstar);
+        uint32_t ip, in, qp, qn;
+        regroup(w, ip, in, qp, qn);
+        const uint32_t mip = tail_mask(kW_IP, tstar), min_ = tail_mask(kW_IN, tstar);
+        const uint32_t mqp = tail_mask(kW_QP, tstar), mqn = tail_mask(kW_QN, tstar);
+        t0i = __dp4a(ip, kOnes & mip, __dp4a(in, kOnes & min_, 0u));
+        t1i = __dp4a(ip, kW_IP & mip, __dp4a(in, kW_IN & min_, 0u));
+        t0q = __dp4a(qp, kOnes & mqp, __dp4a(qn, kOnes & mqn, 0u));
+        t1q = __dp4a(qp, kW_QP & mqp, __dp4a(qn, kW_QN & mqn, 0u));
+        // leave block beta-1: those samples carried index (751 - t*) + t
+        uint4 v = wsums[lane];
+        const uint32_t ib = (uint32_t)kDecim - tstar;
+        v.x -= t0i; v.y -= ib * t0i + t1i; v.z -= t0q; v.w -= ib * t0q + t1q;
+        wsums[lane] = v;
+    }
+    __syncwarp();
+    if (lane < 7) {  // enter block beta with index t - t*
+        uint4 v = wsums[lane + 1];
+        v.x += t0i; v.y += t1i - tstar * t0i; v.z += t0q; v.w += t1q - tstar * t0q;
+        wsums[lane + 1] = v;
+    }
+    __syncwarp();
+    if (lane < 8) {
+        const uint4 v = wsums[lane];
+        BlockSums o;
+        o.s0i = (int32_t)(v.x - kOff0); o.s1i = (int32_t)(v.y - kOff1);
+        o.s0q = (int32_t)(v.z - kOff0); o.s1q = (int32_t)(v.w - kOff1);
+        sums[(size_t)stream * blocks_per_stream + (size_t)sb * 8 + lane] = o;
+    }
+}
+
+// Generic block sums: one warp per 751-sample block, 2-byte loads, any block range / alignment.
+// Used for the blocks a stream has beyond its last full super-block and as an in-library cross-check.
+__global__ void __launch_bounds__(256)
+cic_block_sums_generic_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int first_block, int n_blocks,
+                              int blocks_per_stream, BlockSums *__restrict__ sums) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rel = blockIdx.x * 8 + warp;
+    if (rel >= n_blocks) return;
+    const int blk = first_block + rel;
+    const int stream = blockIdx.y;
+    const uchar2 *p = reinterpret_cast<const uchar2 *>(iq + (size_t)stream * stream_stride_bytes) + (size_t)blk * kDecim;
+    const uint32_t phase0 = (uint32_t)(((size_t)blk * kDecim) & 3u);
+    uint32_t s0i = 0, s1i = 0, s0q = 0, s1q = 0;
+    for (uint32_t i = lane; i < (uint32_t)kDecim; i += 32) {
+        const uchar2 v = p[i];
+        const uint32_t a = v.x, b = v.y;
+        const uint32_t na = (0u - a) & 0xffu, nb = (0u - b) & 0xffu;  // wrapping int8 negate, offset-128 domain
+        uint32_t mi, mq;
+        switch ((phase0 + i) & 3u) {
+        case 0: mi = a; mq = b; break;
+        case 1: mi = nb; mq = a; break;
+        case 2: mi = na; mq = nb; break;
+        default: mi = b; mq = na; break;
+        }
+        s0i += mi; s1i += i * mi; s0q += mq; s1q += i * mq;
+    }
+    s0i = __reduce_add_sync(0xffffffffu, s0i);
+    s1i = __reduce_add_sync(0xffffffffu, s1i);
+    s0q = __reduce_add_sync(0xffffffffu, s0q);
+    s1q = __reduce_add_sync(0xffffffffu, s1q);
+    if (lane == 0) {
+        BlockSums o;
+        o.s0i = (int32_t)(s0i - kOff0); o.s1i = (int32_t)(s1i - kOff1);
+        o.s0q = (int32_t)(s0q - kOff0); o.s1q = (int32_t)(s1q - kOff1);
+        sums[(size_t)stream * blocks_per_stream + blk] = o;
+    }
+}
+
+// Kernel 2: comb (closed form over 4 consecutive block sums) + 57-tap FIR + scale + peak.
+// ref: rtlsdr_ft8d.c:162-200.  One CTA = 256 consecutive outputs of one stream.
+constexpr int kTile = 256;
+constexpr int kHist = kFirTaps - 1;  // 56
+
+__device__ __forceinline__ void comb(const BlockSums *__restrict__ s, int k, int32_t &yi, int32_t &yq) {
+    // y2[k] from blocks k-3..k; blocks before the start of the stream are zero (fresh filter state)
+    uint32_t ai = 0, aq = 0;
+    {
+        const BlockSums b = s[k];
+        ai += 751u * (uint32_t)b.s0i - (uint32_t)b.s1i;
+        aq += 751u * (uint32_t)b.s0q - (uint32_t)b.s1q;
+    }
+    if (k >= 1) {
+        const BlockSums b = s[k - 1];
+        ai += 1502u * (uint32_t)b.s0i - (uint32_t)b.s1i;
+        aq += 1502u * (uint32_t)b.s0q - (uint32_t)b.s1q;
+    }
+    if (k >= 2) {
+        const BlockSums b = s[k - 2];
+        ai += 751u * (uint32_t)b.s0i + (uint32_t)b.s1i;
+        aq += 751u * (uint32_t)b.s0q + (uint32_t)b.s1q;
+    }
+    if (k >= 3) {
+        const BlockSums b = s[k - 3];
+        ai += (uint32_t)b.s1i;
+        aq += (uint32_t)b.s1q;
+    }
+    yi = (int32_t)ai;
+    yq = (int32_t)aq;
+}
+
+__global__ void __launch_bounds__(kTile)
+cic_comb_fir_kernel(const BlockSums *__restrict__ sums, int blocks_per_stream, const float *__restrict__ fir, float *__restrict__ out_i,
+                    float *__restrict__ out_q, uint32_t *__restrict__ count, float *__restrict__ peak, int32_t *__restrict__ y2_out) {
+    __shared__ float s_yi[kTile + kHist], s_yq[kTile + kHist];
+    __shared__ float s_fir[kFirTaps];
+    const int stream = blockIdx.y;
+    const int k0 = blockIdx.x * kTile;
+    const BlockSums *s = sums + (size_t)stream * blocks_per_stream;
+    const int n_out = blocks_per_stream < kSlot ? blocks_per_stream : kSlot;
+    if (threadIdx.x < kFirTaps) s_fir[threadIdx.x] = fir[threadIdx.x];
+    for (int idx = threadIdx.x; idx < kTile + kHist; idx += kTile) {
+        const int k = k0 - kHist + idx;
+        int32_t yi = 0, yq = 0;
+        if (k >= 0 && k < blocks_per_stream) comb(s, k, yi, yq);
+        s_yi[idx] = __int2float_rn(yi);  // (float)Iy2, rtlsdr_ft8d.c:189-190
+        s_yq[idx] = __int2float_rn(yq);
+        if (y2_out && k >= k0 && k < n_out) {
+            y2_out[((size_t)stream * kSlot + k) * 2 + 0] = yi;
+            y2_out[((size_t)stream * kSlot + k) * 2 + 1] = yq;
+        }
+    }
+    __syncthreads();
+    const int k = k0 + threadIdx.x;
+    float vi = 0.0f, vq = 0.0f;
+    if (k < n_out) {
+        float ai = 0.0f, aq = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kFirTaps; ++j) {  // strictly sequential, product rounded before the add (no FMA)
+            ai = __fadd_rn(ai, __fmul_rn(s_yi[threadIdx.x + j], s_fir[j]));
+            aq = __fadd_rn(aq, __fmul_rn(s_yq[threadIdx.x + j], s_fir[j]));
+        }
+        vi = __double2float_rn(__ddiv_rn((double)ai, 32768.0 * 750));  // rtlsdr_ft8d.c:197-198
+        vq = __double2float_rn(__ddiv_rn((double)aq, 32768.0 * 750));
+    }
+    if (k < kSlot) {  // zero tail: decoder() clears [iqIndex, 48000), rtlsdr_ft8d.c:243-246
+        out_i[(size_t)stream * kSlot + k] = vi;
+        out_q[(size_t)stream * kSlot + k] = vq;
+    }
+    float m = fmaxf(fabsf(vi), fabsf(vq));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && peak) atomicMax(reinterpret_cast<unsigned int *>(peak + stream), __float_as_uint(m));
+    if (count && blockIdx.x == 0 && threadIdx.x == 0) count[stream] = (uint32_t)n_out;
+}
+
+// a4 as a standalone pass (the fused pipeline applies the scale inside the waterfall load instead)
+__global__ void condition_kernel(float *__restrict__ d_i, float *__restrict__ d_q, const float *__restrict__ peak) {
+    const int slot = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float p = peak[slot];
+    if (!(p > 1e-24f)) p = 1e-24f;
+    const float scale = __double2float_rn(__ddiv_rn(0.5, (double)p));
+    if (k < kSlot) {
+        d_i[(size_t)slot * kSlot + k] = __fmul_rn(d_i[(size_t)slot * kSlot + k], scale);
+        d_q[(size_t)slot * kSlot + k] = __fmul_rn(d_q[(size_t)slot * kSlot + k], scale);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int blocks_per_stream, BlockSums *d_sums,
+                                  cudaStream_t st, int *launches) {
+    const int supers = blocks_per_stream / 8;
+    if (supers > 0) {
+        dim3 grid((supers + kWarpsPerCta - 1) / kWarpsPerCta, n_streams);
+        cic_block_sums_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, blocks_per_stream, d_sums);
+        ++*launches;
+    }
+    const int rest = blocks_per_stream - supers * 8;
+    if (rest > 0) {
+        dim3 grid((rest + 7) / 8, n_streams);
+        cic_block_sums_generic_kernel<<<grid, 256, 0, st>>>(d_iq, stream_stride_bytes, supers * 8, rest, blocks_per_stream, d_sums);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int first_block, int n_blocks,
+                                          int blocks_per_stream, BlockSums *d_sums, cudaStream_t st, int *launches) {
+    if (n_blocks > 0) {
+        dim3 grid((n_blocks + 7) / 8, n_streams);
+        cic_block_sums_generic_kernel<<<grid, 256, 0, st>>>(d_iq, stream_stride_bytes, first_block, n_blocks, blocks_per_stream, d_sums);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, int blocks_per_stream, int n_streams, const float *d_fir, float *d_i, float *d_q,
+                                uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st, int *launches) {
+    dim3 grid((kSlot + kTile - 1) / kTile, n_streams);
+    cic_comb_fir_kernel<<<grid, kTile, 0, st>>>(d_sums, blocks_per_stream, d_fir, d_i, d_q, d_count, d_peak, d_y2);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_condition(float *d_i, float *d_q, const float *d_peak, int n_slots, cudaStream_t st, int *launches) {
+    dim3 grid((kSlot + 255) / 256, n_slots);
+    condition_kernel<<<grid, 256, 0, st>>>(d_i, d_q, d_peak);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace ft8b200

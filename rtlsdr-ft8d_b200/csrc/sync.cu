@@ -1,0 +1,192 @@
+// sync.cu -- Costas 7x7 sync scoring over the whole waterfall + exact top-K candidate selection.
+// Replaces ft8_find_sync() / ft8_sync_score() / heapify_*(), /root/reference/ft8_lib/ft8/decode.c:35-108,
+// 173-234, 388-435.
+//
+// One CTA per slot.  The slot's waterfall (94 KB for the daemon geometry) is staged in shared memory
+// once; all tosr*fosr*36*(bins-7) positions are scored in parallel in the reference's loop order
+// (time_sub, freq_sub, time_offset, freq_offset); positions with score >= min_score are compacted IN
+// THAT ORDER (ballot + prefix) and then one thread replays the reference's min-heap insertions and the
+// final heap sort over the survivors only.  The replay is what makes the retained set at the cut score
+// and the order among equal scores identical to the reference (they depend on heap history).
+#include "common.cuh"
+
+namespace ft8b200 {
+namespace {
+
+constexpr int kSyncThreads = 1024;
+__constant__ uint8_t c_costas[7] = {3, 1, 4, 0, 6, 5, 2};
+
+struct Geo { int nb, nbins, tosr, fosr, stride, nfo, npos; };
+
+// ref: ft8_sync_score(), decode.c:44-108
+__device__ __forceinline__ int sync_score(const uint8_t *__restrict__ mag, const Geo &g, int ts, int fs, int to, int fo) {
+    const long origin = (((long)to * g.tosr + ts) * g.fosr + fs) * g.nbins + fo;
+    int score = 0, terms = 0;
+#pragma unroll
+    for (int grp = 0; grp < 3; ++grp) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int rel = 36 * grp + k;
+            const int row = to + rel;
+            if (row < 0) continue;
+            if (row >= g.nb) break;  // leaves this group only, like the reference's inner `break`
+            const uint8_t *p = mag + origin + (long)rel * g.stride;
+            const int tone = c_costas[k];
+            const int centre = p[tone];
+            if (tone > 0) { score += centre - p[tone - 1]; ++terms; }
+            if (tone < 7) { score += centre - p[tone + 1]; ++terms; }
+            if (k > 0 && row > 0) { score += centre - p[tone - g.stride]; ++terms; }
+            if (k + 1 < 7 && row + 1 < g.nb) { score += centre - p[tone + g.stride]; ++terms; }
+        }
+    }
+    if (terms > 0) score /= terms;  // truncating division
+    return score;
+}
+
+// candidate_t as one 64-bit word: score | time_offset<<16 | freq_offset<<32 | time_sub<<48 | freq_sub<<56
+__device__ __forceinline__ int cand_score(unsigned long long c) { return (int)(short)(c & 0xffffull); }
+
+__device__ void sift_down(unsigned long long *h, int n) {  // ref: heapify_down, decode.c:388-415
+    int cur = 0;
+    for (;;) {
+        int pick = cur;
+        const int l = 2 * cur + 1, r = l + 1;
+        if (l < n && cand_score(h[l]) < cand_score(h[pick])) pick = l;
+        if (r < n && cand_score(h[r]) < cand_score(h[pick])) pick = r;
+        if (pick == cur) return;
+        const unsigned long long t = h[pick]; h[pick] = h[cur]; h[cur] = t;
+        cur = pick;
+    }
+}
+__device__ void sift_up(unsigned long long *h, int n) {  // ref: heapify_up, decode.c:417-435
+    int cur = n - 1;
+    while (cur > 0) {
+        const int par = (cur - 1) / 2;
+        if (cand_score(h[cur]) >= cand_score(h[par])) return;
+        const unsigned long long t = h[par]; h[par] = h[cur]; h[cur] = t;
+        cur = par;
+    }
+}
+
+template <bool kStage>
+__global__ void __launch_bounds__(kSyncThreads)
+find_sync_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, int n_slots, Geo g, int max_cand, int min_score,
+                 candidate_t *__restrict__ cand_out, int *__restrict__ ncand_out, uint32_t *__restrict__ scratch_all) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_warp_cnt[2][32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wf_bytes = g.nb * g.stride;
+    const int wf_pad = kStage ? ((wf_bytes + 15) & ~15) : 0;
+    unsigned long long *heap = reinterpret_cast<unsigned long long *>(smem + wf_pad);
+    uint32_t *scratch = scratch_all + (size_t)blockIdx.x * g.npos;
+
+    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+        const uint8_t *gmag = mag_all + (size_t)slot * slot_stride;
+        const uint8_t *mag = gmag;
+        if (kStage) {
+            if ((((size_t)gmag) & 15) == 0 && (wf_bytes & 15) == 0) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(gmag);
+                uint4 *dst = reinterpret_cast<uint4 *>(smem);
+                for (int k = tid; k < wf_bytes / 16; k += kSyncThreads) dst[k] = __ldg(src + k);
+            } else {
+                for (int k = tid; k < wf_bytes; k += kSyncThreads) smem[k] = gmag[k];
+            }
+            mag = smem;
+            __syncthreads();
+        }
+        int running = 0, it = 0;
+        for (int base = 0; base < g.npos; base += kSyncThreads, ++it) {
+            const int p = base + tid;
+            bool pass = false;
+            int score = 0;
+            if (p < g.npos) {
+                const int fo = p % g.nfo;
+                int q = p / g.nfo;
+                const int to = q % 36 - 12;
+                q /= 36;
+                const int fs = q % g.fosr, ts = q / g.fosr;
+                score = (int)(short)sync_score(mag, g, ts, fs, to, fo);  // stored as int16_t in candidate_t
+                pass = score >= min_score;
+            }
+            // ordered compaction: position order == the reference's loop order
+            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) s_warp_cnt[it & 1][warp] = __popc(ballot);
+            __syncthreads();
+            const int c = s_warp_cnt[it & 1][lane];
+            const int before = __reduce_add_sync(0xffffffffu, lane < warp ? c : 0);
+            const int tot = __reduce_add_sync(0xffffffffu, c);
+            if (pass) scratch[running + before + __popc(ballot & ((1u << lane) - 1u))] = ((uint32_t)p << 12) | ((uint32_t)score & 0xfffu);
+            running += tot;
+        }
+        __syncthreads();
+
+        if (tid == 0) {  // exact replay of the reference's heap (decode.c:198-231) over the survivors
+            const int n_pass = running;
+            int n = 0;
+            for (int e = 0; e < n_pass; ++e) {
+                const uint32_t v = scratch[e];
+                const int score = ((int)(v << 20)) >> 20;
+                const int p = (int)(v >> 12);
+                if (n == max_cand && score > cand_score(heap[0])) {
+                    heap[0] = heap[n - 1];
+                    --n;
+                    sift_down(heap, n);
+                }
+                if (n < max_cand) {
+                    const int fo = p % g.nfo;
+                    int q = p / g.nfo;
+                    const int to = q % 36 - 12;
+                    q /= 36;
+                    const int fs = q % g.fosr, ts = q / g.fosr;
+                    heap[n] = ((unsigned long long)(uint16_t)(short)score) | ((unsigned long long)(uint16_t)(short)to << 16) |
+                              ((unsigned long long)(uint16_t)(short)fo << 32) | ((unsigned long long)(uint8_t)ts << 48) |
+                              ((unsigned long long)(uint8_t)fs << 56);
+                    ++n;
+                    sift_up(heap, n);
+                }
+            }
+            for (int rest = n; rest > 1;) {  // heap sort -> descending score
+                const unsigned long long t = heap[rest - 1]; heap[rest - 1] = heap[0]; heap[0] = t;
+                --rest;
+                sift_down(heap, rest);
+            }
+            s_total = n;
+            ncand_out[slot] = n;
+        }
+        __syncthreads();
+        {
+            const int n = s_total;
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(cand_out + (size_t)slot * max_cand);
+            for (int k = tid; k < max_cand; k += kSyncThreads) dst[k] = (k < n) ? heap[k] : 0ull;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
+                             int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, uint32_t *d_scratch, int scratch_slots,
+                             cudaStream_t st, int *launches) {
+    Geo g;
+    g.nb = num_blocks; g.nbins = num_bins; g.tosr = time_osr; g.fosr = freq_osr;
+    g.stride = time_osr * freq_osr * num_bins;
+    g.nfo = num_bins - 7;
+    g.npos = time_osr * freq_osr * 36 * g.nfo;
+    const int wf_bytes = g.nb * g.stride;
+    const size_t heap_bytes = (size_t)max_cand * 8;
+    const size_t staged = (size_t)((wf_bytes + 15) & ~15) + heap_bytes;
+    const int grid = n_slots < scratch_slots ? n_slots : scratch_slots;
+    if (staged <= 200 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(find_sync_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
+        if (e != cudaSuccess) return e;
+        find_sync_kernel<true><<<grid, kSyncThreads, staged, st>>>(d_mag, slot_stride, n_slots, g, max_cand, min_score, d_cand, d_ncand, d_scratch);
+    } else {
+        find_sync_kernel<false><<<grid, kSyncThreads, heap_bytes, st>>>(d_mag, slot_stride, n_slots, g, max_cand, min_score, d_cand, d_ncand, d_scratch);
+    }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace ft8b200
