@@ -101,6 +101,17 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _st(stream):
+    """cudaStream_t to launch on: an explicit handle, or (default) torch's current stream so that the
+    library's kernels are ordered with the torch ops that produced/consume the tensors."""
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+        if stream == 0:
+            stream = 1  # cudaStreamLegacy: NULL means "the context's own stream" in the C ABI
+    return C.c_void_p(stream)
+
+
 class Context:
     """One ft8b200_ctx_t on one device. All tensors passed in must live on that device and be contiguous."""
 
@@ -140,7 +151,7 @@ class Context:
         return int(self.L.ft8b200_kernel_launches(C.c_void_p(self.h)))
 
     # ---- stage-wise (device tensors) -------------------------------------------------------------
-    def decimate(self, iq, n_streams: int, bytes_per_stream: int, stride: int | None = None, want_y2: bool = False, stream: int = 0):
+    def decimate(self, iq, n_streams: int, bytes_per_stream: int, stride: int | None = None, want_y2: bool = False, stream: int | None = None):
         import torch
         dev = iq.device
         stride = bytes_per_stream if stride is None else stride
@@ -150,29 +161,29 @@ class Context:
         peak = torch.zeros(n_streams, dtype=torch.float32, device=dev)
         y2 = torch.zeros((n_streams, N_SLOT, 2), dtype=torch.int32, device=dev) if want_y2 else None
         self._chk(self.L.ft8b200_decimate(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_streams, _p(d_i), _p(d_q),
-                                          _p(cnt), _p(peak), _p(y2), C.c_void_p(stream)))
+                                          _p(cnt), _p(peak), _p(y2), _st(stream)))
         return d_i, d_q, cnt, peak, y2
 
-    def condition(self, d_i, d_q, peak, stream: int = 0):
-        self._chk(self.L.ft8b200_condition(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), d_i.shape[0], C.c_void_p(stream)))
+    def condition(self, d_i, d_q, peak, stream: int | None = None):
+        self._chk(self.L.ft8b200_condition(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), d_i.shape[0], _st(stream)))
 
-    def waterfall(self, d_i, d_q, peak=None, stream: int = 0):
+    def waterfall(self, d_i, d_q, peak=None, stream: int | None = None):
         import torch
         n = d_i.shape[0]
         mag = torch.empty((n, WF_BYTES), dtype=torch.uint8, device=d_i.device)
-        self._chk(self.L.ft8b200_waterfall(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), n, _p(mag), C.c_void_p(stream)))
+        self._chk(self.L.ft8b200_waterfall(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), n, _p(mag), _st(stream)))
         return mag
 
-    def find_sync(self, mag, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, stream: int = 0):
+    def find_sync(self, mag, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, stream: int | None = None):
         import torch
         n = mag.shape[0]
         cand = torch.zeros((n, self.K, 8), dtype=torch.uint8, device=mag.device)
         ncand = torch.zeros(n, dtype=torch.int32, device=mag.device)
         self._chk(self.L.ft8b200_find_sync(C.c_void_p(self.h), _p(mag), C.c_size_t(mag.stride(0)), n, num_blocks, num_bins, time_osr, freq_osr,
-                                           _p(cand), _p(ncand), C.c_void_p(stream)))
+                                           _p(cand), _p(ncand), _st(stream)))
         return cand, ncand
 
-    def decode(self, mag, cand, ncand, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, want_plain=False, want_llr=False, stream: int = 0):
+    def decode(self, mag, cand, ncand, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, want_plain=False, want_llr=False, stream: int | None = None):
         import torch
         n = mag.shape[0]
         dev = mag.device
@@ -183,10 +194,10 @@ class Context:
         plain = torch.zeros((n, self.K, 174), dtype=torch.uint8, device=dev) if want_plain else None
         llr = torch.zeros((n, self.K, 174), dtype=torch.float32, device=dev) if want_llr else None
         self._chk(self.L.ft8b200_decode(C.c_void_p(self.h), _p(mag), C.c_size_t(mag.stride(0)), n, num_blocks, num_bins, time_osr, freq_osr,
-                                        _p(cand), _p(ncand), _p(ok), _p(stage), _p(status), _p(msg), _p(plain), _p(llr), C.c_void_p(stream)))
+                                        _p(cand), _p(ncand), _p(ok), _p(stage), _p(status), _p(msg), _p(plain), _p(llr), _st(stream)))
         return ok, stage, status, msg, plain, llr
 
-    def spots(self, cand, ncand, ok, msg, freq_osr=2, want_log=True, stream: int = 0):
+    def spots(self, cand, ncand, ok, msg, freq_osr=2, want_log=True, stream: int | None = None):
         import torch
         n = cand.shape[0]
         dev = cand.device
@@ -196,21 +207,21 @@ class Context:
         ufreq = torch.zeros((n, self.M), dtype=torch.float32, device=dev) if want_log else None
         uscore = torch.zeros((n, self.M), dtype=torch.int32, device=dev) if want_log else None
         self._chk(self.L.ft8b200_spots(C.c_void_p(self.h), n, freq_osr, _p(cand), _p(ncand), _p(ok), _p(msg), _p(res), _p(nres), _p(umsg), _p(ufreq),
-                                       _p(uscore), C.c_void_p(stream)))
+                                       _p(uscore), _st(stream)))
         return res, nres, umsg, ufreq, uscore
 
     # ---- whole path ----------------------------------------------------------------------------------
-    def process_raw(self, iq, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None, stream: int = 0):
+    def process_raw(self, iq, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None, stream: int | None = None):
         stride = bytes_per_stream if stride is None else stride
-        self._chk(self.L.ft8b200_process_raw(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_slots, C.c_void_p(stream)))
+        self._chk(self.L.ft8b200_process_raw(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_slots, _st(stream)))
 
-    def process_slots(self, d_i, d_q, stream: int = 0):
-        self._chk(self.L.ft8b200_process_slots(C.c_void_p(self.h), _p(d_i), _p(d_q), d_i.shape[0], C.c_void_p(stream)))
+    def process_slots(self, d_i, d_q, stream: int | None = None):
+        self._chk(self.L.ft8b200_process_slots(C.c_void_p(self.h), _p(d_i), _p(d_q), d_i.shape[0], _st(stream)))
 
-    def fetch_results(self, n_slots: int, stream: int = 0):
+    def fetch_results(self, n_slots: int, stream: int | None = None):
         res = np.zeros((n_slots, self.M), result_dtype)
         nres = np.zeros(n_slots, np.int32)
-        self._chk(self.L.ft8b200_fetch_results(C.c_void_p(self.h), n_slots, _p(res), _p(nres), C.c_void_p(stream)))
+        self._chk(self.L.ft8b200_fetch_results(C.c_void_p(self.h), n_slots, _p(res), _p(nres), _st(stream)))
         return res, nres
 
     def results_device_ptrs(self):

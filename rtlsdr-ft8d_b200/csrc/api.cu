@@ -160,7 +160,7 @@ ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg_in) {
     ctx->cfg = cfg;
     ctx->sm_count = prop.multiProcessorCount;
     bool okc = true;
-    okc = okc && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    okc = okc && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamDefault) == cudaSuccess;
     // tables, built with the host libm exactly as the reference builds them
     std::vector<float> win(kNfft), thr(257), fir(kFirTaps);
     std::vector<float2> tw(kNfft);

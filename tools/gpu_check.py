@@ -88,17 +88,14 @@ print("raw decim bit-exact:", np.array_equal(gi[0].cpu().numpy().view(np.uint32)
 B = 16
 big = d_raw.repeat(B, 1).contiguous()
 for _ in range(2): ctx.process_raw(big, B)
-ctx.sync()
+torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-st = torch.cuda.ExternalStream(ctx.cuda_stream)
-with torch.cuda.stream(st):
-    e0.record(); ctx.process_raw(big, B); e1.record()
-ctx.sync(); torch.cuda.synchronize()
+e0.record(); ctx.process_raw(big, B); e1.record()
+torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print(f"process_raw x{B}: {ms:.3f} ms -> {B/ms*1e3:.0f} slots/s")
-with torch.cuda.stream(st):
-    e0.record(); ctx.decimate(big, B, raw.size); e1.record()
-ctx.sync(); torch.cuda.synchronize()
+e0.record(); ctx.decimate(big, B, raw.size); e1.record()
+torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print(f"decimate x{B}: {ms:.3f} ms -> {B*72.383488e-3/ms:.1f} GB/s algorithmic")
 print("launches:", ctx.launches())
