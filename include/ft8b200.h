@@ -223,6 +223,10 @@ int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate
  * until fetched. */
 int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots, void *stream);
 int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, int n_slots, void *stream);
+/* Per-stage device timing of the process_* calls: when enabled, CUDA events are recorded on the launching
+ * stream between stages; ms[0..5] = block sums, comb+FIR, waterfall, sync, decode, spots (-1 = stage not run). */
+int ft8b200_set_profiling(ft8b200_ctx_t *ctx, int on);
+int ft8b200_stage_times(ft8b200_ctx_t *ctx, float *ms, int n);
 /* device pointers to the last batch's outputs: results (n_slots x max_messages), counts (n_slots) */
 int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults);
 int ft8b200_fetch_results(ft8b200_ctx_t *ctx, int n_slots, struct decoder_results *h_results, int32_t *h_nresults, void *stream);

@@ -224,6 +224,15 @@ class Context:
         self._chk(self.L.ft8b200_fetch_results(C.c_void_p(self.h), n_slots, _p(res), _p(nres), _st(stream)))
         return res, nres
 
+    def set_profiling(self, on: bool):
+        self._chk(self.L.ft8b200_set_profiling(C.c_void_p(self.h), int(on)))
+
+    def stage_times(self):
+        """ms per stage of the last process_* call: dict(block_sums, comb_fir, waterfall, sync, decode, spots)."""
+        ms = (C.c_float * 6)()
+        self._chk(self.L.ft8b200_stage_times(C.c_void_p(self.h), ms, 6))
+        return dict(zip(("block_sums", "comb_fir", "waterfall", "sync", "decode", "spots"), [float(x) for x in ms]))
+
     def results_device_ptrs(self):
         a, b = C.c_void_p(0), C.c_void_p(0)
         self._chk(self.L.ft8b200_results_device(C.c_void_p(self.h), C.byref(a), C.byref(b)))

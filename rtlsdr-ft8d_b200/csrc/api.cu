@@ -63,6 +63,10 @@ struct ft8b200_ctx {
     DevBuf raw, sums, si, sq, peak, count, mag, cand, ncand, ok, stage, status, msg, results, nresults, table, scratch;
     int scratch_slots = 0;
     int scratch_npos = 0;
+    // optional per-stage timing of the last process_* call (CUDA events on the launching stream)
+    bool profiling = false;
+    cudaEvent_t ev[7] = {};
+    bool ev_valid[7] = {};
     std::mutex mu;
 };
 
@@ -189,6 +193,7 @@ void ft8b200_destroy(ft8b200_ctx_t *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.fir);
     cudaFree(ctx->tb.mon_window); cudaFree(ctx->tb.mon_twiddle); cudaFree(ctx->tb.mon_super);
     DevBuf *bufs[] = {&ctx->raw, &ctx->sums, &ctx->si, &ctx->sq, &ctx->peak, &ctx->count, &ctx->mag, &ctx->cand, &ctx->ncand, &ctx->ok,
@@ -289,19 +294,29 @@ int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate
     return 0;
 }
 
+static void mark(ft8b200_ctx_t *ctx, int k, cudaStream_t st) {
+    if (!ctx->profiling) return;
+    if (!ctx->ev[k]) cudaEventCreate(&ctx->ev[k]);
+    ctx->ev_valid[k] = (cudaEventRecord(ctx->ev[k], st) == cudaSuccess);
+}
+
 // waterfall (already in ctx->mag or produced here) -> sync -> decode -> spots, all on `st`
 static int run_back_end(ft8b200_ctx_t *ctx, int n_slots, cudaStream_t st) {
     int rc;
     const int npos = 2 * 2 * 36 * (256 - 7);
     if ((rc = ensure_scratch(ctx, npos, n_slots))) return rc;
+    mark(ctx, 3, st);
     CU(launch_find_sync(ctx->mag.as<uint8_t>(), kWfBytes, n_slots, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.min_score,
                         ctx->cand.as<candidate_t>(), ctx->ncand.as<int>(), ctx->scratch.as<uint32_t>(), ctx->scratch_slots, st, &ctx->launches));
+    mark(ctx, 4, st);
     CU(launch_decode(ctx->mag.as<uint8_t>(), kWfBytes, n_slots, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
                      ctx->cand.as<candidate_t>(), ctx->ncand.as<int>(), ctx->ok.as<uint8_t>(), ctx->stage.as<uint8_t>(),
                      ctx->status.as<decode_status_t>(), ctx->msg.as<message_t>(), nullptr, nullptr, st, &ctx->launches));
+    mark(ctx, 5, st);
     CU(launch_spots(n_slots, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, 2, ctx->cand.as<candidate_t>(),
                     ctx->ncand.as<int>(), ctx->ok.as<uint8_t>(), ctx->msg.as<message_t>(), ctx->results.as<struct decoder_results>(),
                     ctx->nresults.as<int32_t>(), nullptr, nullptr, nullptr, ctx->table.as<int16_t>(), st, &ctx->launches));
+    mark(ctx, 6, st);
     return 0;
 }
 
@@ -321,9 +336,13 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
     if ((rc = ctx->peak.ensure((size_t)n_slots * sizeof(float)))) return rc;
     if ((rc = ctx->count.ensure((size_t)n_slots * sizeof(uint32_t)))) return rc;
     CU(cudaMemsetAsync(ctx->peak.p, 0, sizeof(float) * n_slots, st));
+    for (bool &v : ctx->ev_valid) v = false;
+    mark(ctx, 0, st);
     CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_slots, blocks, ctx->sums.as<BlockSums>(), st, &ctx->launches));
+    mark(ctx, 1, st);
     CU(launch_cic_comb_fir(ctx->sums.as<BlockSums>(), blocks, n_slots, ctx->tb.fir, ctx->si.as<float>(), ctx->sq.as<float>(),
                            ctx->count.as<uint32_t>(), ctx->peak.as<float>(), nullptr, st, &ctx->launches));
+    mark(ctx, 2, st);
     // decoder()'s normalisation is applied on load inside the waterfall kernel (scale from the slot peak)
     CU(launch_waterfall(ctx->tb, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), n_slots, ctx->mag.as<uint8_t>(), st, &ctx->launches));
     rc = run_back_end(ctx, n_slots, st);
@@ -338,10 +357,33 @@ int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = pick(ctx, stream);
     if ((rc = ensure_slot_buffers(ctx, n_slots))) return rc;
+    for (bool &v : ctx->ev_valid) v = false;
+    mark(ctx, 2, st);
     CU(launch_waterfall(ctx->tb, d_i, d_q, nullptr, n_slots, ctx->mag.as<uint8_t>(), st, &ctx->launches));
     rc = run_back_end(ctx, n_slots, st);
     tally(ctx);
     return rc;
+}
+
+int ft8b200_set_profiling(ft8b200_ctx_t *ctx, int on) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+// ms[0..5] = block sums, comb+FIR, waterfall, sync, decode, spots of the last process_* call (-1 = not run)
+int ft8b200_stage_times(ft8b200_ctx_t *ctx, float *ms, int n) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!ms || n < 6) return fail(FT8B200_EINVAL, "ft8b200_stage_times: need room for 6 floats");
+    for (int k = 0; k < 6; ++k) {
+        ms[k] = -1.0f;
+        if (ctx->ev_valid[k] && ctx->ev_valid[k + 1]) {
+            CU(cudaEventSynchronize(ctx->ev[k + 1]));
+            CU(cudaEventElapsedTime(&ms[k], ctx->ev[k], ctx->ev[k + 1]));
+        }
+    }
+    return 0;
 }
 
 int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults) {

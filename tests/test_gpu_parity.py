@@ -1,0 +1,314 @@
+"""Parity tests proper: the CUDA path, called through the C ABI of libft8b200.so, against the CPU oracle
+on the same seeded inputs, against the committed golden fixtures (made by the unmodified reference), and
+-- at BASELINE.json's full sizes -- through size-independent properties.
+
+Bars (BASELINE.json north_star): candidate lists, LDPC hard decisions, CRC and message text bit-exact;
+decimator floats within 1e-5 relative (asserted BIT-EXACT here, which is stronger); waterfall cells within
++-1 LSB on <= 0.01 % of cells (asserted IDENTICAL here)."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, golden
+from oracle.pyoracle import cand_dtype, msg_dtype, result_dtype, status_dtype
+from tools import ft8enc, synth
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def view(t, dt):
+    a = t.cpu().numpy()
+    return a.view(dt).reshape(a.shape[:-1])
+
+
+def make_slot(oracle, sigs, seed, condition=True):
+    i_s, q_s = synth.slot_f32(sigs, seed)
+    if condition:
+        i_s, q_s, _ = oracle.condition(i_s, q_s, 48000)
+    return i_s, q_s
+
+
+def std_sig(f0=700.0, t0=0.5, snr=-10.0, msg=("CQ", "K1JT", "FN20")):
+    return (ft8enc.tones(ft8enc.pack_std(*msg)), f0, t0, snr)
+
+
+# ------------------------------------------------------------------------------------------- decimator
+def oracle_decim(oracle, iq):
+    n8 = (iq.size // 8) * 8
+    return oracle.decimate_slot(iq[:n8], want_y2=True)
+
+
+@pytest.mark.parametrize("nbytes", [12016 * 40, 12016 * 3 + 1502 * 5 + 8 * 13, 1502 * 7, 1496, 8])
+def test_decimator_random_streams(ctx, oracle, nbytes):
+    """uint8 IQ incl. 0x00/0xFF (the int8 negate wrap), full super-blocks, ragged tails, < 1 block."""
+    rng = np.random.default_rng(nbytes)
+    stride = (nbytes + 15) // 16 * 16
+    iq = rng.integers(0, 256, size=(3, stride), dtype=np.uint8)
+    iq[0, ::53] = 0
+    iq[1, 7::97] = 255
+    iq[2] = rng.integers(118, 139, size=stride, dtype=np.uint8)
+    d_i, d_q, cnt, peak, y2 = ctx.decimate(torch.from_numpy(iq).to(dev()), 3, nbytes, stride=stride, want_y2=True)
+    torch.cuda.synchronize()
+    for s in range(3):
+        oi, oq, oy2i, oy2q = oracle_decim(oracle, iq[s, :nbytes])
+        n = int(cnt[s])
+        assert n == oi.size == (nbytes // 2) // 751
+        gi, gq, gy = d_i[s].cpu().numpy(), d_q[s].cpu().numpy(), y2[s].cpu().numpy()
+        assert np.array_equal(gy[:n, 0], oy2i) and np.array_equal(gy[:n, 1], oy2q), "integer CIC core must be exact"
+        assert bits_equal(gi[:n], oi) and bits_equal(gq[:n], oq), "float outputs bit-exact (spec: <= 1e-5 relative)"
+        assert not gi[n:].any() and not gq[n:].any(), "tail of the 48000-sample buffer is zero (decoder(), rtlsdr_ft8d.c:243-246)"
+        expect_peak = max(np.abs(oi).max(initial=0), np.abs(oq).max(initial=0))
+        assert float(peak[s]) == float(expect_peak)
+
+
+@pytest.mark.parametrize("fill", [0x00, 0xFF, 0x80, 0x7F, 0x01])
+def test_decimator_constant_input(ctx, oracle, fill):
+    nbytes = 12016 * 12
+    iq = np.full(nbytes, fill, np.uint8)
+    d_i, d_q, cnt, peak, y2 = ctx.decimate(torch.from_numpy(iq).to(dev()), 1, nbytes, want_y2=True)
+    oi, oq, oy2i, oy2q = oracle_decim(oracle, iq)
+    n = int(cnt[0])
+    assert np.array_equal(y2[0, :n, 0].cpu().numpy(), oy2i) and np.array_equal(y2[0, :n, 1].cpu().numpy(), oy2q)
+    assert bits_equal(d_i[0, :n].cpu().numpy(), oi) and bits_equal(d_q[0, :n].cpu().numpy(), oq)
+    if fill == 0x80:
+        assert not oi.any() and float(peak[0]) == 0.0
+
+
+def test_decimator_golden(ctx):
+    g = golden("decim_random")
+    iq = g["iq"]
+    nbytes = (iq.size // 8) * 8
+    buf = np.zeros((nbytes + 15) // 16 * 16, np.uint8)
+    buf[:nbytes] = iq[:nbytes]
+    d_i, d_q, cnt, _, _ = ctx.decimate(torch.from_numpy(buf).to(dev()), 1, nbytes, stride=buf.size)
+    n = int(cnt[0])
+    assert n == g["i"].size
+    assert bits_equal(d_i[0, :n].cpu().numpy(), g["i"]) and bits_equal(d_q[0, :n].cpu().numpy(), g["q"])
+
+
+@pytest.fixture(scope="module")
+def raw_slot():
+    """BASELINE config #2: one 15 s slot of raw 2.4 Msps uint8 IQ with one message, 36 M complex samples."""
+    return synth.raw_u8([std_sig(800.0, 0.5, 20.0)], 3)
+
+
+def test_full_raw_slot(ctx, oracle, raw_slot):
+    d_raw = torch.from_numpy(raw_slot).to(dev())
+    d_i, d_q, cnt, peak, _ = ctx.decimate(d_raw, 1, raw_slot.size)
+    oi, oq = oracle.decimate_slot(raw_slot)
+    assert int(cnt[0]) == oi.size == 47936
+    ri = np.zeros(48000, np.float32); rq = np.zeros(48000, np.float32)
+    ri[:oi.size] = oi; rq[:oq.size] = oq
+    assert bits_equal(d_i[0].cpu().numpy(), ri) and bits_equal(d_q[0].cpu().numpy(), rq)
+    # whole path: raw -> spots, against oracle decimate + decoder() conditioning + ft8_subsystem
+    ic, qc, _ = oracle.condition(ri, rq, oi.size)
+    o = oracle.subsystem(ic, qc)
+    ctx.process_raw(d_raw, 1)
+    res, n = ctx.fetch_results(1)
+    assert n[0] == o["n"] >= 1
+    assert res[0].tobytes() == o["results"].tobytes()
+    assert res[0][0]["call"] == b"K1JT" and res[0][0]["loc"] == b"FN20" and res[0][0]["freq"] == 800
+    # end-to-end host entry point gives the same bytes
+    res2, n2 = ctx.process_raw_host(raw_slot, 1)
+    assert n2[0] == n[0] and res2.tobytes() == res.tobytes()
+
+
+def test_raw_batch_properties(ctx, raw_slot):
+    """Full-size properties: every copy of a slot in a batch decodes identically (position independence),
+    a silent slot (all 0x80) yields zero samples and no candidates, and the integer CIC core is linear:
+    y2(a) + y2(b) == y2(a + b - 128) when no byte saturates or hits the -128 wrap."""
+    B = 4
+    big = torch.from_numpy(raw_slot).to(dev()).repeat(B, 1).contiguous()
+    big[2] = 0x80
+    ctx.process_raw(big, B)
+    res, n = ctx.fetch_results(B)
+    assert n[0] == n[1] == n[3] >= 1 and n[2] == 0
+    assert res[0].tobytes() == res[1].tobytes() == res[3].tobytes()
+    rng = np.random.default_rng(5)
+    nbytes = 12016 * 64
+    a = rng.integers(100, 130, size=nbytes, dtype=np.uint8)
+    b = rng.integers(110, 150, size=nbytes, dtype=np.uint8)
+    c = (a.astype(np.int32) + b.astype(np.int32) - 128).astype(np.uint8)
+    y = ctx.decimate(torch.from_numpy(np.stack([a, b, c])).to(dev()), 3, nbytes, want_y2=True)[4].cpu().numpy().astype(np.int64)
+    n_out = nbytes // 2 // 751
+    assert np.array_equal(y[0, :n_out] + y[1, :n_out], y[2, :n_out])
+
+
+# ------------------------------------------------------------------------------------------- waterfall
+@pytest.fixture(scope="module")
+def slots(oracle):
+    out = [make_slot(oracle, [std_sig()], 7)]
+    i_s, q_s, _ = synth.crowded_band(ft8enc, 60, 99)
+    out.append(tuple(oracle.condition(i_s, q_s, 48000)[:2]))
+    i_s, q_s, _ = synth.crowded_band(ft8enc, 25, 5, snr_lo=-18, snr_hi=0)
+    out.append(tuple(oracle.condition(i_s, q_s, 48000)[:2]))
+    out.append(make_slot(oracle, [], 11))  # noise only
+    out.append((np.zeros(48000, np.float32), np.zeros(48000, np.float32)))  # silence: every cell clamps to 0
+    out.append(make_slot(oracle, [std_sig(50.0, 0.0, 5.0), std_sig(1500.0, 2.3, 0.0, ("K1ABC", "W9XYZ", "-15"))], 13))  # band/time edges
+    return out
+
+
+def test_waterfall_parity(ctx, oracle, slots):
+    hi = np.stack([s[0] for s in slots]); hq = np.stack([s[1] for s in slots])
+    mag = ctx.waterfall(torch.from_numpy(hi).to(dev()), torch.from_numpy(hq).to(dev())).cpu().numpy()
+    for s in range(len(slots)):
+        ref = oracle.waterfall(hi[s], hq[s])
+        ndiff = int((mag[s] != ref).sum())
+        assert ndiff == 0, f"slot {s}: {ndiff} of 94208 cells differ (spec allows +-1 LSB on <= 9 cells; this build is exact)"
+
+
+def test_waterfall_applies_decoder_conditioning(ctx, oracle):
+    """Unconditioned samples + slot peak: the kernel applies decoder()'s 0.5/max scale on load (rtlsdr_ft8d.c:248-263)."""
+    i_s, q_s = synth.slot_f32([std_sig()], 21)
+    i_s *= np.float32(3.7e-3); q_s *= np.float32(3.7e-3)
+    ic, qc, _ = oracle.condition(i_s, q_s, 48000)
+    peak = torch.tensor([max(np.abs(i_s).max(), np.abs(q_s).max())], dtype=torch.float32, device=dev())
+    d_i = torch.from_numpy(i_s[None]).to(dev()); d_q = torch.from_numpy(q_s[None]).to(dev())
+    mag = ctx.waterfall(d_i, d_q, peak).cpu().numpy()[0]
+    assert np.array_equal(mag, oracle.waterfall(ic, qc))
+    ctx.condition(d_i, d_q, peak)
+    assert bits_equal(d_i[0].cpu().numpy(), ic) and bits_equal(d_q[0].cpu().numpy(), qc)
+
+
+# ------------------------------------------------------------------------------------------- sync / decode / spots
+def check_slot_against_oracle(oracle, c, mag_np, cand, ncand, ok, stage, status, msg, plain, llr, res, nres, umsg, ufreq, uscore, s, K, M):
+    o = oracle.decode_waterfall(mag_np, max_cand=K, max_msgs=M)
+    gc = view(cand[s], cand_dtype)[: int(ncand[s])]
+    assert int(ncand[s]) == len(o["cands"])
+    assert np.array_equal(gc, o["cands"]), "candidate list must match in content AND order"
+    g_st, g_msg = view(status[s], status_dtype), view(msg[s], msg_dtype)
+    for k, cd in enumerate(o["cands"]):
+        d = oracle.decode(mag_np, cd)
+        assert int(ok[s, k]) == d["ok"], (s, k)
+        assert bits_equal(llr[s, k].cpu().numpy(), d["llr"]), f"slot {s} cand {k}: normalised LLRs"
+        assert np.array_equal(plain[s, k].cpu().numpy(), d["plain"]), f"slot {s} cand {k}: LDPC hard decisions"
+        assert g_st[k]["ldpc_errors"] == d["status"]["ldpc_errors"]
+        st = int(stage[s, k])
+        assert st == (1 if d["status"]["ldpc_errors"] > 0 else 2 if d["status"]["crc_extracted"] != d["status"]["crc_calculated"] else 4 if d["ok"] else 3)
+        if st >= 2:
+            assert g_st[k]["crc_extracted"] == d["status"]["crc_extracted"] and g_st[k]["crc_calculated"] == d["status"]["crc_calculated"]
+        if st >= 3:
+            assert g_st[k]["unpack_status"] == d["status"]["unpack_status"]
+        if d["ok"]:
+            assert g_msg[k].tobytes() == d["msg"].tobytes()
+    assert int(nres[s]) == o["n"]
+    assert view(res[s], result_dtype).tobytes() == o["results"].tobytes(), "decoder_results[] incl. gaps left by non-CQ messages"
+    n = o["n"]
+    assert view(umsg[s], msg_dtype)[:n].tobytes() == o["msgs"].tobytes()
+    assert bits_equal(ufreq[s, :n].cpu().numpy(), o["freq_hz"]) and np.array_equal(uscore[s, :n].cpu().numpy(), o["score"])
+    return o
+
+
+@pytest.mark.parametrize("which", ["k120", "k500"])
+def test_sync_decode_spots_parity(ctx, ctx500, oracle, slots, which):
+    c = ctx if which == "k120" else ctx500
+    mags = np.stack([oracle.waterfall(*s) for s in slots])
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, size=(2, mags.shape[1]), dtype=np.uint8)           # random bytes: thousands of survivors, heap evictions
+    noise[1] = rng.integers(60, 90, size=mags.shape[1], dtype=np.uint8)
+    flat = np.full((1, mags.shape[1]), 77, np.uint8)                                 # constant: every score is 0
+    mags = np.concatenate([mags, noise, flat])
+    d_mag = torch.from_numpy(mags).to(dev())
+    cand, ncand = c.find_sync(d_mag)
+    ok, stage, status, msg, plain, llr = c.decode(d_mag, cand, ncand, want_plain=True, want_llr=True)
+    res, nres, umsg, ufreq, uscore = c.spots(cand, ncand, ok, msg)
+    torch.cuda.synchronize()
+    decoded = 0
+    for s in range(mags.shape[0]):
+        o = check_slot_against_oracle(oracle, c, mags[s], cand, ncand, ok, stage, status, msg, plain, llr, res, nres, umsg, ufreq, uscore, s, c.K, c.M)
+        decoded += o["n"]
+    assert decoded >= 30
+    assert int(ncand[-1]) == 0 and int(ncand[len(slots)]) == c.K
+
+
+def test_min_score_zero_and_small_k(pkg, oracle, slots):
+    """min_score = 0 admits every position (35 856 survivors -> the heap replay is exercised to the full)."""
+    c = pkg.Context(0, max_candidates=7, max_messages=50, min_score=0)
+    mag = oracle.waterfall(*slots[0])
+    cand, ncand = c.find_sync(torch.from_numpy(mag[None]).to(dev()))
+    o = oracle.find_sync(mag, max_cand=7, min_score=0)
+    assert np.array_equal(view(cand[0], cand_dtype)[: int(ncand[0])], o)
+    c.close()
+
+
+@pytest.mark.parametrize("name,src", [("slot_single", "slot_single"), ("slot_crowded_k500", "slot_crowded_k500"), ("slot_crowded_k120", "slot_crowded_k500")])
+def test_golden_slots_on_gpu(ctx, ctx500, name, src):
+    """The committed outputs of the UNMODIFIED reference, stage by stage, without the oracle in between."""
+    g, gi = golden(name), golden(src)
+    c = ctx500 if int(g["kmax"]) == 500 else ctx
+    d_i = torch.from_numpy(gi["i"][None]).to(dev()); d_q = torch.from_numpy(gi["q"][None]).to(dev())
+    mag = c.waterfall(d_i, d_q)
+    assert np.array_equal(mag[0].cpu().numpy(), g["wf"])
+    cand, ncand = c.find_sync(mag)
+    assert np.array_equal(view(cand[0], cand_dtype)[: int(ncand[0])], g["cands"].view(cand_dtype))
+    ok, stage, status, msg, plain, llr = c.decode(mag, cand, ncand, want_plain=True, want_llr=True)
+    n = int(ncand[0])
+    assert np.array_equal(ok[0, :n].cpu().numpy(), g["dec_ok"].astype(np.uint8))
+    assert np.array_equal(plain[0, :n].cpu().numpy(), g["plain"])
+    assert bits_equal(llr[0, :n].cpu().numpy(), g["llr"])
+    g_st = view(status[0], status_dtype)[:n]
+    assert np.array_equal(g_st["ldpc_errors"], g["dec_status"].view(status_dtype)["ldpc_errors"].reshape(-1))
+    okm = g["dec_ok"].astype(bool)
+    assert view(msg[0], msg_dtype)[:n][okm].tobytes() == g["dec_msg"].view(msg_dtype).reshape(-1)[okm].tobytes()
+    c.process_slots(d_i, d_q)
+    res, nres = c.fetch_results(1)
+    assert nres[0] == int(g["n"]) and res[0].tobytes() == g["results"].tobytes()
+
+
+def test_process_slots_batch(ctx, oracle, slots):
+    """BASELINE config #4 in miniature: a batch of independent slots through the fused path."""
+    reps = 5
+    hi = np.stack([s[0] for s in slots] * reps); hq = np.stack([s[1] for s in slots] * reps)
+    res, nres = ctx.process_slots_host(hi, hq)
+    for s, (i_s, q_s) in enumerate(slots):
+        o = oracle.subsystem(i_s, q_s)
+        for r in range(reps):
+            assert nres[s + r * len(slots)] == o["n"]
+            assert res[s + r * len(slots)].tobytes() == o["results"].tobytes()
+
+
+# ------------------------------------------------------------------------------------------- drop-in entry points
+def test_dropin_ft8_subsystem(pkg, oracle, slots):
+    """ft8_subsystem() with the reference's signature on host arrays (rtlsdr_ft8d.h:164)."""
+    for i_s, q_s in slots[:3]:
+        o = oracle.subsystem(i_s, q_s)
+        dec = np.zeros(50, result_dtype)
+        dec["call"] = b"STALE"
+        decodes, n = pkg.ft8_subsystem(i_s, q_s, dec)
+        assert n == o["n"]
+        for k in range(50):
+            if o["results"][k]["call"]:
+                assert decodes[k].tobytes() == o["results"][k].tobytes()
+            else:  # the reference leaves non-CQ slots untouched (rtlsdr_ft8d.c:1509-1520)
+                assert decodes[k]["call"] == b"STALE"
+
+
+def test_dropin_find_sync_and_decode(pkg, oracle, slots):
+    """ft8_find_sync()/ft8_decode() with waterfall_t/candidate_t/message_t/decode_status_t in HOST memory."""
+    mag = oracle.waterfall(*slots[1])
+    heap = pkg.ft8_find_sync(mag, 120, 10)
+    o = oracle.find_sync(mag, 120, 10)
+    assert np.array_equal(heap.view(cand_dtype), o)
+    n_ok = 0
+    for cd in o[:40]:
+        ok, msg, st = pkg.ft8_decode(mag, cd, 20)
+        d = oracle.decode(mag, cd)
+        assert ok == bool(d["ok"])
+        assert st.tobytes() == d["status"].tobytes(), "unwritten status fields must stay unwritten (0xA5 pattern)"
+        if ok:
+            assert msg.tobytes() == d["msg"].tobytes()
+            n_ok += 1
+    assert n_ok >= 3
+    # a candidate find_sync never returned + a different iteration count: served by the uncached single-candidate path
+    cd = np.array([(11, 3, 100, 1, 0)], cand_dtype)[0]
+    for iters in (20, 5):
+        ok, msg, st = pkg.ft8_decode(mag, cd, iters)
+        d = oracle.decode(mag, cd, max_iters=iters)
+        assert ok == bool(d["ok"]) and st.tobytes() == d["status"].tobytes()
+    ok, msg, st = pkg.ft8_decode(mag, o[0], 3)
+    d = oracle.decode(mag, o[0], max_iters=3)
+    assert ok == bool(d["ok"]) and st.tobytes() == d["status"].tobytes()

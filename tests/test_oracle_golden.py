@@ -1,0 +1,65 @@
+"""The CPU oracle (oracle/ft8_oracle*.c) against the committed golden fixtures, which were produced by the
+UNMODIFIED reference (tools/make_golden.py), and against the reference's known-answer constants.
+No GPU, no /root/reference needed."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, golden
+from oracle.pyoracle import cand_dtype
+
+
+def test_kat_pack_encode(oracle):
+    g = golden("kat")
+    # "CQ K1JT FN20QI" -> 00 00 00 20 4d fc dc 8a 14 08 -> 79 tones (rtlsdr_ft8d.c:919-923)
+    assert oracle.pack_std("CQ", "K1JT", "FN20").hex() == "000000204dfcdc8a1408" == g["packed"].tobytes().hex()
+    tones = oracle.tones(g["packed"].tobytes())
+    assert "".join(map(str, tones)) == "3140652000000001005477547106035036373140652547441342116056460065174427143140652"
+    assert np.array_equal(tones, g["tones"])
+
+
+def test_kat_crc(oracle):
+    # ft8_lib/test.c:97-101 (commented out there; its "0x0708" predates the CRC-14 of this ft8_lib).
+    # The pinned value is what the reference's own ftx_compute_crc returns today.
+    g = golden("kat")
+    assert oracle.crc14(bytes([0x11, 0, 0, 0, 0, 0x0E, 0x10, 0x04, 0x01, 0x00, 0, 0]), 76) == int(g["crc_test3"][0])
+
+
+def test_window_table(oracle):
+    assert bits_equal(oracle.sine_window(1024), golden("kat")["window"])
+
+
+def test_decimator_golden(oracle):
+    g = golden("decim_random")
+    i_s, q_s = oracle.decimate_slot(g["iq"][: (g["iq"].size // 8) * 8])
+    assert i_s.size == g["i"].size == 80
+    assert bits_equal(i_s, g["i"]) and bits_equal(q_s, g["q"])
+
+
+@pytest.mark.parametrize("name,src", [("slot_single", "slot_single"), ("slot_crowded_k500", "slot_crowded_k500"), ("slot_crowded_k120", "slot_crowded_k500")])
+def test_slot_golden(oracle, name, src):
+    g = golden(name)
+    gi = golden(src)
+    K, M = int(g["kmax"]), int(g["mmax"])
+    r = oracle.subsystem(gi["i"], gi["q"], max_cand=K, max_msgs=M)
+    assert np.array_equal(r["wf"], g["wf"]), "waterfall bytes"
+    assert np.array_equal(r["cands"], g["cands"].view(cand_dtype)), "candidate list (order included)"
+    assert r["n"] == int(g["n"])
+    assert r["results"].tobytes() == g["results"].tobytes(), "decoder_results[]"
+    for k, c in enumerate(r["cands"]):
+        d = oracle.decode(g["wf"], c)
+        assert d["ok"] == g["dec_ok"][k]
+        assert bits_equal(d["llr"], g["llr"][k]), f"normalised LLRs of candidate {k}"
+        assert np.array_equal(d["plain"], g["plain"][k])
+        assert d["status"].tobytes() == g["dec_status"][k].tobytes(), "status incl. unwritten (0xA5) fields"
+        assert d["msg"].tobytes() == g["dec_msg"][k].tobytes()
+
+
+def test_threshold_table_is_the_quantiser(oracle):
+    """count(thresholds <= x) == clamp((int)(2*10*log10f(x)+240)) on a dense sample of floats + all step neighbours."""
+    thr = oracle.db_thresholds()
+    assert thr[0] == 0 and np.isinf(thr[256]) and np.all(np.diff(thr[1:256]) > 0)
+    rng = np.random.default_rng(0)
+    xs = np.exp(rng.uniform(np.log(1e-12), np.log(1e3), 20000)).astype(np.float32)
+    edge = np.concatenate([np.nextafter(thr[1:256], np.float32(0)), thr[1:256], np.nextafter(thr[1:256], np.float32(np.inf))]).astype(np.float32)
+    for x in np.concatenate([xs, edge, np.float32([1e-12, 1.0, 1e6])]):
+        assert oracle.quantize_db(float(x)) == int(np.searchsorted(thr[1:256], x, side="right")), x
