@@ -1,0 +1,382 @@
+#!/usr/bin/env python3
+"""bench.py -- FT8 15 s-slots decoded per second, from raw 2.4 Msps uint8 RTL IQ (BASELINE.json config #2:
+one 15 s slot = 36 M complex samples through the full CIC+FIR decimation and FT8 decode), batched.
+
+  python bench.py --gpus N --steps K --warmup W                     this repository's CUDA path (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W    the reference's own CPU implementation, all host cores
+
+A "step" is one pass of the whole hot path (decimate -> condition -> waterfall -> Costas sync/top-K ->
+LLR/LDPC/CRC/unpack -> spot table) over one batch of synthetic slots.  `value` times it with the batch already
+resident in HBM (the batch is larger than L2); `e2e` times the same path through the C-ABI call that takes HOST
+buffers (pinned), host->device copies and the device->host read of the spot records inside the timed region.
+`roofline` is for the dominant kernel (cic_block_sums, HBM-bound), timed live with CUDA events on the launching
+stream; `cpu_baseline` is the CPU checker (oracle/_ref = the unmodified reference when it was built, else the
+restatement) timed on this box's host cores on a bounded sample of the same batch.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAW_SLOT_BYTES = 72_000_000
+ALGO_BYTES_PER_SLOT = 72_000_000 + 47_936 * 8  # 2 B/sample in + 8 B per output
+METRIC = "FT8 15s-slots decoded/sec from raw 2.4 Msps uint8 IQ"
+
+
+# --------------------------------------------------------------------------------------------- inputs
+def slot_params(seed: int):
+    """Deterministic message / frequency / time offset of synthetic slot `seed`."""
+    from tools import ft8enc, synth
+    rng = np.random.Generator(np.random.PCG64(0xF78 + seed))
+    to, de, ex = synth.random_message(rng)
+    if seed % 2 == 0:
+        to = "CQ"
+        ex = synth.random_grid(rng)
+    tones = ft8enc.tones(ft8enc.pack_std(to, de, ex))
+    return dict(text=f"{to} {de} {ex}", tones=tones, f_hz=float(rng.uniform(200.0, 1400.0)), t0=float(0.5 + rng.uniform(-0.3, 0.3)),
+                amp=20.0, noise=30.0)
+
+
+def gen_raw_slot_torch(out, seed: int, device):
+    """One 72 MB slot of uint8 IQ: phase-continuous 8-FSK at (f - 600 kHz) + Gaussian noise, offset 127.5, saturating."""
+    import torch
+    p = slot_params(seed)
+    n_s = RAW_SLOT_BYTES // 2
+    n = torch.arange(n_s, device=device, dtype=torch.int64)
+    sym = torch.div(n - int(round(p["t0"] * 2_400_000)), 384_000, rounding_mode="floor")
+    inside = (sym >= 0) & (sym < 79)
+    tone = torch.from_numpy(p["tones"].astype(np.int64)).to(device)[sym.clamp_(0, 78)]
+    del sym, n
+    freq = (tone.to(torch.float64) * 6.25 + (p["f_hz"] - 600_000.0)) * inside
+    del tone
+    phase = torch.cumsum(freq, 0).mul_(2.0 * np.pi / 2_400_000.0).remainder_(2.0 * np.pi).to(torch.float32)
+    del freq
+    g = torch.Generator(device=device)
+    g.manual_seed(1234567 + seed)
+    amp = inside.to(torch.float32) * p["amp"]
+    v = out.view(n_s, 2)
+    v[:, 0] = (torch.cos(phase) * amp + torch.randn(n_s, device=device, generator=g) * p["noise"] + 127.5).round_().clamp_(0, 255).to(torch.uint8)
+    v[:, 1] = (torch.sin(phase) * amp + torch.randn(n_s, device=device, generator=g) * p["noise"] + 127.5).round_().clamp_(0, 255).to(torch.uint8)
+    return p["text"]
+
+
+def gen_batch(n_slots: int, first_seed: int, device):
+    import torch
+    buf = torch.empty((n_slots, RAW_SLOT_BYTES), dtype=torch.uint8, device=device)
+    texts = [gen_raw_slot_torch(buf[s], first_seed + s, device) for s in range(n_slots)]
+    return buf, texts
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """SM clock / throttle-reason sampling DURING the timed region: NVML polled every 2 ms from a thread
+    (nvidia-smi -lms cannot resolve a region that lasts milliseconds)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return
+
+        def loop():
+            while not self.stop_flag:
+                try:
+                    mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    try:
+                        why = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        why = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append((time.time(), float(mhz), int(why)))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1)
+
+    def summary(self, t0: float, t1: float):
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not rows:  # region shorter than one poll: take the nearest samples
+            rows = sorted(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:3]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        why = 0
+        for r in rows:
+            why |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, bit in self.REASONS.items() if why & bit), "samples": len(rows)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+_CPU_SLOTS = None  # numpy uint8 [n, 72e6], shared with forked workers
+
+
+def cpu_kind():
+    from oracle.pyoracle import Reference
+    return "reference" if Reference.available("k120") else "port"
+
+
+def _cpu_one_slot(idx: int):
+    """Raw slot -> spots on the CPU: rtlsdr_callback() in 65536-byte calls, decoder() conditioning, ft8_subsystem()."""
+    from oracle.pyoracle import Oracle, Reference
+    raw = _CPU_SLOTS[idx]
+    orc = Oracle()
+    if cpu_kind() == "reference":
+        ref = Reference("k120", fresh=True)  # private copy: the daemon's decimator state is function-static
+        for o in range(0, raw.size, 65536):
+            ref.callback(raw[o:o + 65536])
+        i_s, q_s, n = ref.rx()
+        i_s, q_s, _ = orc.condition(i_s, q_s, n)  # decoder() itself is thread-bound in the daemon (rtlsdr_ft8d.c:221-285)
+        r = ref.subsystem(i_s, q_s)
+        return int(r["n"])
+    oi, oq = orc.decimate_slot(raw)
+    i_s = np.zeros(48000, np.float32); q_s = np.zeros(48000, np.float32)
+    i_s[:oi.size] = oi; q_s[:oq.size] = oq
+    i_s, q_s, _ = orc.condition(i_s, q_s, oi.size)
+    return int(orc.subsystem(i_s, q_s)["n"])
+
+
+def cpu_run(n_slots: int, workers: int):
+    """Seconds to push slots 0..n_slots-1 of _CPU_SLOTS through the CPU path with `workers` processes."""
+    t0 = time.perf_counter()
+    if workers <= 1:
+        out = [_cpu_one_slot(k) for k in range(n_slots)]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            out = pool.map(_cpu_one_slot, range(n_slots), chunksize=1)
+    return time.perf_counter() - t0, out
+
+
+# --------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slots", type=int, default=32, help="15 s slots per GPU per step")
+    ap.add_argument("--e2e-slots", type=int, default=4, help="slots per step of the host-buffer (e2e) measurement")
+    ap.add_argument("--cpu-slots", type=int, default=16, help="bounded CPU-baseline sample (slots)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "BASELINE config #2 batched: %d x (one 15 s slot of raw 2.4 Msps uint8 RTL IQ, 36 M complex samples, one FT8 message "
+                          "at 20 LSB over 30 LSB noise) per GPU per step -> CIC+FIR decimation -> decoder() conditioning -> waterfall -> "
+                          "sync (K=120) -> LDPC/CRC/unpack -> spot table" % args.slots,
+              "slots_per_gpu_per_step": args.slots, "input_bytes_per_step_per_gpu": args.slots * RAW_SLOT_BYTES,
+              "l2": "inputs larger than L2 (%.1f GB per step per GPU vs 126 MB)" % (args.slots * RAW_SLOT_BYTES / 1e9),
+              "max_candidates": 120, "max_messages": 50, "ldpc_iterations": 20, "parallelism": "slots sharded across GPUs, no data-path collective; "
+              "spot records gathered with NCCL all_gather" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world, config)
+
+    import torch
+    import torch.distributed as dist
+    from ft8b200_loader import load
+    pkg = load()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    B = args.slots
+    batch, texts = gen_batch(B, 100_000 * rank, device)
+    ctx = pkg.Context(local)
+    ctx.set_profiling(True)
+    M = ctx.M
+    res_dev, nres_dev = None, None
+    gathered = torch.empty((world * B, M, 28), dtype=torch.uint8, device=device) if world > 1 else None
+    gathered_n = torch.empty(world * B, dtype=torch.int32, device=device) if world > 1 else None
+
+    def step():
+        nonlocal res_dev, nres_dev
+        ctx.process_raw(batch, B)
+        if world > 1:
+            if res_dev is None:
+                res_dev, nres_dev = ctx.results_tensors(B)
+            dist.all_gather_into_tensor(gathered, res_dev)   # spot records over NVLink
+            dist.all_gather_into_tensor(gathered_n, nres_dev)
+            if rank == 0:
+                return gathered.cpu(), gathered_n.cpu()
+            torch.cuda.current_stream().synchronize()
+            return None
+        return ctx.fetch_results(B)
+
+    for _ in range(args.warmup):
+        out = step()
+    # correctness guard on the first batch: every synthetic slot must decode to its own message
+    if world == 1:
+        res, nres = out
+        got = [(res[s][0]["call"].decode(), res[s][0]["loc"].decode()) if nres[s] else None for s in range(B)]
+        n_good = sum(1 for s in range(B) if nres[s] >= 1)
+    else:
+        n_good = -1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    stage_acc = {}
+    launches0 = ctx.launches()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        for k, v in ctx.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- e2e: host buffers in, host results out, through the C-ABI call
+    Be = min(args.e2e_slots, B)
+    host = torch.empty((Be, RAW_SLOT_BYTES), dtype=torch.uint8, pin_memory=True)
+    host.copy_(batch[:Be])
+    host_np = host.numpy()
+    for _ in range(args.warmup):
+        ctx.process_raw_host(host_np, Be)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        r_e2e, n_e2e = ctx.process_raw_host(host_np, Be)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    sampler.stop()
+    e2e = {"value": world * Be * args.steps / (ms_e2e * 1e-3), "unit": "slots/s", "h2d_bytes_per_step": Be * RAW_SLOT_BYTES,
+           "d2h_bytes_per_step": Be * (M * 28 + 4), "slots_per_step": Be, "api": "ft8b200_process_raw_host (pinned host IQ in, decoder_results out)"}
+
+    # ---- roofline of the dominant kernel (cic_block_sums): algorithmic bytes / CUDA-event time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k1_ms = stage_acc.get("block_sums", 0.0) / args.steps
+    k2_ms = stage_acc.get("comb_fir", 0.0) / args.steps
+    achieved = B * ALGO_BYTES_PER_SLOT / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    roofline = {"kernel": "cic_block_sums_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured, burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_SLOT, "launch_ms": k1_ms,
+                "decimator_ms_incl_comb_fir": k1_ms + k2_ms,
+                "decimator_msps": B * 36.0 / ((k1_ms + k2_ms) * 1e-3) if k1_ms > 0 else None,
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        roofline["traffic"] = tr.get("dram_bytes_per_slot", 0) * B or None
+    except Exception:
+        pass
+
+    out = {"metric": METRIC, "value": value, "unit": "slots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
+           "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+           "decoded_ok_slots_in_first_batch": n_good}
+
+    if rank == 0 and world == 1:
+        global _CPU_SLOTS
+        n_cpu = min(args.cpu_slots, B)
+        _CPU_SLOTS = batch[:n_cpu].cpu().numpy()
+        secs, n_dec = cpu_run(n_cpu, 1)
+        gpu_n = [int(x) for x in nres[:n_cpu]]
+        out["cpu_baseline"] = {"value": n_cpu / secs, "unit": "slots/s", "cores": 1, "kind": cpu_kind(),
+                               "sample": "%d of the step's %d slots, single thread: rtlsdr_callback in 65536-byte calls + decoder() "
+                                         "conditioning + ft8_subsystem (%.2f s)" % (n_cpu, B, secs),
+                               "same_spot_counts_as_gpu": n_dec == gpu_n}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(args, rank, world, config):
+    """The reference's own CPU implementation of the path on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return 0
+    global _CPU_SLOTS
+    cores = os.cpu_count() or 1
+    n = max(cores, 4)
+    try:
+        import torch
+        dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        buf, _ = gen_batch(n, 0, dev)
+        _CPU_SLOTS = buf.cpu().numpy()
+        del buf
+    except Exception as exc:  # pragma: no cover
+        print(json.dumps({"impl": "reference", "unavailable": f"input synthesis failed: {exc}"}))
+        return 0
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(min(n, cores), cores)
+    t = 0.0
+    for _ in range(args.steps):
+        secs, _ = cpu_run(n, cores)
+        t += secs
+    value = n * args.steps / t
+    kind = cpu_kind()
+    cfg = dict(config)
+    cfg["reference_sample"] = "%d slots per step over %d worker processes" % (n, cores)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "slots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
+           "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": value, "unit": "slots/s", "cores": cores, "kind": kind,
+                            "sample": "%d slots per step, one forked process per slot on %d cores (the reference itself is single-threaded)" % (n, cores)},
+           "e2e": {"value": value, "unit": "slots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -238,6 +238,18 @@ class Context:
         self._chk(self.L.ft8b200_results_device(C.c_void_p(self.h), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def results_tensors(self, n_slots: int):
+        """Zero-copy torch views of the last batch's device-resident outputs: (uint8[n, M, 28], int32[n])."""
+        import torch
+        a, b = self.results_device_ptrs()
+
+        class _Arr:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        dev = torch.device("cuda", self.device)
+        return (torch.as_tensor(_Arr(a, (n_slots, self.M, 28), "|u1"), device=dev), torch.as_tensor(_Arr(b, (n_slots,), "<i4"), device=dev))
+
     def workspace_ptrs(self):
         ptrs = [C.c_void_p(0) for _ in range(9)]
         self._chk(self.L.ft8b200_workspace(C.c_void_p(self.h), *[C.byref(p) for p in ptrs]))
