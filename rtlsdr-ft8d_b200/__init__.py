@@ -210,6 +210,21 @@ class Context:
                                        _p(uscore), _st(stream)))
         return res, nres, umsg, ufreq, uscore
 
+    def monitor_waterfall(self, audio, sample_rate=12000, time_osr=2, freq_osr=2, protocol=1, stream: int | None = None):
+        """Batched 12 kHz monitor: audio float32 [n_slots, n_samples] on device -> (mag uint8 [n_slots, bytes], num_blocks)."""
+        import torch
+        n_slots, n_samples = audio.shape
+        block = int(np.float32(sample_rate) * np.float32(0.048 if protocol == 0 else 0.160))
+        bins = int(np.float32(sample_rate) * np.float32(0.048 if protocol == 0 else 0.160) / 2)
+        max_blocks = int(np.float32(7.5 if protocol == 0 else 15.0) / np.float32(0.048 if protocol == 0 else 0.160))
+        nb = min(max_blocks, n_samples // block)
+        stride = time_osr * freq_osr * bins
+        mag = torch.zeros((n_slots, max(nb, 1) * stride), dtype=torch.uint8, device=audio.device)
+        out_nb = C.c_int(0)
+        self._chk(self.L.ft8b200_monitor_waterfall(C.c_void_p(self.h), _p(audio), C.c_size_t(audio.stride(0)), n_samples, n_slots, sample_rate, time_osr,
+                                                   freq_osr, protocol, _p(mag), C.c_size_t(mag.stride(0)), C.byref(out_nb), _st(stream)))
+        return mag, out_nb.value
+
     # ---- whole path ----------------------------------------------------------------------------------
     def process_raw(self, iq, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None, stream: int | None = None):
         stride = bytes_per_stream if stride is None else stride
@@ -270,7 +285,99 @@ class Context:
         return res, nres
 
 
+class Stream:
+    """One receiver stream (ft8b200_stream_t): what rtlsdr_callback() feeds.  Mirrors the daemon's rx_state."""
+
+    def __init__(self, ctx: Context):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.h = self.L.ft8b200_stream_create(C.c_void_p(ctx.h))
+        if not self.h:
+            raise Ft8Error(self.L.ft8b200_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.ft8b200_stream_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def callback(self, buf: np.ndarray):
+        """rtlsdr_callback(samples, samples_count, ctx) with ctx = this stream."""
+        buf = np.ascontiguousarray(buf, np.uint8)
+        self.L.rtlsdr_callback(_p(buf), C.c_uint32(buf.size), C.c_void_p(self.h))
+
+    def flip(self):
+        rc = self.L.ft8b200_stream_flip(C.c_void_p(self.h))
+        if rc:
+            raise Ft8Error(f"ft8b200_stream_flip -> {rc}")
+
+    def count(self) -> int:
+        return int(self.L.ft8b200_stream_count(C.c_void_p(self.h)))
+
+    def fetch(self):
+        i_s = np.zeros(N_SLOT, np.float32)
+        q_s = np.zeros(N_SLOT, np.float32)
+        n = C.c_uint32(0)
+        rc = self.L.ft8b200_stream_fetch(C.c_void_p(self.h), _p(i_s), _p(q_s), C.byref(n))
+        if rc:
+            raise Ft8Error(f"ft8b200_stream_fetch -> {rc}")
+        return i_s, q_s, int(n.value)
+
+    def decode(self):
+        res = np.zeros(self.ctx.M, result_dtype)
+        n = C.c_int32(0)
+        rc = self.L.ft8b200_stream_decode(C.c_void_p(self.h), _p(res), C.byref(n))
+        if rc:
+            raise Ft8Error(f"ft8b200_stream_decode -> {rc}: {self.L.ft8b200_last_error().decode()}")
+        return res, int(n.value)
+
+
+class Monitor:
+    """monitor_init/process/reset/free with the reference's monitor_t / monitor_config_t (ft8_lib/decode_ft8.c:82-224)."""
+
+    def __init__(self, sample_rate=12000, time_osr=2, freq_osr=2, protocol=1, f_min=100.0, f_max=3000.0):
+        self.L = lib()
+        self.cfg = MonitorConfig(f_min, f_max, sample_rate, time_osr, freq_osr, protocol)
+        self.me = MonitorT()
+        self.L.monitor_init(C.byref(self.me), C.byref(self.cfg))
+        self.open = True
+
+    def process(self, frame: np.ndarray):
+        frame = np.ascontiguousarray(frame, np.float32)
+        assert frame.size == self.me.block_size
+        self.L.monitor_process(C.byref(self.me), _p(frame))
+
+    def reset(self):
+        self.L.monitor_reset(C.byref(self.me))
+
+    def mag(self) -> np.ndarray:
+        n = self.me.wf.num_blocks * self.me.wf.block_stride
+        return np.ctypeslib.as_array(C.cast(self.me.wf.mag, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+
+    def find_sync(self, num_candidates=120, min_score=10):
+        heap = np.zeros(num_candidates, cand_dtype)
+        n = self.L.ft8_find_sync(C.byref(self.me.wf), num_candidates, _p(heap), min_score)
+        return heap[:n]
+
+    def decode(self, cand, max_iterations=20):
+        c = np.array([cand], cand_dtype)
+        msg = np.zeros(1, msg_dtype)
+        st = np.frombuffer(bytes([0xA5]) * 12, status_dtype).copy()
+        ok = self.L.ft8_decode(C.byref(self.me.wf), _p(c), _p(msg), max_iterations, _p(st))
+        return bool(ok), msg[0], st[0]
+
+    def close(self):
+        if self.open:
+            self.L.monitor_free(C.byref(self.me))
+            self.open = False
+
+
 # ---- the reference-named drop-in entry points (host pointers) ---------------------------------------
+def rtlsdr_callback(samples: np.ndarray):
+    """rtlsdr_callback(samples, samples_count, NULL): the process-wide default stream, as in the reference."""
+    buf = np.ascontiguousarray(samples, np.uint8)
+    lib().rtlsdr_callback(_p(buf), C.c_uint32(buf.size), C.c_void_p(0))
+
+
 def ft8_subsystem(i_samples: np.ndarray, q_samples: np.ndarray, decodes: np.ndarray | None = None):
     """ft8_subsystem(float*, float*, uint32_t, struct decoder_results*, int32_t*) on host arrays."""
     L = lib()

@@ -223,10 +223,14 @@ int ft8b200_decimate(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_s
     if ((size_t)(blocks / 8) * 12016 > bytes_per_stream) return fail(FT8B200_EINVAL, "internal: super-block overrun");
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = pick(ctx, stream);
-    if ((rc = ctx->sums.ensure((size_t)n_streams * (blocks > 0 ? blocks : 1) * sizeof(BlockSums)))) return rc;
+    const size_t sstride = (size_t)blocks + kHistBlocks;
+    if ((rc = ctx->sums.ensure((size_t)n_streams * sstride * sizeof(BlockSums)))) return rc;
     if (d_peak) CU(cudaMemsetAsync(d_peak, 0, sizeof(float) * n_streams, st));
-    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_streams, blocks, ctx->sums.as<BlockSums>(), st, &ctx->launches));
-    CU(launch_cic_comb_fir(ctx->sums.as<BlockSums>(), blocks, n_streams, ctx->tb.fir, d_i, d_q, d_count, d_peak, d_y2, st, &ctx->launches));
+    // fresh filter state: the history prefix of every stream is zero
+    CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_streams, st));
+    BlockSums *s0 = ctx->sums.as<BlockSums>() + kHistBlocks;
+    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_streams, blocks, s0, sstride, st, &ctx->launches));
+    CU(launch_cic_comb_fir(s0, sstride, blocks, 0, true, n_streams, ctx->tb.fir, d_i, d_q, d_count, d_peak, d_y2, st, &ctx->launches));
     tally(ctx);
     return 0;
 }
@@ -330,17 +334,20 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
     cudaStream_t st = pick(ctx, stream);
     const int blocks = (int)((bytes_per_stream / 2) / kDecim);
     if ((rc = ensure_slot_buffers(ctx, n_slots))) return rc;
-    if ((rc = ctx->sums.ensure((size_t)n_slots * (blocks > 0 ? blocks : 1) * sizeof(BlockSums)))) return rc;
+    const size_t sstride = (size_t)blocks + kHistBlocks;
+    if ((rc = ctx->sums.ensure((size_t)n_slots * sstride * sizeof(BlockSums)))) return rc;
     if ((rc = ctx->si.ensure((size_t)n_slots * kSlot * sizeof(float)))) return rc;
     if ((rc = ctx->sq.ensure((size_t)n_slots * kSlot * sizeof(float)))) return rc;
     if ((rc = ctx->peak.ensure((size_t)n_slots * sizeof(float)))) return rc;
     if ((rc = ctx->count.ensure((size_t)n_slots * sizeof(uint32_t)))) return rc;
     CU(cudaMemsetAsync(ctx->peak.p, 0, sizeof(float) * n_slots, st));
     for (bool &v : ctx->ev_valid) v = false;
+    CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_slots, st));
+    BlockSums *s0 = ctx->sums.as<BlockSums>() + kHistBlocks;
     mark(ctx, 0, st);
-    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_slots, blocks, ctx->sums.as<BlockSums>(), st, &ctx->launches));
+    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_slots, blocks, s0, sstride, st, &ctx->launches));
     mark(ctx, 1, st);
-    CU(launch_cic_comb_fir(ctx->sums.as<BlockSums>(), blocks, n_slots, ctx->tb.fir, ctx->si.as<float>(), ctx->sq.as<float>(),
+    CU(launch_cic_comb_fir(s0, sstride, blocks, 0, true, n_slots, ctx->tb.fir, ctx->si.as<float>(), ctx->sq.as<float>(),
                            ctx->count.as<uint32_t>(), ctx->peak.as<float>(), nullptr, st, &ctx->launches));
     mark(ctx, 2, st);
     // decoder()'s normalisation is applied on load inside the waterfall kernel (scale from the slot peak)
@@ -351,6 +358,10 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
 }
 
 int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, int n_slots, void *stream) {
+    return ft8b200_process_conditioned(ctx, d_i, d_q, nullptr, n_slots, stream);
+}
+
+int ft8b200_process_conditioned(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, const float *d_peak, int n_slots, void *stream) {
     int rc = ctx_enter(ctx);
     if (rc) return rc;
     if (!d_i || !d_q || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_process_slots: bad argument");
@@ -359,7 +370,7 @@ int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q
     if ((rc = ensure_slot_buffers(ctx, n_slots))) return rc;
     for (bool &v : ctx->ev_valid) v = false;
     mark(ctx, 2, st);
-    CU(launch_waterfall(ctx->tb, d_i, d_q, nullptr, n_slots, ctx->mag.as<uint8_t>(), st, &ctx->launches));
+    CU(launch_waterfall(ctx->tb, d_i, d_q, d_peak, n_slots, ctx->mag.as<uint8_t>(), st, &ctx->launches));
     rc = run_back_end(ctx, n_slots, st);
     tally(ctx);
     return rc;

@@ -34,12 +34,15 @@ struct DeviceTables {
 };
 
 // ---- launchers (each returns cudaGetLastError()) ----
-cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int blocks_per_stream,
-                                  BlockSums *d_sums, cudaStream_t st, int *launches);
-cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int first_block, int n_blocks,
-                                          int blocks_per_stream, BlockSums *d_sums, cudaStream_t st, int *launches);
-cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, int blocks_per_stream, int n_streams, const float *d_fir, float *d_i, float *d_q,
-                                uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st, int *launches);
+constexpr int kHistBlocks = 59;  // block sums a flush needs from before its first block: 56 FIR taps + 3 comb delays
+cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int blocks_per_stream, BlockSums *d_sums,
+                                  size_t sums_stride, cudaStream_t st, int *launches);
+cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq_first_block, size_t stream_stride_bytes, int n_streams, uint32_t phase0, int n_blocks,
+                                          BlockSums *d_sums_first_block, size_t sums_stride, cudaStream_t st, int *launches);
+cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int n_blocks, int out_offset, bool zero_fill, int n_streams,
+                                const float *d_fir, float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st,
+                                int *launches);
+cudaError_t launch_shift_history(BlockSums *d_sums_with_prefix, int n_blocks, cudaStream_t st, int *launches);
 cudaError_t launch_condition(float *d_i, float *d_q, const float *d_peak, int n_slots, cudaStream_t st, int *launches);
 cudaError_t launch_waterfall(const DeviceTables &t, const float *d_i, const float *d_q, const float *d_peak, int n_slots, uint8_t *d_mag,
                              cudaStream_t st, int *launches);

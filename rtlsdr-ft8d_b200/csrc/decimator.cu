@@ -140,7 +140,7 @@ constexpr int kWarpsPerCta = 8;
 
 // Kernel 1: block sums of full, 16-byte aligned super-blocks.  One warp per super-block.
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-cic_block_sums_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int supers_per_stream, int blocks_per_stream,
+cic_block_sums_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int supers_per_stream, size_t sums_stride,
                       BlockSums *__restrict__ sums) {
     __shared__ uint4 s_sums[kWarpsPerCta][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -201,29 +201,30 @@ cic_block_sums_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes
         BlockSums o;
         o.s0i = (int32_t)(v.x - kOff0); o.s1i = (int32_t)(v.y - kOff1);
         o.s0q = (int32_t)(v.z - kOff0); o.s1q = (int32_t)(v.w - kOff1);
-        sums[(size_t)stream * blocks_per_stream + (size_t)sb * 8 + lane] = o;
+        sums[(size_t)stream * sums_stride + (size_t)sb * 8 + lane] = o;
     }
 }
 
 // Generic block sums: one warp per 751-sample block, 2-byte loads, any block range / alignment.
-// Used for the blocks a stream has beyond its last full super-block and as an in-library cross-check.
+// Used for the blocks a stream has outside its full, aligned super-blocks (ragged batch tails and the
+// rtlsdr_callback() streams, whose flushes start and end anywhere).  `iq` points at the first byte of the
+// first block of stream 0; `phase0` is (global index of that block's first sample) & 3 for the fs/4 mixer.
 __global__ void __launch_bounds__(256)
-cic_block_sums_generic_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int first_block, int n_blocks,
-                              int blocks_per_stream, BlockSums *__restrict__ sums) {
+cic_block_sums_generic_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, uint32_t phase0, int n_blocks, size_t sums_stride,
+                              BlockSums *__restrict__ sums) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rel = blockIdx.x * 8 + warp;
     if (rel >= n_blocks) return;
-    const int blk = first_block + rel;
     const int stream = blockIdx.y;
-    const uchar2 *p = reinterpret_cast<const uchar2 *>(iq + (size_t)stream * stream_stride_bytes) + (size_t)blk * kDecim;
-    const uint32_t phase0 = (uint32_t)(((size_t)blk * kDecim) & 3u);
+    const uchar2 *p = reinterpret_cast<const uchar2 *>(iq + (size_t)stream * stream_stride_bytes) + (size_t)rel * kDecim;
+    const uint32_t ph = (phase0 + 3u * (uint32_t)rel) & 3u;  // 751 == 3 (mod 4)
     uint32_t s0i = 0, s1i = 0, s0q = 0, s1q = 0;
     for (uint32_t i = lane; i < (uint32_t)kDecim; i += 32) {
         const uchar2 v = p[i];
         const uint32_t a = v.x, b = v.y;
         const uint32_t na = (0u - a) & 0xffu, nb = (0u - b) & 0xffu;  // wrapping int8 negate, offset-128 domain
         uint32_t mi, mq;
-        switch ((phase0 + i) & 3u) {
+        switch ((ph + i) & 3u) {
         case 0: mi = a; mq = b; break;
         case 1: mi = nb; mq = a; break;
         case 2: mi = na; mq = nb; break;
@@ -239,67 +240,56 @@ cic_block_sums_generic_kernel(const uint8_t *__restrict__ iq, size_t stream_stri
         BlockSums o;
         o.s0i = (int32_t)(s0i - kOff0); o.s1i = (int32_t)(s1i - kOff1);
         o.s0q = (int32_t)(s0q - kOff0); o.s1q = (int32_t)(s1q - kOff1);
-        sums[(size_t)stream * blocks_per_stream + blk] = o;
+        sums[(size_t)stream * sums_stride + rel] = o;
     }
 }
 
 // Kernel 2: comb (closed form over 4 consecutive block sums) + 57-tap FIR + scale + peak.
 // ref: rtlsdr_ft8d.c:162-200.  One CTA = 256 consecutive outputs of one stream.
 constexpr int kTile = 256;
-constexpr int kHist = kFirTaps - 1;  // 56
+constexpr int kHist = kFirTaps - 1;  // 56 FIR history samples; they need kHistBlocks = 56 + 3 block sums
 
+// y2[k] from blocks k-3..k.  `s` points at this flush's block 0; the kHistBlocks entries before it hold the
+// previous blocks of the stream (zeros for a fresh filter state), so no index test is needed.
 __device__ __forceinline__ void comb(const BlockSums *__restrict__ s, int k, int32_t &yi, int32_t &yq) {
-    // y2[k] from blocks k-3..k; blocks before the start of the stream are zero (fresh filter state)
-    uint32_t ai = 0, aq = 0;
-    {
-        const BlockSums b = s[k];
-        ai += 751u * (uint32_t)b.s0i - (uint32_t)b.s1i;
-        aq += 751u * (uint32_t)b.s0q - (uint32_t)b.s1q;
-    }
-    if (k >= 1) {
-        const BlockSums b = s[k - 1];
-        ai += 1502u * (uint32_t)b.s0i - (uint32_t)b.s1i;
-        aq += 1502u * (uint32_t)b.s0q - (uint32_t)b.s1q;
-    }
-    if (k >= 2) {
-        const BlockSums b = s[k - 2];
-        ai += 751u * (uint32_t)b.s0i + (uint32_t)b.s1i;
-        aq += 751u * (uint32_t)b.s0q + (uint32_t)b.s1q;
-    }
-    if (k >= 3) {
-        const BlockSums b = s[k - 3];
-        ai += (uint32_t)b.s1i;
-        aq += (uint32_t)b.s1q;
-    }
+    const BlockSums b0 = s[k], b1 = s[k - 1], b2 = s[k - 2], b3 = s[k - 3];
+    const uint32_t ai = (751u * (uint32_t)b0.s0i - (uint32_t)b0.s1i) + (1502u * (uint32_t)b1.s0i - (uint32_t)b1.s1i) +
+                        (751u * (uint32_t)b2.s0i + (uint32_t)b2.s1i) + (uint32_t)b3.s1i;
+    const uint32_t aq = (751u * (uint32_t)b0.s0q - (uint32_t)b0.s1q) + (1502u * (uint32_t)b1.s0q - (uint32_t)b1.s1q) +
+                        (751u * (uint32_t)b2.s0q + (uint32_t)b2.s1q) + (uint32_t)b3.s1q;
     yi = (int32_t)ai;
     yq = (int32_t)aq;
 }
 
+// n_blocks new blocks per stream -> outputs [out_offset, out_offset + n_blocks) of the stream's 48000-sample
+// slot buffer (outputs past 48000 are dropped but the filter keeps running, rtlsdr_ft8d.c:196-200).
+// zero_fill: also clear [out_offset + n_blocks, 48000) -- what decoder() does before it normalises (:243-246).
 __global__ void __launch_bounds__(kTile)
-cic_comb_fir_kernel(const BlockSums *__restrict__ sums, int blocks_per_stream, const float *__restrict__ fir, float *__restrict__ out_i,
-                    float *__restrict__ out_q, uint32_t *__restrict__ count, float *__restrict__ peak, int32_t *__restrict__ y2_out) {
+cic_comb_fir_kernel(const BlockSums *__restrict__ sums, size_t sums_stride, int n_blocks, int out_offset, int zero_fill,
+                    const float *__restrict__ fir, float *__restrict__ out_i, float *__restrict__ out_q, uint32_t *__restrict__ count,
+                    float *__restrict__ peak, int32_t *__restrict__ y2_out) {
     __shared__ float s_yi[kTile + kHist], s_yq[kTile + kHist];
     __shared__ float s_fir[kFirTaps];
     const int stream = blockIdx.y;
     const int k0 = blockIdx.x * kTile;
-    const BlockSums *s = sums + (size_t)stream * blocks_per_stream;
-    const int n_out = blocks_per_stream < kSlot ? blocks_per_stream : kSlot;
+    const BlockSums *s = sums + (size_t)stream * sums_stride;
     if (threadIdx.x < kFirTaps) s_fir[threadIdx.x] = fir[threadIdx.x];
     for (int idx = threadIdx.x; idx < kTile + kHist; idx += kTile) {
-        const int k = k0 - kHist + idx;
+        const int k = k0 - kHist + idx;  // >= -56: inside the history prefix
         int32_t yi = 0, yq = 0;
-        if (k >= 0 && k < blocks_per_stream) comb(s, k, yi, yq);
+        if (k < n_blocks) comb(s, k, yi, yq);
         s_yi[idx] = __int2float_rn(yi);  // (float)Iy2, rtlsdr_ft8d.c:189-190
         s_yq[idx] = __int2float_rn(yq);
-        if (y2_out && k >= k0 && k < n_out) {
-            y2_out[((size_t)stream * kSlot + k) * 2 + 0] = yi;
-            y2_out[((size_t)stream * kSlot + k) * 2 + 1] = yq;
+        if (y2_out && k >= k0 && k < n_blocks && out_offset + k < kSlot) {
+            y2_out[((size_t)stream * kSlot + out_offset + k) * 2 + 0] = yi;
+            y2_out[((size_t)stream * kSlot + out_offset + k) * 2 + 1] = yq;
         }
     }
     __syncthreads();
     const int k = k0 + threadIdx.x;
+    const int o = out_offset + k;
     float vi = 0.0f, vq = 0.0f;
-    if (k < n_out) {
+    if (k < n_blocks && o < kSlot) {
         float ai = 0.0f, aq = 0.0f;
 #pragma unroll
         for (int j = 0; j < kFirTaps; ++j) {  // strictly sequential, product rounded before the add (no FMA)
@@ -309,15 +299,28 @@ cic_comb_fir_kernel(const BlockSums *__restrict__ sums, int blocks_per_stream, c
         vi = __double2float_rn(__ddiv_rn((double)ai, 32768.0 * 750));  // rtlsdr_ft8d.c:197-198
         vq = __double2float_rn(__ddiv_rn((double)aq, 32768.0 * 750));
     }
-    if (k < kSlot) {  // zero tail: decoder() clears [iqIndex, 48000), rtlsdr_ft8d.c:243-246
-        out_i[(size_t)stream * kSlot + k] = vi;
-        out_q[(size_t)stream * kSlot + k] = vq;
+    if (o < kSlot && (k < n_blocks || zero_fill)) {
+        out_i[(size_t)stream * kSlot + o] = vi;
+        out_q[(size_t)stream * kSlot + o] = vq;
     }
     float m = fmaxf(fabsf(vi), fabsf(vq));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && peak) atomicMax(reinterpret_cast<unsigned int *>(peak + stream), __float_as_uint(m));
-    if (count && blockIdx.x == 0 && threadIdx.x == 0) count[stream] = (uint32_t)n_out;
+    for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
+    if ((threadIdx.x & 31) == 0 && peak && m > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(peak + stream), __float_as_uint(m));
+    if (count && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int n_out = out_offset + n_blocks;
+        count[stream] = (uint32_t)(n_out < kSlot ? n_out : kSlot);
+    }
+}
+
+// keep the last kHistBlocks sums of a flush as the history prefix of the next one (regions may overlap)
+__global__ void shift_history_kernel(BlockSums *sums, int n_blocks) {
+    // sums points at the history prefix: entries [0, kHistBlocks) history, [kHistBlocks, kHistBlocks + n_blocks) new
+    const int t = threadIdx.x;
+    BlockSums v = {};
+    if (t < kHistBlocks) v = sums[n_blocks + t];
+    __syncthreads();
+    if (t < kHistBlocks) sums[t] = v;
 }
 
 // a4 as a standalone pass (the fused pipeline applies the scale inside the waterfall load instead)
@@ -335,37 +338,50 @@ __global__ void condition_kernel(float *__restrict__ d_i, float *__restrict__ d_
 
 }  // namespace
 
+// Block sums of `blocks_per_stream` blocks per stream, streams starting at a super-block boundary of their
+// sample stream (mixer phase 0).  d_sums points at block 0 of stream 0 (history prefix before it).
 cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int blocks_per_stream, BlockSums *d_sums,
-                                  cudaStream_t st, int *launches) {
+                                  size_t sums_stride, cudaStream_t st, int *launches) {
     const int supers = blocks_per_stream / 8;
     if (supers > 0) {
         dim3 grid((supers + kWarpsPerCta - 1) / kWarpsPerCta, n_streams);
-        cic_block_sums_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, blocks_per_stream, d_sums);
+        cic_block_sums_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, sums_stride, d_sums);
         ++*launches;
     }
     const int rest = blocks_per_stream - supers * 8;
     if (rest > 0) {
         dim3 grid((rest + 7) / 8, n_streams);
-        cic_block_sums_generic_kernel<<<grid, 256, 0, st>>>(d_iq, stream_stride_bytes, supers * 8, rest, blocks_per_stream, d_sums);
+        cic_block_sums_generic_kernel<<<grid, 256, 0, st>>>(d_iq + (size_t)supers * kSuperBytes, stream_stride_bytes, 0u, rest, sums_stride,
+                                                            d_sums + (size_t)supers * 8);
         ++*launches;
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int first_block, int n_blocks,
-                                          int blocks_per_stream, BlockSums *d_sums, cudaStream_t st, int *launches) {
+cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq_first_block, size_t stream_stride_bytes, int n_streams, uint32_t phase0, int n_blocks,
+                                          BlockSums *d_sums_first_block, size_t sums_stride, cudaStream_t st, int *launches) {
     if (n_blocks > 0) {
         dim3 grid((n_blocks + 7) / 8, n_streams);
-        cic_block_sums_generic_kernel<<<grid, 256, 0, st>>>(d_iq, stream_stride_bytes, first_block, n_blocks, blocks_per_stream, d_sums);
+        cic_block_sums_generic_kernel<<<grid, 256, 0, st>>>(d_iq_first_block, stream_stride_bytes, phase0, n_blocks, sums_stride, d_sums_first_block);
         ++*launches;
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, int blocks_per_stream, int n_streams, const float *d_fir, float *d_i, float *d_q,
-                                uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st, int *launches) {
-    dim3 grid((kSlot + kTile - 1) / kTile, n_streams);
-    cic_comb_fir_kernel<<<grid, kTile, 0, st>>>(d_sums, blocks_per_stream, d_fir, d_i, d_q, d_count, d_peak, d_y2);
+cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int n_blocks, int out_offset, bool zero_fill, int n_streams,
+                                const float *d_fir, float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st,
+                                int *launches) {
+    int span = n_blocks;
+    if (zero_fill && kSlot - out_offset > span) span = kSlot - out_offset;
+    if (span <= 0) return cudaSuccess;
+    dim3 grid((span + kTile - 1) / kTile, n_streams);
+    cic_comb_fir_kernel<<<grid, kTile, 0, st>>>(d_sums, sums_stride, n_blocks, out_offset, zero_fill ? 1 : 0, d_fir, d_i, d_q, d_count, d_peak, d_y2);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shift_history(BlockSums *d_sums_with_prefix, int n_blocks, cudaStream_t st, int *launches) {
+    shift_history_kernel<<<1, 64, 0, st>>>(d_sums_with_prefix, n_blocks);
     ++*launches;
     return cudaGetLastError();
 }

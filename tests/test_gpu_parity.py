@@ -313,3 +313,57 @@ def test_dropin_find_sync_and_decode(pkg, oracle, slots):
     ok, msg, st = pkg.ft8_decode(mag, o[0], 3)
     d = oracle.decode(mag, o[0], max_iters=3)
     assert ok == bool(d["ok"]) and st.tobytes() == d["status"].tobytes()
+
+
+# ------------------------------------------------------------------------------------------- receiver streams
+def test_stream_callback_matches_reference_chunking(pkg, ctx, oracle, raw_slot):
+    """rtlsdr_callback() fed as librtlsdr does (65536-byte buffers), filter state carried across calls and across
+    the 15 s buffer flip (rtlsdr_ft8d.c:80-86, 1339-1354), against the oracle's sample-by-sample streaming decimator."""
+    st = pkg.Stream(ctx)
+    rng = np.random.default_rng(8)
+    second = rng.integers(0, 256, size=65536 * 300 + 8 * 5, dtype=np.uint8)  # second slot: random bytes, ragged end
+    o_state = oracle.new_decim()
+    oi1, oq1 = [], []
+    for o in range(0, raw_slot.size, 65536):
+        chunk = raw_slot[o:o + 65536]
+        st.callback(chunk)
+        a, b = oracle.decim_feed(o_state, chunk, 64)
+        oi1.append(a); oq1.append(b)
+    oi1 = np.concatenate(oi1); oq1 = np.concatenate(oq1)
+    assert st.count() == oi1.size == 47936
+    st.flip()
+    gi, gq, n = st.fetch()
+    assert n == oi1.size
+    assert bits_equal(gi[:n], oi1) and bits_equal(gq[:n], oq1) and not gi[n:].any()
+    res, nres = st.decode()  # decoder(): >= 12 s of samples, condition, ft8_subsystem
+    ic, qc, _ = oracle.condition(gi, gq, n)
+    o = oracle.subsystem(ic, qc)
+    assert nres == o["n"] >= 1 and res.tobytes() == o["results"].tobytes()
+    # second slot continues from the first slot's filter state; odd call sizes (multiples of 8 bytes)
+    oi2, oq2 = [], []
+    sizes = [8, 16, 1496, 65536 - 1520] + [65536] * 299 + [40]
+    o = 0
+    for sz in sizes:
+        chunk = second[o:o + sz]; o += sz
+        st.callback(chunk)
+        a, b = oracle.decim_feed(o_state, chunk, 64)
+        oi2.append(a); oq2.append(b)
+    assert o == second.size
+    oi2 = np.concatenate(oi2); oq2 = np.concatenate(oq2)
+    assert st.count() == oi2.size
+    st.flip()
+    gi, gq, n = st.fetch()
+    assert n == oi2.size and bits_equal(gi[:n], oi2) and bits_equal(gq[:n], oq2)
+    res, nres = st.decode()
+    assert nres == -1, "fewer than 12 s of samples: decoder() skips the slot (rtlsdr_ft8d.c:235-238)"
+    st.close()
+
+
+def test_default_stream_callback(pkg, oracle):
+    """ctx == NULL: the process-wide stream, like the reference's function-static state."""
+    rng = np.random.default_rng(9)
+    buf = rng.integers(0, 256, size=65536 * 3, dtype=np.uint8)
+    for o in range(0, buf.size, 65536):
+        pkg.rtlsdr_callback(buf[o:o + 65536])
+    # an odd-sized buffer is rejected loudly, not half-processed
+    pkg.rtlsdr_callback(buf[:12])
