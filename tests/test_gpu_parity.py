@@ -367,3 +367,60 @@ def test_default_stream_callback(pkg, oracle):
         pkg.rtlsdr_callback(buf[o:o + 65536])
     # an odd-sized buffer is rejected loudly, not half-processed
     pkg.rtlsdr_callback(buf[:12])
+
+
+# ------------------------------------------------------------------------------------------- 12 kHz monitor path (ft8_lib decode_ft8.c)
+@pytest.fixture(scope="module")
+def audio():
+    sigs = [(ft8enc.tones(ft8enc.pack_std("CQ", "K1JT", "FN20")), 1200.0, 0.5, 0.1),
+            (ft8enc.tones(ft8enc.pack_std("K1ABC", "W9XYZ", "-15")), 2100.0, 1.1, 0.05),
+            (ft8enc.tones(ft8enc.pack_std("W9XYZ", "K1ABC", "RR73")), 310.0, 0.1, 0.03)]
+    return synth.audio_12k(sigs, 3)
+
+
+def test_monitor_batch_waterfall(ctx, oracle, audio):
+    """3840-point real FFT frames (kiss_fftr arithmetic), Hann window, 93 x 2 x 2 x 960 cells: identical bytes."""
+    ref, info, _ = oracle.monitor_waterfall(audio)
+    quiet = np.zeros_like(audio)
+    short = np.zeros_like(audio); short[:50_000] = audio[:50_000]
+    batch = torch.from_numpy(np.stack([audio, quiet, short])).to(dev())
+    mag, nb = ctx.monitor_waterfall(batch)
+    assert nb == 93 == int(info[4])
+    mag = mag.cpu().numpy()
+    assert np.array_equal(mag[0], ref), f"{int((mag[0] != ref).sum())} cells differ"
+    assert np.array_equal(mag[1], oracle.monitor_waterfall(quiet)[0])
+    assert np.array_equal(mag[2], oracle.monitor_waterfall(short)[0])
+    # a shorter recording: fewer blocks
+    mag2, nb2 = ctx.monitor_waterfall(batch[:1, :1920 * 40 + 100].contiguous())
+    ref2, info2, _ = oracle.monitor_waterfall(audio[:1920 * 40 + 100])
+    assert nb2 == 40 == int(info2[4]) and np.array_equal(mag2[0].cpu().numpy()[: ref2.size], ref2)
+
+
+def test_monitor_dropin_and_decode(pkg, oracle, audio):
+    """monitor_init/monitor_process/monitor_reset + ft8_find_sync/ft8_decode on the 960-bin waterfall, as decode_ft8 main() uses them."""
+    mon = pkg.Monitor(12000, 2, 2, 1)
+    assert (mon.me.block_size, mon.me.subblock_size, mon.me.nfft, mon.me.wf.max_blocks, mon.me.wf.num_bins) == (1920, 960, 3840, 93, 960)
+    for o in range(0, audio.size - 1920 + 1, 1920):
+        mon.process(audio[o:o + 1920])
+    mon.process(audio[:1920])  # 94th block: silently ignored
+    ref, info, ref_max = oracle.monitor_waterfall(audio)
+    assert mon.me.wf.num_blocks == 93
+    assert np.array_equal(mon.mag(), ref)
+    assert np.float32(mon.me.max_mag) == np.float32(ref_max)
+    heap = mon.find_sync(120, 10)
+    o_heap = oracle.find_sync(ref, 120, 10, num_blocks=93, num_bins=960)
+    assert np.array_equal(heap.view(cand_dtype), o_heap)
+    texts = set()
+    for cd in o_heap:
+        ok, msg, st = mon.decode(cd, 20)
+        d = oracle.decode(ref, cd, num_blocks=93, num_bins=960)
+        assert ok == bool(d["ok"]) and st.tobytes() == d["status"].tobytes()
+        if ok:
+            assert msg["text"] == d["msg"]["text"]
+            texts.add(msg["text"].decode())
+    assert {"CQ K1JT FN20", "K1ABC W9XYZ -15"} <= texts
+    mon.reset()
+    assert mon.me.wf.num_blocks == 0
+    mon.process(audio[:1920])  # history is NOT cleared by reset (decode_ft8.c:220-224)
+    assert mon.me.wf.num_blocks == 1
+    mon.close()
