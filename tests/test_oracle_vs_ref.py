@@ -1,0 +1,181 @@
+"""Pins the CPU restatement (oracle/ft8_oracle*.c) against the UNMODIFIED reference compiled from /root/reference
+(oracle/_ref/libref_*.so, `make -C oracle ref`).  Skipped where the reference build is absent (the committed golden
+fixtures in tests/golden/ cover that case: tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+from oracle.pyoracle import Reference, ReferenceMonitor, cand_dtype
+from tools import ft8enc, synth
+
+pytestmark = pytest.mark.skipif(not (Reference.available("k120") and Reference.available("k500") and ReferenceMonitor.available()),
+                                reason="oracle/_ref not built (needs /root/reference)")
+
+
+def test_reference_selftest_runs():
+    """decoderSelfTest() (rtlsdr_ft8d.c:913-972): the reference decodes its own 'CQ K1JT FN20QI' signal."""
+    assert Reference("k120").lib.ref_selftest() == 1
+
+
+def test_decimator_streaming_vs_rtlsdr_callback(oracle):
+    ref = Reference("k120", fresh=True)
+    rng = np.random.default_rng(3)
+    iq = rng.integers(0, 256, size=65536 * 40, dtype=np.uint8)
+    iq[::977] = 0
+    iq[5::1201] = 255
+    st = oracle.new_decim()
+    outs = []
+    sizes = [65536] * 20 + [8, 16, 751 * 8, 65536 - 8 - 16 - 751 * 8] + [65536] * 19
+    o = 0
+    for s in sizes:
+        chunk = iq[o:o + s]; o += s
+        ref.callback(chunk)
+        outs.append(oracle.decim_feed(st, chunk, 100))
+    i_s = np.concatenate([x[0] for x in outs]); q_s = np.concatenate([x[1] for x in outs])
+    ri, rq, n = ref.rx()
+    assert n == i_s.size == 1745
+    assert bits_equal(ri[:n], i_s) and bits_equal(rq[:n], q_s)
+
+
+def test_buffer_stops_at_48000_but_filter_keeps_running(oracle):
+    """rtlsdr_ft8d.c:196-200: outputs beyond 48000 are dropped; after the flip the state continues."""
+    ref = Reference("k120", fresh=True)
+    rng = np.random.default_rng(4)
+    n_bytes = 2 * 751 * 48100
+    n_bytes -= n_bytes % 65536
+    iq = rng.integers(96, 160, size=n_bytes + 65536 * 4, dtype=np.uint8)
+    st = oracle.new_decim()
+    got_i = []
+    for o in range(0, n_bytes, 65536):
+        ref.callback(iq[o:o + 65536])
+        got_i.append(oracle.decim_feed(st, iq[o:o + 65536], 64)[0])
+    got_i = np.concatenate(got_i)
+    ri, rq, n = ref.rx()
+    assert n == 48000 and got_i.size > 48000
+    assert bits_equal(ri, got_i[:48000])
+    ref.flip()
+    more = []
+    for o in range(n_bytes, iq.size, 65536):
+        ref.callback(iq[o:o + 65536])
+        more.append(oracle.decim_feed(st, iq[o:o + 65536], 64)[0])
+    more = np.concatenate(more)
+    ri, rq, n = ref.rx()
+    assert n == more.size and bits_equal(ri[:n], more)
+
+
+@pytest.mark.parametrize("variant,n_sig,seed", [("k120", 1, 7), ("k120", 25, 5), ("k500", 60, 99), ("k120", 60, 1234), ("k120", 0, 11)])
+def test_subsystem_all_taps(oracle, variant, n_sig, seed):
+    ref = Reference(variant)
+    if n_sig == 1:
+        i_s, q_s = synth.slot_f32([(ft8enc.tones(ft8enc.pack_std("CQ", "K1JT", "FN20")), 700.0, 0.5, -10.0)], seed)
+    elif n_sig == 0:
+        i_s, q_s = synth.slot_f32([], seed)
+    else:
+        i_s, q_s, _ = synth.crowded_band(ft8enc, n_sig, seed)
+    i_s, q_s, _ = oracle.condition(i_s, q_s, 48000)
+    r = ref.subsystem(i_s, q_s)
+    o = oracle.subsystem(i_s, q_s, max_cand=ref.kmax, max_msgs=ref.mmax)
+    assert np.array_equal(o["wf"], r["wf"])
+    assert np.array_equal(o["cands"], r["cands"].view(cand_dtype))
+    assert o["n"] == r["n"] and o["results"].tobytes() == r["results"].tobytes()
+    for k, c in enumerate(r["cands"]):
+        d = oracle.decode(r["wf"], c)
+        assert d["ok"] == r["dec_ok"][k]
+        assert bits_equal(d["llr"], r["llr"][k]) and np.array_equal(d["plain"], r["plain"][k])
+        assert d["status"].tobytes() == r["dec_status"][k].tobytes()
+        assert d["msg"].tobytes() == r["dec_msg"][k].tobytes()
+
+
+def test_find_sync_on_random_waterfalls(oracle):
+    """Heap eviction and tie-breaking paths: random bytes make thousands of positions pass min_score."""
+    ref = Reference("k120")
+    rng = np.random.default_rng(3)
+    for lo, hi, k, ms in [(0, 256, 120, 10), (60, 90, 120, 10), (0, 256, 7, 0), (100, 110, 500, 1)]:
+        mag = rng.integers(lo, hi, size=94208, dtype=np.uint8)
+        assert np.array_equal(oracle.find_sync(mag, k, ms), ref.find_sync(mag, k, ms).view(cand_dtype))
+
+
+def test_bp_decode_fuzz(oracle):
+    ref = Reference("k120")
+    rng = np.random.default_rng(6)
+    for trial in range(60):
+        bits = oracle.encode174(bytes(rng.integers(0, 256, 10, dtype=np.uint8)))
+        llr = ((bits.astype(np.float32) * 2 - 1) * 4.0 + rng.standard_normal(174).astype(np.float32) * (1.0 + 0.1 * trial)).astype(np.float32)
+        for iters in (20, 3):
+            po, eo = oracle.bp_decode(llr, iters)
+            pr, er = ref.bp_decode(llr, iters)
+            assert eo == er and np.array_equal(po, pr)
+    for llr in (np.zeros(174, np.float32), np.full(174, -3.0, np.float32), np.full(174, np.nan, np.float32)):
+        po, eo = oracle.bp_decode(llr)
+        pr, er = ref.bp_decode(llr)
+        assert eo == er and np.array_equal(po, pr)
+
+
+def test_unpack77_fuzz(oracle):
+    """All message types the reference unpacks (0.0 free text, 0.5 telemetry, 1/2 standard, 4 nonstandard) + rejects."""
+    ref = Reference("k120")
+    rng = np.random.default_rng(7)
+    for i3 in range(8):
+        for _ in range(400):
+            a = bytearray(rng.integers(0, 256, 12, dtype=np.uint8))
+            a[9] = (a[9] & 0xC7) | (i3 << 3)
+            rc_o, t_o = oracle.unpack77(bytes(a))
+            rc_r, t_r = ref.unpack77(bytes(a))
+            assert rc_o == rc_r
+            if rc_r >= 0:
+                assert t_o == t_r, (bytes(a).hex(), t_o, t_r)
+    for n28 in list(range(0, 1100)) + [532443, 532444, 2063591, 2063592, 2063592 + 4194303, 2063592 + 4194304]:
+        v = (n28 << 1)
+        a = bytearray(12)
+        a[0] = (v >> 21) & 0xFF; a[1] = (v >> 13) & 0xFF; a[2] = (v >> 5) & 0xFF; a[3] = ((v << 3) & 0xF8) | 0x01
+        a[4] = 0x23; a[5] = 0x45; a[9] = 1 << 3
+        assert oracle.unpack77(bytes(a)) == ref.unpack77(bytes(a))
+
+
+def test_encoder_and_crc_vs_reference(oracle):
+    ref = Reference("k120")
+    rng = np.random.default_rng(8)
+    for _ in range(200):
+        to, de, ex = synth.random_message(rng)
+        text = f"{to} {de} {ex}".strip()
+        p_ref = ref.pack77(text)
+        assert oracle.pack_std(to, de, ex) == p_ref == ft8enc.pack_std(to, de, ex), text
+        assert np.array_equal(oracle.tones(p_ref), ref.tones(p_ref)) and np.array_equal(ft8enc.tones(p_ref), ref.tones(p_ref))
+        blob = bytes(rng.integers(0, 256, 12, dtype=np.uint8))
+        for nbits in (76, 77, 82, 96):
+            assert oracle.crc14(blob, nbits) == ref.crc(blob, nbits) == ft8enc.crc14(blob, nbits)
+    assert oracle.pack_text("HELLO WORLD") == ref.pack77("HELLO WORLD")
+
+
+def test_fft_vs_kiss(oracle):
+    mon = ReferenceMonitor()
+    rng = np.random.default_rng(9)
+    for n in (3840, 1152, 128, 960, 60):
+        x = rng.standard_normal(n).astype(np.float32)
+        assert np.array_equal(oracle.fft_r2c(x).view(np.uint32), mon.fftr(x).view(np.uint32)), n
+
+
+def test_monitor_vs_reference(oracle):
+    mon = ReferenceMonitor()
+    sigs = [(ft8enc.tones(ft8enc.pack_std("CQ", "K1JT", "FN20")), 1200.0, 0.5, 0.1), (ft8enc.tones(ft8enc.pack_std("K1ABC", "W9XYZ", "-15")), 2100.0, 1.1, 0.05)]
+    a = synth.audio_12k(sigs, 3)
+    mo, io, xo = oracle.monitor_waterfall(a)
+    mr, ir, xr = mon.waterfall(a)
+    assert np.array_equal(io, ir) and np.array_equal(mo, mr) and np.float32(xo) == np.float32(xr)
+
+
+def test_log10f_quantiser_is_monotone_over_the_whole_input_range(oracle):
+    """The kernels replace log10f by the step thresholds; that is exact iff the host quantiser is monotone.
+    Checked exhaustively in C over every float in [1e-12, 1e7] would take ~10 s; here: every float within 64 ulp of
+    each threshold plus 2M log-uniform samples, sorted, must quantise to a non-decreasing sequence."""
+    thr = oracle.db_thresholds()
+    near = []
+    for t in thr[1:256]:
+        u = np.float32(t).view(np.uint32)
+        near.append((np.arange(-64, 65, dtype=np.int64) + int(u)).astype(np.uint32).view(np.float32))
+    rng = np.random.default_rng(0)
+    xs = np.concatenate(near + [np.exp(rng.uniform(np.log(1e-12), np.log(1e7), 200000)).astype(np.float32)])
+    xs.sort()
+    q = np.array([oracle.quantize_db(float(x)) for x in xs])
+    assert np.all(np.diff(q) >= 0)
+    assert np.array_equal(q, np.searchsorted(thr[1:256], xs, side="right"))
