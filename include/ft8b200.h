@@ -228,6 +228,10 @@ int ft8b200_process_conditioned(ft8b200_ctx_t *ctx, const float *d_i, const floa
 /* Per-stage device timing of the process_* calls: when enabled, CUDA events are recorded on the launching
  * stream between stages; ms[0..5] = block sums, comb+FIR, waterfall, sync, decode, spots (-1 = stage not run). */
 int ft8b200_set_profiling(ft8b200_ctx_t *ctx, int on);
+/* groups >= 2: ft8b200_process_raw splits the batch into that many slot groups and runs the compute-bound back end of
+ * one group on a high-priority side stream while the HBM-bound decimator of the next group runs on the caller's stream
+ * (default 0 = off; results are identical either way; only worthwhile when a group still holds >= ~64 slots). */
+int ft8b200_set_overlap(ft8b200_ctx_t *ctx, int groups);
 int ft8b200_stage_times(ft8b200_ctx_t *ctx, float *ms, int n);
 /* device pointers to the last batch's outputs: results (n_slots x max_messages), counts (n_slots) */
 int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults);

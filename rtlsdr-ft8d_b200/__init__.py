@@ -242,6 +242,9 @@ class Context:
     def set_profiling(self, on: bool):
         self._chk(self.L.ft8b200_set_profiling(C.c_void_p(self.h), int(on)))
 
+    def set_overlap(self, groups: int):
+        self._chk(self.L.ft8b200_set_overlap(C.c_void_p(self.h), int(groups)))
+
     def stage_times(self):
         """ms per stage of the last process_* call: dict(block_sums, comb_fir, waterfall, sync, decode, spots)."""
         ms = (C.c_float * 6)()

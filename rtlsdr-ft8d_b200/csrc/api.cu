@@ -52,6 +52,8 @@ struct DevBuf {
 };
 }  // namespace
 
+constexpr int kMaxGroups = 16;
+
 struct ft8b200_ctx {
     ft8b200_config_t cfg;
     cudaStream_t stream = nullptr;
@@ -60,13 +62,17 @@ struct ft8b200_ctx {
     uint64_t launches_total = 0;
     int sm_count = 0;
     // workspaces (grown on demand)
-    DevBuf raw, sums, si, sq, peak, count, mag, cand, ncand, ok, stage, status, msg, results, nresults, table, scratch;
+    DevBuf raw, sums, si, sq, peak, count, mag, cand, ncand, ok, stage, status, msg, results, nresults, table, scratch, scores, work, work_total;
     int scratch_slots = 0;
     int scratch_npos = 0;
     // optional per-stage timing of the last process_* call (CUDA events on the launching stream)
     bool profiling = false;
-    cudaEvent_t ev[7] = {};
-    bool ev_valid[7] = {};
+    int overlap = 0;                       // number of slot groups ft8b200_process_raw pipelines (0/1 = off)
+    cudaEvent_t ev[6][kMaxGroups][2] = {};
+    bool ev_valid[6][kMaxGroups] = {};
+    cudaStream_t aux = nullptr;            // high-priority side stream for the back end of a slot group
+    cudaEvent_t ev_join = nullptr;
+    cudaEvent_t ev_group[kMaxGroups] = {};
     std::mutex mu;
 };
 
@@ -105,6 +111,10 @@ int ensure_scratch(ft8b200_ctx_t *ctx, int npos, int n_slots) {
     int want = ctx->sm_count * 2;
     if (want > n_slots) want = n_slots;
     if (want < 1) want = 1;
+    int rc0 = ctx->scores.ensure((size_t)n_slots * npos * sizeof(int16_t));
+    if (rc0) return rc0;
+    if ((rc0 = ctx->work.ensure((size_t)n_slots * ctx->cfg.max_candidates * sizeof(uint32_t)))) return rc0;
+    if ((rc0 = ctx->work_total.ensure(sizeof(unsigned int)))) return rc0;
     if (npos > ctx->scratch_npos || want > ctx->scratch_slots) {
         const int slots = want > ctx->scratch_slots ? want : ctx->scratch_slots;
         const int np = npos > ctx->scratch_npos ? npos : ctx->scratch_npos;
@@ -193,11 +203,14 @@ void ft8b200_destroy(ft8b200_ctx_t *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
-    for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &s : ctx->ev) for (auto &g : s) for (cudaEvent_t e : g) if (e) cudaEventDestroy(e);
+    if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (cudaEvent_t e : ctx->ev_group) if (e) cudaEventDestroy(e);
     cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.fir);
     cudaFree(ctx->tb.mon_window); cudaFree(ctx->tb.mon_twiddle); cudaFree(ctx->tb.mon_super);
     DevBuf *bufs[] = {&ctx->raw, &ctx->sums, &ctx->si, &ctx->sq, &ctx->peak, &ctx->count, &ctx->mag, &ctx->cand, &ctx->ncand, &ctx->ok,
-                      &ctx->stage, &ctx->status, &ctx->msg, &ctx->results, &ctx->nresults, &ctx->table, &ctx->scratch};
+                      &ctx->stage, &ctx->status, &ctx->msg, &ctx->results, &ctx->nresults, &ctx->table, &ctx->scratch, &ctx->scores, &ctx->work, &ctx->work_total};
     for (DevBuf *b : bufs) b->release();
     delete ctx;
 }
@@ -265,7 +278,8 @@ int ft8b200_find_sync(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stri
     std::lock_guard<std::mutex> lk(ctx->mu);
     if ((rc = ensure_scratch(ctx, (int)npos, n_slots))) return rc;
     CU(launch_find_sync(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->cfg.max_candidates, ctx->cfg.min_score,
-                        d_cand, d_ncand, ctx->scratch.as<uint32_t>(), ctx->scratch_slots, pick(ctx, stream), &ctx->launches));
+                        d_cand, d_ncand, ctx->scores.as<int16_t>(), ctx->scratch.as<uint32_t>(), ctx->scratch_slots, nullptr, nullptr, ctx->sm_count,
+                        pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
 }
@@ -278,7 +292,7 @@ int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_
     if (!d_mag || !d_cand || !d_ncand || !d_ok || !d_stage || !d_status || !d_msg || n_slots < 1)
         return fail(FT8B200_EINVAL, "ft8b200_decode: bad argument");
     CU(launch_decode(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
-                     d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, pick(ctx, stream), &ctx->launches));
+                     d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, nullptr, nullptr, pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
 }
@@ -298,29 +312,56 @@ int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate
     return 0;
 }
 
-static void mark(ft8b200_ctx_t *ctx, int k, cudaStream_t st) {
-    if (!ctx->profiling) return;
-    if (!ctx->ev[k]) cudaEventCreate(&ctx->ev[k]);
-    ctx->ev_valid[k] = (cudaEventRecord(ctx->ev[k], st) == cudaSuccess);
+// ---- per-stage timing: one event pair per (stage, group); stage times are summed over the groups -------------
+static void mark(ft8b200_ctx_t *ctx, int stage, int group, bool end, cudaStream_t st) {
+    if (!ctx->profiling || group >= kMaxGroups) return;
+    cudaEvent_t &e = ctx->ev[stage][group][end ? 1 : 0];
+    if (!e) cudaEventCreate(&e);
+    const bool ok = cudaEventRecord(e, st) == cudaSuccess;
+    if (end) ctx->ev_valid[stage][group] = ok && ctx->ev_valid[stage][group];
+    else ctx->ev_valid[stage][group] = ok;
+}
+static void clear_marks(ft8b200_ctx_t *ctx) {
+    for (auto &s : ctx->ev_valid) for (bool &v : s) v = false;
 }
 
-// waterfall (already in ctx->mag or produced here) -> sync -> decode -> spots, all on `st`
-static int run_back_end(ft8b200_ctx_t *ctx, int n_slots, cudaStream_t st) {
-    int rc;
-    const int npos = 2 * 2 * 36 * (256 - 7);
-    if ((rc = ensure_scratch(ctx, npos, n_slots))) return rc;
-    mark(ctx, 3, st);
-    CU(launch_find_sync(ctx->mag.as<uint8_t>(), kWfBytes, n_slots, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.min_score,
-                        ctx->cand.as<candidate_t>(), ctx->ncand.as<int>(), ctx->scratch.as<uint32_t>(), ctx->scratch_slots, st, &ctx->launches));
-    mark(ctx, 4, st);
-    CU(launch_decode(ctx->mag.as<uint8_t>(), kWfBytes, n_slots, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
-                     ctx->cand.as<candidate_t>(), ctx->ncand.as<int>(), ctx->ok.as<uint8_t>(), ctx->stage.as<uint8_t>(),
-                     ctx->status.as<decode_status_t>(), ctx->msg.as<message_t>(), nullptr, nullptr, st, &ctx->launches));
-    mark(ctx, 5, st);
-    CU(launch_spots(n_slots, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, 2, ctx->cand.as<candidate_t>(),
-                    ctx->ncand.as<int>(), ctx->ok.as<uint8_t>(), ctx->msg.as<message_t>(), ctx->results.as<struct decoder_results>(),
-                    ctx->nresults.as<int32_t>(), nullptr, nullptr, nullptr, ctx->table.as<int16_t>(), st, &ctx->launches));
-    mark(ctx, 6, st);
+// waterfall -> sync -> decode -> spots for slots [s0, s0+n) of the context buffers, all on `st`
+static int run_back_end(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, const float *d_peak, int s0, int n, int group, cudaStream_t st) {
+    const size_t K = (size_t)ctx->cfg.max_candidates, M = (size_t)ctx->cfg.max_messages;
+    uint8_t *mag = ctx->mag.as<uint8_t>() + (size_t)s0 * kWfBytes;
+    candidate_t *cand = ctx->cand.as<candidate_t>() + (size_t)s0 * K;
+    int *ncand = ctx->ncand.as<int>() + s0;
+    uint8_t *ok = ctx->ok.as<uint8_t>() + (size_t)s0 * K, *stage = ctx->stage.as<uint8_t>() + (size_t)s0 * K;
+    mark(ctx, 2, group, false, st);
+    // decoder()'s normalisation (when d_peak != NULL) is applied on load inside the waterfall kernel
+    CU(launch_waterfall(ctx->tb, d_i + (size_t)s0 * kSlot, d_q + (size_t)s0 * kSlot, d_peak ? d_peak + s0 : nullptr, n, mag, st, &ctx->launches));
+    mark(ctx, 2, group, true, st);
+    mark(ctx, 3, group, false, st);
+    CU(launch_find_sync(mag, kWfBytes, n, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.min_score, cand, ncand, ctx->scores.as<int16_t>(),
+                        ctx->scratch.as<uint32_t>(), ctx->scratch_slots, ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), ctx->sm_count,
+                        st, &ctx->launches));
+    mark(ctx, 3, group, true, st);
+    mark(ctx, 4, group, false, st);
+    CU(launch_decode(mag, kWfBytes, n, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations, cand, ncand, ok, stage,
+                     ctx->status.as<decode_status_t>() + (size_t)s0 * K, ctx->msg.as<message_t>() + (size_t)s0 * K, nullptr, nullptr,
+                     ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), st, &ctx->launches));
+    mark(ctx, 4, group, true, st);
+    mark(ctx, 5, group, false, st);
+    CU(launch_spots(n, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, 2, cand, ncand, ok, ctx->msg.as<message_t>() + (size_t)s0 * K,
+                    ctx->results.as<struct decoder_results>() + (size_t)s0 * M, ctx->nresults.as<int32_t>() + s0, nullptr, nullptr, nullptr,
+                    ctx->table.as<int16_t>() + (size_t)s0 * M, st, &ctx->launches));
+    mark(ctx, 5, group, true, st);
+    return 0;
+}
+
+static int ensure_aux(ft8b200_ctx_t *ctx) {
+    if (!ctx->aux) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = highest priority
+        CU(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        for (cudaEvent_t &e : ctx->ev_group) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -340,21 +381,49 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
     if ((rc = ctx->sq.ensure((size_t)n_slots * kSlot * sizeof(float)))) return rc;
     if ((rc = ctx->peak.ensure((size_t)n_slots * sizeof(float)))) return rc;
     if ((rc = ctx->count.ensure((size_t)n_slots * sizeof(uint32_t)))) return rc;
+    // Slot groups: the HBM-bound front end (block sums, comb+FIR) of group g+1 runs on the caller's stream while the
+    // compute-bound back end (waterfall, sync, LDPC, spots) of group g runs on a high-priority side stream.
+    int n_groups = 1;
+    if (ctx->overlap > 1 && n_slots >= 2 * ctx->overlap) {
+        n_groups = ctx->overlap;  // a group must stay large enough for the back end to fill the machine
+        if (n_groups > kMaxGroups) n_groups = kMaxGroups;
+    }
+    const int per = (n_slots + n_groups - 1) / n_groups;
+    const int npos = 2 * 2 * 36 * (256 - 7);
+    if ((rc = ensure_scratch(ctx, npos, per))) return rc;
+    cudaStream_t back = st;
+    if (n_groups > 1) {
+        if ((rc = ensure_aux(ctx))) return rc;
+        back = ctx->aux;
+        CU(cudaEventRecord(ctx->ev_join, st));           // the side stream starts after everything already queued on st
+        CU(cudaStreamWaitEvent(back, ctx->ev_join, 0));
+    }
+    clear_marks(ctx);
     CU(cudaMemsetAsync(ctx->peak.p, 0, sizeof(float) * n_slots, st));
-    for (bool &v : ctx->ev_valid) v = false;
-    CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_slots, st));
-    BlockSums *s0 = ctx->sums.as<BlockSums>() + kHistBlocks;
-    mark(ctx, 0, st);
-    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_slots, blocks, s0, sstride, st, &ctx->launches));
-    mark(ctx, 1, st);
-    CU(launch_cic_comb_fir(s0, sstride, blocks, 0, true, n_slots, ctx->tb.fir, ctx->si.as<float>(), ctx->sq.as<float>(),
-                           ctx->count.as<uint32_t>(), ctx->peak.as<float>(), nullptr, st, &ctx->launches));
-    mark(ctx, 2, st);
-    // decoder()'s normalisation is applied on load inside the waterfall kernel (scale from the slot peak)
-    CU(launch_waterfall(ctx->tb, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), n_slots, ctx->mag.as<uint8_t>(), st, &ctx->launches));
-    rc = run_back_end(ctx, n_slots, st);
+    CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_slots, st));  // fresh filter state
+    for (int g = 0, s0 = 0; s0 < n_slots; ++g, s0 += per) {
+        const int n = (n_slots - s0) < per ? (n_slots - s0) : per;
+        BlockSums *sg = ctx->sums.as<BlockSums>() + (size_t)s0 * sstride + kHistBlocks;
+        mark(ctx, 0, g, false, st);
+        CU(launch_cic_block_sums(d_iq + (size_t)s0 * stream_stride_bytes, stream_stride_bytes, n, blocks, sg, sstride, st, &ctx->launches));
+        mark(ctx, 0, g, true, st);
+        mark(ctx, 1, g, false, st);
+        CU(launch_cic_comb_fir(sg, sstride, blocks, 0, true, n, ctx->tb.fir, ctx->si.as<float>() + (size_t)s0 * kSlot,
+                               ctx->sq.as<float>() + (size_t)s0 * kSlot, ctx->count.as<uint32_t>() + s0, ctx->peak.as<float>() + s0, nullptr, st,
+                               &ctx->launches));
+        mark(ctx, 1, g, true, st);
+        if (n_groups > 1) {
+            CU(cudaEventRecord(ctx->ev_group[g], st));
+            CU(cudaStreamWaitEvent(back, ctx->ev_group[g], 0));
+        }
+        if ((rc = run_back_end(ctx, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), s0, n, g, back))) return rc;
+    }
+    if (n_groups > 1) {  // results are ready, in stream order, when this call's work on st completes
+        CU(cudaEventRecord(ctx->ev_join, back));
+        CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    }
     tally(ctx);
-    return rc;
+    return 0;
 }
 
 int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, int n_slots, void *stream) {
@@ -368,10 +437,9 @@ int ft8b200_process_conditioned(ft8b200_ctx_t *ctx, const float *d_i, const floa
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = pick(ctx, stream);
     if ((rc = ensure_slot_buffers(ctx, n_slots))) return rc;
-    for (bool &v : ctx->ev_valid) v = false;
-    mark(ctx, 2, st);
-    CU(launch_waterfall(ctx->tb, d_i, d_q, d_peak, n_slots, ctx->mag.as<uint8_t>(), st, &ctx->launches));
-    rc = run_back_end(ctx, n_slots, st);
+    if ((rc = ensure_scratch(ctx, 2 * 2 * 36 * (256 - 7), n_slots))) return rc;
+    clear_marks(ctx);
+    rc = run_back_end(ctx, d_i, d_q, d_peak, 0, n_slots, 0, st);
     tally(ctx);
     return rc;
 }
@@ -382,17 +450,31 @@ int ft8b200_set_profiling(ft8b200_ctx_t *ctx, int on) {
     return 0;
 }
 
-// ms[0..5] = block sums, comb+FIR, waterfall, sync, decode, spots of the last process_* call (-1 = not run)
+int ft8b200_set_overlap(ft8b200_ctx_t *ctx, int on) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    ctx->overlap = on;
+    return 0;
+}
+
+// ms[0..5] = block sums, comb+FIR, waterfall, sync, decode, spots of the last process_* call, summed over its slot
+// groups (-1 = stage not run).  With overlap on, front-end and back-end stages run concurrently: the sum of the stage
+// times then exceeds the wall time of the call.
 int ft8b200_stage_times(ft8b200_ctx_t *ctx, float *ms, int n) {
     int rc = ctx_enter(ctx);
     if (rc) return rc;
     if (!ms || n < 6) return fail(FT8B200_EINVAL, "ft8b200_stage_times: need room for 6 floats");
     for (int k = 0; k < 6; ++k) {
-        ms[k] = -1.0f;
-        if (ctx->ev_valid[k] && ctx->ev_valid[k + 1]) {
-            CU(cudaEventSynchronize(ctx->ev[k + 1]));
-            CU(cudaEventElapsedTime(&ms[k], ctx->ev[k], ctx->ev[k + 1]));
+        float total = 0.0f;
+        bool any = false;
+        for (int g = 0; g < kMaxGroups; ++g) {
+            if (!ctx->ev_valid[k][g]) continue;
+            float t = 0.0f;
+            CU(cudaEventSynchronize(ctx->ev[k][g][1]));
+            CU(cudaEventElapsedTime(&t, ctx->ev[k][g][0], ctx->ev[k][g][1]));
+            total += t;
+            any = true;
         }
+        ms[k] = any ? total : -1.0f;
     }
     return 0;
 }

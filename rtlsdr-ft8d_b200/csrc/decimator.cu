@@ -246,7 +246,9 @@ cic_block_sums_generic_kernel(const uint8_t *__restrict__ iq, size_t stream_stri
 
 // Kernel 2: comb (closed form over 4 consecutive block sums) + 57-tap FIR + scale + peak.
 // ref: rtlsdr_ft8d.c:162-200.  One CTA = 256 consecutive outputs of one stream.
-constexpr int kTile = 256;
+constexpr int kPerThread = 4;      // outputs per thread
+constexpr int kTileThreads = 128;
+constexpr int kTile = kTileThreads * kPerThread;  // 512 outputs per CTA
 constexpr int kHist = kFirTaps - 1;  // 56 FIR history samples; they need kHistBlocks = 56 + 3 block sums
 
 // y2[k] from blocks k-3..k.  `s` points at this flush's block 0; the kHistBlocks entries before it hold the
@@ -264,17 +266,37 @@ __device__ __forceinline__ void comb(const BlockSums *__restrict__ s, int k, int
 // n_blocks new blocks per stream -> outputs [out_offset, out_offset + n_blocks) of the stream's 48000-sample
 // slot buffer (outputs past 48000 are dropped but the filter keeps running, rtlsdr_ft8d.c:196-200).
 // zero_fill: also clear [out_offset + n_blocks, 48000) -- what decoder() does before it normalises (:243-246).
-__global__ void __launch_bounds__(kTile)
+// Each thread produces kPerThread consecutive outputs from a register window of the (float)y2 history, so the
+// 57-tap FIR costs one shared load per ~4 taps; coefficients sit in constant memory (uniform broadcast).
+__constant__ float c_fir[kFirTaps];
+
+template <int kN>
+__device__ __forceinline__ void fir_window(const float *__restrict__ y, float (&acc)[kN]) {
+    // y[0 .. kN+55]: acc[o] = sum_j y[o+j]*z[j], strictly sequential in j, product rounded before the add (no FMA)
+    float w[kN + kHist];
+#pragma unroll
+    for (int v = 0; v < (kN + kHist) / 4; ++v) {
+        const float4 q = reinterpret_cast<const float4 *>(y)[v];
+        w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+    }
+#pragma unroll
+    for (int o = 0; o < kN; ++o) acc[o] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kFirTaps; ++j) {
+#pragma unroll
+        for (int o = 0; o < kN; ++o) acc[o] = __fadd_rn(acc[o], __fmul_rn(w[o + j], c_fir[j]));
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads)
 cic_comb_fir_kernel(const BlockSums *__restrict__ sums, size_t sums_stride, int n_blocks, int out_offset, int zero_fill,
-                    const float *__restrict__ fir, float *__restrict__ out_i, float *__restrict__ out_q, uint32_t *__restrict__ count,
-                    float *__restrict__ peak, int32_t *__restrict__ y2_out) {
-    __shared__ float s_yi[kTile + kHist], s_yq[kTile + kHist];
-    __shared__ float s_fir[kFirTaps];
+                    float *__restrict__ out_i, float *__restrict__ out_q, uint32_t *__restrict__ count, float *__restrict__ peak,
+                    int32_t *__restrict__ y2_out) {
+    __shared__ __align__(16) float s_yi[kTile + kHist], s_yq[kTile + kHist];
     const int stream = blockIdx.y;
     const int k0 = blockIdx.x * kTile;
     const BlockSums *s = sums + (size_t)stream * sums_stride;
-    if (threadIdx.x < kFirTaps) s_fir[threadIdx.x] = fir[threadIdx.x];
-    for (int idx = threadIdx.x; idx < kTile + kHist; idx += kTile) {
+    for (int idx = threadIdx.x; idx < kTile + kHist; idx += kTileThreads) {
         const int k = k0 - kHist + idx;  // >= -56: inside the history prefix
         int32_t yi = 0, yq = 0;
         if (k < n_blocks) comb(s, k, yi, yq);
@@ -286,24 +308,32 @@ cic_comb_fir_kernel(const BlockSums *__restrict__ sums, size_t sums_stride, int 
         }
     }
     __syncthreads();
-    const int k = k0 + threadIdx.x;
-    const int o = out_offset + k;
-    float vi = 0.0f, vq = 0.0f;
-    if (k < n_blocks && o < kSlot) {
-        float ai = 0.0f, aq = 0.0f;
+    const int kb = k0 + threadIdx.x * kPerThread;  // first of this thread's outputs
+    float vi[kPerThread], vq[kPerThread];
 #pragma unroll
-        for (int j = 0; j < kFirTaps; ++j) {  // strictly sequential, product rounded before the add (no FMA)
-            ai = __fadd_rn(ai, __fmul_rn(s_yi[threadIdx.x + j], s_fir[j]));
-            aq = __fadd_rn(aq, __fmul_rn(s_yq[threadIdx.x + j], s_fir[j]));
+    for (int o = 0; o < kPerThread; ++o) { vi[o] = 0.0f; vq[o] = 0.0f; }
+    if (kb < n_blocks && out_offset + kb < kSlot) {
+        float ai[kPerThread], aq[kPerThread];
+        fir_window<kPerThread>(s_yi + threadIdx.x * kPerThread, ai);
+        fir_window<kPerThread>(s_yq + threadIdx.x * kPerThread, aq);
+#pragma unroll
+        for (int o = 0; o < kPerThread; ++o) {
+            if (kb + o < n_blocks) {
+                vi[o] = __double2float_rn(__ddiv_rn((double)ai[o], 32768.0 * 750));  // rtlsdr_ft8d.c:197-198
+                vq[o] = __double2float_rn(__ddiv_rn((double)aq[o], 32768.0 * 750));
+            }
         }
-        vi = __double2float_rn(__ddiv_rn((double)ai, 32768.0 * 750));  // rtlsdr_ft8d.c:197-198
-        vq = __double2float_rn(__ddiv_rn((double)aq, 32768.0 * 750));
     }
-    if (o < kSlot && (k < n_blocks || zero_fill)) {
-        out_i[(size_t)stream * kSlot + o] = vi;
-        out_q[(size_t)stream * kSlot + o] = vq;
+    float m = 0.0f;
+#pragma unroll
+    for (int o = 0; o < kPerThread; ++o) {
+        const int k = kb + o, pos = out_offset + k;
+        if (pos < kSlot && (k < n_blocks || zero_fill)) {
+            out_i[(size_t)stream * kSlot + pos] = vi[o];
+            out_q[(size_t)stream * kSlot + pos] = vq[o];
+        }
+        m = fmaxf(m, fmaxf(fabsf(vi[o]), fabsf(vq[o])));
     }
-    float m = fmaxf(fabsf(vi), fabsf(vq));
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
     if ((threadIdx.x & 31) == 0 && peak && m > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(peak + stream), __float_as_uint(m));
@@ -374,8 +404,19 @@ cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int
     int span = n_blocks;
     if (zero_fill && kSlot - out_offset > span) span = kSlot - out_offset;
     if (span <= 0) return cudaSuccess;
+    static bool fir_uploaded[64] = {};
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    if (dev_id >= 0 && dev_id < 64 && !fir_uploaded[dev_id]) {  // coefficients live in constant memory, once per device
+        float z[kFirTaps];
+        build_fir(z);
+        cudaError_t e = cudaMemcpyToSymbol(c_fir, z, sizeof(z));
+        if (e != cudaSuccess) return e;
+        fir_uploaded[dev_id] = true;
+    }
+    (void)d_fir;
     dim3 grid((span + kTile - 1) / kTile, n_streams);
-    cic_comb_fir_kernel<<<grid, kTile, 0, st>>>(d_sums, sums_stride, n_blocks, out_offset, zero_fill ? 1 : 0, d_fir, d_i, d_q, d_count, d_peak, d_y2);
+    cic_comb_fir_kernel<<<grid, kTileThreads, 0, st>>>(d_sums, sums_stride, n_blocks, out_offset, zero_fill ? 1 : 0, d_i, d_q, d_count, d_peak, d_y2);
     ++*launches;
     return cudaGetLastError();
 }

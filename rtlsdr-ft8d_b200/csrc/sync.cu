@@ -2,12 +2,13 @@
 // Replaces ft8_find_sync() / ft8_sync_score() / heapify_*(), /root/reference/ft8_lib/ft8/decode.c:35-108,
 // 173-234, 388-435.
 //
-// One CTA per slot.  The slot's waterfall (94 KB for the daemon geometry) is staged in shared memory
-// once; all tosr*fosr*36*(bins-7) positions are scored in parallel in the reference's loop order
-// (time_sub, freq_sub, time_offset, freq_offset); positions with score >= min_score are compacted IN
-// THAT ORDER (ballot + prefix) and then one thread replays the reference's min-heap insertions and the
-// final heap sort over the survivors only.  The replay is what makes the retained set at the cut score
-// and the order among equal scores identical to the reference (they depend on heap history).
+// Two kernels.  sync_score_kernel: a few CTAs per slot, each stages the slot's waterfall (94 KB for the daemon
+// geometry) in shared memory and scores its share of the tosr*fosr*36*(bins-7) positions; scores are stored in the
+// reference's loop order (time_sub, freq_sub, time_offset, freq_offset).  sync_select_kernel: one CTA per slot
+// compacts the positions with score >= min_score IN THAT ORDER (ballot + prefix) and one thread replays the
+// reference's min-heap insertions and the final heap sort over the survivors only.  The replay is what makes the
+// retained set at the cut score and the order among equal scores identical to the reference (they depend on heap
+// history).  The surviving candidates are also appended to a flat work list for the decode kernel.
 #include "common.cuh"
 
 namespace ft8b200 {
@@ -68,45 +69,63 @@ __device__ void sift_up(unsigned long long *h, int n) {  // ref: heapify_up, dec
     }
 }
 
+// Phase 1: score every position.  grid = (chunks, slots): each CTA stages the slot's waterfall in shared memory
+// (when it fits) and scores its share of the positions; scores go to global memory as int16 in position order.
 template <bool kStage>
 __global__ void __launch_bounds__(kSyncThreads)
-find_sync_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, int n_slots, Geo g, int max_cand, int min_score,
-                 candidate_t *__restrict__ cand_out, int *__restrict__ ncand_out, uint32_t *__restrict__ scratch_all) {
+sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int pos_per_chunk, int16_t *__restrict__ scores_all) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int slot = blockIdx.y;
+    const int wf_bytes = g.nb * g.stride;
+    const uint8_t *gmag = mag_all + (size_t)slot * slot_stride;
+    const uint8_t *mag = gmag;
+    if (kStage) {
+        if ((((size_t)gmag) & 15) == 0 && (wf_bytes & 15) == 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(gmag);
+            uint4 *dst = reinterpret_cast<uint4 *>(smem);
+            for (int k = tid; k < wf_bytes / 16; k += kSyncThreads) dst[k] = __ldg(src + k);
+        } else {
+            for (int k = tid; k < wf_bytes; k += kSyncThreads) smem[k] = gmag[k];
+        }
+        mag = smem;
+        __syncthreads();
+    }
+    int16_t *scores = scores_all + (size_t)slot * g.npos;
+    const int p0 = blockIdx.x * pos_per_chunk;
+    int p1 = p0 + pos_per_chunk;
+    if (p1 > g.npos) p1 = g.npos;
+    for (int p = p0 + tid; p < p1; p += kSyncThreads) {
+        const int fo = p % g.nfo;
+        int q = p / g.nfo;
+        const int to = q % 36 - 12;
+        q /= 36;
+        const int fs = q % g.fosr, ts = q / g.fosr;
+        scores[p] = (int16_t)sync_score(mag, g, ts, fs, to, fo);  // stored as int16_t in candidate_t
+    }
+}
+
+// Phase 2: one CTA per slot (looping over slots): ordered compaction of the positions with score >= min_score,
+// then the exact heap replay by one thread, then the candidates are appended to the decode work list.
+__global__ void __launch_bounds__(kSyncThreads)
+sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, int max_cand, int min_score, candidate_t *__restrict__ cand_out,
+                   int *__restrict__ ncand_out, uint32_t *__restrict__ scratch_all, uint32_t *__restrict__ work, unsigned int *__restrict__ work_total) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_warp_cnt[2][32];
-    __shared__ int s_total;
+    __shared__ int s_total, s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wf_bytes = g.nb * g.stride;
-    const int wf_pad = kStage ? ((wf_bytes + 15) & ~15) : 0;
-    unsigned long long *heap = reinterpret_cast<unsigned long long *>(smem + wf_pad);
+    unsigned long long *heap = reinterpret_cast<unsigned long long *>(smem);
     uint32_t *scratch = scratch_all + (size_t)blockIdx.x * g.npos;
 
     for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-        const uint8_t *gmag = mag_all + (size_t)slot * slot_stride;
-        const uint8_t *mag = gmag;
-        if (kStage) {
-            if ((((size_t)gmag) & 15) == 0 && (wf_bytes & 15) == 0) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(gmag);
-                uint4 *dst = reinterpret_cast<uint4 *>(smem);
-                for (int k = tid; k < wf_bytes / 16; k += kSyncThreads) dst[k] = __ldg(src + k);
-            } else {
-                for (int k = tid; k < wf_bytes; k += kSyncThreads) smem[k] = gmag[k];
-            }
-            mag = smem;
-            __syncthreads();
-        }
+        const int16_t *scores = scores_all + (size_t)slot * g.npos;
         int running = 0, it = 0;
         for (int base = 0; base < g.npos; base += kSyncThreads, ++it) {
             const int p = base + tid;
-            bool pass = false;
             int score = 0;
+            bool pass = false;
             if (p < g.npos) {
-                const int fo = p % g.nfo;
-                int q = p / g.nfo;
-                const int to = q % 36 - 12;
-                q /= 36;
-                const int fs = q % g.fosr, ts = q / g.fosr;
-                score = (int)(short)sync_score(mag, g, ts, fs, to, fo);  // stored as int16_t in candidate_t
+                score = scores[p];
                 pass = score >= min_score;
             }
             // ordered compaction: position order == the reference's loop order
@@ -153,12 +172,15 @@ find_sync_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, int n_
             }
             s_total = n;
             ncand_out[slot] = n;
+            s_base = (work && n > 0) ? (int)atomicAdd(work_total, (unsigned int)n) : 0;
         }
         __syncthreads();
         {
             const int n = s_total;
             unsigned long long *dst = reinterpret_cast<unsigned long long *>(cand_out + (size_t)slot * max_cand);
             for (int k = tid; k < max_cand; k += kSyncThreads) dst[k] = (k < n) ? heap[k] : 0ull;
+            if (work)
+                for (int k = tid; k < n; k += kSyncThreads) work[s_base + k] = (uint32_t)slot * (uint32_t)max_cand + (uint32_t)k;
         }
         __syncthreads();
     }
@@ -167,24 +189,38 @@ find_sync_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, int n_
 }  // namespace
 
 cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
-                             int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, uint32_t *d_scratch, int scratch_slots,
-                             cudaStream_t st, int *launches) {
+                             int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_scratch,
+                             int scratch_slots, uint32_t *d_work, unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches) {
     Geo g;
     g.nb = num_blocks; g.nbins = num_bins; g.tosr = time_osr; g.fosr = freq_osr;
     g.stride = time_osr * freq_osr * num_bins;
     g.nfo = num_bins - 7;
     g.npos = time_osr * freq_osr * 36 * g.nfo;
     const int wf_bytes = g.nb * g.stride;
-    const size_t heap_bytes = (size_t)max_cand * 8;
-    const size_t staged = (size_t)((wf_bytes + 15) & ~15) + heap_bytes;
-    const int grid = n_slots < scratch_slots ? n_slots : scratch_slots;
+    const size_t staged = (size_t)((wf_bytes + 15) & ~15);
+    // enough CTAs to fill the machine even for small batches: ~4 per SM, at least 1024 positions each
+    int chunks = (4 * sm_count + n_slots - 1) / n_slots;
+    const int max_chunks = (g.npos + kSyncThreads - 1) / kSyncThreads;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > 12) chunks = 12;
+    if (chunks < 1) chunks = 1;
+    const int per = (g.npos + chunks - 1) / chunks;
+    dim3 grid(chunks, n_slots);
     if (staged <= 200 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(find_sync_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
+        cudaError_t e = cudaFuncSetAttribute(sync_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
         if (e != cudaSuccess) return e;
-        find_sync_kernel<true><<<grid, kSyncThreads, staged, st>>>(d_mag, slot_stride, n_slots, g, max_cand, min_score, d_cand, d_ncand, d_scratch);
+        sync_score_kernel<true><<<grid, kSyncThreads, staged, st>>>(d_mag, slot_stride, g, per, d_scores);
     } else {
-        find_sync_kernel<false><<<grid, kSyncThreads, heap_bytes, st>>>(d_mag, slot_stride, n_slots, g, max_cand, min_score, d_cand, d_ncand, d_scratch);
+        sync_score_kernel<false><<<grid, kSyncThreads, 0, st>>>(d_mag, slot_stride, g, per, d_scores);
     }
+    ++*launches;
+    if (d_work_total) {
+        cudaError_t e = cudaMemsetAsync(d_work_total, 0, sizeof(unsigned int), st);
+        if (e != cudaSuccess) return e;
+    }
+    const int sgrid = n_slots < scratch_slots ? n_slots : scratch_slots;
+    sync_select_kernel<<<sgrid, kSyncThreads, (size_t)max_cand * 8, st>>>(d_scores, n_slots, g, max_cand, min_score, d_cand, d_ncand, d_scratch,
+                                                                          d_work, d_work_total);
     ++*launches;
     return cudaGetLastError();
 }

@@ -424,3 +424,27 @@ def test_monitor_dropin_and_decode(pkg, oracle, audio):
     mon.process(audio[:1920])  # history is NOT cleared by reset (decode_ft8.c:220-224)
     assert mon.me.wf.num_blocks == 1
     mon.close()
+
+
+def test_grouped_overlap_gives_identical_results(ctx, raw_slot):
+    """Large raw batches are split into slot groups whose back end overlaps the next group's decimator on a side
+    stream; that must not change a single byte, and every slot must equal its stand-alone result."""
+    B = 20
+    big = torch.from_numpy(raw_slot).to(dev()).repeat(B, 1).contiguous()
+    big[3] = 0x80                      # a silent slot
+    big[7, : 2 * 751 * 9000] = 0x80    # signal starts late: different peak, same message
+    big[11] = big[11].flip(0)          # garbage
+    outs = []
+    for ov in (0, 2, 5):
+        ctx.set_overlap(ov)
+        ctx.process_raw(big, B)
+        outs.append(ctx.fetch_results(B))
+    ctx.set_overlap(0)
+    for res, n in outs[1:]:
+        assert np.array_equal(n, outs[0][1]) and res.tobytes() == outs[0][0].tobytes()
+    res, n = outs[0]
+    for s in (0, 3, 7, 11, 19):
+        ctx.process_raw(big[s:s + 1], 1)
+        r1, n1 = ctx.fetch_results(1)
+        assert n1[0] == n[s] and r1[0].tobytes() == res[s].tobytes()
+    assert n[0] >= 1 and n[3] == 0
