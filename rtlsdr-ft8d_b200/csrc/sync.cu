@@ -119,29 +119,37 @@ sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, i
 
     for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
         const int16_t *scores = scores_all + (size_t)slot * g.npos;
-        int running = 0, it = 0;
-        for (int base = 0; base < g.npos; base += kSyncThreads, ++it) {
-            const int p = base + tid;
+        // Ordered compaction with ONE block barrier: warp w owns the contiguous positions [w*span, (w+1)*span); it counts
+        // its survivors, the warp totals are prefix-summed, then it writes its survivors at its offset (position order ==
+        // the reference's loop order).  Scores are re-read in the second sweep (L1/L2 hits).
+        const int span = ((g.npos + 31) / 32 + 31) / 32 * 32;  // positions per warp, multiple of 32
+        const int w0 = warp * span;
+        int mine = 0;
+#pragma unroll 4
+        for (int o = 0; o < span; o += 32) {
+            const int p = w0 + o + lane;
+            const bool pass = p < g.npos && scores[p] >= min_score;
+            mine += __popc(__ballot_sync(0xffffffffu, pass));
+        }
+        if (lane == 0) s_warp_cnt[0][warp] = mine;
+        __syncthreads();
+        const int cnt = s_warp_cnt[0][lane];
+        int running = __reduce_add_sync(0xffffffffu, lane < warp ? cnt : 0);
+        const int n_pass_total = __reduce_add_sync(0xffffffffu, cnt);
+#pragma unroll 4
+        for (int o = 0; o < span; o += 32) {
+            const int p = w0 + o + lane;
             int score = 0;
             bool pass = false;
-            if (p < g.npos) {
-                score = scores[p];
-                pass = score >= min_score;
-            }
-            // ordered compaction: position order == the reference's loop order
+            if (p < g.npos) { score = scores[p]; pass = score >= min_score; }
             const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-            if (lane == 0) s_warp_cnt[it & 1][warp] = __popc(ballot);
-            __syncthreads();
-            const int c = s_warp_cnt[it & 1][lane];
-            const int before = __reduce_add_sync(0xffffffffu, lane < warp ? c : 0);
-            const int tot = __reduce_add_sync(0xffffffffu, c);
-            if (pass) scratch[running + before + __popc(ballot & ((1u << lane) - 1u))] = ((uint32_t)p << 12) | ((uint32_t)score & 0xfffu);
-            running += tot;
+            if (pass) scratch[running + __popc(ballot & ((1u << lane) - 1u))] = ((uint32_t)p << 12) | ((uint32_t)score & 0xfffu);
+            running += __popc(ballot);
         }
         __syncthreads();
 
         if (tid == 0) {  // exact replay of the reference's heap (decode.c:198-231) over the survivors
-            const int n_pass = running;
+            const int n_pass = n_pass_total;
             int n = 0;
             for (int e = 0; e < n_pass; ++e) {
                 const uint32_t v = scratch[e];
