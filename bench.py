@@ -183,9 +183,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slots", type=int, default=32, help="15 s slots per GPU per step")
-    ap.add_argument("--e2e-slots", type=int, default=4, help="slots per step of the host-buffer (e2e) measurement")
-    ap.add_argument("--cpu-slots", type=int, default=16, help="bounded CPU-baseline sample (slots)")
+    ap.add_argument("--slots", type=int, default=128, help="15 s slots per GPU per step")
+    ap.add_argument("--e2e-slots", type=int, default=8, help="slots per step of the host-buffer (e2e) measurement")
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight in the pipelined executor")
+    ap.add_argument("--overlap", action="store_true", help="let the back end of batch n share the GPU with the decimator of batch n+1")
+    ap.add_argument("--k1-variant", type=int, default=0, help="0 = streaming cic_block_sums kernel, 1..6 = bulk-copy (TMA) variants")
+    ap.add_argument("--cpu-slots", type=int, default=96, help="bounded CPU-baseline sample (slots)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -197,7 +200,9 @@ def main():
                           "sync (K=120) -> LDPC/CRC/unpack -> spot table" % args.slots,
               "slots_per_gpu_per_step": args.slots, "input_bytes_per_step_per_gpu": args.slots * RAW_SLOT_BYTES,
               "l2": "inputs larger than L2 (%.1f GB per step per GPU vs 126 MB)" % (args.slots * RAW_SLOT_BYTES / 1e9),
-              "max_candidates": 120, "max_messages": 50, "ldpc_iterations": 20, "parallelism": "slots sharded across GPUs, no data-path collective; "
+              "max_candidates": 120, "max_messages": 50, "ldpc_iterations": 20,
+              "executor": "ft8b200_pipe_t depth %d, %s" % (args.depth, "overlap" if args.overlap else "serial (kernels of consecutive batches do not share the GPU)"),
+              "parallelism": "slots sharded across GPUs, no data-path collective; "
               "spot records gathered with NCCL all_gather" if world > 1 else "single GPU"}
 
     if args.impl == "reference":
@@ -214,34 +219,47 @@ def main():
 
     B = args.slots
     batch, texts = gen_batch(B, 100_000 * rank, device)
-    ctx = pkg.Context(local)
-    ctx.set_profiling(True)
-    M = ctx.M
-    res_dev, nres_dev = None, None
+    torch.cuda.synchronize()
+    # The product's batch executor (ft8b200_pipe_t): `depth` batches in flight; in SERIAL mode the kernels of consecutive
+    # batches never share the GPU (each kernel is timed alone), only D2H of the records and host work overlap them.
+    pipe = pkg.Pipe(local, args.depth)
+    pipe.set_mode(serial=not args.overlap, decimator_variant=args.k1_variant)
+    M = pipe.M
     gathered = torch.empty((world * B, M, 28), dtype=torch.uint8, device=device) if world > 1 else None
     gathered_n = torch.empty(world * B, dtype=torch.int32, device=device) if world > 1 else None
 
-    def step():
-        nonlocal res_dev, nres_dev
-        ctx.process_raw(batch, B)
+    def collect():
+        """Oldest batch -> host records on rank 0 (multi-GPU: one NCCL all_gather of the fixed-size spot records)."""
         if world > 1:
-            if res_dev is None:
-                res_dev, nres_dev = ctx.results_tensors(B)
+            res_dev, nres_dev = pipe.collect_device()
             dist.all_gather_into_tensor(gathered, res_dev)   # spot records over NVLink
             dist.all_gather_into_tensor(gathered_n, nres_dev)
             if rank == 0:
                 return gathered.cpu(), gathered_n.cpu()
             torch.cuda.current_stream().synchronize()
             return None
-        return ctx.fetch_results(B)
+        return pipe.collect(B)
 
-    for _ in range(args.warmup):
-        out = step()
+    def run(steps):
+        out = None
+        for _ in range(steps):
+            if pipe.in_flight() == pipe.depth:
+                out = collect()
+            pipe.submit(batch, B)
+        while pipe.in_flight():
+            out = collect()
+        return out
+
+    out = run(args.warmup)
     # correctness guard on the first batch: every synthetic slot must decode to its own message
     if world == 1:
         res, nres = out
-        got = [(res[s][0]["call"].decode(), res[s][0]["loc"].decode()) if nres[s] else None for s in range(B)]
-        n_good = sum(1 for s in range(B) if nres[s] >= 1)
+        def slot_ok(s):  # CQ messages must come back with their call sign; other messages only count as a decode (a15)
+            if nres[s] < 1:
+                return False
+            to, de = texts[s].split()[:2]
+            return to != "CQ" or any(r["call"] == de.encode() for r in res[s][:nres[s]])
+        n_good = sum(1 for s in range(B) if slot_ok(s))
     else:
         n_good = -1
 
@@ -253,21 +271,20 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    stage_acc = {}
-    launches0 = ctx.launches()
+    pipe.set_profiling(True)
+    launches0 = pipe.launches()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
     e0.record()
-    for _ in range(args.steps):
-        step()
-        for k, v in ctx.stage_times().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    run(args.steps)
     e1.record()
     barrier()
     t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
-    launches = ctx.launches() - launches0
+    launches = pipe.launches() - launches0
+    stage_acc, n_prof = pipe.stage_times()
+    pipe.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -275,17 +292,26 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
     clocks = sampler.summary(t_wall0, t_wall1)
 
-    # ---- e2e: host buffers in, host results out, through the C-ABI call
+    # ---- e2e: host buffers in, host results out, through the C-ABI calls that take HOST memory
     Be = min(args.e2e_slots, B)
     host = torch.empty((Be, RAW_SLOT_BYTES), dtype=torch.uint8, pin_memory=True)
     host.copy_(batch[:Be])
     host_np = host.numpy()
-    for _ in range(args.warmup):
-        ctx.process_raw_host(host_np, Be)
+
+    def run_host(steps):
+        out = None
+        for _ in range(steps):
+            if pipe.in_flight() == pipe.depth:
+                out = pipe.collect(Be)
+            pipe.submit_host(host_np, Be)
+        while pipe.in_flight():
+            out = pipe.collect(Be)
+        return out
+
+    run_host(args.warmup)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        r_e2e, n_e2e = ctx.process_raw_host(host_np, Be)
+    r_e2e, n_e2e = run_host(args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -295,7 +321,10 @@ def main():
     ms_e2e = float(t.item())
     sampler.stop()
     e2e = {"value": world * Be * args.steps / (ms_e2e * 1e-3), "unit": "slots/s", "h2d_bytes_per_step": Be * RAW_SLOT_BYTES,
-           "d2h_bytes_per_step": Be * (M * 28 + 4), "slots_per_step": Be, "api": "ft8b200_process_raw_host (pinned host IQ in, decoder_results out)"}
+           "d2h_bytes_per_step": Be * (M * 28 + 4), "slots_per_step": Be, "same_results_as_device_path": bool(world > 1 or (
+               np.array_equal(n_e2e, nres[:Be]) and r_e2e.tobytes() == res[:Be].tobytes())),
+           "h2d_gbs": world * Be * RAW_SLOT_BYTES * args.steps / (ms_e2e * 1e-3) / 1e9,
+           "api": "ft8b200_pipe_submit_host / ft8b200_pipe_collect (pinned host IQ in, decoder_results out, %d batches in flight)" % pipe.depth}
 
     # ---- roofline of the dominant kernel (cic_block_sums): algorithmic bytes / CUDA-event time
     peaks = {}
@@ -304,8 +333,9 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    k1_ms = stage_acc.get("block_sums", 0.0) / args.steps
-    k2_ms = stage_acc.get("comb_fir", 0.0) / args.steps
+    n_prof = max(n_prof, 1)
+    k1_ms = stage_acc.get("block_sums", 0.0) / n_prof
+    k2_ms = stage_acc.get("comb_fir", 0.0) / n_prof
     achieved = B * ALGO_BYTES_PER_SLOT / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
     roofline = {"kernel": "cic_block_sums_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
@@ -313,10 +343,12 @@ def main():
                 "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_SLOT, "launch_ms": k1_ms,
                 "decimator_ms_incl_comb_fir": k1_ms + k2_ms,
                 "decimator_msps": B * 36.0 / ((k1_ms + k2_ms) * 1e-3) if k1_ms > 0 else None,
-                "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}}
+                "timed": "CUDA events around every launch of the kernel inside the timed region (%d launches)" % n_prof,
+                "stage_ms_per_step": {k: v / n_prof for k, v in stage_acc.items()}}
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))  # one `ncu --set full` capture, per slot
         roofline["traffic"] = tr.get("dram_bytes_per_slot", 0) * B or None
+        roofline["traffic_source"] = tr.get("source")
     except Exception:
         pass
 
@@ -348,7 +380,7 @@ def reference_arm(args, rank, world, config):
         return 0
     global _CPU_SLOTS
     cores = os.cpu_count() or 1
-    n = max(cores, 4)
+    n = max(4 * cores, 16)  # a few slots per worker per step
     try:
         import torch
         dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")

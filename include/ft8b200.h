@@ -153,6 +153,7 @@ void monitor_free(monitor_t *me);
 #define FT8B200_EINVAL (-2)   /* bad argument */
 #define FT8B200_ECUDA (-3)    /* a CUDA call or kernel failed */
 #define FT8B200_ENOMEM (-4)
+#define FT8B200_EBUSY (-5)    /* ft8b200_pipe_submit*: every lane is in flight, collect a batch first */
 
 #define FT8B200_SLOT_SAMPLES 48000  /* 15 s at 3200 sps per rail (rtlsdr_ft8d.h:34-35) */
 #define FT8B200_DECIM 751           /* input samples per output sample (rtlsdr_ft8d.c:156-160) */
@@ -161,6 +162,7 @@ void monitor_free(monitor_t *me);
 
 typedef struct ft8b200_ctx ft8b200_ctx_t;
 typedef struct ft8b200_stream ft8b200_stream_t;
+typedef struct ft8b200_pipe ft8b200_pipe_t;
 
 typedef struct {
     int device;          /* CUDA device ordinal */
@@ -233,9 +235,21 @@ int ft8b200_set_profiling(ft8b200_ctx_t *ctx, int on);
  * (default 0 = off; results are identical either way; only worthwhile when a group still holds >= ~64 slots). */
 int ft8b200_set_overlap(ft8b200_ctx_t *ctx, int groups);
 int ft8b200_stage_times(ft8b200_ctx_t *ctx, float *ms, int n);
+/* on: ft8b200_process_raw runs its back end (waterfall ... spots) on the context's high-priority side stream even for a
+ * single slot group, and ft8b200_front_event() returns the cudaEvent_t (as void*) recorded on the launching stream right
+ * after the decimator of the last call -- what ft8b200_pipe_t chains its lanes with. */
+int ft8b200_set_side_backend(ft8b200_ctx_t *ctx, int on);
+/* Which cic_block_sums kernel the decimator uses: 0 = streaming (one warp per super-block, whole-GPU grid),
+ * >= 1 = persistent bulk-copy kernel (one CTA per SM: a producer thread feeding a shared-memory ring with cp.async.bulk,
+ * consumer warps doing the arithmetic) which leaves most of each SM free for the back-end kernels of another batch.
+ * Results are identical. */
+int ft8b200_set_decimator_variant(ft8b200_ctx_t *ctx, int variant);
+void *ft8b200_front_event(ft8b200_ctx_t *ctx);
 /* device pointers to the last batch's outputs: results (n_slots x max_messages), counts (n_slots) */
 int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults);
 int ft8b200_fetch_results(ft8b200_ctx_t *ctx, int n_slots, struct decoder_results *h_results, int32_t *h_nresults, void *stream);
+/* same without the final synchronisation: h_results/h_nresults must be pinned and are valid once `stream` reaches this point */
+int ft8b200_fetch_results_async(ft8b200_ctx_t *ctx, int n_slots, struct decoder_results *h_results, int32_t *h_nresults, void *stream);
 /* intermediate device buffers of the last batch (for tests / profiling): any pointer may be NULL */
 int ft8b200_workspace(ft8b200_ctx_t *ctx, float **d_i, float **d_q, float **d_peak, uint8_t **d_mag, candidate_t **d_cand, int **d_ncand,
                       uint8_t **d_ok, decode_status_t **d_status, message_t **d_msg);
@@ -245,6 +259,40 @@ int ft8b200_process_raw_host(ft8b200_ctx_t *ctx, const uint8_t *h_iq, size_t byt
                              struct decoder_results *h_results, int32_t *h_nresults);
 int ft8b200_process_slots_host(ft8b200_ctx_t *ctx, const float *h_i, const float *h_q, int n_slots,
                                struct decoder_results *h_results, int32_t *h_nresults);
+
+/* Pipelined executor: `depth` lanes (contexts) on one GPU keep that many batches in flight, in order.  The HBM-bound
+ * decimator of batch n+1 runs while the compute-bound back end of batch n finishes on a high-priority stream; host input
+ * is copied H2D on the lane's own stream (overlapping the previous batch's kernels); spot records come back through
+ * pinned buffers, so the host blocks only in ft8b200_pipe_collect().  This is the daemon's "receive slot n+1 while slot
+ * n decodes" double buffering (rtlsdr_ft8d.c:221-285,1336-1354) across batches.  Results are identical to
+ * ft8b200_process_raw + ft8b200_fetch_results.
+ *   submit*  : 0, FT8B200_EBUSY when `depth` batches are already in flight, or another error (ft8b200_pipe_error)
+ *   collect  : waits for the OLDEST batch in flight, copies its records out, returns its slot count (>0) or an error (<0)
+ * Device input passed to ft8b200_pipe_submit must be complete (synchronised) and stay untouched until collected;
+ * host input of ft8b200_pipe_submit_host should be pinned (cudaHostAlloc/cudaHostRegister) for the copy to be async. */
+ft8b200_pipe_t *ft8b200_pipe_create(const ft8b200_config_t *cfg, int depth);
+/* FT8B200_PIPE_OVERLAP (default): as described above.  FT8B200_PIPE_SERIAL: the kernels of batch n+1 start when batch n
+ * has completed, so only H2D copies, D2H of the records and host work overlap the kernels (each kernel then runs alone
+ * on the GPU, which is what the per-kernel roofline is quoted for).  decimator_variant >= 0 also selects the
+ * cic_block_sums kernel of every lane (ft8b200_set_decimator_variant), -1 leaves it. */
+#define FT8B200_PIPE_OVERLAP 0
+#define FT8B200_PIPE_SERIAL 1
+int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant);
+void ft8b200_pipe_destroy(ft8b200_pipe_t *p);
+const char *ft8b200_pipe_error(ft8b200_pipe_t *p);
+int ft8b200_pipe_depth(ft8b200_pipe_t *p);
+int ft8b200_pipe_in_flight(ft8b200_pipe_t *p);
+int ft8b200_pipe_submit(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots);
+int ft8b200_pipe_submit_host(ft8b200_pipe_t *p, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots);
+int ft8b200_pipe_collect(ft8b200_pipe_t *p, struct decoder_results *h_results, int32_t *h_nresults, int capacity_slots);
+/* same wait, but hands out the DEVICE buffers of the oldest batch (n_slots x max_messages records, n_slots counts) instead of
+ * copying to the host -- for a collective on the records (NCCL all_gather).  They stay valid until that lane is submitted
+ * to again, i.e. finish (synchronise) the collective before the next ft8b200_pipe_submit*. */
+int ft8b200_pipe_collect_device(ft8b200_pipe_t *p, struct decoder_results **d_results, int32_t **d_nresults);
+/* per-stage device times summed over the batches collected since profiling was switched on (ms[0..5] as ft8b200_stage_times) */
+int ft8b200_pipe_set_profiling(ft8b200_pipe_t *p, int on);
+int ft8b200_pipe_stage_times(ft8b200_pipe_t *p, double *ms, int n, uint64_t *batches);
+uint64_t ft8b200_pipe_kernel_launches(ft8b200_pipe_t *p);
 
 /* Receiver streams for rtlsdr_callback(): persistent decimator state, double-buffered 15 s slots. */
 ft8b200_stream_t *ft8b200_stream_create(ft8b200_ctx_t *ctx);

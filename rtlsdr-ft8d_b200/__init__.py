@@ -242,6 +242,10 @@ class Context:
     def set_profiling(self, on: bool):
         self._chk(self.L.ft8b200_set_profiling(C.c_void_p(self.h), int(on)))
 
+    def set_decimator_variant(self, variant: int):
+        """0 = streaming cic_block_sums kernel; >= 1 = persistent bulk-copy (TMA) kernel, shape index 1..6."""
+        self._chk(self.L.ft8b200_set_decimator_variant(C.c_void_p(self.h), int(variant)))
+
     def set_overlap(self, groups: int):
         self._chk(self.L.ft8b200_set_overlap(C.c_void_p(self.h), int(groups)))
 
@@ -286,6 +290,85 @@ class Context:
         nres = np.zeros(n, np.int32)
         self._chk(self.L.ft8b200_process_slots_host(C.c_void_p(self.h), _p(i_host), _p(q_host), n, _p(res), _p(nres)))
         return res, nres
+
+
+class Pipe:
+    """ft8b200_pipe_t: `depth` batches in flight on one GPU (see include/ft8b200.h)."""
+
+    def __init__(self, device: int = 0, depth: int = 2, max_candidates: int = 120, max_messages: int = 50, min_score: int = 10,
+                 ldpc_iterations: int = 20):
+        self.L = lib()
+        self.L.ft8b200_pipe_create.restype = C.c_void_p
+        self.L.ft8b200_pipe_error.restype = C.c_char_p
+        self.L.ft8b200_pipe_kernel_launches.restype = C.c_uint64
+        self.cfg = Config(device, 1, max_candidates, max_messages, min_score, ldpc_iterations)
+        self.h = self.L.ft8b200_pipe_create(C.byref(self.cfg), depth)
+        if not self.h:
+            raise Ft8Error(self.L.ft8b200_last_error().decode())
+        self.depth = depth
+        self.M = max_messages
+
+    def close(self):
+        if self.h:
+            self.L.ft8b200_pipe_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise Ft8Error(f"ft8b200 pipe error {rc}: {self.L.ft8b200_pipe_error(C.c_void_p(self.h)).decode()}")
+        return rc
+
+    def in_flight(self) -> int:
+        return self.L.ft8b200_pipe_in_flight(C.c_void_p(self.h))
+
+    def set_mode(self, serial: bool, decimator_variant: int = -1):
+        self._chk(self.L.ft8b200_pipe_set_mode(C.c_void_p(self.h), 1 if serial else 0, int(decimator_variant)))
+
+    def submit(self, iq, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None):
+        """iq: device tensor (already complete on the device) -> queued on the next lane."""
+        stride = bytes_per_stream if stride is None else stride
+        self._chk(self.L.ft8b200_pipe_submit(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_slots))
+
+    def submit_host(self, iq_host, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES):
+        self._chk(self.L.ft8b200_pipe_submit_host(C.c_void_p(self.h), _p(iq_host), C.c_size_t(bytes_per_stream), n_slots))
+
+    def collect(self, capacity_slots: int):
+        res = np.zeros((capacity_slots, self.M), result_dtype)
+        nres = np.zeros(capacity_slots, np.int32)
+        n = self._chk(self.L.ft8b200_pipe_collect(C.c_void_p(self.h), _p(res), _p(nres), capacity_slots))
+        return res[:n], nres[:n]
+
+    def collect_device(self):
+        """Oldest batch as zero-copy torch views of the lane's device buffers: (uint8[n, M, 28], int32[n])."""
+        import torch
+        a, b = C.c_void_p(0), C.c_void_p(0)
+        n = self._chk(self.L.ft8b200_pipe_collect_device(C.c_void_p(self.h), C.byref(a), C.byref(b)))
+
+        class _Arr:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        dev = torch.device("cuda", self.cfg.device)
+        return (torch.as_tensor(_Arr(a.value, (n, self.M, 28), "|u1"), device=dev), torch.as_tensor(_Arr(b.value, (n,), "<i4"), device=dev))
+
+    def set_profiling(self, on: bool):
+        self._chk(self.L.ft8b200_pipe_set_profiling(C.c_void_p(self.h), int(on)))
+
+    def stage_times(self):
+        """(dict of summed ms per stage, number of batches) since profiling was switched on."""
+        ms = (C.c_double * 6)()
+        nb = C.c_uint64(0)
+        self._chk(self.L.ft8b200_pipe_stage_times(C.c_void_p(self.h), ms, 6, C.byref(nb)))
+        return dict(zip(("block_sums", "comb_fir", "waterfall", "sync", "decode", "spots"), [float(x) for x in ms])), int(nb.value)
+
+    def launches(self) -> int:
+        return int(self.L.ft8b200_pipe_kernel_launches(C.c_void_p(self.h)))
 
 
 class Stream:

@@ -68,6 +68,9 @@ struct ft8b200_ctx {
     // optional per-stage timing of the last process_* call (CUDA events on the launching stream)
     bool profiling = false;
     int overlap = 0;                       // number of slot groups ft8b200_process_raw pipelines (0/1 = off)
+    int k1_variant = 0;                    // 0 = streaming cic_block_sums kernel, >= 1 = persistent bulk-copy kernel (shape index)
+    bool side_back = false;                // back end on the high-priority side stream even with a single group (pipe lanes)
+    cudaEvent_t ev_front = nullptr;        // recorded on the launching stream when the last process_raw's decimator was queued
     cudaEvent_t ev[6][kMaxGroups][2] = {};
     bool ev_valid[6][kMaxGroups] = {};
     cudaStream_t aux = nullptr;            // high-priority side stream for the back end of a slot group
@@ -173,6 +176,7 @@ ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg_in) {
     ft8b200_ctx_t *ctx = new ft8b200_ctx();
     ctx->cfg = cfg;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("FT8B200_K1")) ctx->k1_variant = atoi(e);  // experiments; ft8b200_set_decimator_variant is the API
     bool okc = true;
     okc = okc && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamDefault) == cudaSuccess;
     // tables, built with the host libm exactly as the reference builds them
@@ -242,7 +246,7 @@ int ft8b200_decimate(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_s
     // fresh filter state: the history prefix of every stream is zero
     CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_streams, st));
     BlockSums *s0 = ctx->sums.as<BlockSums>() + kHistBlocks;
-    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_streams, blocks, s0, sstride, st, &ctx->launches));
+    CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_streams, blocks, s0, sstride, ctx->k1_variant, ctx->sm_count, st, &ctx->launches));
     CU(launch_cic_comb_fir(s0, sstride, blocks, 0, true, n_streams, ctx->tb.fir, d_i, d_q, d_count, d_peak, d_y2, st, &ctx->launches));
     tally(ctx);
     return 0;
@@ -392,7 +396,8 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
     const int npos = 2 * 2 * 36 * (256 - 7);
     if ((rc = ensure_scratch(ctx, npos, per))) return rc;
     cudaStream_t back = st;
-    if (n_groups > 1) {
+    const bool side = n_groups > 1 || ctx->side_back;
+    if (side) {
         if ((rc = ensure_aux(ctx))) return rc;
         back = ctx->aux;
         CU(cudaEventRecord(ctx->ev_join, st));           // the side stream starts after everything already queued on st
@@ -405,20 +410,21 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
         const int n = (n_slots - s0) < per ? (n_slots - s0) : per;
         BlockSums *sg = ctx->sums.as<BlockSums>() + (size_t)s0 * sstride + kHistBlocks;
         mark(ctx, 0, g, false, st);
-        CU(launch_cic_block_sums(d_iq + (size_t)s0 * stream_stride_bytes, stream_stride_bytes, n, blocks, sg, sstride, st, &ctx->launches));
+        CU(launch_cic_block_sums(d_iq + (size_t)s0 * stream_stride_bytes, stream_stride_bytes, n, blocks, sg, sstride, ctx->k1_variant, ctx->sm_count, st, &ctx->launches));
         mark(ctx, 0, g, true, st);
         mark(ctx, 1, g, false, st);
         CU(launch_cic_comb_fir(sg, sstride, blocks, 0, true, n, ctx->tb.fir, ctx->si.as<float>() + (size_t)s0 * kSlot,
                                ctx->sq.as<float>() + (size_t)s0 * kSlot, ctx->count.as<uint32_t>() + s0, ctx->peak.as<float>() + s0, nullptr, st,
                                &ctx->launches));
         mark(ctx, 1, g, true, st);
-        if (n_groups > 1) {
+        if (side) {
             CU(cudaEventRecord(ctx->ev_group[g], st));
             CU(cudaStreamWaitEvent(back, ctx->ev_group[g], 0));
+            ctx->ev_front = ctx->ev_group[g];
         }
         if ((rc = run_back_end(ctx, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), s0, n, g, back))) return rc;
     }
-    if (n_groups > 1) {  // results are ready, in stream order, when this call's work on st completes
+    if (side) {  // results are ready, in stream order, when this call's work on st completes
         CU(cudaEventRecord(ctx->ev_join, back));
         CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     }
@@ -455,6 +461,21 @@ int ft8b200_set_overlap(ft8b200_ctx_t *ctx, int on) {
     ctx->overlap = on;
     return 0;
 }
+
+int ft8b200_set_side_backend(ft8b200_ctx_t *ctx, int on) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    ctx->side_back = on != 0;
+    if (!on) ctx->ev_front = nullptr;
+    return 0;
+}
+
+int ft8b200_set_decimator_variant(ft8b200_ctx_t *ctx, int variant) {
+    if (!ctx || variant < 0 || variant > 6) return fail(FT8B200_EINVAL, "ft8b200_set_decimator_variant: bad argument");
+    ctx->k1_variant = variant;
+    return 0;
+}
+
+void *ft8b200_front_event(ft8b200_ctx_t *ctx) { return ctx ? ctx->ev_front : nullptr; }
 
 // ms[0..5] = block sums, comb+FIR, waterfall, sync, decode, spots of the last process_* call, summed over its slot
 // groups (-1 = stage not run).  With overlap on, front-end and back-end stages run concurrently: the sum of the stage
@@ -496,6 +517,18 @@ int ft8b200_fetch_results(ft8b200_ctx_t *ctx, int n_slots, struct decoder_result
     CU(cudaMemcpyAsync(h_results, ctx->results.p, (size_t)n_slots * M * sizeof(struct decoder_results), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_nresults, ctx->nresults.p, (size_t)n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ft8b200_fetch_results_async(ft8b200_ctx_t *ctx, int n_slots, struct decoder_results *h_results, int32_t *h_nresults, void *stream) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!h_results || !h_nresults || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_fetch_results_async: bad argument");
+    cudaStream_t st = pick(ctx, stream);
+    const size_t M = (size_t)ctx->cfg.max_messages;
+    if (ctx->results.bytes < (size_t)n_slots * M * sizeof(struct decoder_results)) return fail(FT8B200_EINVAL, "ft8b200_fetch_results_async: no such batch");
+    CU(cudaMemcpyAsync(h_results, ctx->results.p, (size_t)n_slots * M * sizeof(struct decoder_results), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_nresults, ctx->nresults.p, (size_t)n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return 0;
 }
 

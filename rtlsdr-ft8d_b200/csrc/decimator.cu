@@ -72,10 +72,17 @@ struct IterInfo {
     static constexpr int ibase = 8 * c0 - kDecim * bF;                // in-block index of lane 0's first sample
 };
 
-template <int K>
+// kSmem: the super-block has been staged in shared memory (bulk-copy kernel) instead of being streamed from global
+template <bool kSmem>
+__device__ __forceinline__ uint4 ld_chunk(const uint4 *p) {
+    if (kSmem) return *p;  // LDS.128, consecutive lanes -> consecutive 16-byte chunks: conflict-free
+    return ldg_stream(p);
+}
+
+template <int K, bool kSmem = false>
 __device__ __forceinline__ uint4 load_chunk(const uint4 *base, int lane) {
     using I = IterInfo<K>;
-    if (I::nvalid == 32 || lane < I::nvalid) return ldg_stream(base + I::c0 + lane);
+    if (I::nvalid == 32 || lane < I::nvalid) return ld_chunk<kSmem>(base + I::c0 + lane);
     return make_uint4(0u, 0u, 0u, 0u);  // contributes nothing to the unsigned sums
 }
 
@@ -112,12 +119,12 @@ __device__ __forceinline__ void process_chunk(const uint4 w, int lane, uint32_t 
     }
 }
 
-template <int G>
+template <int G, bool kSmem = false>
 __device__ __forceinline__ void load_group(uint4 (&buf)[4], const uint4 *base, int lane) {
-    buf[0] = load_chunk<4 * G + 0>(base, lane);
-    buf[1] = load_chunk<4 * G + 1>(base, lane);
-    buf[2] = load_chunk<4 * G + 2>(base, lane);
-    buf[3] = load_chunk<4 * G + 3>(base, lane);
+    buf[0] = load_chunk<4 * G + 0, kSmem>(base, lane);
+    buf[1] = load_chunk<4 * G + 1, kSmem>(base, lane);
+    buf[2] = load_chunk<4 * G + 2, kSmem>(base, lane);
+    buf[3] = load_chunk<4 * G + 3, kSmem>(base, lane);
 }
 template <int G>
 __device__ __forceinline__ void process_group(const uint4 (&buf)[4], int lane, uint32_t lane8, Acc &A, Acc &B, uint4 *wsums) {
@@ -136,47 +143,43 @@ __device__ __forceinline__ uint32_t tail_mask(uint32_t sample_idx_word, uint32_t
     return m;
 }
 
-constexpr int kWarpsPerCta = 8;
-
-// Kernel 1: block sums of full, 16-byte aligned super-blocks.  One warp per super-block.
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-cic_block_sums_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int supers_per_stream, size_t sums_stride,
-                      BlockSums *__restrict__ sums) {
-    __shared__ uint4 s_sums[kWarpsPerCta][8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sb = blockIdx.x * kWarpsPerCta + warp;
-    if (sb >= supers_per_stream) return;  // whole warp leaves together
-    const int stream = blockIdx.y;
-    const uint4 *base = reinterpret_cast<const uint4 *>(iq + (size_t)stream * stream_stride_bytes + (size_t)sb * kSuperBytes);
-    uint4 *wsums = s_sums[warp];
+// One warp, one super-block: 8 block sums into out[0..7].  `base` = the super-block's 751 chunks (global or staged in
+// shared memory); `wsums` = 8 x uint4 of per-warp shared scratch.  `release` (kSmem only) is called once every read of
+// the staged copy has completed, so the producer may refill the stage while the results are still being written.
+template <bool kSmem, class Release>
+__device__ __forceinline__ void super_block_sums(const uint4 *base, int lane, uint4 *wsums, BlockSums *__restrict__ out, Release release) {
     const uint32_t lane8 = 8u * (uint32_t)lane;
-
     Acc A = {0u, 0u, 0u, 0u}, B = {0u, 0u, 0u, 0u};
     uint4 b0[4], b1[4];
-    load_group<0>(b0, base, lane);
-    load_group<1>(b1, base, lane);
+    load_group<0, kSmem>(b0, base, lane);
+    load_group<1, kSmem>(b1, base, lane);
     process_group<0>(b0, lane, lane8, A, B, wsums);
-    load_group<2>(b0, base, lane);
+    load_group<2, kSmem>(b0, base, lane);
     process_group<1>(b1, lane, lane8, A, B, wsums);
-    load_group<3>(b1, base, lane);
+    load_group<3, kSmem>(b1, base, lane);
     process_group<2>(b0, lane, lane8, A, B, wsums);
-    load_group<4>(b0, base, lane);
+    load_group<4, kSmem>(b0, base, lane);
     process_group<3>(b1, lane, lane8, A, B, wsums);
-    load_group<5>(b1, base, lane);
-    process_group<4>(b0, lane, lane8, A, B, wsums);
-    process_group<5>(b1, lane, lane8, A, B, wsums);
-    __syncwarp();
-
-    // Boundary fix-up: the chunk holding sample 751*beta (beta = 1..7) was summed whole into block
-    // beta-1 with in-block indices >= 751; move its tail (samples t >= t*) into block beta.
-    uint32_t t0i = 0, t1i = 0, t0q = 0, t1q = 0, tstar = 0;
+    load_group<5, kSmem>(b1, base, lane);
+    // Boundary fix-up operand: the chunk holding sample 751*beta (beta = 1..7) is summed whole into block beta-1
+    // with in-block indices >= 751; its tail (samples t >= t*) is moved into block beta below.
+    uint4 wfix = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t tstar = 0;
     if (lane < 7) {
         const uint32_t beta = (uint32_t)lane + 1u;
         const uint32_t cstar = (kDecim * beta) >> 3;
         tstar = kDecim * beta - 8u * cstar;  // = 8 - beta, never 0 for beta < 8
-        const uint4 w = ldg_stream(base + cstar);
+        wfix = ld_chunk<kSmem>(base + cstar);
+    }
+    release();
+    process_group<4>(b0, lane, lane8, A, B, wsums);
+    process_group<5>(b1, lane, lane8, A, B, wsums);
+    __syncwarp();
+
+    uint32_t t0i = 0, t1i = 0, t0q = 0, t1q = 0;
+    if (lane < 7) {
         uint32_t ip, in, qp, qn;
-        regroup(w, ip, in, qp, qn);
+        regroup(wfix, ip, in, qp, qn);
         const uint32_t mip = tail_mask(kW_IP, tstar), min_ = tail_mask(kW_IN, tstar);
         const uint32_t mqp = tail_mask(kW_QP, tstar), mqn = tail_mask(kW_QN, tstar);
         t0i = __dp4a(ip, kOnes & mip, __dp4a(in, kOnes & min_, 0u));
@@ -201,7 +204,146 @@ cic_block_sums_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes
         BlockSums o;
         o.s0i = (int32_t)(v.x - kOff0); o.s1i = (int32_t)(v.y - kOff1);
         o.s0q = (int32_t)(v.z - kOff0); o.s1q = (int32_t)(v.w - kOff1);
-        sums[(size_t)stream * sums_stride + (size_t)sb * 8 + lane] = o;
+        out[lane] = o;
+    }
+    __syncwarp();  // wsums is reused by this warp's next super-block
+}
+
+constexpr int kWarpsPerCta = 8;
+
+// Kernel 1: block sums of full, 16-byte aligned super-blocks.  One warp per super-block.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+cic_block_sums_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int supers_per_stream, size_t sums_stride,
+                      BlockSums *__restrict__ sums) {
+    __shared__ uint4 s_sums[kWarpsPerCta][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sb = blockIdx.x * kWarpsPerCta + warp;
+    if (sb >= supers_per_stream) return;  // whole warp leaves together
+    const int stream = blockIdx.y;
+    const uint4 *base = reinterpret_cast<const uint4 *>(iq + (size_t)stream * stream_stride_bytes + (size_t)sb * kSuperBytes);
+    uint4 *wsums = s_sums[warp];
+    super_block_sums<false>(base, lane, wsums, sums + (size_t)stream * sums_stride + (size_t)sb * 8, [] {});
+}
+
+// ---- Kernel 1, bulk-copy variant: persistent CTAs, one producer thread + kC consumer warps, kS-stage shared-memory ring ----
+// The streaming variant above needs ~1500 resident threads per SM to keep enough loads in flight (128 B per thread), so
+// nothing else fits on the SM while it runs.  Here the bytes in flight live in shared memory instead of registers: one
+// elected thread issues 12 016-byte cp.async.bulk copies (the TMA engine, SASS UBLKCP) into a ring of kS stages guarded by
+// full/empty mbarriers, and kC consumer warps pull staged super-blocks off the ring (LDS.128) and run the same
+// PRMT/DP4A/REDUX arithmetic.  One CTA per SM with (kC+1) warps and kS x 12 KB of shared memory sustains the same HBM
+// rate and leaves most of the SM's threads, registers and shared memory to the back-end kernels of the previous batch
+// (ft8b200_pipe_t overlaps them).  Work is handed out dynamically (global counter, kGrab super-blocks at a time) so SMs
+// that are slowed down by co-resident CTAs simply take fewer super-blocks.
+constexpr int kStageBytes = 12032;  // 12016 rounded up to a multiple of 128
+constexpr int kGrab = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int kC, int kS>
+__global__ void __launch_bounds__((kC + 1) * 32, 1)
+cic_block_sums_tma_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int supers_per_stream, int total_supers, size_t sums_stride,
+                          BlockSums *__restrict__ sums, unsigned int *__restrict__ work_counter) {
+    extern __shared__ __align__(128) uint8_t s_ring[];  // kS stages of kStageBytes
+    __shared__ __align__(8) uint64_t s_full[kS], s_empty[kS];
+    __shared__ int s_item[kS];                    // global super-block index staged in each stage (-1 = no more work)
+    __shared__ unsigned int s_next;               // CTA-local sequence number handed to the consumer warps
+    __shared__ volatile unsigned int s_issued;    // items the producer has armed so far (consumers never wait on a stage before that)
+    __shared__ uint4 s_sums[kC][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < kS; ++k) { mbar_init(&s_full[k], 1); mbar_init(&s_empty[k], 1); }
+        s_next = 0;
+        s_issued = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kC) {  // ---- producer: one thread
+        if (lane != 0) return;
+        uint32_t j = 0;
+        auto src_of = [&](unsigned int item) {
+            const unsigned int stream = item / (unsigned int)supers_per_stream, sb = item - stream * (unsigned int)supers_per_stream;
+            return iq + (size_t)stream * stream_stride_bytes + (size_t)sb * kSuperBytes;
+        };
+        // (Requesting the next run into L2 with cp.async.bulk.prefetch.L2 was measured and dropped: 3.4 TB/s instead of 5.3.)
+        unsigned int cur = 0, have = 0;
+        for (;;) {
+            if (have == 0) { cur = atomicAdd(work_counter, (unsigned int)kGrab); have = kGrab; }
+            const unsigned int item = cur++;
+            --have;
+            if (item >= (unsigned int)total_supers) break;
+            const uint32_t st = j % kS, ph = (j / kS) & 1u;
+            mbar_wait(&s_empty[st], ph ^ 1u);
+            s_item[st] = (int)item;
+            mbar_arrive_expect_tx(&s_full[st], (uint32_t)kSuperBytes);
+            bulk_g2s(s_ring + (size_t)st * kStageBytes, src_of(item), (uint32_t)kSuperBytes, &s_full[st]);
+            ++j;
+            __threadfence_block();
+            s_issued = j;
+        }
+        for (int c = 0; c < kC; ++c, ++j) {  // one end marker per consumer warp
+            const uint32_t st = j % kS, ph = (j / kS) & 1u;
+            mbar_wait(&s_empty[st], ph ^ 1u);
+            s_item[st] = -1;
+            mbar_arrive(&s_full[st]);
+            __threadfence_block();
+            s_issued = j + 1;
+        }
+        // every producer has made its last grab once all of them got here: the last one re-arms the counters for the
+        // next launch that uses this pair (no memset node between launches)
+        if (atomicAdd(work_counter + 1, 1u) == gridDim.x - 1) { work_counter[0] = 0u; work_counter[1] = 0u; }
+        return;
+    }
+
+    // ---- consumers
+    uint4 *wsums = s_sums[warp];
+    for (;;) {
+        unsigned int j = 0;
+        if (lane == 0) j = atomicAdd(&s_next, 1u);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        const uint32_t st = j % kS, ph = (j / kS) & 1u;
+        // A parity wait is only exact when the waiter is at most one phase ahead of the barrier.  Consumers claim items
+        // freely, so first wait until the producer has armed item j (then full[st] is in exactly phase j / kS).
+        while (s_issued <= j) __nanosleep(32);
+        mbar_wait(&s_full[st], ph);
+        const int item = s_item[st];
+        uint64_t *empty = &s_empty[st];
+        if (item < 0) {  // end marker: hand the stage back (the producer may need it for another warp's marker) and leave
+            if (lane == 0) mbar_arrive(empty);
+            break;
+        }
+        const int stream = item / supers_per_stream, sb = item - stream * supers_per_stream;
+        super_block_sums<true>(reinterpret_cast<const uint4 *>(s_ring + (size_t)st * kStageBytes), lane, wsums,
+                               sums + (size_t)stream * sums_stride + (size_t)sb * 8, [empty, lane] {
+                                   __syncwarp();  // every lane's shared-memory reads of this stage have been issued and returned
+                                   if (lane == 0) mbar_arrive(empty);
+                               });
     }
 }
 
@@ -368,12 +510,61 @@ __global__ void condition_kernel(float *__restrict__ d_i, float *__restrict__ d_
 
 }  // namespace
 
+// counter pairs {next super-block, finished CTAs} for the bulk-copy kernel: zeroed once, re-armed by the kernel itself
+constexpr int kCounterPairs = 256;
+static unsigned int *counter_pool(int dev) {
+    static unsigned int *pool[64] = {};
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!pool[dev]) {
+        if (cudaMalloc(&pool[dev], kCounterPairs * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        cudaMemset(pool[dev], 0, kCounterPairs * 2 * sizeof(unsigned int));
+    }
+    return pool[dev];
+}
+
+template <int kC, int kS>
+static cudaError_t launch_tma(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int supers, BlockSums *d_sums, size_t sums_stride,
+                              int sm_count, unsigned int *counter, cudaStream_t st) {
+    const int smem = kS * kStageBytes;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(cic_block_sums_tma_kernel<kC, kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const long total = (long)supers * n_streams;
+    int grid = sm_count;
+    if ((long)grid * kC > total) grid = (int)((total + kC - 1) / kC);
+    cic_block_sums_tma_kernel<kC, kS><<<grid, (kC + 1) * 32, smem, st>>>(d_iq, stream_stride_bytes, supers, (int)total, sums_stride, d_sums, counter);
+    return cudaGetLastError();
+}
+
 // Block sums of `blocks_per_stream` blocks per stream, streams starting at a super-block boundary of their
 // sample stream (mixer phase 0).  d_sums points at block 0 of stream 0 (history prefix before it).
+// variant 0: streaming kernel (one warp per super-block, grid over all of them); variant >= 1: persistent bulk-copy
+// kernel (shape selected by the variant number), for running underneath other kernels.
 cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int blocks_per_stream, BlockSums *d_sums,
-                                  size_t sums_stride, cudaStream_t st, int *launches) {
+                                  size_t sums_stride, int variant, int sm_count, cudaStream_t st, int *launches) {
     const int supers = blocks_per_stream / 8;
-    if (supers > 0) {
+    if (supers > 0 && variant >= 1 && (long)supers * n_streams < (1l << 31)) {
+        static unsigned int next_pair = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        unsigned int *pool = counter_pool(dev);
+        if (!pool) return cudaErrorMemoryAllocation;
+        unsigned int *counter = pool + 2 * (next_pair++ % kCounterPairs);
+        cudaError_t e;
+        switch (variant) {
+        case 2: e = launch_tma<12, 8>(d_iq, stream_stride_bytes, n_streams, supers, d_sums, sums_stride, sm_count, counter, st); break;
+        case 3: e = launch_tma<16, 8>(d_iq, stream_stride_bytes, n_streams, supers, d_sums, sums_stride, sm_count, counter, st); break;
+        case 4: e = launch_tma<6, 4>(d_iq, stream_stride_bytes, n_streams, supers, d_sums, sums_stride, sm_count, counter, st); break;
+        case 5: e = launch_tma<8, 10>(d_iq, stream_stride_bytes, n_streams, supers, d_sums, sums_stride, sm_count, counter, st); break;
+        case 6: e = launch_tma<16, 12>(d_iq, stream_stride_bytes, n_streams, supers, d_sums, sums_stride, sm_count, counter, st); break;
+        default: e = launch_tma<8, 6>(d_iq, stream_stride_bytes, n_streams, supers, d_sums, sums_stride, sm_count, counter, st); break;
+        }
+        if (e != cudaSuccess) return e;
+        ++*launches;
+    } else if (supers > 0) {
         dim3 grid((supers + kWarpsPerCta - 1) / kWarpsPerCta, n_streams);
         cic_block_sums_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, sums_stride, d_sums);
         ++*launches;

@@ -1,0 +1,239 @@
+// pipe.cu -- ft8b200_pipe_t: a small in-order executor that keeps several slot batches in flight on one GPU.
+//
+// Why: one batch through ft8b200_process_raw() is an HBM-bound front end (cic_block_sums + comb/FIR, ~11 us per slot)
+// followed by a latency/issue-bound back end (waterfall, sync, LDPC, spot table) that uses almost no DRAM bandwidth.
+// Run back to back they leave the memory system idle for a third of the step, and every step also pays the host's
+// launch latency and the blocking D2H of the spot records.  The pipe owns `depth` lanes (one ft8b200_ctx_t each: private
+// workspaces, a launching stream and a high-priority side stream for the back end) and chains them so that
+//   * the front end of batch n+1 starts as soon as the front end of batch n has been issued and finished
+//     (front ends never compete with each other for DRAM),
+//   * the back end of batch n runs on its lane's high-priority stream underneath the front end of batch n+1,
+//   * host input (ft8b200_pipe_submit_host) is copied H2D on the lane's own stream, so the PCIe copy of batch n+1
+//     overlaps all of batch n's kernels, and
+//   * spot records return through pinned per-lane buffers with an async D2H; the host only blocks in collect().
+// Results are bit-identical to the unpipelined calls (tests/test_gpu_parity.py::test_pipe_*): the kernels and their
+// per-batch buffers are the same, only the stream topology differs.
+//
+// Reference counterpart: the daemon's double-buffered rx_state + decoder thread (rtlsdr_ft8d.c:221-285, 1336-1354),
+// i.e. "receive slot n+1 while slot n decodes" -- here across batches of slots on one GPU.
+#include "common.cuh"
+
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Lane {
+    ft8b200_ctx_t *ctx = nullptr;
+    cudaStream_t st = nullptr;
+    uint8_t *d_raw = nullptr;
+    size_t raw_bytes = 0;
+    struct decoder_results *h_res = nullptr;
+    int32_t *h_n = nullptr;
+    size_t res_slots = 0;
+    cudaEvent_t done = nullptr;
+    int n_slots = 0;
+};
+
+}  // namespace
+
+struct ft8b200_pipe {
+    ft8b200_config_t cfg;
+    std::vector<Lane> lanes;
+    int head = 0;    // oldest batch in flight
+    int count = 0;   // batches in flight
+    cudaEvent_t prev_front = nullptr;  // front-end-done event of the most recently submitted batch
+    cudaEvent_t prev_done = nullptr;   // completion event of the most recently submitted batch
+    int mode = FT8B200_PIPE_OVERLAP;
+    bool profiling = false;
+    double stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t batches = 0, slots = 0;
+    std::string err;
+};
+
+namespace {
+
+int pfail(ft8b200_pipe_t *p, int code, const std::string &msg) {
+    p->err = msg;
+    return code;
+}
+#define PCU(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) return pfail(p, FT8B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+int lane_results(ft8b200_pipe_t *p, Lane &l, int n_slots) {
+    if ((size_t)n_slots <= l.res_slots) return 0;
+    if (l.h_res) cudaFreeHost(l.h_res);
+    if (l.h_n) cudaFreeHost(l.h_n);
+    l.h_res = nullptr; l.h_n = nullptr; l.res_slots = 0;
+    PCU(cudaMallocHost(&l.h_res, (size_t)n_slots * p->cfg.max_messages * sizeof(struct decoder_results)));
+    PCU(cudaMallocHost(&l.h_n, (size_t)n_slots * sizeof(int32_t)));
+    l.res_slots = (size_t)n_slots;
+    return 0;
+}
+
+// queue one batch on the next free lane; `h_iq` (host) or `d_iq` (device) holds the raw IQ
+int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t bytes_per_stream, size_t stride, int n_slots) {
+    if (!p) return FT8B200_EINVAL;
+    if ((!h_iq && !d_iq) || n_slots < 1 || (bytes_per_stream & 7)) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_submit: bad argument");
+    if (p->count == (int)p->lanes.size()) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_submit: every lane is in flight, collect first");
+    PCU(cudaSetDevice(p->cfg.device));
+    Lane &l = p->lanes[(p->head + p->count) % p->lanes.size()];
+    int rc = lane_results(p, l, n_slots);
+    if (rc) return rc;
+    if (h_iq) {
+        stride = (bytes_per_stream + 15) & ~(size_t)15;
+        const size_t need = stride * (size_t)n_slots + 16;
+        if (need > l.raw_bytes) {
+            if (l.d_raw) cudaFree(l.d_raw);
+            l.d_raw = nullptr; l.raw_bytes = 0;
+            PCU(cudaMalloc(&l.d_raw, need));
+            l.raw_bytes = need;
+        }
+        if (stride == bytes_per_stream) PCU(cudaMemcpyAsync(l.d_raw, h_iq, bytes_per_stream * n_slots, cudaMemcpyHostToDevice, l.st));
+        else PCU(cudaMemcpy2DAsync(l.d_raw, stride, h_iq, bytes_per_stream, bytes_per_stream, n_slots, cudaMemcpyHostToDevice, l.st));
+        d_iq = l.d_raw;
+    }
+    if (p->mode == FT8B200_PIPE_OVERLAP) {
+        // front ends are serialised across lanes: this batch's decimator starts when the previous batch's has finished
+        if (p->prev_front) PCU(cudaStreamWaitEvent(l.st, p->prev_front, 0));
+    } else if (p->prev_done) {
+        // kernels of consecutive batches never share the GPU; only copies and host work overlap them
+        PCU(cudaStreamWaitEvent(l.st, p->prev_done, 0));
+    }
+    if ((rc = ft8b200_process_raw(l.ctx, d_iq, bytes_per_stream, stride, n_slots, nullptr))) return pfail(p, rc, ft8b200_last_error());
+    p->prev_front = reinterpret_cast<cudaEvent_t>(ft8b200_front_event(l.ctx));
+    if ((rc = ft8b200_fetch_results_async(l.ctx, n_slots, l.h_res, l.h_n, nullptr))) return pfail(p, rc, ft8b200_last_error());
+    PCU(cudaEventRecord(l.done, l.st));
+    p->prev_done = l.done;
+    l.n_slots = n_slots;
+    ++p->count;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+ft8b200_pipe_t *ft8b200_pipe_create(const ft8b200_config_t *cfg_in, int depth) {
+    if (depth < 1 || depth > 8) return nullptr;
+    ft8b200_pipe_t *p = new ft8b200_pipe();
+    ft8b200_default_config(&p->cfg);
+    if (cfg_in) p->cfg = *cfg_in;
+    p->lanes.resize((size_t)depth);
+    for (Lane &l : p->lanes) {
+        l.ctx = ft8b200_create(&p->cfg);  // fails (NULL + ft8b200_last_error) without an sm_100 device: no fallback
+        if (!l.ctx || cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming) != cudaSuccess) {
+            ft8b200_pipe_destroy(p);
+            return nullptr;
+        }
+        l.st = reinterpret_cast<cudaStream_t>(ft8b200_cuda_stream(l.ctx));
+        ft8b200_set_side_backend(l.ctx, depth > 1);
+    }
+    return p;
+}
+
+int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant) {
+    if (!p || (mode != FT8B200_PIPE_OVERLAP && mode != FT8B200_PIPE_SERIAL)) return FT8B200_EINVAL;
+    if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_set_mode: batches in flight");
+    p->mode = mode;
+    for (Lane &l : p->lanes) {
+        ft8b200_set_side_backend(l.ctx, mode == FT8B200_PIPE_OVERLAP && p->lanes.size() > 1);
+        if (decimator_variant >= 0 && ft8b200_set_decimator_variant(l.ctx, decimator_variant)) return pfail(p, FT8B200_EINVAL, ft8b200_last_error());
+    }
+    p->prev_front = nullptr;
+    return 0;
+}
+
+void ft8b200_pipe_destroy(ft8b200_pipe_t *p) {
+    if (!p) return;
+    cudaSetDevice(p->cfg.device);
+    for (Lane &l : p->lanes) {
+        if (l.st) cudaStreamSynchronize(l.st);
+        if (l.ctx) ft8b200_destroy(l.ctx);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.d_raw) cudaFree(l.d_raw);
+        if (l.h_res) cudaFreeHost(l.h_res);
+        if (l.h_n) cudaFreeHost(l.h_n);
+    }
+    delete p;
+}
+
+const char *ft8b200_pipe_error(ft8b200_pipe_t *p) { return p ? p->err.c_str() : "null pipe"; }
+int ft8b200_pipe_depth(ft8b200_pipe_t *p) { return p ? (int)p->lanes.size() : 0; }
+int ft8b200_pipe_in_flight(ft8b200_pipe_t *p) { return p ? p->count : 0; }
+
+int ft8b200_pipe_submit(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots) {
+    return submit(p, nullptr, d_iq, bytes_per_stream, stream_stride_bytes, n_slots);
+}
+
+int ft8b200_pipe_submit_host(ft8b200_pipe_t *p, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots) {
+    return submit(p, h_iq, nullptr, bytes_per_stream, bytes_per_stream, n_slots);
+}
+
+static int pop(ft8b200_pipe_t *p, struct decoder_results *h_results, int32_t *h_nresults, int capacity_slots, struct decoder_results **d_results,
+               int32_t **d_nresults) {
+    if (!p) return FT8B200_EINVAL;
+    if (p->count == 0) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_collect: nothing in flight");
+    Lane &l = p->lanes[p->head];
+    if (h_results && (capacity_slots < l.n_slots || !h_nresults)) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_collect: result buffers too small");
+    PCU(cudaSetDevice(p->cfg.device));
+    PCU(cudaEventSynchronize(l.done));
+    if (h_results) {
+        memcpy(h_results, l.h_res, (size_t)l.n_slots * p->cfg.max_messages * sizeof(struct decoder_results));
+        memcpy(h_nresults, l.h_n, (size_t)l.n_slots * sizeof(int32_t));
+    }
+    if (d_results || d_nresults) {
+        int rc = ft8b200_results_device(l.ctx, d_results, d_nresults);
+        if (rc) return pfail(p, rc, ft8b200_last_error());
+    }
+    if (p->profiling) {
+        float ms[6];
+        if (ft8b200_stage_times(l.ctx, ms, 6) == 0)
+            for (int k = 0; k < 6; ++k) if (ms[k] > 0) p->stage_ms[k] += ms[k];
+    }
+    ++p->batches;
+    p->slots += (uint64_t)l.n_slots;
+    p->head = (p->head + 1) % (int)p->lanes.size();
+    --p->count;
+    return l.n_slots;
+}
+
+int ft8b200_pipe_collect(ft8b200_pipe_t *p, struct decoder_results *h_results, int32_t *h_nresults, int capacity_slots) {
+    if (!h_results || !h_nresults) return p ? pfail(p, FT8B200_EINVAL, "ft8b200_pipe_collect: null result buffer") : FT8B200_EINVAL;
+    return pop(p, h_results, h_nresults, capacity_slots, nullptr, nullptr);
+}
+
+int ft8b200_pipe_collect_device(ft8b200_pipe_t *p, struct decoder_results **d_results, int32_t **d_nresults) {
+    return pop(p, nullptr, nullptr, 0, d_results, d_nresults);
+}
+
+int ft8b200_pipe_set_profiling(ft8b200_pipe_t *p, int on) {
+    if (!p) return FT8B200_EINVAL;
+    p->profiling = on != 0;
+    for (Lane &l : p->lanes) ft8b200_set_profiling(l.ctx, on);
+    for (double &v : p->stage_ms) v = 0.0;
+    p->batches = 0;
+    p->slots = 0;
+    return 0;
+}
+
+// sums over the batches collected since profiling was switched on: ms[0..5] as ft8b200_stage_times, *batches = how many
+int ft8b200_pipe_stage_times(ft8b200_pipe_t *p, double *ms, int n, uint64_t *batches) {
+    if (!p || !ms || n < 6) return FT8B200_EINVAL;
+    for (int k = 0; k < 6; ++k) ms[k] = p->stage_ms[k];
+    if (batches) *batches = p->batches;
+    return 0;
+}
+
+uint64_t ft8b200_pipe_kernel_launches(ft8b200_pipe_t *p) {
+    uint64_t n = 0;
+    if (p) for (Lane &l : p->lanes) n += ft8b200_kernel_launches(l.ctx);
+    return n;
+}
+
+}  // extern "C"

@@ -82,7 +82,7 @@ void pump(ft8b200_stream_t *s) {
     if (a0 > b0)
         CK(launch_cic_block_sums_generic(ptr(b0), 0, 1, (uint32_t)((b0 * kDecim) & 3u), (int)(a0 - b0), out, 0, s->st, &s->launches));
     if (a1 > a0)
-        CK(launch_cic_block_sums(ptr(a0), 0, 1, (int)(a1 - a0), out + (a0 - b0), 0, s->st, &s->launches));
+        CK(launch_cic_block_sums(ptr(a0), 0, 1, (int)(a1 - a0), out + (a0 - b0), 0, 0, 0, s->st, &s->launches));
     if (b1 > a1)
         CK(launch_cic_block_sums_generic(ptr(a1), 0, 1, (uint32_t)((a1 * kDecim) & 3u), (int)(b1 - a1), out + (a1 - b0), 0, s->st, &s->launches));
     const int buf = s->buffer_index;

@@ -15,34 +15,8 @@ namespace ft8b200 {
 namespace {
 
 constexpr int kSyncThreads = 1024;
-__constant__ uint8_t c_costas[7] = {3, 1, 4, 0, 6, 5, 2};
 
 struct Geo { int nb, nbins, tosr, fosr, stride, nfo, npos; };
-
-// ref: ft8_sync_score(), decode.c:44-108
-__device__ __forceinline__ int sync_score(const uint8_t *__restrict__ mag, const Geo &g, int ts, int fs, int to, int fo) {
-    const long origin = (((long)to * g.tosr + ts) * g.fosr + fs) * g.nbins + fo;
-    int score = 0, terms = 0;
-#pragma unroll
-    for (int grp = 0; grp < 3; ++grp) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const int rel = 36 * grp + k;
-            const int row = to + rel;
-            if (row < 0) continue;
-            if (row >= g.nb) break;  // leaves this group only, like the reference's inner `break`
-            const uint8_t *p = mag + origin + (long)rel * g.stride;
-            const int tone = c_costas[k];
-            const int centre = p[tone];
-            if (tone > 0) { score += centre - p[tone - 1]; ++terms; }
-            if (tone < 7) { score += centre - p[tone + 1]; ++terms; }
-            if (k > 0 && row > 0) { score += centre - p[tone - g.stride]; ++terms; }
-            if (k + 1 < 7 && row + 1 < g.nb) { score += centre - p[tone + g.stride]; ++terms; }
-        }
-    }
-    if (terms > 0) score /= terms;  // truncating division
-    return score;
-}
 
 // candidate_t as one 64-bit word: score | time_offset<<16 | freq_offset<<32 | time_sub<<48 | freq_sub<<56
 __device__ __forceinline__ int cand_score(unsigned long long c) { return (int)(short)(c & 0xffffull); }
@@ -69,39 +43,84 @@ __device__ void sift_up(unsigned long long *h, int n) {  // ref: heapify_up, dec
     }
 }
 
-// Phase 1: score every position.  grid = (chunks, slots): each CTA stages the slot's waterfall in shared memory
-// (when it fits) and scores its share of the positions; scores go to global memory as int16 in position order.
-template <bool kStage>
-__global__ void __launch_bounds__(kSyncThreads)
-sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int pos_per_chunk, int16_t *__restrict__ scores_all) {
+// Phase 1: score every position.  For a fixed (time_sub, freq_sub) every byte a score touches lies in ONE sub-plane of
+// the waterfall: mag[((row*tosr + ts)*fosr + fs)*nbins + bin] for row < nb, bin < nbins (nb x nbins bytes: 23.5 KB for
+// the daemon geometry, 89 KB for the 12 kHz monitor).  grid = (planes * splits, slots): a CTA stages its plane compactly
+// in shared memory ([row][bin]) and scores the positions of that plane for its share of the 36 time offsets; thread t
+// owns frequency offsets t, t + blockDim, ... so a warp reads 32 consecutive bytes per access (one wavefront) and the
+// row-range tests are uniform across the CTA.  Scores go to global memory as int16 in the reference's loop order.
+constexpr int kScoreThreads = 256;
+
+// ref: ft8_sync_score(), decode.c:44-108, on the compact plane (`nbins` = row pitch)
+template <int kBins>
+__device__ __forceinline__ int sync_score_plane(const uint8_t *__restrict__ plane, int nb, int nbins_rt, int to, int fo) {
+    const int nbins = kBins > 0 ? kBins : nbins_rt;
+    int score = 0, terms = 0;
+#pragma unroll
+    for (int grp = 0; grp < 3; ++grp) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int row = to + 36 * grp + k;
+            if (row < 0) continue;
+            if (row >= nb) break;  // leaves this group only, like the reference's inner `break`
+            constexpr int kCostas[7] = {3, 1, 4, 0, 6, 5, 2};
+            const int tone = kCostas[k];
+            const uint8_t *p = plane + row * nbins + fo + tone;
+            const int centre = p[0];
+            if (tone > 0) { score += centre - p[-1]; ++terms; }
+            if (tone < 7) { score += centre - p[1]; ++terms; }
+            if (k > 0 && row > 0) { score += centre - p[-nbins]; ++terms; }
+            if (k + 1 < 7 && row + 1 < nb) { score += centre - p[nbins]; ++terms; }
+        }
+    }
+    if (terms > 0) score /= terms;  // truncating division
+    return score;
+}
+
+template <int kBins, bool kStage>
+__global__ void __launch_bounds__(kScoreThreads)
+sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int splits, int to_per_cta, int16_t *__restrict__ scores_all) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x;
     const int slot = blockIdx.y;
-    const int wf_bytes = g.nb * g.stride;
-    const uint8_t *gmag = mag_all + (size_t)slot * slot_stride;
-    const uint8_t *mag = gmag;
+    const int plane_id = blockIdx.x / splits, split = blockIdx.x - plane_id * splits;  // plane_id = ts*fosr + fs
+    const int nbins = kBins > 0 ? kBins : g.nbins;
+    const uint8_t *gplane = mag_all + (size_t)slot * slot_stride + (size_t)plane_id * nbins;  // row r at gplane + r*stride
+    const int to0 = -12 + split * to_per_cta;
+    int to1 = to0 + to_per_cta;
+    if (to1 > 24) to1 = 24;
+    const uint8_t *plane;
+    int pitch;
     if (kStage) {
-        if ((((size_t)gmag) & 15) == 0 && (wf_bytes & 15) == 0) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(gmag);
-            uint4 *dst = reinterpret_cast<uint4 *>(smem);
-            for (int k = tid; k < wf_bytes / 16; k += kSyncThreads) dst[k] = __ldg(src + k);
+        // rows this CTA can touch: [to0 - 1, to1 - 1 + 72 + 6 + 1], clipped
+        int r0 = to0 - 1, r1 = to1 + 79;
+        if (r0 < 0) r0 = 0;
+        if (r1 > g.nb) r1 = g.nb;
+        if (((((size_t)gplane) | (size_t)g.stride | (size_t)nbins) & 15) == 0) {
+            const int vec_per_row = nbins >> 4;
+            for (int v = tid; v < (r1 - r0) * vec_per_row; v += kScoreThreads) {
+                const int r = r0 + v / vec_per_row, c = v - (v / vec_per_row) * vec_per_row;
+                reinterpret_cast<uint4 *>(smem + (size_t)r * nbins)[c] = __ldg(reinterpret_cast<const uint4 *>(gplane + (size_t)r * g.stride) + c);
+            }
         } else {
-            for (int k = tid; k < wf_bytes; k += kSyncThreads) smem[k] = gmag[k];
+            for (int v = tid; v < (r1 - r0) * nbins; v += kScoreThreads) {
+                const int r = r0 + v / nbins, c = v - (v / nbins) * nbins;
+                smem[(size_t)r * nbins + c] = gplane[(size_t)r * g.stride + c];
+            }
         }
-        mag = smem;
+        plane = smem;
+        pitch = nbins;
         __syncthreads();
+    } else {
+        plane = gplane;
+        pitch = g.stride;
     }
-    int16_t *scores = scores_all + (size_t)slot * g.npos;
-    const int p0 = blockIdx.x * pos_per_chunk;
-    int p1 = p0 + pos_per_chunk;
-    if (p1 > g.npos) p1 = g.npos;
-    for (int p = p0 + tid; p < p1; p += kSyncThreads) {
-        const int fo = p % g.nfo;
-        int q = p / g.nfo;
-        const int to = q % 36 - 12;
-        q /= 36;
-        const int fs = q % g.fosr, ts = q / g.fosr;
-        scores[p] = (int16_t)sync_score(mag, g, ts, fs, to, fo);  // stored as int16_t in candidate_t
+    int16_t *scores = scores_all + (size_t)slot * g.npos + (size_t)plane_id * 36 * g.nfo;
+    for (int to = to0; to < to1; ++to) {
+        for (int fo = tid; fo < g.nfo; fo += kScoreThreads) {
+            const int sc = kStage ? sync_score_plane<kBins>(plane, g.nb, pitch, to, fo) : sync_score_plane<0>(plane, g.nb, pitch, to, fo);
+            scores[(to + 12) * g.nfo + fo] = (int16_t)sc;  // stored as int16_t in candidate_t
+        }
     }
 }
 
@@ -204,22 +223,27 @@ cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slo
     g.stride = time_osr * freq_osr * num_bins;
     g.nfo = num_bins - 7;
     g.npos = time_osr * freq_osr * 36 * g.nfo;
-    const int wf_bytes = g.nb * g.stride;
-    const size_t staged = (size_t)((wf_bytes + 15) & ~15);
-    // enough CTAs to fill the machine even for small batches: ~4 per SM, at least 1024 positions each
-    int chunks = (4 * sm_count + n_slots - 1) / n_slots;
-    const int max_chunks = (g.npos + kSyncThreads - 1) / kSyncThreads;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks > 12) chunks = 12;
-    if (chunks < 1) chunks = 1;
-    const int per = (g.npos + chunks - 1) / chunks;
-    dim3 grid(chunks, n_slots);
+    // one CTA per (slot, sub-plane, share of the 36 time offsets); enough CTAs to fill the machine for small batches
+    const int planes = time_osr * freq_osr;
+    int splits = (4 * sm_count + n_slots * planes - 1) / (n_slots * planes);
+    if (splits > 6) splits = 6;
+    if (splits < 1) splits = 1;
+    const int to_per_cta = (36 + splits - 1) / splits;
+    splits = (36 + to_per_cta - 1) / to_per_cta;
+    dim3 grid(planes * splits, n_slots);
+    const size_t staged = ((size_t)g.nb * g.nbins + 15) & ~(size_t)15;
     if (staged <= 200 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(sync_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
-        if (e != cudaSuccess) return e;
-        sync_score_kernel<true><<<grid, kSyncThreads, staged, st>>>(d_mag, slot_stride, g, per, d_scores);
+        if (g.nbins == 256) {
+            sync_score_kernel<256, true><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
+        } else {
+            if (staged > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(sync_score_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
+                if (e != cudaSuccess) return e;
+            }
+            sync_score_kernel<0, true><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
+        }
     } else {
-        sync_score_kernel<false><<<grid, kSyncThreads, 0, st>>>(d_mag, slot_stride, g, per, d_scores);
+        sync_score_kernel<0, false><<<grid, kScoreThreads, 0, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
     }
     ++*launches;
     if (d_work_total) {

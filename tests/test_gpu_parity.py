@@ -448,3 +448,83 @@ def test_grouped_overlap_gives_identical_results(ctx, raw_slot):
         r1, n1 = ctx.fetch_results(1)
         assert n1[0] == n[s] and r1[0].tobytes() == res[s].tobytes()
     assert n[0] >= 1 and n[3] == 0
+
+
+# ------------------------------------------------------------------------------------------- pipelined executor
+def _mixed_batch(raw_slot, B):
+    big = torch.from_numpy(raw_slot).to(dev()).repeat(B, 1).contiguous()
+    big[1] = 0x80                      # a silent slot
+    big[2, : 2 * 751 * 9000] = 0x80    # signal starts late: different peak, same message
+    big[3] = big[3].flip(0)            # garbage
+    return big
+
+
+@pytest.mark.parametrize("depth,serial,variant", [(1, False, 0), (2, False, 0), (2, True, 0), (3, False, 5), (2, True, 1)])
+def test_pipe_matches_unpipelined(pkg, ctx, oracle, raw_slot, depth, serial, variant):
+    """ft8b200_pipe_t (several batches in flight, back end on a side stream, optional bulk-copy decimator) returns exactly
+    the records of ft8b200_process_raw + ft8b200_fetch_results, batch after batch, for device and for host input; the
+    first slot is also checked against the CPU oracle."""
+    B = 6
+    big = _mixed_batch(raw_slot, B)
+    torch.cuda.synchronize()
+    ctx.process_raw(big, B)
+    ref_res, ref_n = ctx.fetch_results(B)
+    oi, oq = oracle.decimate_slot(raw_slot)
+    ri = np.zeros(48000, np.float32); rq = np.zeros(48000, np.float32)
+    ri[:oi.size] = oi; rq[:oq.size] = oq
+    o = oracle.subsystem(*oracle.condition(ri, rq, oi.size)[:2])
+    assert ref_n[0] == o["n"] >= 1 and ref_res[0].tobytes() == o["results"].tobytes()
+
+    pipe = pkg.Pipe(0, depth)
+    pipe.set_mode(serial, variant)
+    outs = []
+    sizes = [B, 2, B, 1, 4, B, 3]
+    for n in sizes:
+        if pipe.in_flight() == pipe.depth:
+            outs.append(pipe.collect(B))
+        pipe.submit(big[:n], n)
+    with pytest.raises(pkg.Ft8Error):   # FT8B200_EBUSY only when every lane is in flight
+        while True:
+            pipe.submit(big[:1], 1)
+            sizes.append(1)
+    while pipe.in_flight():
+        outs.append(pipe.collect(B))
+    assert [len(o[1]) for o in outs] == sizes
+    for (res, n), k in zip(outs, sizes):
+        assert np.array_equal(n, ref_n[:k]) and res.tobytes() == ref_res[:k].tobytes()
+    with pytest.raises(pkg.Ft8Error):
+        pipe.collect(B)                 # nothing in flight
+
+    host = big[:4].cpu().numpy()
+    houts = []
+    for n in (4, 1, 3, 4):
+        if pipe.in_flight() == pipe.depth:
+            houts.append(pipe.collect(B))
+        pipe.submit_host(host[:n], n)
+    while pipe.in_flight():
+        houts.append(pipe.collect(B))
+    for (res, n), k in zip(houts, (4, 1, 3, 4)):
+        assert np.array_equal(n, ref_n[:k]) and res.tobytes() == ref_res[:k].tobytes()
+    assert pipe.launches() > 0
+    pipe.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+def test_bulk_copy_decimator_variants(pkg, oracle, variant):
+    """The persistent cp.async.bulk + mbarrier cic_block_sums kernel (every ring shape) is bit-identical to the oracle,
+    including batches smaller than one CTA's consumer count and ragged tails handled by the generic kernel."""
+    c = pkg.Context(0)
+    c.set_decimator_variant(variant)
+    rng = np.random.default_rng(40 + variant)
+    for nstreams, nbytes in ((1, 12016 * 3), (3, 12016 * 40 + 1502 * 4), (2, 12016 * 700 + 8 * 11), (5, 12016 * 17)):
+        stride = (nbytes + 15) // 16 * 16
+        iq = rng.integers(0, 256, size=(nstreams, stride), dtype=np.uint8)
+        d_i, d_q, cnt, peak, y2 = c.decimate(torch.from_numpy(iq).to(dev()), nstreams, nbytes, stride, want_y2=True)
+        for s in range(nstreams):
+            oi, oq, oy2i, oy2q = oracle_decim(oracle, iq[s, :nbytes])
+            n = int(cnt[s])
+            assert n == oi.size
+            assert bits_equal(d_i[s, :n].cpu().numpy(), oi) and bits_equal(d_q[s, :n].cpu().numpy(), oq)
+            gy = y2[s].cpu().numpy()
+            assert np.array_equal(gy[:n, 0], oy2i) and np.array_equal(gy[:n, 1], oy2q)
+    c.close()
