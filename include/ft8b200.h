@@ -193,6 +193,15 @@ uint64_t ft8b200_kernel_launches(ft8b200_ctx_t *ctx);
 int ft8b200_decimate(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams,
                      float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, void *stream);
 
+/* Continuous receiver streams cut into consecutive slots (BASELINE config #5): stream s holds slots_per_stream x
+ * bytes_per_slot bytes of one receiver; the decimator runs THROUGH the slot boundaries (filter history is the real
+ * preceding samples) and output row s*slots_per_stream + g receives the samples whose decimation instant falls into
+ * slot g -- 47 936 or 47 937 per 72 000 000-byte slot, exactly what rx_state's buffers hold when main() flips them every
+ * 15 s between callbacks (rtlsdr_ft8d.c:1339-1354).  Output arrays have n_streams*slots_per_stream rows. */
+int ft8b200_decimate_streams(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams,
+                             int slots_per_stream, size_t bytes_per_slot, float *d_i, float *d_q, uint32_t *d_count, float *d_peak,
+                             int32_t *d_y2, void *stream);
+
 /* a4: in-place decoder() conditioning of n_slots x 48000 samples using d_peak (rtlsdr_ft8d.c:242-263) */
 int ft8b200_condition(ft8b200_ctx_t *ctx, float *d_i, float *d_q, const float *d_peak, int n_slots, void *stream);
 
@@ -224,6 +233,9 @@ int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate
  * 3200 sps samples (d_i/d_q) -> decoder_results.  Results stay on the device (ft8b200_results_device)
  * until fetched. */
 int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots, void *stream);
+/* whole path over continuous streams (see ft8b200_decimate_streams): n_streams*slots_per_stream result rows */
+int ft8b200_process_raw_streams(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams,
+                                int slots_per_stream, size_t bytes_per_slot, void *stream);
 int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, int n_slots, void *stream);
 /* same, but the samples are NOT yet conditioned: d_peak[slot] = max(|I|,|Q|) and decoder()'s 0.5/peak scale is applied on load */
 int ft8b200_process_conditioned(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, const float *d_peak, int n_slots, void *stream);

@@ -164,6 +164,30 @@ class Context:
                                           _p(cnt), _p(peak), _p(y2), _st(stream)))
         return d_i, d_q, cnt, peak, y2
 
+    def decimate_streams(self, iq, n_streams: int, slots_per_stream: int, bytes_per_slot: int, bytes_per_stream: int | None = None,
+                         stride: int | None = None, want_y2: bool = False, stream: int | None = None):
+        """Continuous streams cut into consecutive slots: rows = n_streams * slots_per_stream."""
+        import torch
+        dev = iq.device
+        bytes_per_stream = slots_per_stream * bytes_per_slot if bytes_per_stream is None else bytes_per_stream
+        stride = bytes_per_stream if stride is None else stride
+        rows = n_streams * slots_per_stream
+        d_i = torch.empty((rows, N_SLOT), dtype=torch.float32, device=dev)
+        d_q = torch.empty_like(d_i)
+        cnt = torch.zeros(rows, dtype=torch.int32, device=dev)
+        peak = torch.zeros(rows, dtype=torch.float32, device=dev)
+        y2 = torch.zeros((rows, N_SLOT, 2), dtype=torch.int32, device=dev) if want_y2 else None
+        self._chk(self.L.ft8b200_decimate_streams(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_streams,
+                                                  slots_per_stream, C.c_size_t(bytes_per_slot), _p(d_i), _p(d_q), _p(cnt), _p(peak), _p(y2), _st(stream)))
+        return d_i, d_q, cnt, peak, y2
+
+    def process_raw_streams(self, iq, n_streams: int, slots_per_stream: int, bytes_per_slot: int = RAW_SLOT_BYTES, bytes_per_stream: int | None = None,
+                            stride: int | None = None, stream: int | None = None):
+        bytes_per_stream = slots_per_stream * bytes_per_slot if bytes_per_stream is None else bytes_per_stream
+        stride = bytes_per_stream if stride is None else stride
+        self._chk(self.L.ft8b200_process_raw_streams(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_streams,
+                                                     slots_per_stream, C.c_size_t(bytes_per_slot), _st(stream)))
+
     def condition(self, d_i, d_q, peak, stream: int | None = None):
         self._chk(self.L.ft8b200_condition(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), d_i.shape[0], _st(stream)))
 

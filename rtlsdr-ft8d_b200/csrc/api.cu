@@ -228,13 +228,15 @@ int ft8b200_sync(ft8b200_ctx_t *ctx) {
 }
 uint64_t ft8b200_kernel_launches(ft8b200_ctx_t *ctx) { return ctx ? ctx->launches_total : 0; }
 
-int ft8b200_decimate(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams, float *d_i,
-                     float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, void *stream) {
+static int decimate_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams, int segs,
+                         size_t seg_bytes, float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, void *stream) {
     int rc = ctx_enter(ctx);
     if (rc) return rc;
     if (!d_iq || !d_i || !d_q || n_streams < 1) return fail(FT8B200_EINVAL, "ft8b200_decimate: null buffer or n_streams < 1");
     if ((bytes_per_stream & 7) || (stream_stride_bytes & 15) || (((size_t)d_iq) & 15))
         return fail(FT8B200_EINVAL, "ft8b200_decimate: byte counts must be multiples of 8, stream stride and base 16-byte aligned");
+    if (segs < 1 || (segs > 1 && (seg_bytes < 8 || (seg_bytes & 7) || seg_bytes * (size_t)segs > bytes_per_stream || seg_bytes / 2 / kDecim + 1 > (size_t)kSlot)))
+        return fail(FT8B200_EINVAL, "ft8b200_decimate_streams: slots_per_stream * bytes_per_slot must fit the stream, bytes_per_slot a multiple of 8 and <= one 48000-sample slot");
     const int blocks = (int)((bytes_per_stream / 2) / kDecim);
     // the 128-bit loads of the last super-block may read up to 14 bytes past the last complete block
     if ((size_t)(blocks / 8) * 12016 > bytes_per_stream) return fail(FT8B200_EINVAL, "internal: super-block overrun");
@@ -242,14 +244,27 @@ int ft8b200_decimate(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_s
     cudaStream_t st = pick(ctx, stream);
     const size_t sstride = (size_t)blocks + kHistBlocks;
     if ((rc = ctx->sums.ensure((size_t)n_streams * sstride * sizeof(BlockSums)))) return rc;
-    if (d_peak) CU(cudaMemsetAsync(d_peak, 0, sizeof(float) * n_streams, st));
+    if (d_peak) CU(cudaMemsetAsync(d_peak, 0, sizeof(float) * n_streams * segs, st));
     // fresh filter state: the history prefix of every stream is zero
     CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_streams, st));
     BlockSums *s0 = ctx->sums.as<BlockSums>() + kHistBlocks;
     CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_streams, blocks, s0, sstride, ctx->k1_variant, ctx->sm_count, st, &ctx->launches));
-    CU(launch_cic_comb_fir(s0, sstride, blocks, 0, true, n_streams, ctx->tb.fir, d_i, d_q, d_count, d_peak, d_y2, st, &ctx->launches));
+    CU(launch_cic_comb_fir(s0, sstride, blocks, 0, true, n_streams, ctx->tb.fir, d_i, d_q, d_count, d_peak, d_y2, st, &ctx->launches, segs,
+                           (long long)(seg_bytes / 2)));
     tally(ctx);
     return 0;
+}
+
+int ft8b200_decimate(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams, float *d_i,
+                     float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, void *stream) {
+    return decimate_impl(ctx, d_iq, bytes_per_stream, stream_stride_bytes, n_streams, 1, 0, d_i, d_q, d_count, d_peak, d_y2, stream);
+}
+
+int ft8b200_decimate_streams(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams,
+                             int slots_per_stream, size_t bytes_per_slot, float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2,
+                             void *stream) {
+    return decimate_impl(ctx, d_iq, bytes_per_stream, stream_stride_bytes, n_streams, slots_per_stream, bytes_per_slot, d_i, d_q, d_count, d_peak,
+                         d_y2, stream);
 }
 
 int ft8b200_condition(ft8b200_ctx_t *ctx, float *d_i, float *d_q, const float *d_peak, int n_slots, void *stream) {
@@ -369,22 +384,26 @@ static int ensure_aux(ft8b200_ctx_t *ctx) {
     return 0;
 }
 
-int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots, void *stream) {
+static int process_raw_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots, int segs,
+                            size_t seg_bytes, void *stream) {
     int rc = ctx_enter(ctx);
     if (rc) return rc;
     if (!d_iq || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_process_raw: bad argument");
     if ((bytes_per_stream & 7) || (stream_stride_bytes & 15) || (((size_t)d_iq) & 15))
         return fail(FT8B200_EINVAL, "ft8b200_process_raw: byte counts must be multiples of 8, stream stride and base 16-byte aligned");
+    if (segs < 1 || (segs > 1 && (seg_bytes < 8 || (seg_bytes & 7) || seg_bytes * (size_t)segs > bytes_per_stream || seg_bytes / 2 / kDecim + 1 > (size_t)kSlot)))
+        return fail(FT8B200_EINVAL, "ft8b200_process_raw_streams: slots_per_stream * bytes_per_slot must fit the stream, bytes_per_slot a multiple of 8 and <= one 48000-sample slot");
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = pick(ctx, stream);
     const int blocks = (int)((bytes_per_stream / 2) / kDecim);
-    if ((rc = ensure_slot_buffers(ctx, n_slots))) return rc;
+    const int n_rows = n_slots * segs;  // 15 s slots to decode: (receiver stream, consecutive slot)
+    if ((rc = ensure_slot_buffers(ctx, n_rows))) return rc;
     const size_t sstride = (size_t)blocks + kHistBlocks;
     if ((rc = ctx->sums.ensure((size_t)n_slots * sstride * sizeof(BlockSums)))) return rc;
-    if ((rc = ctx->si.ensure((size_t)n_slots * kSlot * sizeof(float)))) return rc;
-    if ((rc = ctx->sq.ensure((size_t)n_slots * kSlot * sizeof(float)))) return rc;
-    if ((rc = ctx->peak.ensure((size_t)n_slots * sizeof(float)))) return rc;
-    if ((rc = ctx->count.ensure((size_t)n_slots * sizeof(uint32_t)))) return rc;
+    if ((rc = ctx->si.ensure((size_t)n_rows * kSlot * sizeof(float)))) return rc;
+    if ((rc = ctx->sq.ensure((size_t)n_rows * kSlot * sizeof(float)))) return rc;
+    if ((rc = ctx->peak.ensure((size_t)n_rows * sizeof(float)))) return rc;
+    if ((rc = ctx->count.ensure((size_t)n_rows * sizeof(uint32_t)))) return rc;
     // Slot groups: the HBM-bound front end (block sums, comb+FIR) of group g+1 runs on the caller's stream while the
     // compute-bound back end (waterfall, sync, LDPC, spots) of group g runs on a high-priority side stream.
     int n_groups = 1;
@@ -394,7 +413,7 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
     }
     const int per = (n_slots + n_groups - 1) / n_groups;
     const int npos = 2 * 2 * 36 * (256 - 7);
-    if ((rc = ensure_scratch(ctx, npos, per))) return rc;
+    if ((rc = ensure_scratch(ctx, npos, per * segs))) return rc;
     cudaStream_t back = st;
     const bool side = n_groups > 1 || ctx->side_back;
     if (side) {
@@ -404,25 +423,26 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
         CU(cudaStreamWaitEvent(back, ctx->ev_join, 0));
     }
     clear_marks(ctx);
-    CU(cudaMemsetAsync(ctx->peak.p, 0, sizeof(float) * n_slots, st));
+    CU(cudaMemsetAsync(ctx->peak.p, 0, sizeof(float) * n_rows, st));
     CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_slots, st));  // fresh filter state
     for (int g = 0, s0 = 0; s0 < n_slots; ++g, s0 += per) {
         const int n = (n_slots - s0) < per ? (n_slots - s0) : per;
+        const int r0 = s0 * segs, nr = n * segs;
         BlockSums *sg = ctx->sums.as<BlockSums>() + (size_t)s0 * sstride + kHistBlocks;
         mark(ctx, 0, g, false, st);
         CU(launch_cic_block_sums(d_iq + (size_t)s0 * stream_stride_bytes, stream_stride_bytes, n, blocks, sg, sstride, ctx->k1_variant, ctx->sm_count, st, &ctx->launches));
         mark(ctx, 0, g, true, st);
         mark(ctx, 1, g, false, st);
-        CU(launch_cic_comb_fir(sg, sstride, blocks, 0, true, n, ctx->tb.fir, ctx->si.as<float>() + (size_t)s0 * kSlot,
-                               ctx->sq.as<float>() + (size_t)s0 * kSlot, ctx->count.as<uint32_t>() + s0, ctx->peak.as<float>() + s0, nullptr, st,
-                               &ctx->launches));
+        CU(launch_cic_comb_fir(sg, sstride, blocks, 0, true, n, ctx->tb.fir, ctx->si.as<float>() + (size_t)r0 * kSlot,
+                               ctx->sq.as<float>() + (size_t)r0 * kSlot, ctx->count.as<uint32_t>() + r0, ctx->peak.as<float>() + r0, nullptr, st,
+                               &ctx->launches, segs, (long long)(seg_bytes / 2)));
         mark(ctx, 1, g, true, st);
         if (side) {
             CU(cudaEventRecord(ctx->ev_group[g], st));
             CU(cudaStreamWaitEvent(back, ctx->ev_group[g], 0));
             ctx->ev_front = ctx->ev_group[g];
         }
-        if ((rc = run_back_end(ctx, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), s0, n, g, back))) return rc;
+        if ((rc = run_back_end(ctx, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), r0, nr, g, back))) return rc;
     }
     if (side) {  // results are ready, in stream order, when this call's work on st completes
         CU(cudaEventRecord(ctx->ev_join, back));
@@ -430,6 +450,15 @@ int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_pe
     }
     tally(ctx);
     return 0;
+}
+
+int ft8b200_process_raw(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots, void *stream) {
+    return process_raw_impl(ctx, d_iq, bytes_per_stream, stream_stride_bytes, n_slots, 1, 0, stream);
+}
+
+int ft8b200_process_raw_streams(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams,
+                                int slots_per_stream, size_t bytes_per_slot, void *stream) {
+    return process_raw_impl(ctx, d_iq, bytes_per_stream, stream_stride_bytes, n_streams, slots_per_stream, bytes_per_slot, stream);
 }
 
 int ft8b200_process_slots(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, int n_slots, void *stream) {

@@ -41,7 +41,7 @@ cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq_first_block, size_
                                           BlockSums *d_sums_first_block, size_t sums_stride, cudaStream_t st, int *launches);
 cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int n_blocks, int out_offset, bool zero_fill, int n_streams,
                                 const float *d_fir, float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st,
-                                int *launches);
+                                int *launches, int segs = 1, long long seg_samples = 0);
 cudaError_t launch_shift_history(BlockSums *d_sums_with_prefix, int n_blocks, cudaStream_t st, int *launches);
 cudaError_t launch_condition(float *d_i, float *d_q, const float *d_peak, int n_slots, cudaStream_t st, int *launches);
 cudaError_t launch_waterfall(const DeviceTables &t, const float *d_i, const float *d_q, const float *d_peak, int n_slots, uint8_t *d_mag,

@@ -430,14 +430,33 @@ __device__ __forceinline__ void fir_window(const float *__restrict__ y, float (&
     }
 }
 
+// Slot segments of a continuous stream (BASELINE config #5: consecutive 15 s slots of one receiver): with segs > 1 the
+// row blockIdx.y is (stream, segment); segment g takes the outputs whose decimation instant 750 + 751*k falls inside
+// input samples [g*seg_samples, (g+1)*seg_samples) -- what the daemon gets when main() flips the rx buffer every 15 s
+// between two callbacks (rtlsdr_ft8d.c:1339-1354) -- i.e. 47 936 or 47 937 outputs per slot.  Because the filter has no
+// integrator state, a segment simply starts reading block sums further into the stream; its FIR/comb history is the
+// real preceding blocks.
+__device__ __forceinline__ int seg_first_block(int seg, long long seg_samples) {
+    const long long first_sample = (long long)seg * seg_samples;
+    return first_sample <= 750 ? 0 : (int)((first_sample - 750 + kDecim - 1) / kDecim);
+}
+
 __global__ void __launch_bounds__(kTileThreads)
-cic_comb_fir_kernel(const BlockSums *__restrict__ sums, size_t sums_stride, int n_blocks, int out_offset, int zero_fill,
-                    float *__restrict__ out_i, float *__restrict__ out_q, uint32_t *__restrict__ count, float *__restrict__ peak,
-                    int32_t *__restrict__ y2_out) {
+cic_comb_fir_kernel(const BlockSums *__restrict__ sums, size_t sums_stride, int n_blocks, int out_offset, int zero_fill, int segs,
+                    long long seg_samples, float *__restrict__ out_i, float *__restrict__ out_q, uint32_t *__restrict__ count,
+                    float *__restrict__ peak, int32_t *__restrict__ y2_out) {
     __shared__ __align__(16) float s_yi[kTile + kHist], s_yq[kTile + kHist];
-    const int stream = blockIdx.y;
+    const int stream = blockIdx.y;  // output row: (receiver stream, segment)
     const int k0 = blockIdx.x * kTile;
-    const BlockSums *s = sums + (size_t)stream * sums_stride;
+    const BlockSums *s = sums + (size_t)(stream / segs) * sums_stride;
+    if (segs > 1) {
+        const int seg = stream % segs;
+        const int b0 = seg_first_block(seg, seg_samples);
+        int b1 = seg_first_block(seg + 1, seg_samples);
+        if (b1 > n_blocks) b1 = n_blocks;
+        n_blocks = b1 > b0 ? b1 - b0 : 0;
+        s += b0;
+    }
     for (int idx = threadIdx.x; idx < kTile + kHist; idx += kTileThreads) {
         const int k = k0 - kHist + idx;  // >= -56: inside the history prefix
         int32_t yi = 0, yq = 0;
@@ -591,8 +610,9 @@ cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq_first_block, size_
 
 cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int n_blocks, int out_offset, bool zero_fill, int n_streams,
                                 const float *d_fir, float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st,
-                                int *launches) {
+                                int *launches, int segs, long long seg_samples) {
     int span = n_blocks;
+    if (segs > 1) span = (int)(seg_samples / kDecim) + 2;  // outputs of one segment
     if (zero_fill && kSlot - out_offset > span) span = kSlot - out_offset;
     if (span <= 0) return cudaSuccess;
     static bool fir_uploaded[64] = {};
@@ -606,8 +626,10 @@ cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int
         fir_uploaded[dev_id] = true;
     }
     (void)d_fir;
-    dim3 grid((span + kTile - 1) / kTile, n_streams);
-    cic_comb_fir_kernel<<<grid, kTileThreads, 0, st>>>(d_sums, sums_stride, n_blocks, out_offset, zero_fill ? 1 : 0, d_i, d_q, d_count, d_peak, d_y2);
+    if (segs < 1) segs = 1;
+    dim3 grid((span + kTile - 1) / kTile, n_streams * segs);
+    cic_comb_fir_kernel<<<grid, kTileThreads, 0, st>>>(d_sums, sums_stride, n_blocks, out_offset, zero_fill ? 1 : 0, segs, seg_samples, d_i, d_q,
+                                                       d_count, d_peak, d_y2);
     ++*launches;
     return cudaGetLastError();
 }

@@ -528,3 +528,78 @@ def test_bulk_copy_decimator_variants(pkg, oracle, variant):
             gy = y2[s].cpu().numpy()
             assert np.array_equal(gy[:n, 0], oy2i) and np.array_equal(gy[:n, 1], oy2q)
     c.close()
+
+
+# ------------------------------------------------------------------------------------------- config #5: continuous streams
+def oracle_stream_slots(oracle, iq, slots, bytes_per_slot, chunk):
+    """The reference's behaviour for one receiver: rtlsdr_callback() in `chunk`-byte calls with persistent filter state,
+    rx buffer flipped every bytes_per_slot bytes (between two callbacks, like main()'s 15 s timer)."""
+    st = oracle.new_decim()
+    out = []
+    for g in range(slots):
+        parts = [oracle.decim_feed(st, iq[o:o + chunk], chunk // 2 // 751 + 2, want_y2=True)
+                 for o in range(g * bytes_per_slot, (g + 1) * bytes_per_slot, chunk)]
+        out.append(tuple(np.concatenate([p[k] for p in parts]) for k in range(4)))
+    return out
+
+
+@pytest.mark.parametrize("bytes_per_slot,slots,chunk", [(1502 * 400 + 600, 5, 6200), (12016 * 50, 3, 12016 * 10), (1502 * 92 + 8, 8, 23032)])
+def test_stream_batches_cross_slot_boundaries(ctx, oracle, bytes_per_slot, slots, chunk):
+    """BASELINE config #5 at reduced size: consecutive slots of continuous streams, decimated in ONE launch, equal the
+    reference's callback-by-callback outputs with the filter state carried across the slot flip: per-slot sample counts
+    (the decimation phase drifts), integer CIC outputs, float samples, peaks."""
+    assert bytes_per_slot % chunk == 0
+    n_streams = 3
+    rng = np.random.default_rng(bytes_per_slot)
+    stride = (slots * bytes_per_slot + 15) // 16 * 16 + 32
+    iq = rng.integers(0, 256, size=(n_streams, stride), dtype=np.uint8)
+    iq[1] = rng.integers(120, 137, size=stride, dtype=np.uint8)
+    d_i, d_q, cnt, peak, y2 = ctx.decimate_streams(torch.from_numpy(iq).to(dev()), n_streams, slots, bytes_per_slot,
+                                                   bytes_per_stream=slots * bytes_per_slot, stride=stride, want_y2=True)
+    counts = set()
+    for s in range(n_streams):
+        ref = oracle_stream_slots(oracle, iq[s], slots, bytes_per_slot, chunk)
+        for g, (oi, oq, oy2i, oy2q) in enumerate(ref):
+            r = s * slots + g
+            n = int(cnt[r])
+            counts.add(n)
+            assert n == oi.size
+            gy = y2[r].cpu().numpy()
+            assert np.array_equal(gy[:n, 0], oy2i) and np.array_equal(gy[:n, 1], oy2q)
+            assert bits_equal(d_i[r, :n].cpu().numpy(), oi) and bits_equal(d_q[r, :n].cpu().numpy(), oq)
+            assert not d_i[r, n:].any() and not d_q[r, n:].any()
+            assert float(peak[r]) == float(max(np.abs(oi).max(initial=0), np.abs(oq).max(initial=0)))
+    if slots * (bytes_per_slot // 2 % 751) >= 751:
+        assert len(counts) > 1, "the decimation phase drifts by more than one output over these slots, so the per-slot counts must differ"
+
+
+def test_streams_full_size_whole_path(ctx, oracle, raw_slot):
+    """Full-size slots: 2 receivers x 3 consecutive 72 MB slots in one call.  Slot 0 of each stream equals the fresh-state
+    single-slot result; later slots equal the oracle's continuing stream (47 936 / 47 937 samples) end to end."""
+    slots, n_streams = 3, 2
+    one = torch.from_numpy(raw_slot).to(dev())
+    big = one.repeat(n_streams, slots).contiguous()
+    big[1, 72_000_000:2 * 72_000_000] = 0x80      # a silent middle slot on the second receiver
+    torch.cuda.synchronize()
+    d_i, d_q, cnt, peak, _ = ctx.decimate_streams(big, n_streams, slots, 72_000_000)
+    first = [0 if g == 0 else -((750 - g * 36_000_000) // 751) for g in range(slots + 1)]   # ceil((g*N - 750) / 751)
+    first[slots] = min(first[slots], slots * 36_000_000 // 751)
+    assert cnt.cpu().tolist() == [first[g + 1] - first[g] for g in range(slots)] * n_streams  # 47 936 each (47 937 first appears in slot 11)
+    ctx.process_raw_streams(big, n_streams, slots)
+    res, n = ctx.fetch_results(n_streams * slots)
+    ctx.process_raw(one[None], 1)
+    r1, n1 = ctx.fetch_results(1)
+    assert n[0] == n[3] == n1[0] >= 1 and res[0].tobytes() == res[3].tobytes() == r1[0].tobytes()
+    assert n[4] == 0
+    # oracle: continue the first receiver's stream through its second slot
+    st = oracle.new_decim()
+    host = big[0].cpu().numpy()
+    for g in range(2):
+        parts = [oracle.decim_feed(st, host[o:o + 600_000], 600_000 // 2 // 751 + 2) for o in range(g * 72_000_000, (g + 1) * 72_000_000, 600_000)]
+    oi = np.concatenate([p[0] for p in parts]); oq = np.concatenate([p[1] for p in parts])
+    assert oi.size == int(cnt[1])
+    assert bits_equal(d_i[1, :oi.size].cpu().numpy(), oi) and bits_equal(d_q[1, :oq.size].cpu().numpy(), oq)
+    ri = np.zeros(48000, np.float32); rq = np.zeros(48000, np.float32)
+    ri[:oi.size] = oi; rq[:oq.size] = oq
+    o = oracle.subsystem(*oracle.condition(ri, rq, oi.size)[:2])
+    assert n[1] == o["n"] and res[1].tobytes() == o["results"].tobytes()
