@@ -251,6 +251,10 @@ int ft8b200_stage_times(ft8b200_ctx_t *ctx, float *ms, int n);
  * single slot group, and ft8b200_front_event() returns the cudaEvent_t (as void*) recorded on the launching stream right
  * after the decimator of the last call -- what ft8b200_pipe_t chains its lanes with. */
 int ft8b200_set_side_backend(ft8b200_ctx_t *ctx, int on);
+/* Protocol that ft8b200_find_sync / ft8b200_decode score and demap: PROTO_FT8 (default) or PROTO_FT4 (ft4_sync_score,
+ * ft4_extract_likelihood and the descrambling of decode.c:110-171,236-263,355-363).  The drop-in ft8_find_sync / ft8_decode
+ * take it from waterfall_t.protocol like the reference; the daemon path (ft8b200_process_*) is FT8 by definition. */
+int ft8b200_set_protocol(ft8b200_ctx_t *ctx, int protocol);
 /* Which cic_block_sums kernel the decimator uses: 0 = streaming (one warp per super-block, whole-GPU grid),
  * >= 1 = persistent bulk-copy kernel (one CTA per SM: a producer thread feeding a shared-memory ring with cp.async.bulk,
  * consumer warps doing the arithmetic) which leaves most of each SM free for the back-end kernels of another batch.

@@ -110,6 +110,7 @@ int orc_decode_waterfall(const orc_waterfall_t *wf, int max_candidates, int max_
 int orc_pack_std(const char *call_to, const char *call_de, const char *extra, uint8_t *payload10);
 void orc_pack_text(const char *text, uint8_t *payload10);
 void orc_encode_tones(const uint8_t *payload10, uint8_t *tones79);
+void orc_encode_tones_ft4(const uint8_t *payload10, uint8_t *tones105);
 void orc_encode174(const uint8_t *payload10, uint8_t *bits174);
 
 #ifdef __cplusplus

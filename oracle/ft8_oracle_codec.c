@@ -21,7 +21,31 @@ static long wf_index(const orc_waterfall_t *wf, const orc_candidate_t *c) { /* r
     return o;
 }
 
+/* ref: ft4_sync_score, decode.c:110-171: four 4-symbol groups at symbols 1, 34, 67, 100, one Costas array each */
+static int orc_sync_score_ft4(const orc_waterfall_t *wf, const orc_candidate_t *c) {
+    const uint8_t *base = wf->mag + wf_index(wf, c);
+    const int stride = wf->block_stride;
+    int total = 0, terms = 0;
+    for (int grp = 0; grp < 4; ++grp) {
+        for (int k = 0; k < 4; ++k) {
+            const int rel = 1 + 33 * grp + k;
+            const int row = c->time_offset + rel;
+            if (row < 0) continue;
+            if (row >= wf->num_blocks) break;
+            const uint8_t *p = base + (long)rel * stride;
+            const int tone = kFt4tCostas[grp][k];
+            if (tone > 0) { total += p[tone] - p[tone - 1]; ++terms; }
+            if (tone < 3) { total += p[tone] - p[tone + 1]; ++terms; }
+            if (k > 0 && row > 0) { total += p[tone] - p[tone - stride]; ++terms; }
+            if (k + 1 < 4 && row + 1 < wf->num_blocks) { total += p[tone] - p[tone + stride]; ++terms; }
+        }
+    }
+    if (terms > 0) total /= terms;
+    return total;
+}
+
 int orc_sync_score(const orc_waterfall_t *wf, const orc_candidate_t *c) {
+    if (wf->protocol == 0) return orc_sync_score_ft4(wf, c); /* PROTO_FT4 == 0, constants.h:6-10 */
     const uint8_t *base = wf->mag + wf_index(wf, c);
     const int stride = wf->block_stride;
     int total = 0, terms = 0;
@@ -108,6 +132,20 @@ static inline float fmax4(float a, float b, float c, float d) { return fmax2(fma
 
 void orc_extract_llr(const orc_waterfall_t *wf, const orc_candidate_t *c, float *llr) {
     const uint8_t *base = wf->mag + wf_index(wf, c);
+    if (wf->protocol == 0) { /* ref: ft4_extract_likelihood / ft4_extract_symbol, decode.c:236-263, 438-450 */
+        for (int k = 0; k < 87; ++k) {
+            const int sym = k + (k < 29 ? 5 : (k < 58 ? 9 : 13));
+            const int row = c->time_offset + sym;
+            float *o = llr + 2 * k;
+            if (row < 0 || row >= wf->num_blocks) { o[0] = o[1] = 0; continue; }
+            const uint8_t *p = base + (long)sym * wf->block_stride;
+            float s[4];
+            for (int j = 0; j < 4; ++j) s[j] = (float)p[kFt4tGray[j]];
+            o[0] = fmax2(s[2], s[3]) - fmax2(s[0], s[1]);
+            o[1] = fmax2(s[1], s[3]) - fmax2(s[0], s[2]);
+        }
+        return;
+    }
     for (int k = 0; k < 58; ++k) {
         const int sym = k + (k < 29 ? 7 : 14);
         const int row = c->time_offset + sym;
@@ -388,6 +426,8 @@ int orc_decode(const orc_waterfall_t *wf, const orc_candidate_t *c, int max_iter
     a91[10] = 0;
     st->crc_calculated = orc_crc14(a91, 82);
     if (st->crc_extracted != st->crc_calculated) return 0;
+    if (wf->protocol == 0) /* FT4 scrambles the 77 message bits before CRC/FEC, decode.c:355-363 */
+        for (int k = 0; k < 10; ++k) a91[k] ^= kFt4tXor[k];
     char text[40];
     st->unpack_status = orc_unpack77(a91, text);
     if (st->unpack_status < 0) return 0;
@@ -543,6 +583,21 @@ void orc_encode174(const uint8_t *payload, uint8_t *bits) {
         int acc = 0;
         for (int k = 0; k < FT8T_K; ++k) acc ^= bits[k] & ((kFt8tGen[r][k >> 3] >> (7 - (k & 7))) & 1);
         bits[FT8T_K + r] = (uint8_t)acc;
+    }
+}
+
+void orc_encode_tones_ft4(const uint8_t *payload, uint8_t *tones) { /* ref: ft4_encode, encode.c:126-195; 105 tones */
+    uint8_t scrambled[10], bits[FT8T_N];
+    for (int k = 0; k < 10; ++k) scrambled[k] = payload[k] ^ kFt4tXor[k];
+    orc_encode174(scrambled, bits);
+    int k = 0;
+    for (int s = 0; s < 105; ++s) {
+        if (s == 0 || s == 104) tones[s] = 0; /* ramp symbols */
+        else if (s < 5) tones[s] = kFt4tCostas[0][s - 1];
+        else if (s >= 34 && s < 38) tones[s] = kFt4tCostas[1][s - 34];
+        else if (s >= 67 && s < 71) tones[s] = kFt4tCostas[2][s - 67];
+        else if (s >= 100) tones[s] = kFt4tCostas[3][s - 100];
+        else { tones[s] = kFt4tGray[(bits[k] << 1) | bits[k + 1]]; k += 2; }
     }
 }
 

@@ -266,6 +266,10 @@ class Context:
     def set_profiling(self, on: bool):
         self._chk(self.L.ft8b200_set_profiling(C.c_void_p(self.h), int(on)))
 
+    def set_protocol(self, protocol: int):
+        """0 = FT4, 1 = FT8 (ftx_protocol_t) for find_sync / decode."""
+        self._chk(self.L.ft8b200_set_protocol(C.c_void_p(self.h), int(protocol)))
+
     def set_decimator_variant(self, variant: int):
         """0 = streaming cic_block_sums kernel; >= 1 = persistent bulk-copy (TMA) kernel, shape index 1..6."""
         self._chk(self.L.ft8b200_set_decimator_variant(C.c_void_p(self.h), int(variant)))

@@ -68,6 +68,7 @@ struct ft8b200_ctx {
     // optional per-stage timing of the last process_* call (CUDA events on the launching stream)
     bool profiling = false;
     int overlap = 0;                       // number of slot groups ft8b200_process_raw pipelines (0/1 = off)
+    int protocol = PROTO_FT8;              // what ft8b200_find_sync / ft8b200_decode score and demap (ft8b200_set_protocol)
     int k1_variant = 0;                    // 0 = streaming cic_block_sums kernel, >= 1 = persistent bulk-copy kernel (shape index)
     bool side_back = false;                // back end on the high-priority side stream even with a single group (pipe lanes)
     cudaEvent_t ev_front = nullptr;        // recorded on the launching stream when the last process_raw's decimator was queued
@@ -296,7 +297,7 @@ int ft8b200_find_sync(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stri
     if (npos >= (1l << 20)) return fail(FT8B200_EINVAL, "ft8b200_find_sync: waterfall too large (position index exceeds 20 bits)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if ((rc = ensure_scratch(ctx, (int)npos, n_slots))) return rc;
-    CU(launch_find_sync(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->cfg.max_candidates, ctx->cfg.min_score,
+    CU(launch_find_sync(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->protocol, ctx->cfg.max_candidates, ctx->cfg.min_score,
                         d_cand, d_ncand, ctx->scores.as<int16_t>(), ctx->scratch.as<uint32_t>(), ctx->scratch_slots, nullptr, nullptr, ctx->sm_count,
                         pick(ctx, stream), &ctx->launches));
     tally(ctx);
@@ -310,7 +311,7 @@ int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_
     if (rc) return rc;
     if (!d_mag || !d_cand || !d_ncand || !d_ok || !d_stage || !d_status || !d_msg || n_slots < 1)
         return fail(FT8B200_EINVAL, "ft8b200_decode: bad argument");
-    CU(launch_decode(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
+    CU(launch_decode(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->protocol, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
                      d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, nullptr, nullptr, pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
@@ -356,12 +357,12 @@ static int run_back_end(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, 
     CU(launch_waterfall(ctx->tb, d_i + (size_t)s0 * kSlot, d_q + (size_t)s0 * kSlot, d_peak ? d_peak + s0 : nullptr, n, mag, st, &ctx->launches));
     mark(ctx, 2, group, true, st);
     mark(ctx, 3, group, false, st);
-    CU(launch_find_sync(mag, kWfBytes, n, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.min_score, cand, ncand, ctx->scores.as<int16_t>(),
+    CU(launch_find_sync(mag, kWfBytes, n, 92, 256, 2, 2, PROTO_FT8, ctx->cfg.max_candidates, ctx->cfg.min_score, cand, ncand, ctx->scores.as<int16_t>(),
                         ctx->scratch.as<uint32_t>(), ctx->scratch_slots, ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), ctx->sm_count,
                         st, &ctx->launches));
     mark(ctx, 3, group, true, st);
     mark(ctx, 4, group, false, st);
-    CU(launch_decode(mag, kWfBytes, n, 92, 256, 2, 2, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations, cand, ncand, ok, stage,
+    CU(launch_decode(mag, kWfBytes, n, 92, 256, 2, 2, PROTO_FT8, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations, cand, ncand, ok, stage,
                      ctx->status.as<decode_status_t>() + (size_t)s0 * K, ctx->msg.as<message_t>() + (size_t)s0 * K, nullptr, nullptr,
                      ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), st, &ctx->launches));
     mark(ctx, 4, group, true, st);
@@ -495,6 +496,12 @@ int ft8b200_set_side_backend(ft8b200_ctx_t *ctx, int on) {
     if (!ctx) return fail(FT8B200_EINVAL, "null context");
     ctx->side_back = on != 0;
     if (!on) ctx->ev_front = nullptr;
+    return 0;
+}
+
+int ft8b200_set_protocol(ft8b200_ctx_t *ctx, int protocol) {
+    if (!ctx || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return fail(FT8B200_EINVAL, "ft8b200_set_protocol: PROTO_FT4 or PROTO_FT8");
+    ctx->protocol = protocol;
     return 0;
 }
 

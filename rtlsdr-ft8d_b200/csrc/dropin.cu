@@ -32,7 +32,7 @@ struct DecodeCache {
     bool valid = false;
     uint64_t key = 0;
     int iters = 0;
-    int nb = 0, nbins = 0, tosr = 0, fosr = 0;
+    int nb = 0, nbins = 0, tosr = 0, fosr = 0, proto = 1;
     std::vector<candidate_t> cand;
     std::vector<uint8_t> ok, stage;
     std::vector<decode_status_t> status;
@@ -133,8 +133,8 @@ void ft8_subsystem(float *iSamples, float *qSamples, uint32_t samples_len, struc
 
 int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap[], int min_score) {
     ft8b200_ctx_t *ctx = default_ctx();
-    if (power->protocol != PROTO_FT8) {
-        fprintf(stderr, "libft8b200: ft8_find_sync: only PROTO_FT8 is implemented (FT4 is out of scope, see DESIGN.md)\n");
+    if (power->protocol != PROTO_FT8 && power->protocol != PROTO_FT4) {
+        fprintf(stderr, "libft8b200: ft8_find_sync: unknown protocol %d\n", (int)power->protocol);
         abort();
     }
     if (num_candidates <= 0) return 0;
@@ -156,12 +156,12 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
             die("ft8_find_sync (scratch)");
         scratch_npos = npos;
     }
-    if (launch_find_sync(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, num_candidates, min_score,
+    if (launch_find_sync(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, num_candidates, min_score,
                          g_s.cand, g_s.ncand, scores, scratch, 1, nullptr, nullptr, 148, st, &launches) != cudaSuccess) die("ft8_find_sync (kernel)");
     // decode everything now; ft8_decode() will look the answers up
     ft8b200_config_t cfg;
     ft8b200_default_config(&cfg);
-    if (launch_decode(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, num_candidates, cfg.ldpc_iterations,
+    if (launch_decode(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, num_candidates, cfg.ldpc_iterations,
                       g_s.cand, g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, st, &launches) != cudaSuccess)
         die("ft8_find_sync (decode kernel)");
     int n = 0;
@@ -180,6 +180,7 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
     g_cache.key = hash_bytes(power->mag, bytes);
     g_cache.iters = cfg.ldpc_iterations;
     g_cache.nb = power->num_blocks; g_cache.nbins = power->num_bins; g_cache.tosr = power->time_osr; g_cache.fosr = power->freq_osr;
+    g_cache.proto = (int)power->protocol;
     g_cache.valid = true;
     memcpy(heap, g_cache.cand.data(), sizeof(candidate_t) * (size_t)n);
     return n;
@@ -194,15 +195,15 @@ static void write_status(decode_status_t *status, const decode_status_t &s, int 
 
 bool ft8_decode(const waterfall_t *power, const candidate_t *cand, message_t *message, int max_iterations, decode_status_t *status) {
     ft8b200_ctx_t *ctx = default_ctx();
-    if (power->protocol != PROTO_FT8) {
-        fprintf(stderr, "libft8b200: ft8_decode: only PROTO_FT8 is implemented (FT4 is out of scope, see DESIGN.md)\n");
+    if (power->protocol != PROTO_FT8 && power->protocol != PROTO_FT4) {
+        fprintf(stderr, "libft8b200: ft8_decode: unknown protocol %d\n", (int)power->protocol);
         abort();
     }
     std::lock_guard<std::mutex> lk(g_mu);
     const size_t bytes = (size_t)power->num_blocks * power->block_stride;
     const uint64_t key = hash_bytes(power->mag, bytes);
     if (g_cache.valid && g_cache.key == key && g_cache.iters == max_iterations && g_cache.nb == power->num_blocks &&
-        g_cache.nbins == power->num_bins && g_cache.tosr == power->time_osr && g_cache.fosr == power->freq_osr) {
+        g_cache.nbins == power->num_bins && g_cache.tosr == power->time_osr && g_cache.fosr == power->freq_osr && g_cache.proto == (int)power->protocol) {
         for (size_t k = 0; k < g_cache.cand.size(); ++k) {
             if (memcmp(&g_cache.cand[k], cand, sizeof(candidate_t)) == 0) {
                 write_status(status, g_cache.status[k], g_cache.stage[k]);
@@ -221,7 +222,7 @@ bool ft8_decode(const waterfall_t *power, const candidate_t *cand, message_t *me
     bool okc = cudaMemcpyAsync(g_s.mag, power->mag, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess &&
                cudaMemcpyAsync(g_s.cand, cand, sizeof(candidate_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
                cudaMemcpyAsync(g_s.ncand, &one, sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess &&
-               launch_decode(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, 1, max_iterations, g_s.cand,
+               launch_decode(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, 1, max_iterations, g_s.cand,
                              g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, st, &launches) == cudaSuccess &&
                cudaMemcpyAsync(&okv, g_s.ok, 1, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                cudaMemcpyAsync(&stage, g_s.stage, 1, cudaMemcpyDeviceToHost, st) == cudaSuccess &&

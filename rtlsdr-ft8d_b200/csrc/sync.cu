@@ -51,33 +51,37 @@ __device__ void sift_up(unsigned long long *h, int n) {  // ref: heapify_up, dec
 // row-range tests are uniform across the CTA.  Scores go to global memory as int16 in the reference's loop order.
 constexpr int kScoreThreads = 256;
 
-// ref: ft8_sync_score(), decode.c:44-108, on the compact plane (`nbins` = row pitch)
-template <int kBins>
+// ref: ft8_sync_score(), decode.c:44-108 / ft4_sync_score(), decode.c:110-171, on the compact plane (`nbins` = row pitch)
+// FT8: 3 groups of 7 symbols at 0, 36, 72 sharing one Costas array, 8 tones.  FT4: 4 groups of 4 symbols at 1, 34, 67,
+// 100, one Costas array per group, 4 tones.
+template <int kBins, bool kFt4>
 __device__ __forceinline__ int sync_score_plane(const uint8_t *__restrict__ plane, int nb, int nbins_rt, int to, int fo) {
     const int nbins = kBins > 0 ? kBins : nbins_rt;
+    constexpr int kGroups = kFt4 ? 4 : 3, kLen = kFt4 ? 4 : 7, kFirst = kFt4 ? 1 : 0, kStep = kFt4 ? 33 : 36, kTop = kFt4 ? 3 : 7;
+    constexpr int kCostas8[7] = {3, 1, 4, 0, 6, 5, 2};
+    constexpr int kCostas4[4][4] = {{0, 1, 3, 2}, {1, 0, 2, 3}, {2, 3, 1, 0}, {3, 2, 0, 1}};
     int score = 0, terms = 0;
 #pragma unroll
-    for (int grp = 0; grp < 3; ++grp) {
+    for (int grp = 0; grp < kGroups; ++grp) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const int row = to + 36 * grp + k;
+        for (int k = 0; k < kLen; ++k) {
+            const int row = to + kFirst + kStep * grp + k;
             if (row < 0) continue;
             if (row >= nb) break;  // leaves this group only, like the reference's inner `break`
-            constexpr int kCostas[7] = {3, 1, 4, 0, 6, 5, 2};
-            const int tone = kCostas[k];
+            const int tone = kFt4 ? kCostas4[grp][k < 4 ? k : 0] : kCostas8[k];
             const uint8_t *p = plane + row * nbins + fo + tone;
             const int centre = p[0];
             if (tone > 0) { score += centre - p[-1]; ++terms; }
-            if (tone < 7) { score += centre - p[1]; ++terms; }
+            if (tone < kTop) { score += centre - p[1]; ++terms; }
             if (k > 0 && row > 0) { score += centre - p[-nbins]; ++terms; }
-            if (k + 1 < 7 && row + 1 < nb) { score += centre - p[nbins]; ++terms; }
+            if (k + 1 < kLen && row + 1 < nb) { score += centre - p[nbins]; ++terms; }
         }
     }
     if (terms > 0) score /= terms;  // truncating division
     return score;
 }
 
-template <int kBins, bool kStage>
+template <int kBins, bool kStage, bool kFt4>
 __global__ void __launch_bounds__(kScoreThreads)
 sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int splits, int to_per_cta, int16_t *__restrict__ scores_all) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -92,8 +96,8 @@ sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g
     const uint8_t *plane;
     int pitch;
     if (kStage) {
-        // rows this CTA can touch: [to0 - 1, to1 - 1 + 72 + 6 + 1], clipped
-        int r0 = to0 - 1, r1 = to1 + 79;
+        // rows this CTA can touch: [to0 - 1, (to1 - 1) + last sync symbol + 1], clipped (last sync symbol: 78 FT8, 103 FT4)
+        int r0 = to0 - 1, r1 = to1 + (kFt4 ? 104 : 79);
         if (r0 < 0) r0 = 0;
         if (r1 > g.nb) r1 = g.nb;
         if (((((size_t)gplane) | (size_t)g.stride | (size_t)nbins) & 15) == 0) {
@@ -118,7 +122,7 @@ sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g
     int16_t *scores = scores_all + (size_t)slot * g.npos + (size_t)plane_id * 36 * g.nfo;
     for (int to = to0; to < to1; ++to) {
         for (int fo = tid; fo < g.nfo; fo += kScoreThreads) {
-            const int sc = kStage ? sync_score_plane<kBins>(plane, g.nb, pitch, to, fo) : sync_score_plane<0>(plane, g.nb, pitch, to, fo);
+            const int sc = kStage ? sync_score_plane<kBins, kFt4>(plane, g.nb, pitch, to, fo) : sync_score_plane<0, kFt4>(plane, g.nb, pitch, to, fo);
             scores[(to + 12) * g.nfo + fo] = (int16_t)sc;  // stored as int16_t in candidate_t
         }
     }
@@ -216,7 +220,7 @@ sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, i
 }  // namespace
 
 cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
-                             int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_scratch,
+                             int protocol, int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_scratch,
                              int scratch_slots, uint32_t *d_work, unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches) {
     Geo g;
     g.nb = num_blocks; g.nbins = num_bins; g.tosr = time_osr; g.fosr = freq_osr;
@@ -232,18 +236,21 @@ cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slo
     splits = (36 + to_per_cta - 1) / to_per_cta;
     dim3 grid(planes * splits, n_slots);
     const size_t staged = ((size_t)g.nb * g.nbins + 15) & ~(size_t)15;
+    const bool ft4 = protocol == PROTO_FT4;
     if (staged <= 200 * 1024) {
-        if (g.nbins == 256) {
-            sync_score_kernel<256, true><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
+        if (g.nbins == 256 && !ft4) {
+            sync_score_kernel<256, true, false><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
         } else {
+            auto kern = ft4 ? sync_score_kernel<0, true, true> : sync_score_kernel<0, true, false>;
             if (staged > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(sync_score_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
                 if (e != cudaSuccess) return e;
             }
-            sync_score_kernel<0, true><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
+            kern<<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
         }
     } else {
-        sync_score_kernel<0, false><<<grid, kScoreThreads, 0, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
+        auto kern = ft4 ? sync_score_kernel<0, false, true> : sync_score_kernel<0, false, false>;
+        kern<<<grid, kScoreThreads, 0, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
     }
     ++*launches;
     if (d_work_total) {

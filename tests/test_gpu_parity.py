@@ -603,3 +603,84 @@ def test_streams_full_size_whole_path(ctx, oracle, raw_slot):
     ri[:oi.size] = oi; rq[:oq.size] = oq
     o = oracle.subsystem(*oracle.condition(ri, rq, oi.size)[:2])
     assert n[1] == o["n"] and res[1].tobytes() == o["results"].tobytes()
+
+
+# ------------------------------------------------------------------------------------------- FT4
+def ft4_audio(seed, n=6):
+    rng = np.random.default_rng(seed)
+    sigs, texts = [], []
+    for k in range(n):
+        to, de, ex = synth.random_message(rng)
+        if k % 2 == 0:
+            to = "CQ"
+        sigs.append((ft8enc.tones_ft4(ft8enc.pack_std(to, de, ex)), float(rng.uniform(300.0, 2600.0)), float(0.3 + rng.uniform(0.0, 0.9)),
+                     float(rng.uniform(0.03, 0.15))))
+        texts.append(f"{to} {de} {ex}")
+    return synth.audio_12k(sigs, seed, n_samples=90_000, symbol_period=0.048), texts
+
+
+def test_ft4_batched(pkg, oracle):
+    """FT4 through the batched device API: 7.5 s monitor waterfall (576-sample symbols, 1152-point real FFT, 288 bins),
+    ft4_sync_score + top-K, 87x2 LLRs, LDPC, CRC, descrambling, unpack -- all identical to the CPU oracle
+    (itself pinned to the unmodified reference by tests/test_oracle_vs_ref.py::test_ft4_vs_reference)."""
+    c = pkg.Context(0)
+    c.set_protocol(0)
+    audios, texts = zip(*[ft4_audio(s) for s in (11, 12, 13)])
+    noise = np.random.default_rng(1).standard_normal(90_000).astype(np.float32) * 0.05
+    batch = np.stack(list(audios) + [noise])
+    mag, nb = c.monitor_waterfall(torch.from_numpy(batch).to(dev()), protocol=0)
+    refs = [oracle.monitor_waterfall(a, protocol=0) for a in batch]
+    assert nb == int(refs[0][1][4]) == 156
+    dims = dict(num_blocks=nb, num_bins=288, time_osr=2, freq_osr=2)
+    hm = mag.cpu().numpy()
+    for s in range(batch.shape[0]):
+        assert np.array_equal(hm[s][: refs[s][0].size], refs[s][0]), f"FT4 waterfall {s}: {(hm[s][:refs[s][0].size] != refs[s][0]).sum()} cells differ"
+    cand, ncand = c.find_sync(mag, **dims)
+    ok, stage, status, msg, plain, llr = c.decode(mag, cand, ncand, want_plain=True, want_llr=True, **dims)
+    torch.cuda.synchronize()
+    g_cand, g_ok = view(cand, cand_dtype), ok.cpu().numpy()
+    g_st, g_msg = view(status, status_dtype), view(msg, msg_dtype)
+    decoded = set()
+    for s in range(batch.shape[0]):
+        o_heap = oracle.find_sync(refs[s][0], c.K, 10, protocol=0, **dims)
+        n = int(ncand[s])
+        assert n == o_heap.size and g_cand[s, :n].tobytes() == o_heap.tobytes()
+        for k in range(n):
+            d = oracle.decode(refs[s][0], o_heap[k], 20, protocol=0, **dims)
+            assert bool(g_ok[s, k]) == bool(d["ok"])
+            assert np.array_equal(llr[s, k].cpu().numpy().view(np.uint32), d["llr"].view(np.uint32))
+            assert np.array_equal(plain[s, k].cpu().numpy(), d["plain"])
+            assert g_st[s, k]["ldpc_errors"] == d["status"]["ldpc_errors"]
+            if d["ok"]:
+                assert g_st[s, k].tobytes() == d["status"].tobytes()
+                assert g_msg[s, k]["text"] == d["msg"]["text"] and g_msg[s, k]["hash"] == d["msg"]["hash"]
+                decoded.add(d["msg"]["text"].decode())
+    assert len(decoded & {t for tt in texts for t in tt}) >= 10
+    c.close()
+
+
+def test_ft4_dropin(pkg, oracle):
+    """monitor_init(protocol = PROTO_FT4) / monitor_process / ft8_find_sync / ft8_decode with host structs, as
+    `decode_ft8 -ft4` drives them (ft8_lib/decode_ft8.c:240-243,286-330)."""
+    audio, texts = ft4_audio(21)
+    mon = pkg.Monitor(12000, 2, 2, 0)
+    assert (mon.me.block_size, mon.me.subblock_size, mon.me.nfft, mon.me.wf.max_blocks, mon.me.wf.num_bins) == (576, 288, 1152, 156, 288)
+    for o in range(0, audio.size - 576 + 1, 576):
+        mon.process(audio[o:o + 576])
+    ref, info, ref_max = oracle.monitor_waterfall(audio, protocol=0)
+    assert mon.me.wf.num_blocks == int(info[4]) and np.array_equal(mon.mag(), ref)
+    assert np.float32(mon.me.max_mag) == np.float32(ref_max)
+    dims = dict(num_blocks=int(info[4]), num_bins=288, time_osr=2, freq_osr=2, protocol=0)
+    heap = mon.find_sync(120, 10)
+    o_heap = oracle.find_sync(ref, 120, 10, **dims)
+    assert np.array_equal(heap.view(cand_dtype), o_heap)
+    got = set()
+    for cd in o_heap:
+        ok, msg, st = mon.decode(cd, 20)
+        d = oracle.decode(ref, cd, 20, **dims)
+        assert ok == bool(d["ok"]) and st.tobytes() == d["status"].tobytes()
+        if ok:
+            assert msg["text"] == d["msg"]["text"]
+            got.add(msg["text"].decode())
+    assert len(got & set(texts)) >= 4
+    mon.close()

@@ -179,3 +179,51 @@ def test_log10f_quantiser_is_monotone_over_the_whole_input_range(oracle):
     q = np.array([oracle.quantize_db(float(x)) for x in xs])
     assert np.all(np.diff(q) >= 0)
     assert np.array_equal(q, np.searchsorted(thr[1:256], xs, side="right"))
+
+
+def ft4_audio(seed, n=5):
+    rng = np.random.default_rng(seed)
+    sigs, texts = [], []
+    for k in range(n):
+        to, de, ex = synth.random_message(rng)
+        if k % 2 == 0:
+            to = "CQ"
+        sigs.append((ft8enc.tones_ft4(ft8enc.pack_std(to, de, ex)), float(rng.uniform(300.0, 2600.0)), float(0.3 + rng.uniform(0.0, 0.9)),
+                     float(rng.uniform(0.03, 0.15))))
+        texts.append(f"{to} {de} {ex}")
+    return synth.audio_12k(sigs, seed, n_samples=90_000, symbol_period=0.048), texts
+
+
+def test_ft4_vs_reference(oracle):
+    """FT4 through the restatement == the unmodified reference at every tap: encoder tones, the 7.5 s / 576-sample
+    monitor waterfall (kiss_fftr 1152), ft4_sync_score + heap order, 87x2 LLRs, LDPC, CRC, descrambling, text."""
+    ref = Reference("k120")
+    mon = ReferenceMonitor()
+    # encoder: Python restatement vs the oracle's C vs (through decode) the reference
+    payload = ft8enc.pack_std("CQ", "K1JT", "FN20")
+    t4 = np.zeros(105, np.uint8)
+    oracle.lib.orc_encode_tones_ft4(payload, t4.ctypes.data_as(__import__("ctypes").c_void_p))
+    assert np.array_equal(t4, ft8enc.tones_ft4(payload))
+    decoded_any = 0
+    for seed in (1, 2):
+        audio, texts = ft4_audio(seed)
+        mo, io, xo = oracle.monitor_waterfall(audio, protocol=0)
+        mr, ir, xr = mon.waterfall(audio, protocol=0)
+        assert np.array_equal(io, ir) and np.array_equal(mo, mr) and np.float32(xo) == np.float32(xr)
+        assert int(io[0]) == 576 and int(io[2]) == 1152 and int(io[5]) == 288
+        dims = dict(num_blocks=int(io[4]), num_bins=int(io[5]), time_osr=2, freq_osr=2, protocol=0)
+        for K, ms in ((120, 10), (40, 0)):
+            co = oracle.find_sync(mo, K, ms, **dims)
+            cr = ref.find_sync(mo, K, ms, **dims)
+            assert co.tobytes() == cr.tobytes()
+        got = set()
+        for c in co[:60]:
+            do, dr = oracle.decode(mo, c, 20, **dims), ref.decode(mo, c, 20, **dims)
+            assert do["ok"] == dr["ok"]
+            assert np.array_equal(do["llr"].view(np.uint32), dr["llr"].view(np.uint32)) and np.array_equal(do["plain"], dr["plain"])
+            assert do["status"]["ldpc_errors"] == dr["status"]["ldpc_errors"]
+            if do["ok"]:
+                assert do["msg"].tobytes() == dr["msg"].tobytes() and do["status"].tobytes() == dr["status"].tobytes()
+                got.add(do["msg"]["text"].decode())
+        decoded_any += len(got & set(texts))
+    assert decoded_any >= 4, "the synthetic FT4 signals must actually decode"

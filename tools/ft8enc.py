@@ -110,3 +110,29 @@ def tones(payload: bytes) -> np.ndarray:
             out[s] = gray[(bits[k] << 2) | (bits[k + 1] << 1) | bits[k + 2]]
             k += 3
     return out
+
+
+def tones_ft4(payload: bytes) -> np.ndarray:
+    """FT4 channel symbols (105 tones: ramp, 4 Costas groups, 87 two-bit data symbols), ft8_lib/ft8/encode.c:126-195:
+    the 77 message bits are scrambled with the protocol's fixed sequence before CRC and parity."""
+    xor = _table("kFt4tXor")
+    scrambled = bytes(b ^ int(x) for b, x in zip(payload[:10], xor))
+    bits = encode174(scrambled)
+    costas, gray = _table("kFt4tCostas"), _table("kFt4tGray")
+    out = np.zeros(105, np.uint8)
+    k = 0
+    for s in range(105):
+        if s == 0 or s == 104:
+            out[s] = 0
+        elif s < 5:
+            out[s] = costas[0][s - 1]
+        elif 34 <= s < 38:
+            out[s] = costas[1][s - 34]
+        elif 67 <= s < 71:
+            out[s] = costas[2][s - 67]
+        elif s >= 100:
+            out[s] = costas[3][s - 100]
+        else:
+            out[s] = gray[(bits[k] << 1) | bits[k + 1]]
+            k += 2
+    return out

@@ -121,18 +121,20 @@ def crowded_band(oracle, n_signals: int, seed: int, f_lo=50.0, f_hi=1500.0, snr_
     return i_s, q_s, texts
 
 
-def audio_12k(signals, seed: int, noise_sigma: float = 0.05, n_samples: int = 180_000, fs: int = 12_000):
-    """Real audio at 12 kHz for the ft8_lib monitor path: signals = (tones[79], f0_hz, t0_sec, amplitude).
-    1920 samples per symbol, phase-continuous 8-FSK, white Gaussian noise.  Returns float32[n_samples]."""
+def audio_12k(signals, seed: int, noise_sigma: float = 0.05, n_samples: int = 180_000, fs: int = 12_000, symbol_period: float = 0.16):
+    """Real audio at 12 kHz for the ft8_lib monitor path: signals = (tones, f0_hz, t0_sec, amplitude).
+    FT8: 79 tones, 0.16 s symbols (1920 samples), 6.25 Hz spacing.  FT4: 105 tones, symbol_period=0.048 (576 samples,
+    20.83 Hz spacing), n_samples=90_000.  Phase-continuous FSK, white Gaussian noise.  Returns float32[n_samples]."""
     rng = np.random.Generator(np.random.PCG64(seed))
     x = rng.standard_normal(n_samples) * noise_sigma
-    sym = int(round(fs * 0.16))
+    sym = int(round(fs * symbol_period))
+    tone_hz = 1.0 / symbol_period
     t = np.arange(sym, dtype=np.float64) / fs
     for tones, f0, t0, amp in signals:
         start = int(round(t0 * fs))
         phase = 0.0
         for k, tone in enumerate(np.asarray(tones, dtype=np.int64)):
-            f = f0 + float(tone) * TONE_HZ
+            f = f0 + float(tone) * tone_hz
             lo = start + k * sym
             a, b = max(lo, 0), min(lo + sym, n_samples)
             if a < b:
