@@ -224,10 +224,11 @@ int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_
 
 /* a15: the daemon's duplicate table + CQ filter, one slot per thread.  d_results: n_slots x max_messages
  * (zeroed here first), d_nresults: n_slots; optional first-seen unique message log: d_umsg (n_slots x
- * max_messages message_t), d_ufreq (float), d_uscore (int32). */
+ * max_messages message_t), d_ufreq (float), d_uscore (int32), d_ucand (int32, optional: index of the candidate
+ * that produced the entry). */
 int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate_t *d_cand, const int *d_ncand, const uint8_t *d_ok,
                   const message_t *d_msg, struct decoder_results *d_results, int32_t *d_nresults, message_t *d_umsg, float *d_ufreq,
-                  int32_t *d_uscore, void *stream);
+                  int32_t *d_uscore, int32_t *d_ucand, void *stream);
 
 /* Whole path on device buffers owned by the context: raw uint8 IQ (d_iq != NULL) or conditioned
  * 3200 sps samples (d_i/d_q) -> decoder_results.  Results stay on the device (ft8b200_results_device)
@@ -321,6 +322,33 @@ uint32_t ft8b200_stream_count(ft8b200_stream_t *s);
 int ft8b200_stream_fetch(ft8b200_stream_t *s, float *h_i, float *h_q, uint32_t *n_valid);
 /* decoder() (rtlsdr_ft8d.c:221-285) for the slot closed by the last flip: skip if < 12 s, condition, decode */
 int ft8b200_stream_decode(ft8b200_stream_t *s, struct decoder_results *h_results, int32_t *h_nresults);
+
+/* ---- on-disk formats and whole recordings (csrc/files.cu) --------------------------------------------------------
+ * Readers return the samples UNSCALED plus their peak max(|I|,|Q|): the reference's "normalise @ -3 dB" is applied on the
+ * device (ft8b200_process_conditioned / ft8b200_condition).  Buffers hold 48000 floats; the tail is zero-filled.
+ * replaces: readRawIQfile / readC2file (rtlsdr_ft8d.c:744-856), load_wav (ft8_lib/common/wave.c:66-128). */
+int ft8b200_read_iq_file(const char *path, float *h_i, float *h_q, float *peak);                      /* -> pairs read, 0 = cannot open */
+int ft8b200_read_c2_file(const char *path, float *h_i, float *h_q, float *peak, double *dial_freq, int *type, char *name15);
+int ft8b200_load_wav(float *signal, int *num_samples, int *sample_rate, const char *path);            /* load_wav()'s contract; -3 = cannot open */
+int ft8b200_load_wav_s16(int16_t *raw_s16, float *signal, int *num_samples, int *sample_rate, const char *path);
+/* decodeRecordedFile() (rtlsdr_ft8d.c:859-887) for a batch of .iq / .c2 files: n x max_messages records, n counts */
+int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n, struct decoder_results *h_results, int32_t *h_nresults,
+                            int32_t *h_samples);
+/* one line of decode_ft8's output: "000000 %3d %+4.2f %4.0f ~  %s" = score, time_sec, freq_hz, text (decode_ft8.c:399-401) */
+typedef struct {
+    char text[25];
+    uint16_t hash;
+    int16_t score;
+    float time_sec;
+    float freq_hz;
+} ft8b200_decoded_t;
+/* decode_ft8 main() (ft8_lib/decode_ft8.c:272-409) for n device-resident float recordings / n WAV files, FT8 or FT4:
+ * h_out holds max_out_per_recording (>= max_messages) entries per recording, first-seen unique messages in candidate order. */
+int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride, int n_samples, int n, int sample_rate, int protocol,
+                         ft8b200_decoded_t *h_out, int32_t *h_count, int max_out_per_recording);
+int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n, int protocol, ft8b200_decoded_t *h_out, int32_t *h_count,
+                             int max_out_per_recording, int32_t *h_status);
+int ft8b200_get_config(ft8b200_ctx_t *ctx, ft8b200_config_t *cfg);
 
 /* 12 kHz monitor waterfall, batched: n_slots x n_samples real audio -> u8[n_slots][blocks][time_osr][freq_osr][bins] */
 int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t slot_stride_samples, int n_samples, int n_slots,

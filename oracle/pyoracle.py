@@ -231,6 +231,42 @@ class Oracle:
         return dict(n=n, results=res, msgs=msgs, freq_hz=np.array(rep.freq_hz[:k], np.float32), score=np.array(rep.score[:k], np.int32),
                     cands=cands[:rep.n_cand].copy(), wf=wf)
 
+    def decode_ft8_lines(self, audio: np.ndarray, sample_rate=12000, protocol=1, max_cand=120, min_score=10, iters=20, max_msgs=50):
+        """decode_ft8's main() (ft8_lib/decode_ft8.c:296-406) on one recording -> its stdout lines:
+        monitor waterfall, ft8_find_sync, then per candidate ft8_decode + the hash table of first-seen unique messages."""
+        mag, info, _ = self.monitor_waterfall(audio, sample_rate, 2, 2, protocol)
+        dims = dict(num_blocks=int(info[4]), num_bins=int(info[5]), time_osr=2, freq_osr=2, protocol=protocol)
+        if dims["num_blocks"] == 0:
+            return []
+        sp = np.float32(0.048 if protocol == 0 else 0.160)
+        table = [None] * max_msgs
+        lines = []
+        for c in self.find_sync(mag, max_cand, min_score, **dims):
+            if c["score"] < min_score:
+                continue
+            freq = (np.float32(c["freq_offset"]) + np.float32(c["freq_sub"]) / np.float32(2)) / sp
+            tsec = (np.float32(c["time_offset"]) + np.float32(c["time_sub"]) / np.float32(2)) * sp
+            d = self.decode(mag, c, iters, **dims)
+            if not d["ok"]:
+                continue
+            h, text = int(d["msg"]["hash"]), d["msg"]["text"]
+            idx = h % max_msgs
+            dup = False
+            for _ in range(max_msgs):
+                if table[idx] is None:
+                    break
+                if table[idx] == (h, text):
+                    dup = True
+                    break
+                idx = (idx + 1) % max_msgs
+            else:
+                continue  # table full: the reference would spin forever (decode_ft8.c:369-388)
+            if dup:
+                continue
+            table[idx] = (h, text)
+            lines.append("000000 %3d %+4.2f %4.0f ~  %s" % (int(c["score"]), float(tsec), float(freq), text.decode()))
+        return lines
+
     # -- encoder ----------------------------------------------------------------------
     def pack_std(self, call_to: str, call_de: str, extra: str) -> bytes:
         b = C.create_string_buffer(10)
@@ -413,6 +449,31 @@ class ReferenceMonitor:
         y = np.zeros(x.size // 2 + 1, np.complex64)
         self.lib.refmon_fftr(x.size, _ptr(x), _ptr(y))
         return y
+
+    def decode_ft8_stdout(self, wav_path: str, ft4: bool = False):
+        """Run the reference's own main() (decode_ft8 [-ft4] file.wav) in-process and return its stdout lines."""
+        import tempfile
+        args = [b"decode_ft8"] + ([b"-ft4"] if ft4 else []) + [wav_path.encode()]
+        argv = (C.c_char_p * (len(args) + 1))(*args, None)
+        libc = C.CDLL(None)
+        libc.fflush(None)
+        with tempfile.TemporaryFile() as tmp:
+            saved, saved_err = os.dup(1), os.dup(2)
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            os.dup2(tmp.fileno(), 1)
+            os.dup2(devnull, 2)  # LOG(LOG_INFO, ...) chatter
+            try:
+                rc = self.lib.ref_decode_ft8_main(len(args), argv)
+                libc.fflush(None)
+            finally:
+                os.dup2(saved, 1)
+                os.dup2(saved_err, 2)
+                os.close(saved); os.close(saved_err); os.close(devnull)
+            tmp.seek(0)
+            out = tmp.read().decode("ascii", "replace")
+        if rc != 0:
+            raise IOError(f"decode_ft8 main -> {rc}")
+        return [l for l in out.splitlines() if l.startswith("000000")]
 
     def load_wav(self, path, max_samples=15 * 12000):
         sig = np.zeros(max_samples, np.float32)

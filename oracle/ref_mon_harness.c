@@ -7,6 +7,10 @@
 #include "decode_ft8.c"
 #undef main
 
+/* linked with -Wl,--wrap=malloc: every malloc() in the reference objects returns zeroed memory, so the uninitialised
+ * last_frame of monitor_init() (decode_ft8.c:131) is deterministic, also inside the reference's own main() */
+void *__wrap_malloc(size_t n) { return calloc(1, n); }
+
 int refmon_sizeof_monitor(void) { return (int)sizeof(monitor_t); }
 monitor_t *refmon_new(float f_min, float f_max, int sample_rate, int time_osr, int freq_osr, int protocol) {
     monitor_config_t cfg = { f_min, f_max, sample_rate, time_osr, freq_osr, (ftx_protocol_t)protocol };

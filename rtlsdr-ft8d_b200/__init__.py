@@ -231,7 +231,7 @@ class Context:
         ufreq = torch.zeros((n, self.M), dtype=torch.float32, device=dev) if want_log else None
         uscore = torch.zeros((n, self.M), dtype=torch.int32, device=dev) if want_log else None
         self._chk(self.L.ft8b200_spots(C.c_void_p(self.h), n, freq_osr, _p(cand), _p(ncand), _p(ok), _p(msg), _p(res), _p(nres), _p(umsg), _p(ufreq),
-                                       _p(uscore), _st(stream)))
+                                       _p(uscore), C.c_void_p(0), _st(stream)))
         return res, nres, umsg, ufreq, uscore
 
     def monitor_waterfall(self, audio, sample_rate=12000, time_osr=2, freq_osr=2, protocol=1, stream: int | None = None):
@@ -522,3 +522,71 @@ def ft8_decode(mag: np.ndarray, cand, max_iterations=20, num_blocks=92, num_bins
     st = np.frombuffer(bytes([0xA5]) * 12, status_dtype).copy()
     ok = L.ft8_decode(C.byref(wf), _p(c), _p(msg), max_iterations, _p(st))
     return bool(ok), msg[0], st[0]
+
+
+# ---- on-disk formats and whole recordings (csrc/files.cu) -------------------------------------------------
+decoded_dtype = np.dtype([("text", "S25"), ("_pad", "u1"), ("hash", "<u2"), ("score", "<i2"), ("_pad2", "<u2"), ("time_sec", "<f4"), ("freq_hz", "<f4")])
+assert decoded_dtype.itemsize == 40
+
+
+def read_iq_file(path: str):
+    """-> (I[48000], Q[48000], n_pairs, peak): unscaled samples of a .iq recording (readRawIQfile without its normalisation)."""
+    i_s = np.zeros(N_SLOT, np.float32); q_s = np.zeros(N_SLOT, np.float32)
+    peak = C.c_float(0)
+    n = lib().ft8b200_read_iq_file(path.encode(), _p(i_s), _p(q_s), C.byref(peak))
+    return i_s, q_s, int(n), float(peak.value)
+
+
+def read_c2_file(path: str):
+    i_s = np.zeros(N_SLOT, np.float32); q_s = np.zeros(N_SLOT, np.float32)
+    peak, freq, ty = C.c_float(0), C.c_double(0), C.c_int(0)
+    name = C.create_string_buffer(15)
+    n = lib().ft8b200_read_c2_file(path.encode(), _p(i_s), _p(q_s), C.byref(peak), C.byref(freq), C.byref(ty), name)
+    return i_s, q_s, int(n), float(peak.value), float(freq.value), int(ty.value), name.raw[:14]
+
+
+def load_wav(path: str, max_samples: int = 15 * 12000):
+    """load_wav() of ft8_lib/common/wave.c: -> (float32 signal, sample_rate); raises IOError(code) like a negative return."""
+    sig = np.zeros(max_samples, np.float32)
+    n, sr = C.c_int(max_samples), C.c_int(0)
+    rc = lib().ft8b200_load_wav(_p(sig), C.byref(n), C.byref(sr), path.encode())
+    if rc < 0:
+        raise IOError(rc)
+    return sig[:n.value].copy(), int(sr.value)
+
+
+def _paths(paths):
+    arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+    return arr
+
+
+def decode_iq_files(ctx: Context, paths):
+    n = len(paths)
+    res = np.zeros((n, ctx.M), result_dtype)
+    nres = np.zeros(n, np.int32)
+    ns = np.zeros(n, np.int32)
+    ctx._chk(ctx.L.ft8b200_decode_iq_files(C.c_void_p(ctx.h), _paths(paths), n, _p(res), _p(nres), _p(ns)))
+    return res, nres, ns
+
+
+def decode_audio(ctx: Context, audio, sample_rate=12000, protocol=1):
+    """audio: float32 device tensor [n, n_samples] -> list of decoded_dtype arrays (decode_ft8's output per recording)."""
+    n, n_samples = audio.shape
+    out = np.zeros((n, ctx.M), decoded_dtype)
+    cnt = np.zeros(n, np.int32)
+    ctx._chk(ctx.L.ft8b200_decode_audio(C.c_void_p(ctx.h), _p(audio), C.c_size_t(audio.stride(0)), n_samples, n, sample_rate, protocol, _p(out), _p(cnt), ctx.M))
+    return [out[k, :cnt[k]] for k in range(n)]
+
+
+def decode_wav_files(ctx: Context, paths, protocol=1):
+    n = len(paths)
+    out = np.zeros((n, ctx.M), decoded_dtype)
+    cnt = np.zeros(n, np.int32)
+    status = np.zeros(n, np.int32)
+    ctx._chk(ctx.L.ft8b200_decode_wav_files(C.c_void_p(ctx.h), _paths(paths), n, protocol, _p(out), _p(cnt), ctx.M, _p(status)))
+    return [out[k, :cnt[k]] for k in range(n)], status
+
+
+def format_decoded(rec) -> str:
+    """One line of decode_ft8's stdout (decode_ft8.c:401)."""
+    return "000000 %3d %+4.2f %4.0f ~  %s" % (int(rec["score"]), float(rec["time_sec"]), float(rec["freq_hz"]), rec["text"].decode())

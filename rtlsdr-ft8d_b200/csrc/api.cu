@@ -220,6 +220,12 @@ void ft8b200_destroy(ft8b200_ctx_t *ctx) {
     delete ctx;
 }
 
+int ft8b200_get_config(ft8b200_ctx_t *ctx, ft8b200_config_t *cfg) {
+    if (!ctx || !cfg) return fail(FT8B200_EINVAL, "ft8b200_get_config: null argument");
+    *cfg = ctx->cfg;
+    return 0;
+}
+
 void *ft8b200_cuda_stream(ft8b200_ctx_t *ctx) { return ctx ? ctx->stream : nullptr; }
 int ft8b200_sync(ft8b200_ctx_t *ctx) {
     int rc = ctx_enter(ctx);
@@ -319,7 +325,7 @@ int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_
 
 int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate_t *d_cand, const int *d_ncand, const uint8_t *d_ok,
                   const message_t *d_msg, struct decoder_results *d_results, int32_t *d_nresults, message_t *d_umsg, float *d_ufreq,
-                  int32_t *d_uscore, void *stream) {
+                  int32_t *d_uscore, int32_t *d_ucand, void *stream) {
     int rc = ctx_enter(ctx);
     if (rc) return rc;
     if (!d_cand || !d_ncand || !d_ok || !d_msg || !d_results || !d_nresults || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_spots: bad argument");
@@ -327,7 +333,7 @@ int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate
     std::lock_guard<std::mutex> lk(ctx->mu);
     if ((rc = ctx->table.ensure((size_t)n_slots * ctx->cfg.max_messages * sizeof(int16_t)))) return rc;
     CU(launch_spots(n_slots, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, freq_osr, d_cand, d_ncand, d_ok, d_msg, d_results,
-                    d_nresults, d_umsg, d_ufreq, d_uscore, ctx->table.as<int16_t>(), pick(ctx, stream), &ctx->launches));
+                    d_nresults, d_umsg, d_ufreq, d_uscore, d_ucand, ctx->table.as<int16_t>(), pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
 }
@@ -368,7 +374,7 @@ static int run_back_end(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, 
     mark(ctx, 4, group, true, st);
     mark(ctx, 5, group, false, st);
     CU(launch_spots(n, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, 2, cand, ncand, ok, ctx->msg.as<message_t>() + (size_t)s0 * K,
-                    ctx->results.as<struct decoder_results>() + (size_t)s0 * M, ctx->nresults.as<int32_t>() + s0, nullptr, nullptr, nullptr,
+                    ctx->results.as<struct decoder_results>() + (size_t)s0 * M, ctx->nresults.as<int32_t>() + s0, nullptr, nullptr, nullptr, nullptr,
                     ctx->table.as<int16_t>() + (size_t)s0 * M, st, &ctx->launches));
     mark(ctx, 5, group, true, st);
     return 0;

@@ -684,3 +684,89 @@ def test_ft4_dropin(pkg, oracle):
             got.add(msg["text"].decode())
     assert len(got & set(texts)) >= 4
     mon.close()
+
+
+# ------------------------------------------------------------------------------------------- recordings on disk
+def _write_wav(path, pcm):
+    import wave
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(12000)
+        w.writeframes(np.ascontiguousarray(pcm, np.int16).tobytes())
+
+
+def test_real_recordings_match_reference_stdout(pkg, ctx, tmp_path):
+    """Three of the reference's real-world 12 kHz recordings, as WAV files, through ft8b200_decode_wav_files in ONE batch:
+    every printed line (score, time, frequency, text, order) equals the stdout of the reference's own `decode_ft8` main()
+    stored in tests/golden/recordings_12k.npz."""
+    g = golden("recordings_12k")
+    paths = []
+    for k, pcm in enumerate(g["pcm"]):
+        paths.append(str(tmp_path / f"rec{k}.wav"))
+        _write_wav(paths[-1], pcm)
+    paths.append(str(tmp_path / "missing.wav"))
+    outs, status = pkg.decode_wav_files(ctx, paths)
+    assert list(status) == [0, 0, 0, -3] and len(outs[3]) == 0
+    total = 0
+    for k in range(3):
+        assert [pkg.format_decoded(r) for r in outs[k]] == str(g["lines"][k]).split("\n"), str(g["names"][k])
+        total += len(outs[k])
+    assert total == 47
+
+
+def test_wav_batch_ft4_and_short_files(pkg, ctx, oracle, tmp_path):
+    """Synthetic recordings as s16 WAV files: FT4 (7.5 s) and FT8 files of different lengths in one call each,
+    against the oracle's decode_ft8 chain on the same quantised samples."""
+    a4, _ = ft4_audio(31)
+    a4b, _ = ft4_audio(32)
+    pcm4 = [np.clip(np.round(a * 20000), -32768, 32767).astype(np.int16) for a in (a4, a4b)]
+    paths = []
+    for k, p in enumerate(pcm4):
+        paths.append(tmp_path / f"ft4_{k}.wav"); _write_wav(paths[-1], p)
+    outs, status = pkg.decode_wav_files(ctx, [str(p) for p in paths], protocol=0)
+    n = 0
+    for k, p in enumerate(pcm4):
+        want = oracle.decode_ft8_lines(p.astype(np.float32) / np.float32(32768.0), 12000, protocol=0)
+        assert [pkg.format_decoded(r) for r in outs[k]] == want
+        n += len(want)
+    assert n >= 6
+    sigs = [(ft8enc.tones(ft8enc.pack_std("CQ", "K1JT", "FN20")), 1200.0, 0.5, 0.1), (ft8enc.tones(ft8enc.pack_std("K1ABC", "W9XYZ", "-15")), 2100.0, 1.1, 0.05)]
+    a8 = synth.audio_12k(sigs, 3)
+    pcm8 = np.clip(np.round(a8 * 20000), -32768, 32767).astype(np.int16)
+    lens = [180_000, 180_000, 150_000, 1000]
+    paths = []
+    for k, L in enumerate(lens):
+        paths.append(tmp_path / f"ft8_{k}.wav"); _write_wav(paths[-1], pcm8[:L])
+    outs, status = pkg.decode_wav_files(ctx, [str(p) for p in paths])
+    for k, L in enumerate(lens):
+        want = oracle.decode_ft8_lines(pcm8[:L].astype(np.float32) / np.float32(32768.0), 12000)
+        assert [pkg.format_decoded(r) for r in outs[k]] == want
+    assert len(outs[0]) >= 2 and len(outs[3]) == 0
+
+
+def test_iq_and_c2_files(pkg, ctx, oracle, slots, tmp_path):
+    """decodeRecordedFile() for a batch: .iq / .c2 files (unnormalised amplitudes, a short recording, a missing file, a
+    wrong extension) -> decoder_results identical to readRawIQfile's normalisation + ft8_subsystem on the CPU."""
+    paths, want = [], []
+    for k, (i_s, q_s) in enumerate(slots[:3]):
+        n = 48000 if k != 1 else 41000
+        gain = np.float32([0.02, 7.5, 1.0][k])
+        inter = np.empty(2 * n, np.float32)
+        inter[0::2] = i_s[:n] * gain; inter[1::2] = -(q_s[:n] * gain)
+        if k == 2:
+            p = tmp_path / f"s{k}.c2"
+            with open(p, "wb") as f:
+                f.write(b"000000_0000.c2".ljust(14, b"\0") + np.int32(2).tobytes() + np.float64(7.074).tobytes() + inter.tobytes())
+        else:
+            p = tmp_path / f"s{k}.iq"
+            inter.tofile(p)
+        paths.append(str(p))
+        fi = np.zeros(48000, np.float32); fq = np.zeros(48000, np.float32)
+        fi[:n] = inter[0::2]; fq[:n] = -inter[1::2]
+        ci, cq, _ = oracle.condition(fi, fq, n)   # same expression as readRawIQfile's normalisation (rtlsdr_ft8d.c:762-778)
+        want.append(oracle.subsystem(ci, cq))
+    paths += [str(tmp_path / "missing.iq"), str(tmp_path / "wrong.txt")]
+    res, nres, ns = pkg.decode_iq_files(ctx, paths)
+    assert list(ns) == [48000, 41000, 48000, 0, 0] and nres[3] == 0 and nres[4] == 0
+    for k in range(3):
+        assert nres[k] == want[k]["n"] and res[k].tobytes() == want[k]["results"].tobytes()
+    assert nres[0] >= 1

@@ -63,3 +63,37 @@ def test_threshold_table_is_the_quantiser(oracle):
     edge = np.concatenate([np.nextafter(thr[1:256], np.float32(0)), thr[1:256], np.nextafter(thr[1:256], np.float32(np.inf))]).astype(np.float32)
     for x in np.concatenate([xs, edge, np.float32([1e-12, 1.0, 1e6])]):
         assert oracle.quantize_db(float(x)) == int(np.searchsorted(thr[1:256], x, side="right")), x
+
+
+def test_oracle_reproduces_reference_stdout_on_real_recordings(oracle):
+    """tests/golden/recordings_12k.npz: three of the reference's own real-world WAVs (PCM) + the stdout of its own
+    `decode_ft8` main() on them (tools/make_golden.py).  The restatement must print the same lines."""
+    g = golden("recordings_12k")
+    for name, pcm, lines in zip(g["names"], g["pcm"], g["lines"]):
+        audio = pcm.astype(np.float32) / np.float32(32768.0)
+        assert oracle.decode_ft8_lines(audio, 12000) == str(lines).split("\n"), str(name)
+
+
+def test_wav_and_iq_readers_without_gpu(pkg, tmp_path):
+    """The host-side readers (csrc/files.cu) need no device: WAV written with Python's wave module, error codes of load_wav."""
+    import wave
+    g = golden("recordings_12k")
+    path = str(tmp_path / "r.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(12000)
+        w.writeframes(g["pcm"][0].tobytes())
+    sig, sr = pkg.load_wav(path)
+    assert sr == 12000 and np.array_equal(sig, g["pcm"][0].astype(np.float32) / np.float32(32768.0))
+    with pytest.raises(IOError) as e:
+        pkg.load_wav(path, max_samples=1000)      # more samples than the caller's buffer: -2 like the reference
+    assert e.value.args[0] == -2
+    stereo = str(tmp_path / "s.wav")
+    with wave.open(stereo, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(12000)
+        w.writeframes(g["pcm"][0][:2000].tobytes())
+    with pytest.raises(IOError) as e:
+        pkg.load_wav(stereo)                      # not mono: -1 like the reference
+    assert e.value.args[0] == -1
+    with pytest.raises(IOError) as e:
+        pkg.load_wav(str(tmp_path / "nope.wav"))  # the reference would crash on fread(NULL); here -3
+    assert e.value.args[0] == -3

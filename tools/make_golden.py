@@ -56,6 +56,23 @@ def main():
     slot_fixture("slot_crowded_k500", i_s, q_s, "k500")
     slot_fixture("slot_crowded_k120", i_s, q_s, "k120", store_input=False)  # same input as slot_crowded_k500
 
+    # --- real-world 12 kHz recordings (the reference's own test WAVs) through the reference's own main():
+    #     input PCM + the exact stdout lines of `decode_ft8 file.wav` (ft8_lib/decode_ft8.c:226-409)
+    from oracle.pyoracle import ReferenceMonitor
+    import wave
+    mon = ReferenceMonitor()
+    pcm, lines, names = [], [], []
+    for rel in ("ft8_lib/tests/191111_110130.wav", "ft8_lib/tests/20m_busy/test_06.wav", "ft8_lib/tests/websdr_test4.wav"):
+        path = os.path.join("/root/reference", rel)
+        with wave.open(path, "rb") as w:
+            assert (w.getnchannels(), w.getsampwidth(), w.getframerate()) == (1, 2, 12000)
+            pcm.append(np.frombuffer(w.readframes(w.getnframes()), np.int16).copy())
+        out = mon.decode_ft8_stdout(path)
+        lines.append("\n".join(out))
+        names.append(rel)
+        print(rel, len(out), "messages")
+    np.savez_compressed(os.path.join(OUT, "recordings_12k.npz"), names=np.array(names), pcm=np.stack(pcm), lines=np.array(lines))
+
     # --- known answers
     R = Reference("k120")
     p = R.pack77("CQ K1JT FN20QI")
