@@ -42,39 +42,24 @@ def slot_params(seed: int):
     if seed % 2 == 0:
         to = "CQ"
         ex = synth.random_grid(rng)
-    tones = ft8enc.tones(ft8enc.pack_std(to, de, ex))
-    return dict(text=f"{to} {de} {ex}", tones=tones, f_hz=float(rng.uniform(200.0, 1400.0)), t0=float(0.5 + rng.uniform(-0.3, 0.3)),
+    return dict(text=f"{to} {de} {ex}", f_hz=float(rng.uniform(200.0, 1400.0)), t0=float(0.5 + rng.uniform(-0.3, 0.3)),
                 amp=20.0, noise=30.0)
 
 
-def gen_raw_slot_torch(out, seed: int, device):
-    """One 72 MB slot of uint8 IQ: phase-continuous 8-FSK at (f - 600 kHz) + Gaussian noise, offset 127.5, saturating."""
-    import torch
-    p = slot_params(seed)
-    n_s = RAW_SLOT_BYTES // 2
-    n = torch.arange(n_s, device=device, dtype=torch.int64)
-    sym = torch.div(n - int(round(p["t0"] * 2_400_000)), 384_000, rounding_mode="floor")
-    inside = (sym >= 0) & (sym < 79)
-    tone = torch.from_numpy(p["tones"].astype(np.int64)).to(device)[sym.clamp_(0, 78)]
-    del sym, n
-    freq = (tone.to(torch.float64) * 6.25 + (p["f_hz"] - 600_000.0)) * inside
-    del tone
-    phase = torch.cumsum(freq, 0).mul_(2.0 * np.pi / 2_400_000.0).remainder_(2.0 * np.pi).to(torch.float32)
-    del freq
-    g = torch.Generator(device=device)
-    g.manual_seed(1234567 + seed)
-    amp = inside.to(torch.float32) * p["amp"]
-    v = out.view(n_s, 2)
-    v[:, 0] = (torch.cos(phase) * amp + torch.randn(n_s, device=device, generator=g) * p["noise"] + 127.5).round_().clamp_(0, 255).to(torch.uint8)
-    v[:, 1] = (torch.sin(phase) * amp + torch.randn(n_s, device=device, generator=g) * p["noise"] + 127.5).round_().clamp_(0, 255).to(torch.uint8)
-    return p["text"]
-
-
-def gen_batch(n_slots: int, first_seed: int, device):
-    import torch
-    buf = torch.empty((n_slots, RAW_SLOT_BYTES), dtype=torch.uint8, device=device)
-    texts = [gen_raw_slot_torch(buf[s], first_seed + s, device) for s in range(n_slots)]
-    return buf, texts
+def gen_batch(n_slots: int, first_seed: int, device, ctx=None):
+    """n_slots x 72 MB of uint8 IQ made ON THE DEVICE by the library's synthesiser (csrc/synth.cu): one FT8 message per
+    slot as phase-continuous 8-FSK at (f - 600 kHz), 20 LSB over 30 LSB of noise, offset 128, saturating."""
+    from ft8b200_loader import load
+    pkg = load()
+    own = ctx is None
+    if own:
+        ctx = pkg.Context(device.index or 0)
+    params = [slot_params(first_seed + s) for s in range(n_slots)]
+    sig = pkg.make_signals((pkg.pack77_std(*p["text"].split()), p["f_hz"], p["t0"], p["amp"]) for p in params)
+    buf = ctx.synth_raw(sig, np.arange(n_slots + 1, dtype=np.int32), params[0]["noise"], 0xF78, first_slot_index=first_seed)
+    if own:
+        ctx.close()
+    return buf, [p["text"] for p in params]
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -354,7 +339,7 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": "slots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-           "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+           "data": "synthetic (generated on the device by ft8b200_synth_raw)", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
            "decoded_ok_slots_in_first_batch": n_good}
 
     if rank == 0 and world == 1:

@@ -350,6 +350,30 @@ int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n
                              int max_out_per_recording, int32_t *h_status);
 int ft8b200_get_config(ft8b200_ctx_t *ctx, ft8b200_config_t *cfg);
 
+/* ---- device-side signal synthesis (csrc/synth.cu): the step before the path -------------------------------------
+ * message -> 77-bit payload (host) -> CRC/LDPC/Gray/Costas symbols -> phase-continuous FSK + noise (device).
+ * replaces for benchmarking/testing: pack77 (ft8_lib/ft8/pack.c), ft8_encode/ft4_encode (ft8/encode.c:22-195) and the
+ * modulators of decoderSelfTest (rtlsdr_ft8d.c:937-955) / gen_ft8 (gen_ft8.c:28-102).  The waveform generator is integer
+ * (32-bit phase accumulators, table cosine, counter-hash noise) so that a CPU twin reproduces it bit for bit. */
+typedef struct {
+    uint8_t payload[10];  /* 77-bit message, MSB first (ft8b200_pack77_std or any packer) */
+    uint8_t reserved[2];
+    float f0_hz;          /* frequency of tone 0 as the decoder will see it */
+    float t0_sec;         /* start of symbol 0 */
+    float amp;            /* raw path: amplitude in LSB; float paths: linear amplitude */
+} ft8b200_signal_t;
+int ft8b200_pack77_std(const char *call_to, const char *call_de, const char *extra, uint8_t *payload10);
+/* n payloads (10 bytes each, host) -> n x 105 channel symbols (host; FT8 uses the first 79), computed on the device */
+int ft8b200_encode_tones(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, int protocol, uint8_t *h_tones);
+/* Slot s holds signals h_first[s] .. h_first[s+1]-1 (h_first has n_slots+1 entries).  Noise stream of slot s is selected by
+ * (seed, first_slot_index + s): a batch generated in pieces or on several GPUs equals one generated at once. */
+int ft8b200_synth_raw(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, const int *h_first, int n_slots, float noise_lsb, uint64_t seed,
+                      int first_slot_index, uint8_t *d_iq, size_t slot_stride_bytes, size_t bytes_per_slot, void *stream);
+int ft8b200_synth_slots(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, const int *h_first, int n_slots, float noise_sigma, uint64_t seed,
+                        int first_slot_index, float *d_i, float *d_q, size_t slot_stride_samples, int n_samples, void *stream);
+int ft8b200_synth_audio(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, const int *h_first, int n_slots, int protocol, float noise_sigma,
+                        uint64_t seed, int first_slot_index, float *d_audio, size_t slot_stride_samples, int n_samples, void *stream);
+
 /* 12 kHz monitor waterfall, batched: n_slots x n_samples real audio -> u8[n_slots][blocks][time_osr][freq_osr][bins] */
 int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t slot_stride_samples, int n_samples, int n_slots,
                               int sample_rate, int time_osr, int freq_osr, int protocol, uint8_t *d_mag, size_t mag_slot_stride,

@@ -113,6 +113,13 @@ void orc_encode_tones(const uint8_t *payload10, uint8_t *tones79);
 void orc_encode_tones_ft4(const uint8_t *payload10, uint8_t *tones105);
 void orc_encode174(const uint8_t *payload10, uint8_t *bits174);
 
+/* ---- CPU twin of the device signal synthesiser (csrc/synth.cu); layout mirrors ft8b200_signal_t ---- */
+typedef struct { uint8_t payload[10]; uint8_t reserved[2]; float f0_hz, t0_sec, amp; } orc_signal_t;
+void orc_synth_tones(const orc_signal_t *sig, int ft4, uint8_t *tones105);
+void orc_synth_raw(const orc_signal_t *sigs, int n_sigs, float noise_lsb, uint64_t seed, int slot_index, uint8_t *iq, long long n_samples);
+void orc_synth_float(int kind, int ft4, const orc_signal_t *sigs, int n_sigs, float noise_sigma, uint64_t seed, int slot_index, float *out_i,
+                     float *out_q, int n_samples);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,13 +47,17 @@ class SlotReport(C.Structure):
                 ("score", C.c_int * 512)]
 
 
+signal_dtype = np.dtype([("payload", "u1", 10), ("reserved", "u1", 2), ("f0_hz", "<f4"), ("t0_sec", "<f4"), ("amp", "<f4")])
+assert signal_dtype.itemsize == 24
+
+
 def _ptr(a, t=C.c_void_p):
     return a.ctypes.data_as(t)
 
 
 def build_restatement(force: bool = False) -> str:
     so = os.path.join(HERE, "libft8oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("ft8_oracle.c", "ft8_oracle_codec.c", "ft8_oracle.h", "ft8_tables.h")]
+    srcs = [os.path.join(HERE, f) for f in ("ft8_oracle.c", "ft8_oracle_codec.c", "ft8_oracle_synth.c", "ft8_oracle.h", "ft8_tables.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "restate"], stdout=subprocess.DEVNULL)
     return so
@@ -266,6 +270,23 @@ class Oracle:
             table[idx] = (h, text)
             lines.append("000000 %3d %+4.2f %4.0f ~  %s" % (int(c["score"]), float(tsec), float(freq), text.decode()))
         return lines
+
+    # -- CPU twin of the device signal synthesiser (csrc/synth.cu) ------------------------------------
+    def synth_raw(self, signals: np.ndarray, noise_lsb: float, seed: int, slot_index: int, n_samples: int) -> np.ndarray:
+        """signals: array of signal_dtype -> uint8[2*n_samples] interleaved I,Q (one slot)."""
+        signals = np.ascontiguousarray(signals, signal_dtype)
+        out = np.zeros(2 * n_samples, np.uint8)
+        self.lib.orc_synth_raw(_ptr(signals), signals.size, C.c_float(noise_lsb), C.c_uint64(seed), slot_index, _ptr(out), C.c_longlong(n_samples))
+        return out
+
+    def synth_float(self, kind: int, ft4: bool, signals: np.ndarray, noise_sigma: float, seed: int, slot_index: int, n_samples: int):
+        """kind 1: complex 3200 sps -> (I, Q); kind 2: real 12 kHz audio -> (x, None)."""
+        signals = np.ascontiguousarray(signals, signal_dtype)
+        oi = np.zeros(n_samples, np.float32)
+        oq = np.zeros(n_samples, np.float32) if kind == 1 else None
+        self.lib.orc_synth_float(kind, int(ft4), _ptr(signals), signals.size, C.c_float(noise_sigma), C.c_uint64(seed), slot_index, _ptr(oi),
+                                 _ptr(oq) if oq is not None else None, n_samples)
+        return oi, oq
 
     # -- encoder ----------------------------------------------------------------------
     def pack_std(self, call_to: str, call_de: str, extra: str) -> bytes:

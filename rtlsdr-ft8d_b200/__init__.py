@@ -30,6 +30,27 @@ status_dtype = np.dtype([("ldpc_errors", "<i4"), ("crc_extracted", "<u2"), ("crc
 result_dtype = np.dtype([("call", "S13"), ("loc", "S7"), ("freq", "<i4"), ("snr", "<i4")])
 
 
+signal_dtype = np.dtype([("payload", "u1", 10), ("reserved", "u1", 2), ("f0_hz", "<f4"), ("t0_sec", "<f4"), ("amp", "<f4")])
+
+
+def pack77_std(call_to: str, call_de: str, extra: str) -> bytes:
+    """Standard (type 1) message -> 10-byte payload (host code of csrc/synth.cu); raises ValueError if not representable."""
+    b = C.create_string_buffer(10)
+    if lib().ft8b200_pack77_std(call_to.encode(), call_de.encode(), extra.encode(), b) != 0:
+        raise ValueError(f"cannot pack {call_to} {call_de} {extra}")
+    return b.raw
+
+
+def make_signals(items):
+    """items: iterable of (payload bytes, f0_hz, t0_sec, amp) -> signal_dtype array."""
+    items = list(items)
+    out = np.zeros(len(items), signal_dtype)
+    for k, (payload, f0, t0, amp) in enumerate(items):
+        out[k]["payload"] = np.frombuffer(payload, np.uint8)
+        out[k]["f0_hz"], out[k]["t0_sec"], out[k]["amp"] = f0, t0, amp
+    return out
+
+
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("max_slots", C.c_int), ("max_candidates", C.c_int), ("max_messages", C.c_int),
                 ("min_score", C.c_int), ("ldpc_iterations", C.c_int)]
@@ -249,6 +270,51 @@ class Context:
                                                    freq_osr, protocol, _p(mag), C.c_size_t(mag.stride(0)), C.byref(out_nb), _st(stream)))
         return mag, out_nb.value
 
+    # ---- device-side signal synthesis (csrc/synth.cu) ---------------------------------------------------
+    @staticmethod
+    def _sig_args(signals, first):
+        signals = np.ascontiguousarray(signals, signal_dtype)
+        first = np.ascontiguousarray(first, np.int32)
+        assert first[0] == 0 and first[-1] == signals.size
+        return signals, first
+
+    def synth_raw(self, signals, first, noise_lsb: float, seed: int, first_slot_index: int = 0, bytes_per_slot: int = RAW_SLOT_BYTES, out=None):
+        """signals: signal_dtype array, first: int32[n_slots+1] -> uint8 device tensor [n_slots, bytes_per_slot] of raw RTL IQ."""
+        import torch
+        signals, first = self._sig_args(signals, first)
+        n_slots = first.size - 1
+        stride = (bytes_per_slot + 15) // 16 * 16
+        if out is None:
+            out = torch.empty((n_slots, stride), dtype=torch.uint8, device=torch.device("cuda", self.device))
+        self._chk(self.L.ft8b200_synth_raw(C.c_void_p(self.h), _p(signals), _p(first), n_slots, C.c_float(noise_lsb), C.c_uint64(seed), first_slot_index,
+                                           _p(out), C.c_size_t(out.stride(0)), C.c_size_t(bytes_per_slot), _st(None)))
+        return out
+
+    def synth_slots(self, signals, first, noise_sigma: float, seed: int, first_slot_index: int = 0, n_samples: int = N_SLOT):
+        import torch
+        signals, first = self._sig_args(signals, first)
+        n_slots = first.size - 1
+        d_i = torch.empty((n_slots, n_samples), dtype=torch.float32, device=torch.device("cuda", self.device))
+        d_q = torch.empty_like(d_i)
+        self._chk(self.L.ft8b200_synth_slots(C.c_void_p(self.h), _p(signals), _p(first), n_slots, C.c_float(noise_sigma), C.c_uint64(seed), first_slot_index,
+                                             _p(d_i), _p(d_q), C.c_size_t(n_samples), n_samples, _st(None)))
+        return d_i, d_q
+
+    def synth_audio(self, signals, first, protocol: int, noise_sigma: float, seed: int, first_slot_index: int = 0, n_samples: int = 180_000):
+        import torch
+        signals, first = self._sig_args(signals, first)
+        n_slots = first.size - 1
+        d_a = torch.empty((n_slots, n_samples), dtype=torch.float32, device=torch.device("cuda", self.device))
+        self._chk(self.L.ft8b200_synth_audio(C.c_void_p(self.h), _p(signals), _p(first), n_slots, protocol, C.c_float(noise_sigma), C.c_uint64(seed),
+                                             first_slot_index, _p(d_a), C.c_size_t(n_samples), n_samples, _st(None)))
+        return d_a
+
+    def encode_tones(self, payloads, protocol: int = 1) -> np.ndarray:
+        payloads = np.ascontiguousarray(payloads, np.uint8).reshape(-1, 10)
+        tones = np.zeros((payloads.shape[0], 105), np.uint8)
+        self._chk(self.L.ft8b200_encode_tones(C.c_void_p(self.h), _p(payloads), payloads.shape[0], protocol, _p(tones)))
+        return tones[:, :79] if protocol == 1 else tones
+
     # ---- whole path ----------------------------------------------------------------------------------
     def process_raw(self, iq, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None, stream: int | None = None):
         stride = bytes_per_stream if stride is None else stride
@@ -256,6 +322,10 @@ class Context:
 
     def process_slots(self, d_i, d_q, stream: int | None = None):
         self._chk(self.L.ft8b200_process_slots(C.c_void_p(self.h), _p(d_i), _p(d_q), d_i.shape[0], _st(stream)))
+
+    def process_conditioned(self, d_i, d_q, peak, stream: int | None = None):
+        """Unconditioned samples + their peak max(|I|,|Q|) per slot: decoder()'s 0.5/peak scale is applied on load."""
+        self._chk(self.L.ft8b200_process_conditioned(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), d_i.shape[0], _st(stream)))
 
     def fetch_results(self, n_slots: int, stream: int | None = None):
         res = np.zeros((n_slots, self.M), result_dtype)

@@ -770,3 +770,77 @@ def test_iq_and_c2_files(pkg, ctx, oracle, slots, tmp_path):
     for k in range(3):
         assert nres[k] == want[k]["n"] and res[k].tobytes() == want[k]["results"].tobytes()
     assert nres[0] >= 1
+
+
+# ------------------------------------------------------------------------------------------- device-side synthesis
+def _random_signals(pkg, rng, n, f_lo, f_hi, t_lo, t_hi, amp):
+    items, texts = [], []
+    for _ in range(n):
+        to, de, ex = synth.random_message(rng)
+        items.append((pkg.pack77_std(to, de, ex), float(rng.uniform(f_lo, f_hi)), float(rng.uniform(t_lo, t_hi)), amp))
+        texts.append(f"{to} {de} {ex}")
+    return pkg.make_signals(items), texts
+
+
+def test_encode_tones_on_device(pkg, ctx, oracle):
+    rng = np.random.default_rng(17)
+    payloads = np.stack([np.frombuffer(oracle.pack_std(*synth.random_message(rng)), np.uint8) for _ in range(200)])
+    t8 = ctx.encode_tones(payloads, 1)
+    t4 = ctx.encode_tones(payloads, 0)
+    for k in range(payloads.shape[0]):
+        assert np.array_equal(t8[k], oracle.tones(payloads[k].tobytes()))
+        assert np.array_equal(t4[k], ft8enc.tones_ft4(payloads[k].tobytes()))
+
+
+def test_synth_matches_cpu_twin_and_decodes(pkg, ctx, oracle):
+    """ft8b200_synth_raw / _slots / _audio == oracle/ft8_oracle_synth.c bit for bit (bytes, float bit patterns), for
+    several slots with several signals each, and the noise stream depends only on (seed, slot index)."""
+    rng = np.random.default_rng(23)
+    # raw bytes: 3 slots x 400 000 samples, signals starting inside the window (incl. negative start)
+    sigs, first = [], [0]
+    for s in range(3):
+        g, _ = _random_signals(pkg, rng, s + 1, 200.0, 1400.0, -0.05, 0.05, 20.0 + 10 * s)
+        sigs.append(g); first.append(first[-1] + g.size)
+    allsig = np.concatenate(sigs)
+    n_samp = 400_000
+    raw = ctx.synth_raw(allsig, first, 30.0, 99, first_slot_index=5, bytes_per_slot=2 * n_samp).cpu().numpy()
+    for s in range(3):
+        want = oracle.synth_raw(sigs[s], 30.0, 99, 5 + s, n_samp)
+        assert np.array_equal(raw[s, :2 * n_samp], want), f"raw slot {s}"
+    again = ctx.synth_raw(sigs[2], [0, sigs[2].size], 30.0, 99, first_slot_index=7, bytes_per_slot=2 * n_samp).cpu().numpy()
+    assert np.array_equal(again[0, :2 * n_samp], raw[2, :2 * n_samp]), "slot content must not depend on its position in the batch"
+    assert 25.0 < raw[0, 1::2].astype(np.float64).std() < 40.0   # ~30 LSB of noise + a 20 LSB tone
+    # complex 3200 sps slots
+    g, texts = _random_signals(pkg, rng, 4, 100.0, 1400.0, 0.2, 1.5, 0.3)
+    d_i, d_q = ctx.synth_slots(np.concatenate([g, g[:1]]), [0, 4, 5], 1.0, 5)
+    for s, part in enumerate((g, g[:1])):
+        wi, wq = oracle.synth_float(1, False, part, 1.0, 5, s, 48000)
+        assert bits_equal(d_i[s].cpu().numpy(), wi) and bits_equal(d_q[s].cpu().numpy(), wq)
+    peak = torch.maximum(d_i.abs().amax(1), d_q.abs().amax(1))
+    ctx.process_conditioned(d_i, d_q, peak)
+    res, n = ctx.fetch_results(2)
+    o = oracle.subsystem(*oracle.condition(*oracle.synth_float(1, False, g, 1.0, 5, 0, 48000), 48000)[:2])
+    assert n[0] == o["n"] >= 3 and res[0].tobytes() == o["results"].tobytes()
+    # 12 kHz audio, FT8 and FT4
+    for proto, n_samp in ((1, 180_000), (0, 90_000)):
+        g, texts = _random_signals(pkg, rng, 3, 300.0, 2500.0, 0.3, 1.0, 0.1)
+        d_a = ctx.synth_audio(g, [0, 3], proto, 0.05, 11, n_samples=n_samp)
+        wa, _ = oracle.synth_float(2, proto == 0, g, 0.05, 11, 0, n_samp)
+        assert bits_equal(d_a[0].cpu().numpy(), wa)
+        lines = [pkg.format_decoded(r) for r in pkg.decode_audio(ctx, d_a, 12000, proto)[0]]
+        assert lines == oracle.decode_ft8_lines(wa, 12000, protocol=proto)
+        assert {l.split("~  ")[1] for l in lines} == set(texts)
+
+
+def test_synth_full_raw_slots_decode(pkg, ctx):
+    """Full-size config #2 inputs made on the device: 4 raw 72 MB slots, one message each -> the whole path decodes them."""
+    rng = np.random.default_rng(31)
+    g, texts = _random_signals(pkg, rng, 4, 300.0, 1300.0, 0.3, 0.8, 20.0)
+    for k in range(4):
+        texts[k] = "CQ " + " ".join(texts[k].split()[1:2]) + " FN20"
+        g[k]["payload"] = np.frombuffer(pkg.pack77_std(*texts[k].split()), np.uint8)
+    raw = ctx.synth_raw(g, [0, 1, 2, 3, 4], 30.0, 1)
+    ctx.process_raw(raw, 4)
+    res, n = ctx.fetch_results(4)
+    for k in range(4):
+        assert n[k] >= 1 and res[k][0]["call"].decode() == texts[k].split()[1] and res[k][0]["loc"] == b"FN20"

@@ -97,3 +97,37 @@ def test_wav_and_iq_readers_without_gpu(pkg, tmp_path):
     with pytest.raises(IOError) as e:
         pkg.load_wav(str(tmp_path / "nope.wav"))  # the reference would crash on fread(NULL); here -3
     assert e.value.args[0] == -3
+
+
+def test_pack77_std_matches_the_restated_packer(pkg, oracle):
+    """ft8b200_pack77_std (host code of csrc/synth.cu) == the oracle's restatement of pack77 for standard messages
+    (itself pinned to the reference), and rejects what the type-1 format cannot carry."""
+    from tools import ft8enc, synth
+    rng = np.random.default_rng(9)
+    msgs = [synth.random_message(rng) for _ in range(300)] + [("CQ", "K1JT", "FN20"), ("DE", "W9XYZ", ""), ("QRZ", "K1ABC", "RR73"),
+                                                                ("K1ABC", "W9XYZ", "R-15"), ("K1ABC", "W9XYZ", "+07"), ("CQ", "9A9A", "JN75")]
+    for to, de, ex in msgs:
+        assert pkg.pack77_std(to, de, ex) == oracle.pack_std(to, de, ex) == ft8enc.pack_std(to, de, ex), (to, de, ex)
+    for bad in (("CQ", "TOOLONGCALL", "FN20"), ("CQ", "K1JT", "ZZ99"), ("CQ", "K1JT", "+1X")):
+        with pytest.raises(ValueError):
+            pkg.pack77_std(*bad)
+
+
+def test_cpu_twin_signals_decode_on_the_oracle(pkg, oracle):
+    """The integer signal generator's CPU twin (oracle/ft8_oracle_synth.c): a 3200 sps slot with three messages and a
+    12 kHz FT4 recording decode to exactly those messages through the restated reference path."""
+    from oracle.pyoracle import signal_dtype
+    texts = [("CQ", "K1JT", "FN20"), ("K1ABC", "W9XYZ", "-15"), ("CQ", "9A9A", "JN75")]
+    sig = np.zeros(3, signal_dtype)
+    for k, t in enumerate(texts):
+        sig[k]["payload"] = np.frombuffer(pkg.pack77_std(*t), np.uint8)
+        sig[k]["f0_hz"], sig[k]["t0_sec"], sig[k]["amp"] = 300.0 + 400.0 * k, 0.4 + 0.3 * k, 0.25
+    i_s, q_s = oracle.synth_float(1, False, sig, 1.0, 77, 0, 48000)
+    ci, cq, _ = oracle.condition(i_s, q_s, 48000)
+    got = {m["text"].decode() for m in oracle.subsystem(ci, cq)["msgs"]}
+    assert got == {" ".join(t) for t in texts}
+    sig["f0_hz"] = [500.0, 1200.0, 2100.0]
+    sig["amp"] = 0.1
+    a, _ = oracle.synth_float(2, True, sig, 0.05, 78, 0, 90_000)
+    lines = oracle.decode_ft8_lines(a, 12000, protocol=0)
+    assert {l.split("~  ")[1] for l in lines} == {" ".join(t) for t in texts}
