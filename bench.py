@@ -200,7 +200,10 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # the all_gather of the spot records must not queue behind the decimator's 190k-CTA grid: high-priority NCCL stream
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
 
     B = args.slots
     batch, texts = gen_batch(B, 100_000 * rank, device)
@@ -212,16 +215,20 @@ def main():
     M = pipe.M
     gathered = torch.empty((world * B, M, 28), dtype=torch.uint8, device=device) if world > 1 else None
     gathered_n = torch.empty(world * B, dtype=torch.int32, device=device) if world > 1 else None
+    gather_done = torch.cuda.Event()
 
     def collect():
         """Oldest batch -> host records on rank 0 (multi-GPU: one NCCL all_gather of the fixed-size spot records)."""
+        if world > 1 and os.environ.get("BENCH_NOGATHER"):
+            return pipe.collect(B)   # diagnostic only: how fast would the ranks run without the collective
         if world > 1:
             res_dev, nres_dev = pipe.collect_device()
             dist.all_gather_into_tensor(gathered, res_dev)   # spot records over NVLink
             dist.all_gather_into_tensor(gathered_n, nres_dev)
+            gather_done.record()
+            pipe.depend_on(gather_done)   # the lane's buffers are rewritten only after the collective has read them
             if rank == 0:
-                return gathered.cpu(), gathered_n.cpu()
-            torch.cuda.current_stream().synchronize()
+                return gathered.cpu(), gathered_n.cpu()   # every step's records reach the host on rank 0
             return None
         return pipe.collect(B)
 

@@ -306,6 +306,10 @@ int ft8b200_pipe_collect(ft8b200_pipe_t *p, struct decoder_results *h_results, i
  * copying to the host -- for a collective on the records (NCCL all_gather).  They stay valid until that lane is submitted
  * to again, i.e. finish (synchronise) the collective before the next ft8b200_pipe_submit*. */
 int ft8b200_pipe_collect_device(ft8b200_pipe_t *p, struct decoder_results **d_results, int32_t **d_nresults);
+/* One-shot stream dependency: the kernels of the NEXT submitted batch start only after `cuda_event` (a cudaEvent_t recorded by
+ * the caller, e.g. behind an NCCL all_gather that reads the device buffers handed out by ft8b200_pipe_collect_device) has
+ * completed -- ordering on the device, no host synchronisation. */
+int ft8b200_pipe_depend_on(ft8b200_pipe_t *p, void *cuda_event);
 /* per-stage device times summed over the batches collected since profiling was switched on (ms[0..5] as ft8b200_stage_times) */
 int ft8b200_pipe_set_profiling(ft8b200_pipe_t *p, int on);
 int ft8b200_pipe_stage_times(ft8b200_pipe_t *p, double *ms, int n, uint64_t *batches);

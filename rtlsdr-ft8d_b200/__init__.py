@@ -425,6 +425,10 @@ class Pipe:
     def in_flight(self) -> int:
         return self.L.ft8b200_pipe_in_flight(C.c_void_p(self.h))
 
+    def depend_on(self, event):
+        """event: torch.cuda.Event already recorded; the next submitted batch waits for it on the device."""
+        self._chk(self.L.ft8b200_pipe_depend_on(C.c_void_p(self.h), C.c_void_p(event.cuda_event)))
+
     def set_mode(self, serial: bool, decimator_variant: int = -1):
         self._chk(self.L.ft8b200_pipe_set_mode(C.c_void_p(self.h), 1 if serial else 0, int(decimator_variant)))
 

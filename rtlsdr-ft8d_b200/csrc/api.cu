@@ -179,7 +179,9 @@ ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg_in) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("FT8B200_K1")) ctx->k1_variant = atoi(e);  // experiments; ft8b200_set_decimator_variant is the API
     bool okc = true;
-    okc = okc && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamDefault) == cudaSuccess;
+    // non-blocking: work queued here must not serialise with whatever the host application does on the legacy NULL stream
+    // (e.g. a synchronous cudaMemcpy of gathered records would otherwise wait for every batch in flight)
+    okc = okc && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     // tables, built with the host libm exactly as the reference builds them
     std::vector<float> win(kNfft), thr(257), fir(kFirTaps);
     std::vector<float2> tw(kNfft);

@@ -47,6 +47,7 @@ struct ft8b200_pipe {
     cudaEvent_t prev_front = nullptr;  // front-end-done event of the most recently submitted batch
     cudaEvent_t prev_done = nullptr;   // completion event of the most recently submitted batch
     int mode = FT8B200_PIPE_OVERLAP;
+    cudaEvent_t dependency = nullptr;  // one-shot: the next submit's kernels wait for this event (ft8b200_pipe_depend_on)
     bool profiling = false;
     double stage_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t batches = 0, slots = 0;
@@ -97,6 +98,10 @@ int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t b
         if (stride == bytes_per_stream) PCU(cudaMemcpyAsync(l.d_raw, h_iq, bytes_per_stream * n_slots, cudaMemcpyHostToDevice, l.st));
         else PCU(cudaMemcpy2DAsync(l.d_raw, stride, h_iq, bytes_per_stream, bytes_per_stream, n_slots, cudaMemcpyHostToDevice, l.st));
         d_iq = l.d_raw;
+    }
+    if (p->dependency) {  // e.g. a collective still reading this lane's previous results
+        PCU(cudaStreamWaitEvent(l.st, p->dependency, 0));
+        p->dependency = nullptr;
     }
     if (p->mode == FT8B200_PIPE_OVERLAP) {
         // front ends are serialised across lanes: this batch's decimator starts when the previous batch's has finished
@@ -210,6 +215,12 @@ int ft8b200_pipe_collect(ft8b200_pipe_t *p, struct decoder_results *h_results, i
 
 int ft8b200_pipe_collect_device(ft8b200_pipe_t *p, struct decoder_results **d_results, int32_t **d_nresults) {
     return pop(p, nullptr, nullptr, 0, d_results, d_nresults);
+}
+
+int ft8b200_pipe_depend_on(ft8b200_pipe_t *p, void *cuda_event) {
+    if (!p) return FT8B200_EINVAL;
+    p->dependency = reinterpret_cast<cudaEvent_t>(cuda_event);
+    return 0;
 }
 
 int ft8b200_pipe_set_profiling(ft8b200_pipe_t *p, int on) {
