@@ -118,7 +118,7 @@ int ensure_scratch(ft8b200_ctx_t *ctx, int npos, int n_slots) {
     int rc0 = ctx->scores.ensure((size_t)n_slots * npos * sizeof(int16_t));
     if (rc0) return rc0;
     if ((rc0 = ctx->work.ensure((size_t)n_slots * ctx->cfg.max_candidates * sizeof(uint32_t)))) return rc0;
-    if ((rc0 = ctx->work_total.ensure(sizeof(unsigned int)))) return rc0;
+    if ((rc0 = ctx->work_total.ensure(4 * sizeof(unsigned int)))) return rc0;
     if (npos > ctx->scratch_npos || want > ctx->scratch_slots) {
         const int slots = want > ctx->scratch_slots ? want : ctx->scratch_slots;
         const int np = npos > ctx->scratch_npos ? npos : ctx->scratch_npos;
@@ -198,6 +198,13 @@ ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg_in) {
     okc = okc && cudaMemcpy(ctx->tb.db_thresholds, thr.data(), 257 * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
     okc = okc && cudaMemcpy(ctx->tb.fir, fir.data(), kFirTaps * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
     okc = okc && upload_ldpc_tables() == cudaSuccess;
+    {
+        std::vector<float> blob(waterfall_blob_floats());
+        build_waterfall_tables(win.data(), tw.data(), thr.data(), blob.data());
+        okc = okc && cudaMalloc(&ctx->tb.wf_blob, blob.size() * sizeof(float)) == cudaSuccess;
+        okc = okc && cudaMemcpy(ctx->tb.wf_blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+        okc = okc && upload_waterfall_constants(blob.data()) == cudaSuccess;
+    }
     if (!okc) {
         cuda_fail(cudaGetLastError(), "context initialisation");
         ft8b200_destroy(ctx);
@@ -214,7 +221,7 @@ void ft8b200_destroy(ft8b200_ctx_t *ctx) {
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (cudaEvent_t e : ctx->ev_group) if (e) cudaEventDestroy(e);
-    cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.fir);
+    cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.fir); cudaFree(ctx->tb.wf_blob);
     cudaFree(ctx->tb.mon_window); cudaFree(ctx->tb.mon_twiddle); cudaFree(ctx->tb.mon_super);
     DevBuf *bufs[] = {&ctx->raw, &ctx->sums, &ctx->si, &ctx->sq, &ctx->peak, &ctx->count, &ctx->mag, &ctx->cand, &ctx->ncand, &ctx->ok,
                       &ctx->stage, &ctx->status, &ctx->msg, &ctx->results, &ctx->nresults, &ctx->table, &ctx->scratch, &ctx->scores, &ctx->work, &ctx->work_total};
@@ -289,8 +296,8 @@ int ft8b200_waterfall(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, co
     int rc = ctx_enter(ctx);
     if (rc) return rc;
     if (!d_i || !d_q || !d_mag || n_slots < 1) return fail(FT8B200_EINVAL, "ft8b200_waterfall: bad argument");
-    if (((size_t)d_mag) & 15) return fail(FT8B200_EINVAL, "ft8b200_waterfall: d_mag must be 16-byte aligned");
-    CU(launch_waterfall(ctx->tb, d_i, d_q, d_peak, n_slots, d_mag, pick(ctx, stream), &ctx->launches));
+    if ((((size_t)d_mag) | ((size_t)d_i) | ((size_t)d_q)) & 15) return fail(FT8B200_EINVAL, "ft8b200_waterfall: d_i, d_q and d_mag must be 16-byte aligned");
+    CU(launch_waterfall(ctx->tb, d_i, d_q, d_peak, n_slots, d_mag, ctx->sm_count, pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
 }
@@ -320,7 +327,7 @@ int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_
     if (!d_mag || !d_cand || !d_ncand || !d_ok || !d_stage || !d_status || !d_msg || n_slots < 1)
         return fail(FT8B200_EINVAL, "ft8b200_decode: bad argument");
     CU(launch_decode(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->protocol, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
-                     d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, nullptr, nullptr, pick(ctx, stream), &ctx->launches));
+                     d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, nullptr, nullptr, ctx->sm_count, pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
 }
@@ -362,7 +369,7 @@ static int run_back_end(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, 
     uint8_t *ok = ctx->ok.as<uint8_t>() + (size_t)s0 * K, *stage = ctx->stage.as<uint8_t>() + (size_t)s0 * K;
     mark(ctx, 2, group, false, st);
     // decoder()'s normalisation (when d_peak != NULL) is applied on load inside the waterfall kernel
-    CU(launch_waterfall(ctx->tb, d_i + (size_t)s0 * kSlot, d_q + (size_t)s0 * kSlot, d_peak ? d_peak + s0 : nullptr, n, mag, st, &ctx->launches));
+    CU(launch_waterfall(ctx->tb, d_i + (size_t)s0 * kSlot, d_q + (size_t)s0 * kSlot, d_peak ? d_peak + s0 : nullptr, n, mag, ctx->sm_count, st, &ctx->launches));
     mark(ctx, 2, group, true, st);
     mark(ctx, 3, group, false, st);
     CU(launch_find_sync(mag, kWfBytes, n, 92, 256, 2, 2, PROTO_FT8, ctx->cfg.max_candidates, ctx->cfg.min_score, cand, ncand, ctx->scores.as<int16_t>(),
@@ -372,7 +379,7 @@ static int run_back_end(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, 
     mark(ctx, 4, group, false, st);
     CU(launch_decode(mag, kWfBytes, n, 92, 256, 2, 2, PROTO_FT8, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations, cand, ncand, ok, stage,
                      ctx->status.as<decode_status_t>() + (size_t)s0 * K, ctx->msg.as<message_t>() + (size_t)s0 * K, nullptr, nullptr,
-                     ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), st, &ctx->launches));
+                     ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), ctx->sm_count, st, &ctx->launches));
     mark(ctx, 4, group, true, st);
     mark(ctx, 5, group, false, st);
     CU(launch_spots(n, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, 2, cand, ncand, ok, ctx->msg.as<message_t>() + (size_t)s0 * K,

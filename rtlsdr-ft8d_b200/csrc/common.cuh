@@ -26,6 +26,7 @@ struct DeviceTables {
     float2 *twiddle1024;   // ((float)cos, (float)sin)(-2*pi*k/1024)      kiss_fft.c:351-357
     float *db_thresholds;  // [257] smallest x with quantise(x) >= k       rtlsdr_ft8d.c:1416,1425-1427
     float *fir;            // [57]                                          rtlsdr_ft8d.c:93-110
+    float *wf_blob;        // the three tables above re-laid-out for waterfall1024_kernel (build_waterfall_tables)
     // monitor (12 kHz) tables, built lazily per nfft
     float *mon_window;     // fft_norm-free Hann, nfft floats
     float2 *mon_twiddle;   // nfft/2 complex twiddles
@@ -45,14 +46,17 @@ cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int
 cudaError_t launch_shift_history(BlockSums *d_sums_with_prefix, int n_blocks, cudaStream_t st, int *launches);
 cudaError_t launch_condition(float *d_i, float *d_q, const float *d_peak, int n_slots, cudaStream_t st, int *launches);
 cudaError_t launch_waterfall(const DeviceTables &t, const float *d_i, const float *d_q, const float *d_peak, int n_slots, uint8_t *d_mag,
-                             cudaStream_t st, int *launches);
+                             int sm_count, cudaStream_t st, int *launches);
+void build_waterfall_tables(const float *window, const float2 *tw, const float *thr257, float *blob);
+int waterfall_blob_floats();
+cudaError_t upload_waterfall_constants(const float *blob_host);
 cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
                              int protocol, int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_scratch,
                              int scratch_slots, uint32_t *d_work, unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches);
 cudaError_t launch_decode(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
                           int protocol, int max_cand, int max_iters, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage,
                           decode_status_t *d_status, message_t *d_msg, uint8_t *d_plain, float *d_llr, const uint32_t *d_work,
-                          const unsigned int *d_work_total, cudaStream_t st, int *launches);
+                          const unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches);
 cudaError_t launch_spots(int n_slots, int max_cand, int max_msgs, int min_score, int freq_osr, const candidate_t *d_cand, const int *d_ncand,
                          const uint8_t *d_ok, const message_t *d_msg, struct decoder_results *d_results, int32_t *d_nresults,
                          message_t *d_umsg, float *d_ufreq, int32_t *d_uscore, int32_t *d_ucand, int16_t *d_table, cudaStream_t st, int *launches);

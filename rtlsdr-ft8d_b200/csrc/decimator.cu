@@ -412,6 +412,16 @@ __device__ __forceinline__ void comb(const BlockSums *__restrict__ s, int k, int
 // 57-tap FIR costs one shared load per ~4 taps; coefficients sit in constant memory (uniform broadcast).
 __constant__ float c_fir[kFirTaps];
 
+// (float)((double)sum / (32768.0 * 750)), rtlsdr_ft8d.c:197-198, without the FP64 divide: 24 576 000 = 375 * 2^16, and a float
+// quotient sum/375 can neither be nor come within 2^-34 (relative) of a midpoint between two floats (sum has 24 significant
+// bits, 375 * midpoint has >= 25 and is odd in its last place), so rounding the exact quotient once to float equals rounding it
+// to double first; the 2^-16 is exact while the result stays normal.  Verified over every float mantissa on the CPU
+// (tests/test_oracle_golden.py::test_fir_scale_identity); tiny inputs (never produced by the filter) take the FP64 form.
+__device__ __forceinline__ float scale_out(float sum) {
+    if (fabsf(sum) < 1e-20f) return __double2float_rn(__ddiv_rn((double)sum, 32768.0 * 750));
+    return __fmul_rn(__fdiv_rn(sum, 375.0f), 1.52587890625e-05f);
+}
+
 template <int kN>
 __device__ __forceinline__ void fir_window(const float *__restrict__ y, float (&acc)[kN]) {
     // y[0 .. kN+55]: acc[o] = sum_j y[o+j]*z[j], strictly sequential in j, product rounded before the add (no FMA)
@@ -480,8 +490,8 @@ cic_comb_fir_kernel(const BlockSums *__restrict__ sums, size_t sums_stride, int 
 #pragma unroll
         for (int o = 0; o < kPerThread; ++o) {
             if (kb + o < n_blocks) {
-                vi[o] = __double2float_rn(__ddiv_rn((double)ai[o], 32768.0 * 750));  // rtlsdr_ft8d.c:197-198
-                vq[o] = __double2float_rn(__ddiv_rn((double)aq[o], 32768.0 * 750));
+                vi[o] = scale_out(ai[o]);  // rtlsdr_ft8d.c:197-198
+                vq[o] = scale_out(aq[o]);
             }
         }
     }

@@ -162,7 +162,7 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
     ft8b200_config_t cfg;
     ft8b200_default_config(&cfg);
     if (launch_decode(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, num_candidates, cfg.ldpc_iterations,
-                      g_s.cand, g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, st, &launches) != cudaSuccess)
+                      g_s.cand, g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, 148, st, &launches) != cudaSuccess)
         die("ft8_find_sync (decode kernel)");
     int n = 0;
     g_cache.cand.resize((size_t)num_candidates); g_cache.ok.resize((size_t)num_candidates); g_cache.stage.resize((size_t)num_candidates);
@@ -223,7 +223,7 @@ bool ft8_decode(const waterfall_t *power, const candidate_t *cand, message_t *me
                cudaMemcpyAsync(g_s.cand, cand, sizeof(candidate_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
                cudaMemcpyAsync(g_s.ncand, &one, sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess &&
                launch_decode(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, 1, max_iterations, g_s.cand,
-                             g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, st, &launches) == cudaSuccess &&
+                             g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, 148, st, &launches) == cudaSuccess &&
                cudaMemcpyAsync(&okv, g_s.ok, 1, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                cudaMemcpyAsync(&stage, g_s.stage, 1, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                cudaMemcpyAsync(&s, g_s.status, sizeof(s), cudaMemcpyDeviceToHost, st) == cudaSuccess &&

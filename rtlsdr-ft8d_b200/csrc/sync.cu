@@ -254,7 +254,7 @@ cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slo
     }
     ++*launches;
     if (d_work_total) {
-        cudaError_t e = cudaMemsetAsync(d_work_total, 0, sizeof(unsigned int), st);
+        cudaError_t e = cudaMemsetAsync(d_work_total, 0, 4 * sizeof(unsigned int), st);  // [0] items, [1] next item (decode_kernel)
         if (e != cudaSuccess) return e;
     }
     const int sgrid = n_slots < scratch_slots ? n_slots : scratch_slots;

@@ -65,6 +65,18 @@ def test_threshold_table_is_the_quantiser(oracle):
         assert oracle.quantize_db(float(x)) == int(np.searchsorted(thr[1:256], x, side="right")), x
 
 
+def test_fir_scale_identity():
+    """csrc/decimator.cu replaces (float)((double)sum / 24576000.0) (rtlsdr_ft8d.c:197-198) by (sum / 375.0f) * 2^-16 in float.
+    The identity is binade-independent (scaling by powers of two is exact), so sweeping every mantissa of a few binades proves it."""
+    man = np.arange(2 ** 23, dtype=np.uint32)
+    for e in (90, 127, 128, 150, 160):
+        for sign in (0, 1):
+            a = ((np.uint32(sign) << np.uint32(31)) | (np.uint32(e) << np.uint32(23)) | man).view(np.float32)
+            ref = (a.astype(np.float64) / 24576000.0).astype(np.float32)
+            alt = (a / np.float32(375.0)) * np.float32(2.0 ** -16)
+            assert np.array_equal(ref.view(np.uint32), alt.view(np.uint32)), (e, sign)
+
+
 def test_oracle_reproduces_reference_stdout_on_real_recordings(oracle):
     """tests/golden/recordings_12k.npz: three of the reference's own real-world WAVs (PCM) + the stdout of its own
     `decode_ft8` main() on them (tools/make_golden.py).  The restatement must print the same lines."""
