@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slots", type=int, default=128, help="15 s slots per GPU per step")
+    ap.add_argument("--slots", type=int, default=512, help="15 s slots per GPU per step (36.9 GB of raw IQ per GPU at 512)")
     ap.add_argument("--e2e-slots", type=int, default=8, help="slots per step of the host-buffer (e2e) measurement")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight in the pipelined executor")
     ap.add_argument("--overlap", action="store_true", help="let the back end of batch n share the GPU with the decimator of batch n+1")

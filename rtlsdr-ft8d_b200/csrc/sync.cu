@@ -128,6 +128,127 @@ sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g
     }
 }
 
+// FT8 fast path.  Every term of a score is a difference between a cell P[r][c] and one of its four neighbours, and WHICH
+// neighbours take part depends only on the Costas index k (k = 0 has no earlier symbol, k = 6 no later one, k = 3 is tone 0
+// and has no lower neighbour; tone 7 never occurs) and on the row being the first/last of the waterfall.  So the CTA first
+// turns its tile of the plane into four 16-bit planes, with a = P - P[c+1], b = P - P[c-1], u = r > 0 ? P - P[r-1] : 0,
+// d = r + 1 < nb ? P - P[r+1] : 0:
+//     W0 = a + b + d   (k = 0)     Wm = a + b + u + d   (k = 1,2,4,5)     W3 = a + u + d   (k = 3)     W6 = a + b + u   (k = 6)
+// each stored with a bias of +1024 (so two cells are computed per 32-bit integer operation without borrows between the halves)
+// and with 12 rows before and >= 10 rows after the waterfall holding the biased zero: the reference's `row < 0 -> continue` and
+// `row >= nb -> break` become zero contributions, and a score is 21 loads at compile-time offsets plus 21 adds, minus 21 * 1024.
+// The number of terms it is divided by depends on the time offset only (exact truncating division by multiply-high).
+// The sums are the same integers as the reference's, so the scores are too.
+// grid = (planes * tiles, slots); a tile is kTileF frequency offsets (all 36 time offsets, all rows).
+constexpr int kTileF = 64;
+constexpr int kTilePitch = kTileF + 8;   // 16-bit elements per derived row (71 needed: fo .. fo + 6), 18 groups of 4
+constexpr int kRawPitch = kTileF + 16;   // raw bytes per row: columns fo0 - 4 .. fo0 + 75, whole aligned words
+constexpr int kPadBefore = 12;           // time offsets start at -12
+constexpr uint32_t kBias2 = 0x04000400u; // biased zero, two cells
+__host__ __device__ constexpr int fast_rows(int nb) { return kPadBefore + (nb > 102 ? nb : 102); }  // last row touched: 23 + 72 + 6
+
+// two 16-bit lanes per word, every lane stays non-negative: a' = P + 256 - N in [1, 511]
+__device__ __forceinline__ uint32_t diff2(uint32_t p2, uint32_t n2) { return p2 + 0x01000100u - n2; }
+
+__global__ void __launch_bounds__(kScoreThreads)
+sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int tiles, int16_t *__restrict__ scores_all) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t s_magic[36];
+    const int tid = threadIdx.x, slot = blockIdx.y;
+    const int plane_id = blockIdx.x / tiles, tile = blockIdx.x - plane_id * tiles;
+    const int fo0 = tile * kTileF;
+    const int nb = g.nb, nbins = g.nbins;
+    const int rows = fast_rows(nb);
+    uint8_t *raw = smem;                                                   // [nb][kRawPitch]
+    uint16_t *w0 = reinterpret_cast<uint16_t *>(smem + (((size_t)nb * kRawPitch + 15) & ~(size_t)15));
+    const int plane_elems = rows * kTilePitch;
+    const uint8_t *gplane = mag_all + (size_t)slot * slot_stride + (size_t)plane_id * nbins;  // row r at gplane + r*stride
+
+    // raw tile: words covering columns [fo0 - 4, fo0 + 76), zero outside [0, nbins)
+    constexpr int kWordsPerRow = kRawPitch / 4;
+    for (int v = tid; v < nb * kWordsPerRow; v += kScoreThreads) {
+        const int r = v / kWordsPerRow, wi = v - r * kWordsPerRow;
+        const int c = fo0 - 4 + 4 * wi;
+        uint32_t word = 0;
+        if (c >= 0 && c + 4 <= nbins) word = __ldg(reinterpret_cast<const uint32_t *>(gplane + (size_t)r * g.stride + c));
+        reinterpret_cast<uint32_t *>(raw + (size_t)r * kRawPitch)[wi] = word;
+    }
+    if (tid < 36) {  // number of terms of a score at time offset to = tid - 12 (ft8_sync_score's num_average) -> 2^32 / terms + 1
+        const int to = tid - 12;
+        int terms = 0;
+        for (int grp = 0; grp < 3; ++grp)
+            for (int k = 0; k < 7; ++k) {
+                const int row = to + 36 * grp + k;
+                if (row < 0) continue;
+                if (row >= nb) break;
+                terms += (k == 3 ? 1 : 2) + ((k > 0 && row > 0) ? 1 : 0) + ((k < 6 && row + 1 < nb) ? 1 : 0);
+            }
+        s_magic[tid] = terms > 1 ? (0xffffffffu / (uint32_t)terms + 1u) : 0u;  // 0: divide by 1 (or nothing to divide)
+    }
+    __syncthreads();
+    constexpr int kGroups = kTilePitch / 4;  // 18 groups of 4 cells per row
+    for (int v = tid; v < rows * kGroups; v += kScoreThreads) {
+        const int rp = v / kGroups, q = v - rp * kGroups;
+        const int r = rp - kPadBefore;
+        uint2 o0, om, o3, o6;
+        if (r < 0 || r >= nb) {
+            o0 = om = o3 = o6 = make_uint2(kBias2, kBias2);
+        } else {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(raw + (size_t)r * kRawPitch) + q;  // words: [0] left, [1] the 4 cells, [2] right
+            const uint32_t wl = row[0], wc = row[1], wr = row[2];
+            const uint32_t p01 = __byte_perm(wc, 0u, 0x4140), p23 = __byte_perm(wc, 0u, 0x4342);    // (P0,P1) (P2,P3) as 16-bit lanes
+            const uint32_t l01 = __byte_perm(p01, wl, 0x1017), l23 = __byte_perm(wc, 0u, 0x4241);   // (P-1,P0) (P1,P2); p01/p23 supply the zero bytes
+            const uint32_t r23 = __byte_perm(p23, wr, 0x1412);                                      // (P3,P4)
+            const uint32_t a01 = diff2(p01, l23), a23 = diff2(p23, r23);   // P - right neighbour (right of (P0,P1) is (P1,P2))
+            const uint32_t b01 = diff2(p01, l01), b23 = diff2(p23, l23);   // P - left neighbour
+            uint32_t u01 = 0x01000100u, u23 = 0x01000100u, d01 = 0x01000100u, d23 = 0x01000100u;
+            if (r > 0) {
+                const uint32_t wu = row[-kWordsPerRow + 1];
+                u01 = diff2(p01, __byte_perm(wu, 0u, 0x4140)); u23 = diff2(p23, __byte_perm(wu, 0u, 0x4342));
+            }
+            if (r + 1 < nb) {
+                const uint32_t wd = row[kWordsPerRow + 1];
+                d01 = diff2(p01, __byte_perm(wd, 0u, 0x4140)); d23 = diff2(p23, __byte_perm(wd, 0u, 0x4342));
+            }
+            const uint32_t k1 = 0x01000100u;
+            const uint32_t ab01 = a01 + b01, ab23 = a23 + b23, ud01 = u01 + d01, ud23 = u23 + d23;
+            o0 = make_uint2(ab01 + d01 + k1, ab23 + d23 + k1);
+            om = make_uint2(ab01 + ud01, ab23 + ud23);
+            o3 = make_uint2(a01 + ud01 + k1, a23 + ud23 + k1);
+            o6 = make_uint2(ab01 + u01 + k1, ab23 + u23 + k1);
+        }
+        uint2 *dst = reinterpret_cast<uint2 *>(w0 + (size_t)rp * kTilePitch) + q;
+        dst[0] = o0;
+        dst[plane_elems / 4] = om;
+        dst[2 * (plane_elems / 4)] = o3;
+        dst[3 * (plane_elems / 4)] = o6;
+    }
+    __syncthreads();
+    const int fl = tid & (kTileF - 1), fo = fo0 + fl;
+    if (fo >= g.nfo) return;
+    int16_t *scores = scores_all + (size_t)slot * g.npos + (size_t)plane_id * 36 * g.nfo;
+    constexpr int kCostas8[7] = {3, 1, 4, 0, 6, 5, 2};
+    for (int ti = tid / kTileF; ti < 36; ti += kScoreThreads / kTileF) {  // warp-uniform time offset to = ti - 12: padded row = ti + 36 grp + k
+        const uint16_t *b0 = w0 + ti * kTilePitch + fl, *bm = b0 + plane_elems, *b3 = bm + plane_elems, *b6 = b3 + plane_elems;
+        int sum = 0;
+#pragma unroll
+        for (int grp = 0; grp < 3; ++grp) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const uint16_t *w = k == 0 ? b0 : (k == 3 ? b3 : (k == 6 ? b6 : bm));
+                sum += w[(36 * grp + k) * kTilePitch + kCostas8[k]];
+            }
+        }
+        int score = sum - 21 * 1024;
+        const uint32_t magic = s_magic[ti];
+        if (magic) {  // truncating division by the number of terms
+            const uint32_t mag_q = __umulhi((uint32_t)(score < 0 ? -score : score), magic);
+            score = score < 0 ? -(int)mag_q : (int)mag_q;
+        }
+        scores[ti * g.nfo + fo] = (int16_t)score;
+    }
+}
+
 // Phase 2: one CTA per slot (looping over slots): ordered compaction of the positions with score >= min_score,
 // then the exact heap replay by one thread, then the candidates are appended to the decode work list.
 __global__ void __launch_bounds__(kSyncThreads)
@@ -237,7 +358,14 @@ cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slo
     dim3 grid(planes * splits, n_slots);
     const size_t staged = ((size_t)g.nb * g.nbins + 15) & ~(size_t)15;
     const bool ft4 = protocol == PROTO_FT4;
-    if (staged <= 200 * 1024) {
+    const size_t fast_smem = (((size_t)g.nb * kRawPitch + 15) & ~(size_t)15) + (size_t)4 * fast_rows(g.nb) * kTilePitch * sizeof(int16_t);
+    if (!ft4 && fast_smem <= 96 * 1024 && (((size_t)d_mag | slot_stride | (size_t)g.stride | (size_t)g.nbins) & 3) == 0) {
+        // FT8 fast path: derived int16 planes per (plane, tile of 64 frequency offsets)
+        const int tiles = (g.nfo + kTileF - 1) / kTileF;
+        cudaError_t e = cudaFuncSetAttribute(sync_score_ft8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return e;
+        sync_score_ft8_kernel<<<dim3(planes * tiles, n_slots), kScoreThreads, fast_smem, st>>>(d_mag, slot_stride, g, tiles, d_scores);
+    } else if (staged <= 200 * 1024) {
         if (g.nbins == 256 && !ft4) {
             sync_score_kernel<256, true, false><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
         } else {
