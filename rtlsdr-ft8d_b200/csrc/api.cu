@@ -112,7 +112,7 @@ int ensure_slot_buffers(ft8b200_ctx_t *ctx, int n_slots) {
 
 int ensure_scratch(ft8b200_ctx_t *ctx, int npos, int n_slots) {
     // one compaction list per resident CTA of the sync kernel (it loops over slots)
-    int want = ctx->sm_count * 2;
+    int want = ctx->sm_count * 6;  // 256-thread CTAs, 6 resident per SM
     if (want > n_slots) want = n_slots;
     if (want < 1) want = 1;
     int rc0 = ctx->scores.ensure((size_t)n_slots * npos * sizeof(int16_t));

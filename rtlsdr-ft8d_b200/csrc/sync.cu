@@ -14,7 +14,7 @@
 namespace ft8b200 {
 namespace {
 
-constexpr int kSyncThreads = 1024;
+constexpr int kSyncThreads = 256;  // small CTAs: the heap replay is one thread's latency, so many slots should be resident per SM
 
 struct Geo { int nb, nbins, tosr, fosr, stride, nfo, npos; };
 
@@ -266,7 +266,8 @@ sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, i
         // Ordered compaction with ONE block barrier: warp w owns the contiguous positions [w*span, (w+1)*span); it counts
         // its survivors, the warp totals are prefix-summed, then it writes its survivors at its offset (position order ==
         // the reference's loop order).  Scores are re-read in the second sweep (L1/L2 hits).
-        const int span = ((g.npos + 31) / 32 + 31) / 32 * 32;  // positions per warp, multiple of 32
+        constexpr int kSelWarps = kSyncThreads / 32;
+        const int span = ((g.npos + kSelWarps - 1) / kSelWarps + 31) / 32 * 32;  // positions per warp, multiple of 32
         const int w0 = warp * span;
         int mine = 0;
 #pragma unroll 4
@@ -277,7 +278,7 @@ sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, i
         }
         if (lane == 0) s_warp_cnt[0][warp] = mine;
         __syncthreads();
-        const int cnt = s_warp_cnt[0][lane];
+        const int cnt = lane < kSelWarps ? s_warp_cnt[0][lane] : 0;
         int running = __reduce_add_sync(0xffffffffu, lane < warp ? cnt : 0);
         const int n_pass_total = __reduce_add_sync(0xffffffffu, cnt);
 #pragma unroll 4
