@@ -170,8 +170,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=512, help="15 s slots per GPU per step (36.9 GB of raw IQ per GPU at 512)")
     ap.add_argument("--e2e-slots", type=int, default=8, help="slots per step of the host-buffer (e2e) measurement")
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight in the pipelined executor")
-    ap.add_argument("--overlap", action="store_true", help="let the back end of batch n share the GPU with the decimator of batch n+1")
+    ap.add_argument("--chunks", type=int, default=4, help="executor batches per step: a step's slots are submitted to ft8b200_pipe_t in this many batches")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the pipelined executor")
+    ap.add_argument("--back-sms", type=int, default=40, help="SMs of the back-end partition (waterfall/sync/LDPC of batch n next to the decimator "
+                                                             "of batch n+1 on the other SMs); 0 = no partition, kernels of consecutive batches run serially")
+    ap.add_argument("--overlap", action="store_true", help="(without a partition) let the back end of batch n time-share the GPU with the decimator of batch n+1")
     ap.add_argument("--k1-variant", type=int, default=0, help="0 = streaming cic_block_sums kernel, 1..6 = bulk-copy (TMA) variants")
     ap.add_argument("--cpu-slots", type=int, default=96, help="bounded CPU-baseline sample (slots)")
     args = ap.parse_args()
@@ -186,7 +189,10 @@ def main():
               "slots_per_gpu_per_step": args.slots, "input_bytes_per_step_per_gpu": args.slots * RAW_SLOT_BYTES,
               "l2": "inputs larger than L2 (%.1f GB per step per GPU vs 126 MB)" % (args.slots * RAW_SLOT_BYTES / 1e9),
               "max_candidates": 120, "max_messages": 50, "ldpc_iterations": 20,
-              "executor": "ft8b200_pipe_t depth %d, %s" % (args.depth, "overlap" if args.overlap else "serial (kernels of consecutive batches do not share the GPU)"),
+              "executor": "ft8b200_pipe_t depth %d, %d batches of %d slots per step, %s" % (
+                  args.depth, args.chunks, args.slots // max(args.chunks, 1),
+                  ("SM partition: back end of batch n on >= %d SMs, decimator of batch n+1 on the others" % args.back_sms) if args.back_sms > 0 else
+                  ("overlap (time-shared)" if args.overlap else "serial (kernels of consecutive batches do not share the GPU)")),
               "parallelism": "slots sharded across GPUs, no data-path collective; "
               "spot records gathered with NCCL all_gather" if world > 1 else "single GPU"}
 
@@ -206,21 +212,27 @@ def main():
         dist.init_process_group("nccl", device_id=device, pg_options=opts)
 
     B = args.slots
+    if args.chunks < 1 or B % args.chunks:
+        raise SystemExit("--slots must be a multiple of --chunks")
+    Bc = B // args.chunks   # slots per executor batch
     batch, texts = gen_batch(B, 100_000 * rank, device)
     torch.cuda.synchronize()
     # The product's batch executor (ft8b200_pipe_t): `depth` batches in flight; in SERIAL mode the kernels of consecutive
     # batches never share the GPU (each kernel is timed alone), only D2H of the records and host work overlap them.
     pipe = pkg.Pipe(local, args.depth)
     pipe.set_mode(serial=not args.overlap, decimator_variant=args.k1_variant)
+    if args.back_sms > 0:
+        # green contexts: disjoint SM sets for the HBM-bound decimator and the issue-bound back end (ft8b200_pipe_set_partition)
+        config["sm_partition"] = dict(zip(("front_sms", "back_sms"), pipe.set_partition(args.back_sms)))
     M = pipe.M
-    gathered = torch.empty((world * B, M, 28), dtype=torch.uint8, device=device) if world > 1 else None
-    gathered_n = torch.empty(world * B, dtype=torch.int32, device=device) if world > 1 else None
+    gathered = torch.empty((world * Bc, M, 28), dtype=torch.uint8, device=device) if world > 1 else None
+    gathered_n = torch.empty(world * Bc, dtype=torch.int32, device=device) if world > 1 else None
     gather_done = torch.cuda.Event()
 
     def collect():
         """Oldest batch -> host records on rank 0 (multi-GPU: one NCCL all_gather of the fixed-size spot records)."""
         if world > 1 and os.environ.get("BENCH_NOGATHER"):
-            return pipe.collect(B)   # diagnostic only: how fast would the ranks run without the collective
+            return pipe.collect(Bc)   # diagnostic only: how fast would the ranks run without the collective
         if world > 1:
             res_dev, nres_dev = pipe.collect_device()
             dist.all_gather_into_tensor(gathered, res_dev)   # spot records over NVLink
@@ -228,19 +240,25 @@ def main():
             gather_done.record()
             pipe.depend_on(gather_done)   # the lane's buffers are rewritten only after the collective has read them
             if rank == 0:
-                return gathered.cpu(), gathered_n.cpu()   # every step's records reach the host on rank 0
+                return gathered.cpu(), gathered_n.cpu()   # every batch's records reach the host on rank 0
             return None
-        return pipe.collect(B)
+        return pipe.collect(Bc)
 
     def run(steps):
-        out = None
+        """`steps` passes over the B resident slots, each submitted as args.chunks executor batches; every batch's spot
+        records are read back.  Returns the records of the last pass in slot order."""
+        outs = []
         for _ in range(steps):
-            if pipe.in_flight() == pipe.depth:
-                out = collect()
-            pipe.submit(batch, B)
+            for c in range(args.chunks):
+                if pipe.in_flight() == pipe.depth:
+                    outs.append(collect())
+                pipe.submit(batch[c * Bc:(c + 1) * Bc], Bc)
         while pipe.in_flight():
-            out = collect()
-        return out
+            outs.append(collect())
+        last = outs[-args.chunks:]
+        if last[0] is None:
+            return None
+        return np.concatenate([np.asarray(o[0]) for o in last]), np.concatenate([np.asarray(o[1]) for o in last])
 
     out = run(args.warmup)
     # correctness guard on the first batch: every synthetic slot must decode to its own message
@@ -328,18 +346,20 @@ def main():
     n_prof = max(n_prof, 1)
     k1_ms = stage_acc.get("block_sums", 0.0) / n_prof
     k2_ms = stage_acc.get("comb_fir", 0.0) / n_prof
-    achieved = B * ALGO_BYTES_PER_SLOT / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    achieved = Bc * ALGO_BYTES_PER_SLOT / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
     roofline = {"kernel": "cic_block_sums_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured, burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_SLOT, "launch_ms": k1_ms,
+                "algorithmic_bytes_per_launch": Bc * ALGO_BYTES_PER_SLOT, "slots_per_launch": Bc, "launch_ms": k1_ms,
                 "decimator_ms_incl_comb_fir": k1_ms + k2_ms,
-                "decimator_msps": B * 36.0 / ((k1_ms + k2_ms) * 1e-3) if k1_ms > 0 else None,
+                "decimator_msps": Bc * 36.0 / ((k1_ms + k2_ms) * 1e-3) if k1_ms > 0 else None,
                 "timed": "CUDA events around every launch of the kernel inside the timed region (%d launches)" % n_prof,
-                "stage_ms_per_step": {k: v / n_prof for k, v in stage_acc.items()}}
+                "stage_ms_per_launch": {k: v / n_prof for k, v in stage_acc.items()},
+                "stage_note": "with an SM partition the back-end stages (comb_fir ... spots) run on the back-end SMs concurrently with the "
+                              "next batch's block sums: their times overlap it and do not add to the step" if args.back_sms > 0 else "stages run back to back"}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))  # one `ncu --set full` capture, per slot
-        roofline["traffic"] = tr.get("dram_bytes_per_slot", 0) * B or None
+        roofline["traffic"] = tr.get("dram_bytes_per_slot", 0) * Bc or None
         roofline["traffic_source"] = tr.get("source")
     except Exception:
         pass

@@ -248,6 +248,8 @@ int ft8b200_set_profiling(ft8b200_ctx_t *ctx, int on);
  * (default 0 = off; results are identical either way; only worthwhile when a group still holds >= ~64 slots). */
 int ft8b200_set_overlap(ft8b200_ctx_t *ctx, int groups);
 int ft8b200_stage_times(ft8b200_ctx_t *ctx, float *ms, int n);
+/* begin/end of each stage of the last process_* call in ms since `ref_event` (a timing cudaEvent_t recorded earlier) */
+int ft8b200_stage_marks(ft8b200_ctx_t *ctx, void *ref_event, float *begin_ms, float *end_ms, int n);
 /* on: ft8b200_process_raw runs its back end (waterfall ... spots) on the context's high-priority side stream even for a
  * single slot group, and ft8b200_front_event() returns the cudaEvent_t (as void*) recorded on the launching stream right
  * after the decimator of the last call -- what ft8b200_pipe_t chains its lanes with. */
@@ -261,6 +263,10 @@ int ft8b200_set_protocol(ft8b200_ctx_t *ctx, int protocol);
  * consumer warps doing the arithmetic) which leaves most of each SM free for the back-end kernels of another batch.
  * Results are identical. */
 int ft8b200_set_decimator_variant(ft8b200_ctx_t *ctx, int variant);
+/* Run the context's work on caller-owned streams (cudaStream_t as void*): `front_stream` replaces the context's launching
+ * stream, `back_stream` its back-end side stream, whose kernels size their persistent grids for `back_sm_count` SMs.
+ * NULL restores the context's own stream.  Used by ft8b200_pipe_set_partition with green-context streams. */
+int ft8b200_set_partition_streams(ft8b200_ctx_t *ctx, void *front_stream, void *back_stream, int back_sm_count);
 void *ft8b200_front_event(ft8b200_ctx_t *ctx);
 /* device pointers to the last batch's outputs: results (n_slots x max_messages), counts (n_slots) */
 int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults);
@@ -295,6 +301,12 @@ ft8b200_pipe_t *ft8b200_pipe_create(const ft8b200_config_t *cfg, int depth);
 #define FT8B200_PIPE_OVERLAP 0
 #define FT8B200_PIPE_SERIAL 1
 int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant);
+/* Spatial partition (CUDA green contexts, resolved from the driver at run time): the HBM-bound front end (cic_block_sums,
+ * comb+FIR) of batch n+1 runs on one disjoint set of SMs while the issue/latency-bound back end (waterfall, sync, LDPC,
+ * spots) of batch n runs on the other `back_sms` SMs (rounded up by the driver to its granularity, 8 SMs on sm_100; the
+ * sizes actually provisioned come back through front_sms/back_sms, either may be NULL).  Implies FT8B200_PIPE_OVERLAP.
+ * back_sms == 0 removes the partition.  Results are identical in every mode.  Needs depth >= 2 and no batch in flight. */
+int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms, int *back_sms_out);
 void ft8b200_pipe_destroy(ft8b200_pipe_t *p);
 const char *ft8b200_pipe_error(ft8b200_pipe_t *p);
 int ft8b200_pipe_depth(ft8b200_pipe_t *p);
@@ -313,6 +325,9 @@ int ft8b200_pipe_depend_on(ft8b200_pipe_t *p, void *cuda_event);
 /* per-stage device times summed over the batches collected since profiling was switched on (ms[0..5] as ft8b200_stage_times) */
 int ft8b200_pipe_set_profiling(ft8b200_pipe_t *p, int on);
 int ft8b200_pipe_stage_times(ft8b200_pipe_t *p, double *ms, int n, uint64_t *batches);
+/* device timeline of those batches: 12 floats each (begin, end of the six stages, ms since profiling was switched on);
+ * returns how many batches were written.  Shows what actually overlapped. */
+int ft8b200_pipe_timeline(ft8b200_pipe_t *p, float *out, int max_batches);
 uint64_t ft8b200_pipe_kernel_launches(ft8b200_pipe_t *p);
 
 /* Receiver streams for rtlsdr_callback(): persistent decimator state, double-buffered 15 s slots. */

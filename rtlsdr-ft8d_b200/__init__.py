@@ -432,6 +432,19 @@ class Pipe:
     def set_mode(self, serial: bool, decimator_variant: int = -1):
         self._chk(self.L.ft8b200_pipe_set_mode(C.c_void_p(self.h), 1 if serial else 0, int(decimator_variant)))
 
+    def timeline(self, max_batches: int = 64):
+        """float32[n, 6, 2]: begin/end (ms since set_profiling(True)) of the six stages of each collected batch."""
+        out = np.zeros((max_batches, 6, 2), np.float32)
+        n = self._chk(self.L.ft8b200_pipe_timeline(C.c_void_p(self.h), _p(out), max_batches))
+        return out[:n]
+
+    def set_partition(self, back_sms: int):
+        """Disjoint SM sets (green contexts) for the front end of batch n+1 and the back end of batch n; 0 removes it.
+        Returns (front_sms, back_sms) as provisioned by the driver."""
+        f, b = C.c_int(0), C.c_int(0)
+        self._chk(self.L.ft8b200_pipe_set_partition(C.c_void_p(self.h), int(back_sms), C.byref(f), C.byref(b)))
+        return f.value, b.value
+
     def submit(self, iq, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None):
         """iq: device tensor (already complete on the device) -> queued on the next lane."""
         stride = bytes_per_stream if stride is None else stride

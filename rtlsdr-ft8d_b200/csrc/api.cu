@@ -56,7 +56,8 @@ constexpr int kMaxGroups = 16;
 
 struct ft8b200_ctx {
     ft8b200_config_t cfg;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;         // effective launching stream: own_stream, or the front-end partition's stream
+    cudaStream_t own_stream = nullptr;
     DeviceTables tb = {};
     int launches = 0;
     uint64_t launches_total = 0;
@@ -71,10 +72,13 @@ struct ft8b200_ctx {
     int protocol = PROTO_FT8;              // what ft8b200_find_sync / ft8b200_decode score and demap (ft8b200_set_protocol)
     int k1_variant = 0;                    // 0 = streaming cic_block_sums kernel, >= 1 = persistent bulk-copy kernel (shape index)
     bool side_back = false;                // back end on the high-priority side stream even with a single group (pipe lanes)
-    cudaEvent_t ev_front = nullptr;        // recorded on the launching stream when the last process_raw's decimator was queued
+    cudaEvent_t ev_front = nullptr;        // recorded on the launching stream right after the last process_raw's cic_block_sums
+    cudaEvent_t ev_k1 = nullptr;
     cudaEvent_t ev[6][kMaxGroups][2] = {};
     bool ev_valid[6][kMaxGroups] = {};
     cudaStream_t aux = nullptr;            // high-priority side stream for the back end of a slot group
+    cudaStream_t own_aux = nullptr;
+    int sm_back = 0;                       // SMs the back-end kernels size their persistent grids for (0 = sm_count)
     cudaEvent_t ev_join = nullptr;
     cudaEvent_t ev_group[kMaxGroups] = {};
     std::mutex mu;
@@ -181,7 +185,8 @@ ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg_in) {
     bool okc = true;
     // non-blocking: work queued here must not serialise with whatever the host application does on the legacy NULL stream
     // (e.g. a synchronous cudaMemcpy of gathered records would otherwise wait for every batch in flight)
-    okc = okc && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    okc = okc && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ctx->stream = ctx->own_stream;
     // tables, built with the host libm exactly as the reference builds them
     std::vector<float> win(kNfft), thr(257), fir(kFirTaps);
     std::vector<float2> tw(kNfft);
@@ -216,10 +221,13 @@ ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg_in) {
 void ft8b200_destroy(ft8b200_ctx_t *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
-    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
     for (auto &s : ctx->ev) for (auto &g : s) for (cudaEvent_t e : g) if (e) cudaEventDestroy(e);
-    if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
+    if (ctx->aux) cudaStreamSynchronize(ctx->aux);
+    if (ctx->own_aux) { cudaStreamSynchronize(ctx->own_aux); cudaStreamDestroy(ctx->own_aux); }
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     for (cudaEvent_t e : ctx->ev_group) if (e) cudaEventDestroy(e);
     cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.fir); cudaFree(ctx->tb.wf_blob);
     cudaFree(ctx->tb.mon_window); cudaFree(ctx->tb.mon_twiddle); cudaFree(ctx->tb.mon_super);
@@ -367,19 +375,20 @@ static int run_back_end(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, 
     candidate_t *cand = ctx->cand.as<candidate_t>() + (size_t)s0 * K;
     int *ncand = ctx->ncand.as<int>() + s0;
     uint8_t *ok = ctx->ok.as<uint8_t>() + (size_t)s0 * K, *stage = ctx->stage.as<uint8_t>() + (size_t)s0 * K;
+    const int sms = (ctx->sm_back > 0 && st == ctx->aux) ? ctx->sm_back : ctx->sm_count;  // persistent grids fit the back-end partition
     mark(ctx, 2, group, false, st);
     // decoder()'s normalisation (when d_peak != NULL) is applied on load inside the waterfall kernel
-    CU(launch_waterfall(ctx->tb, d_i + (size_t)s0 * kSlot, d_q + (size_t)s0 * kSlot, d_peak ? d_peak + s0 : nullptr, n, mag, ctx->sm_count, st, &ctx->launches));
+    CU(launch_waterfall(ctx->tb, d_i + (size_t)s0 * kSlot, d_q + (size_t)s0 * kSlot, d_peak ? d_peak + s0 : nullptr, n, mag, sms, st, &ctx->launches));
     mark(ctx, 2, group, true, st);
     mark(ctx, 3, group, false, st);
     CU(launch_find_sync(mag, kWfBytes, n, 92, 256, 2, 2, PROTO_FT8, ctx->cfg.max_candidates, ctx->cfg.min_score, cand, ncand, ctx->scores.as<int16_t>(),
-                        ctx->scratch.as<uint32_t>(), ctx->scratch_slots, ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), ctx->sm_count,
+                        ctx->scratch.as<uint32_t>(), ctx->scratch_slots, ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), sms,
                         st, &ctx->launches));
     mark(ctx, 3, group, true, st);
     mark(ctx, 4, group, false, st);
     CU(launch_decode(mag, kWfBytes, n, 92, 256, 2, 2, PROTO_FT8, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations, cand, ncand, ok, stage,
                      ctx->status.as<decode_status_t>() + (size_t)s0 * K, ctx->msg.as<message_t>() + (size_t)s0 * K, nullptr, nullptr,
-                     ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), ctx->sm_count, st, &ctx->launches));
+                     ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), sms, st, &ctx->launches));
     mark(ctx, 4, group, true, st);
     mark(ctx, 5, group, false, st);
     CU(launch_spots(n, ctx->cfg.max_candidates, ctx->cfg.max_messages, ctx->cfg.min_score, 2, cand, ncand, ok, ctx->msg.as<message_t>() + (size_t)s0 * K,
@@ -393,8 +402,12 @@ static int ensure_aux(ft8b200_ctx_t *ctx) {
     if (!ctx->aux) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = highest priority
-        CU(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&ctx->own_aux, cudaStreamNonBlocking, hi));
+        ctx->aux = ctx->own_aux;
+    }
+    if (!ctx->ev_join) {
         CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_k1, cudaEventDisableTiming));
         for (cudaEvent_t &e : ctx->ev_group) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     return 0;
@@ -448,15 +461,28 @@ static int process_raw_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t byte
         mark(ctx, 0, g, false, st);
         CU(launch_cic_block_sums(d_iq + (size_t)s0 * stream_stride_bytes, stream_stride_bytes, n, blocks, sg, sstride, ctx->k1_variant, ctx->sm_count, st, &ctx->launches));
         mark(ctx, 0, g, true, st);
-        mark(ctx, 1, g, false, st);
-        CU(launch_cic_comb_fir(sg, sstride, blocks, 0, true, n, ctx->tb.fir, ctx->si.as<float>() + (size_t)r0 * kSlot,
-                               ctx->sq.as<float>() + (size_t)r0 * kSlot, ctx->count.as<uint32_t>() + r0, ctx->peak.as<float>() + r0, nullptr, st,
-                               &ctx->launches, segs, (long long)(seg_bytes / 2)));
-        mark(ctx, 1, g, true, st);
-        if (side) {
+        if (side && s0 + per >= n_slots) {
+            // the next batch's block sums (another lane) may start now: comb+FIR below is 2 % of the front end's bytes and
+            // fills the ramp-up of that kernel instead of leaving the memory system idle between batches
+            CU(cudaEventRecord(ctx->ev_k1, st));
+            ctx->ev_front = ctx->ev_k1;
+        }
+        // With an SM partition the comb+FIR pass belongs to the back end's SM set: it is a whole-GPU grid, and on the front
+        // set its CTAs would queue ahead of the next batch's block sums (measured: the two then run back to back).
+        cudaStream_t fst = st;
+        if (side && ctx->sm_back > 0) {
             CU(cudaEventRecord(ctx->ev_group[g], st));
             CU(cudaStreamWaitEvent(back, ctx->ev_group[g], 0));
-            ctx->ev_front = ctx->ev_group[g];
+            fst = back;
+        }
+        mark(ctx, 1, g, false, fst);
+        CU(launch_cic_comb_fir(sg, sstride, blocks, 0, true, n, ctx->tb.fir, ctx->si.as<float>() + (size_t)r0 * kSlot,
+                               ctx->sq.as<float>() + (size_t)r0 * kSlot, ctx->count.as<uint32_t>() + r0, ctx->peak.as<float>() + r0, nullptr, fst,
+                               &ctx->launches, segs, (long long)(seg_bytes / 2)));
+        mark(ctx, 1, g, true, fst);
+        if (side && fst == st) {
+            CU(cudaEventRecord(ctx->ev_group[g], st));
+            CU(cudaStreamWaitEvent(back, ctx->ev_group[g], 0));
         }
         if ((rc = run_back_end(ctx, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), r0, nr, g, back))) return rc;
     }
@@ -514,6 +540,17 @@ int ft8b200_set_side_backend(ft8b200_ctx_t *ctx, int on) {
     return 0;
 }
 
+int ft8b200_set_partition_streams(ft8b200_ctx_t *ctx, void *front_stream, void *back_stream, int back_sm_count) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux) cudaStreamSynchronize(ctx->aux);
+    ctx->stream = front_stream ? reinterpret_cast<cudaStream_t>(front_stream) : ctx->own_stream;
+    ctx->aux = back_stream ? reinterpret_cast<cudaStream_t>(back_stream) : ctx->own_aux;
+    ctx->sm_back = back_stream ? back_sm_count : 0;
+    return 0;
+}
+
 int ft8b200_set_protocol(ft8b200_ctx_t *ctx, int protocol) {
     if (!ctx || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return fail(FT8B200_EINVAL, "ft8b200_set_protocol: PROTO_FT4 or PROTO_FT8");
     ctx->protocol = protocol;
@@ -547,6 +584,30 @@ int ft8b200_stage_times(ft8b200_ctx_t *ctx, float *ms, int n) {
             any = true;
         }
         ms[k] = any ? total : -1.0f;
+    }
+    return 0;
+}
+
+// Timeline of the last process_* call: begin_ms[k] / end_ms[k] = device time of stage k's first start / last end mark,
+// measured from `ref_event` (a timing-enabled cudaEvent_t recorded earlier by the caller); -1 = stage not run.
+int ft8b200_stage_marks(ft8b200_ctx_t *ctx, void *ref_event, float *begin_ms, float *end_ms, int n) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!ref_event || !begin_ms || !end_ms || n < 6) return fail(FT8B200_EINVAL, "ft8b200_stage_marks: bad argument");
+    cudaEvent_t ref = reinterpret_cast<cudaEvent_t>(ref_event);
+    for (int k = 0; k < 6; ++k) {
+        float b = -1.0f, e = -1.0f;
+        for (int g = 0; g < kMaxGroups; ++g) {
+            if (!ctx->ev_valid[k][g]) continue;
+            float t0 = 0.0f, t1 = 0.0f;
+            CU(cudaEventSynchronize(ctx->ev[k][g][1]));
+            CU(cudaEventElapsedTime(&t0, ref, ctx->ev[k][g][0]));
+            CU(cudaEventElapsedTime(&t1, ref, ctx->ev[k][g][1]));
+            if (b < 0.0f || t0 < b) b = t0;
+            if (t1 > e) e = t1;
+        }
+        begin_ms[k] = b;
+        end_ms[k] = e;
     }
     return 0;
 }

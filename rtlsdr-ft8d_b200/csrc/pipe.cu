@@ -18,6 +18,7 @@
 // i.e. "receive slot n+1 while slot n decodes" -- here across batches of slots on one GPU.
 #include "common.cuh"
 
+#include <cuda.h>  // types and prototypes only: the driver entry points are resolved through cudaGetDriverEntryPoint, libcuda is not linked
 #include <string.h>
 
 #include <string>
@@ -35,7 +36,51 @@ struct Lane {
     size_t res_slots = 0;
     cudaEvent_t done = nullptr;
     int n_slots = 0;
+    CUstream part_front = nullptr, part_back = nullptr;  // streams of the two SM partitions (ft8b200_pipe_set_partition)
 };
+
+// Spatial partition of the GPU (CUDA green contexts): the HBM-bound front end (cic_block_sums, comb+FIR) of batch n+1 owns
+// `front_sms` SMs, the issue/latency-bound back end (waterfall, sync, LDPC, spots) of batch n owns the other `back_sms`.
+// Time-sharing the same SMs was measured not to pay (the back-end CTAs displace decimator CTAs, whose loads in flight are
+// what saturates HBM); with disjoint SM sets the decimator keeps its residency and the back end runs in its shadow.
+struct Partition {
+    CUgreenCtx front = nullptr, back = nullptr;
+    int front_sms = 0, back_sms = 0;
+};
+
+struct DriverApi {
+    decltype(&cuDeviceGet) DeviceGet = nullptr;
+    decltype(&cuDeviceGetDevResource) DeviceGetDevResource = nullptr;
+    decltype(&cuDevSmResourceSplitByCount) DevSmResourceSplitByCount = nullptr;
+    decltype(&cuDevResourceGenerateDesc) DevResourceGenerateDesc = nullptr;
+    decltype(&cuGreenCtxCreate) GreenCtxCreate = nullptr;
+    decltype(&cuGreenCtxDestroy) GreenCtxDestroy = nullptr;
+    decltype(&cuGreenCtxStreamCreate) GreenCtxStreamCreate = nullptr;
+    decltype(&cuStreamDestroy) StreamDestroy = nullptr;
+    bool ok = false;
+};
+
+const DriverApi &driver_api() {
+    static DriverApi api = [] {
+        DriverApi a;
+        bool ok = true;
+        auto get = [&](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) ok = false;
+        };
+        get("cuDeviceGet", reinterpret_cast<void **>(&a.DeviceGet));
+        get("cuDeviceGetDevResource", reinterpret_cast<void **>(&a.DeviceGetDevResource));
+        get("cuDevSmResourceSplitByCount", reinterpret_cast<void **>(&a.DevSmResourceSplitByCount));
+        get("cuDevResourceGenerateDesc", reinterpret_cast<void **>(&a.DevResourceGenerateDesc));
+        get("cuGreenCtxCreate", reinterpret_cast<void **>(&a.GreenCtxCreate));
+        get("cuGreenCtxDestroy", reinterpret_cast<void **>(&a.GreenCtxDestroy));
+        get("cuGreenCtxStreamCreate", reinterpret_cast<void **>(&a.GreenCtxStreamCreate));
+        get("cuStreamDestroy", reinterpret_cast<void **>(&a.StreamDestroy));
+        a.ok = ok;
+        return a;
+    }();
+    return api;
+}
 
 }  // namespace
 
@@ -51,6 +96,9 @@ struct ft8b200_pipe {
     bool profiling = false;
     double stage_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t batches = 0, slots = 0;
+    cudaEvent_t t_ref = nullptr;           // recorded when profiling is switched on: origin of the timeline
+    std::vector<float> timeline;           // 12 floats per collected batch: begin/end of the 6 stages, ms since t_ref
+    Partition part;
     std::string err;
 };
 
@@ -142,9 +190,12 @@ ft8b200_pipe_t *ft8b200_pipe_create(const ft8b200_config_t *cfg_in, int depth) {
     return p;
 }
 
+static void partition_release(ft8b200_pipe_t *p);
+
 int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant) {
     if (!p || (mode != FT8B200_PIPE_OVERLAP && mode != FT8B200_PIPE_SERIAL)) return FT8B200_EINVAL;
     if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_set_mode: batches in flight");
+    if (p->part.front || p->part.back) partition_release(p);  // both modes time-share the whole GPU
     p->mode = mode;
     for (Lane &l : p->lanes) {
         ft8b200_set_side_backend(l.ctx, mode == FT8B200_PIPE_OVERLAP && p->lanes.size() > 1);
@@ -154,9 +205,80 @@ int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant) {
     return 0;
 }
 
+// drop the SM partition: lanes go back to their own streams, the green contexts and their streams are destroyed
+static void partition_release(ft8b200_pipe_t *p) {
+    const DriverApi &d = driver_api();
+    for (Lane &l : p->lanes) {
+        if (!l.part_front && !l.part_back) continue;
+        if (l.ctx) {
+            ft8b200_set_partition_streams(l.ctx, nullptr, nullptr, 0);  // synchronises both streams first
+            l.st = reinterpret_cast<cudaStream_t>(ft8b200_cuda_stream(l.ctx));
+        }
+        if (l.part_front) d.StreamDestroy(l.part_front);
+        if (l.part_back) d.StreamDestroy(l.part_back);
+        l.part_front = l.part_back = nullptr;
+    }
+    if (p->part.front) d.GreenCtxDestroy(p->part.front);
+    if (p->part.back) d.GreenCtxDestroy(p->part.back);
+    p->part = Partition();
+}
+
+int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_out, int *back_sms_out) {
+    if (!p || back_sms < 0) return FT8B200_EINVAL;
+    if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_set_partition: batches in flight");
+    PCU(cudaSetDevice(p->cfg.device));
+    const DriverApi &d = driver_api();
+    if (p->part.front || p->part.back) partition_release(p);
+    p->prev_front = nullptr;
+    if (back_sms == 0) {
+        if (front_sms_out) *front_sms_out = 0;
+        if (back_sms_out) *back_sms_out = 0;
+        return 0;
+    }
+    if (p->lanes.size() < 2) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_set_partition: needs a pipe of depth >= 2");
+    if (!d.ok) return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_set_partition: the CUDA driver does not export the green-context API");
+#define PDRV(call)                                                                                                  \
+    do {                                                                                                            \
+        CUresult r__ = (call);                                                                                      \
+        if (r__ != CUDA_SUCCESS) {                                                                                  \
+            partition_release(p);                                                                                   \
+            return pfail(p, FT8B200_ECUDA, std::string(#call) + ": CUresult " + std::to_string((int)r__));          \
+        }                                                                                                           \
+    } while (0)
+    CUdevice dev;
+    PDRV(d.DeviceGet(&dev, p->cfg.device));
+    CUdevResource all, back, front;
+    PDRV(d.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+    if ((unsigned)back_sms >= all.sm.smCount) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_set_partition: back_sms must leave SMs for the front end");
+    unsigned int groups = 1;
+    PDRV(d.DevSmResourceSplitByCount(&back, &groups, &all, &front, 0, (unsigned)back_sms));  // rounds up to the architecture's granularity
+    if (groups != 1 || front.sm.smCount == 0) { partition_release(p); return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_set_partition: the driver could not split the SMs that way"); }
+    CUdevResourceDesc dfront, dback;
+    PDRV(d.DevResourceGenerateDesc(&dback, &back, 1));
+    PDRV(d.DevResourceGenerateDesc(&dfront, &front, 1));
+    PDRV(d.GreenCtxCreate(&p->part.back, dback, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    PDRV(d.GreenCtxCreate(&p->part.front, dfront, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    p->part.front_sms = (int)front.sm.smCount;
+    p->part.back_sms = (int)back.sm.smCount;
+    for (Lane &l : p->lanes) {
+        PDRV(d.GreenCtxStreamCreate(&l.part_front, p->part.front, CU_STREAM_NON_BLOCKING, 0));
+        PDRV(d.GreenCtxStreamCreate(&l.part_back, p->part.back, CU_STREAM_NON_BLOCKING, 0));
+        int rc = ft8b200_set_partition_streams(l.ctx, l.part_front, l.part_back, p->part.back_sms);
+        if (rc) { partition_release(p); return pfail(p, rc, ft8b200_last_error()); }
+        l.st = reinterpret_cast<cudaStream_t>(ft8b200_cuda_stream(l.ctx));
+        ft8b200_set_side_backend(l.ctx, 1);
+    }
+#undef PDRV
+    p->mode = FT8B200_PIPE_OVERLAP;
+    if (front_sms_out) *front_sms_out = p->part.front_sms;
+    if (back_sms_out) *back_sms_out = p->part.back_sms;
+    return 0;
+}
+
 void ft8b200_pipe_destroy(ft8b200_pipe_t *p) {
     if (!p) return;
     cudaSetDevice(p->cfg.device);
+    partition_release(p);
     for (Lane &l : p->lanes) {
         if (l.st) cudaStreamSynchronize(l.st);
         if (l.ctx) ft8b200_destroy(l.ctx);
@@ -165,6 +287,7 @@ void ft8b200_pipe_destroy(ft8b200_pipe_t *p) {
         if (l.h_res) cudaFreeHost(l.h_res);
         if (l.h_n) cudaFreeHost(l.h_n);
     }
+    if (p->t_ref) cudaEventDestroy(p->t_ref);
     delete p;
 }
 
@@ -200,6 +323,9 @@ static int pop(ft8b200_pipe_t *p, struct decoder_results *h_results, int32_t *h_
         float ms[6];
         if (ft8b200_stage_times(l.ctx, ms, 6) == 0)
             for (int k = 0; k < 6; ++k) if (ms[k] > 0) p->stage_ms[k] += ms[k];
+        float tb[6], te[6];
+        if (p->t_ref && ft8b200_stage_marks(l.ctx, p->t_ref, tb, te, 6) == 0)
+            for (int k = 0; k < 6; ++k) { p->timeline.push_back(tb[k]); p->timeline.push_back(te[k]); }
     }
     ++p->batches;
     p->slots += (uint64_t)l.n_slots;
@@ -230,7 +356,23 @@ int ft8b200_pipe_set_profiling(ft8b200_pipe_t *p, int on) {
     for (double &v : p->stage_ms) v = 0.0;
     p->batches = 0;
     p->slots = 0;
+    p->timeline.clear();
+    if (on) {
+        PCU(cudaSetDevice(p->cfg.device));
+        if (!p->t_ref) PCU(cudaEventCreate(&p->t_ref));
+        PCU(cudaEventRecord(p->t_ref, p->lanes[0].st));
+    }
     return 0;
+}
+
+// Device timeline of the batches collected since profiling was switched on: 12 floats per batch (begin, end of block sums,
+// comb+FIR, waterfall, sync, decode, spots in ms since that moment).  Returns the number of batches written (<= max_batches).
+int ft8b200_pipe_timeline(ft8b200_pipe_t *p, float *out, int max_batches) {
+    if (!p || !out || max_batches < 0) return FT8B200_EINVAL;
+    int n = (int)(p->timeline.size() / 12);
+    if (n > max_batches) n = max_batches;
+    memcpy(out, p->timeline.data(), (size_t)n * 12 * sizeof(float));
+    return n;
 }
 
 // sums over the batches collected since profiling was switched on: ms[0..5] as ft8b200_stage_times, *batches = how many

@@ -509,6 +509,66 @@ def test_pipe_matches_unpipelined(pkg, ctx, oracle, raw_slot, depth, serial, var
     pipe.close()
 
 
+@pytest.mark.parametrize("depth,back_sms", [(2, 8), (3, 40), (2, 100)])
+def test_pipe_sm_partition(pkg, ctx, oracle, raw_slot, depth, back_sms):
+    """ft8b200_pipe_set_partition: decimator of batch n+1 and back end of batch n on disjoint SM sets (green contexts).
+    Same records as the unpipelined call for device and host input, through partition changes, removal and mode switches;
+    the first slot is also checked against the CPU oracle."""
+    B = 6
+    big = _mixed_batch(raw_slot, B)
+    torch.cuda.synchronize()
+    ctx.process_raw(big, B)
+    ref_res, ref_n = ctx.fetch_results(B)
+    oi, oq = oracle.decimate_slot(raw_slot)
+    ri = np.zeros(48000, np.float32); rq = np.zeros(48000, np.float32)
+    ri[:oi.size] = oi; rq[:oq.size] = oq
+    o = oracle.subsystem(*oracle.condition(ri, rq, oi.size)[:2])
+    assert ref_n[0] == o["n"] >= 1 and ref_res[0].tobytes() == o["results"].tobytes()
+
+    pipe = pkg.Pipe(0, depth)
+    host = big[:4].cpu().numpy()
+
+    def rounds():
+        outs, sizes = [], [B, 2, B, 1, 4, B, 3]
+        for n in sizes:
+            if pipe.in_flight() == pipe.depth:
+                outs.append(pipe.collect(B))
+            pipe.submit(big[:n], n)
+        for n in (4, 1, 3):
+            if pipe.in_flight() == pipe.depth:
+                outs.append(pipe.collect(B))
+            pipe.submit_host(host[:n], n)
+            sizes.append(n)
+        while pipe.in_flight():
+            outs.append(pipe.collect(B))
+        assert [len(o[1]) for o in outs] == sizes
+        for (res, n), k in zip(outs, sizes):
+            assert np.array_equal(n, ref_n[:k]) and res.tobytes() == ref_res[:k].tobytes()
+
+    f, b = pipe.set_partition(back_sms)
+    assert b >= back_sms and f >= 1 and f + b <= torch.cuda.get_device_properties(0).multi_processor_count
+    rounds()
+    pipe.submit(big[:1], 1)
+    with pytest.raises(pkg.Ft8Error):   # not while a batch is in flight
+        pipe.set_partition(16)
+    pipe.collect(B)
+    f2, b2 = pipe.set_partition(16)     # re-partition
+    assert b2 >= 16
+    rounds()
+    assert pipe.set_partition(0) == (0, 0)   # back to time sharing
+    rounds()
+    pipe.set_partition(back_sms)
+    pipe.set_mode(True)                 # a mode switch drops the partition
+    rounds()
+    with pytest.raises(pkg.Ft8Error):
+        pipe.set_partition(10 ** 6)
+    pipe.close()
+    one = pkg.Pipe(0, 1)
+    with pytest.raises(pkg.Ft8Error):   # nothing to overlap with a single lane
+        one.set_partition(16)
+    one.close()
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_bulk_copy_decimator_variants(pkg, oracle, variant):
     """The persistent cp.async.bulk + mbarrier cic_block_sums kernel (every ring shape) is bit-identical to the oracle,
