@@ -398,6 +398,49 @@ int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t s
                               int sample_rate, int time_osr, int freq_osr, int protocol, uint8_t *d_mag, size_t mag_slot_stride,
                               int *num_blocks_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Reporting records: the step after the hot path.  HOST code, no sockets: these
+ * build the bytes / strings the daemon's reporters emit; sending them stays with the caller.
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces: rtlsdr_ft8d.h:130-134 (24 bytes) -- dial frequency and identity of the receiving station */
+struct decoder_options {
+    uint32_t freq;
+    char rcall[13];
+    char rloc[7];
+};
+
+/* The four form fields webClusterSpots() posts for one spot (buffer sizes of rtlsdr_ft8d.c:599-602; longer values truncate) */
+typedef struct {
+    char mycall[16]; /* "_mycall" */
+    char dxcall[12]; /* "_dxcall" */
+    char freq[10];   /* "_freq": kHz, "%8f" of a float */
+    char info[100];  /* "_info":  "M2M FT8 [<rx locator> - <tx locator>]" */
+} ft8b200_cluster_form_t;
+
+#define FT8B200_PSK_MAX_DATAGRAM 1600
+
+/* replaces: postSpots(), rtlsdr_ft8d.c:365-552 (the packet-building part; the UDP send at :554-582 stays with the caller).
+ * One PSKreporter IPFIX datagram: header, the two template sets, the receiver record (call, locator, app_version) and one
+ * sender record per spot (call, dial + freq, (int8)snr - 20, "FT8", locator, source 1, unixtime), until the sender set has
+ * grown past 1200 bytes.  app_version NULL = ft8b200_report_app_version().  The reference uses sequence 1 and a per-process
+ * rand() id.  Returns the datagram length, or -1 (bad argument / `cap` too small; FT8B200_PSK_MAX_DATAGRAM always fits). */
+int ft8b200_pskreporter_datagram(const struct decoder_results *spots, uint32_t n_spots, const struct decoder_options *station,
+                                 const char *app_version, uint32_t unixtime, uint32_t sequence, uint32_t random_id, uint8_t *out,
+                                 size_t cap, uint32_t *n_reported);
+/* The same for the records of a batch (the layout ft8b200_fetch_results / ft8b200_pipe_collect return: spots[n_slots][max_messages],
+ * n_spots[n_slots]): datagram s at out + s*stride, its length in lengths[s] (0 for a slot without spots, which sends nothing);
+ * sequence numbers count up from first_sequence over the datagrams actually built.  Returns the number of datagrams, or -1. */
+int ft8b200_pskreporter_batch(const struct decoder_results *spots, const int32_t *n_spots, int n_slots, int max_messages,
+                              const struct decoder_options *station, const char *app_version, const uint32_t *unixtime,
+                              uint32_t first_sequence, uint32_t random_id, uint8_t *out, size_t stride, int32_t *lengths);
+/* replaces: the field formatting of webClusterSpots(), rtlsdr_ft8d.c:603-606 (the curl POST stays with the caller) */
+int ft8b200_webcluster_form(const struct decoder_results *spot, const struct decoder_options *station, ft8b200_cluster_form_t *form);
+/* replaces: printSpots(), rtlsdr_ft8d.c:635-663: the console table (or the "No spot <UTC time>" line) into `out`.
+ * Returns the number of characters needed, excluding the terminator (snprintf convention), or -1. */
+int ft8b200_format_spots(const struct decoder_results *spots, uint32_t n_spots, uint32_t dial_freq, uint32_t unixtime, char *out, size_t cap);
+const char *ft8b200_report_app_version(void);
+
 #ifdef __cplusplus
 }
 #endif

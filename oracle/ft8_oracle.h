@@ -120,6 +120,12 @@ void orc_synth_raw(const orc_signal_t *sigs, int n_sigs, float noise_lsb, uint64
 void orc_synth_float(int kind, int ft4, const orc_signal_t *sigs, int n_sigs, float noise_sigma, uint64_t seed, int slot_index, float *out_i,
                      float *out_q, int n_samples);
 
+/* ---- f4: reporting formats (ft8_oracle_report.c; ref rtlsdr_ft8d.c:365-663) ---- */
+int orc_pskreporter_datagram(const orc_result_t *spots, uint32_t n_spots, const char *rcall, const char *rloc, uint32_t dial_freq,
+                             const char *app_version, uint32_t unixtime, uint32_t sequence, uint32_t random_id, unsigned char *out /* >= 2048 */);
+void orc_webcluster_form(const orc_result_t *spot, const char *rcall, const char *rloc, uint32_t dial_freq, char *out /* 4 x 112 */);
+int orc_print_spots(const orc_result_t *spots, uint32_t n_spots, uint32_t dial_freq, uint32_t unixtime, char *out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,7 +57,7 @@ def _ptr(a, t=C.c_void_p):
 
 def build_restatement(force: bool = False) -> str:
     so = os.path.join(HERE, "libft8oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("ft8_oracle.c", "ft8_oracle_codec.c", "ft8_oracle_synth.c", "ft8_oracle.h", "ft8_tables.h")]
+    srcs = [os.path.join(HERE, f) for f in ("ft8_oracle.c", "ft8_oracle_codec.c", "ft8_oracle_synth.c", "ft8_oracle_report.c", "ft8_oracle.h", "ft8_tables.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "restate"], stdout=subprocess.DEVNULL)
     return so
@@ -288,6 +288,27 @@ class Oracle:
                                  _ptr(oq) if oq is not None else None, n_samples)
         return oi, oq
 
+    # -- reporting formats (ft8_oracle_report.c) -----------------------------------------------------------
+    def pskreporter_datagram(self, spots: np.ndarray, rcall: str, rloc: str, dial_freq: int, app_version: str, unixtime: int,
+                             sequence: int = 1, random_id: int = 0) -> bytes:
+        spots = np.ascontiguousarray(spots, result_dtype)
+        out = C.create_string_buffer(4096)
+        n = self.lib.orc_pskreporter_datagram(_ptr(spots), C.c_uint32(spots.size), rcall.encode(), rloc.encode(), C.c_uint32(dial_freq),
+                                              app_version.encode(), C.c_uint32(unixtime), C.c_uint32(sequence), C.c_uint32(random_id), out)
+        return out.raw[:n]
+
+    def webcluster_form(self, spot: np.ndarray, rcall: str, rloc: str, dial_freq: int) -> dict:
+        spot = np.ascontiguousarray(spot, result_dtype).reshape(1)
+        out = C.create_string_buffer(4 * 112)
+        self.lib.orc_webcluster_form(_ptr(spot), rcall.encode(), rloc.encode(), C.c_uint32(dial_freq), out)
+        return {k: out.raw[i * 112:(i + 1) * 112].split(b"\0")[0] for i, k in enumerate(("_mycall", "_dxcall", "_freq", "_info"))}
+
+    def print_spots(self, spots: np.ndarray, dial_freq: int, unixtime: int) -> str:
+        spots = np.ascontiguousarray(spots, result_dtype)
+        out = C.create_string_buffer(1 << 16)
+        self.lib.orc_print_spots(_ptr(spots), C.c_uint32(spots.size), C.c_uint32(dial_freq), C.c_uint32(unixtime), out, C.c_size_t(1 << 16))
+        return out.value.decode()
+
     # -- encoder ----------------------------------------------------------------------
     def pack_std(self, call_to: str, call_de: str, extra: str) -> bytes:
         b = C.create_string_buffer(10)
@@ -504,3 +525,43 @@ class ReferenceMonitor:
         if rc < 0:
             raise IOError(f"load_wav({path}) -> {rc}")
         return sig[:n.value].copy(), sr.value
+
+
+class ReferenceReport:
+    """The reference daemon's own reporting functions (postSpots / webClusterSpots / printSpots) with network, clock and stdout
+    captured (oracle/_ref/libref_report.so, see ref_report_harness.c for the two lines edited in a temp copy)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libref_report.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = L = C.CDLL(path)
+        L.ref_report_app_version.restype = C.c_char_p
+        self.app_version = L.ref_report_app_version().decode()
+        self.max_messages = L.ref_report_max_messages()
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_report.so"))
+
+    def post_spots(self, spots: np.ndarray, rcall: str, rloc: str, dial_freq: int, unixtime: int) -> bytes:
+        """-> the datagram postSpots() hands to send(); bytes 12..15 are the process-wide rand() id."""
+        spots = np.ascontiguousarray(spots, result_dtype)
+        assert spots.size <= self.max_messages
+        out = C.create_string_buffer(4096)
+        n = self.lib.ref_post_spots(_ptr(spots), C.c_uint32(spots.size), rcall.encode(), rloc.encode(), C.c_uint32(dial_freq), C.c_uint32(unixtime), out, 4096)
+        return out.raw[:n] if n > 0 else b""
+
+    def print_spots(self, spots: np.ndarray, dial_freq: int, unixtime: int) -> str:
+        spots = np.ascontiguousarray(spots, result_dtype)
+        out = C.create_string_buffer(1 << 16)
+        self.lib.ref_print_spots(_ptr(spots), C.c_uint32(spots.size), C.c_uint32(dial_freq), C.c_uint32(unixtime), out, 1 << 16)
+        return out.value.decode()
+
+    def webcluster(self, spots: np.ndarray, rcall: str, rloc: str, dial_freq: int) -> list:
+        """-> one {field name: value} dict per spot, as passed to curl_formadd()."""
+        spots = np.ascontiguousarray(spots, result_dtype)
+        out = C.create_string_buffer(224 * 4 * max(spots.size, 1))
+        k = self.lib.ref_webcluster_spots(_ptr(spots), C.c_uint32(spots.size), rcall.encode(), rloc.encode(), C.c_uint32(dial_freq), out, 4 * max(spots.size, 1))
+        pairs = [(out.raw[(2 * i) * 112:(2 * i + 1) * 112].split(b"\0")[0].decode(), out.raw[(2 * i + 1) * 112:(2 * i + 2) * 112].split(b"\0")[0]) for i in range(k)]
+        return [dict(pairs[4 * j:4 * j + 4]) for j in range(k // 4)]

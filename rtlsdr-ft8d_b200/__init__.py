@@ -677,3 +677,67 @@ def decode_wav_files(ctx: Context, paths, protocol=1):
 def format_decoded(rec) -> str:
     """One line of decode_ft8's stdout (decode_ft8.c:401)."""
     return "000000 %3d %+4.2f %4.0f ~  %s" % (int(rec["score"]), float(rec["time_sec"]), float(rec["freq_hz"]), rec["text"].decode())
+
+
+# ---- reporting records (csrc/report.cu): host code, no GPU involved ---------------------------------------
+options_dtype = np.dtype([("freq", "<u4"), ("rcall", "S13"), ("rloc", "S7")])
+cluster_form_dtype = np.dtype([("mycall", "S16"), ("dxcall", "S12"), ("freq", "S10"), ("info", "S100")])
+PSK_MAX_DATAGRAM = 1600
+
+
+def station(rcall: str, rloc: str, dial_freq: int) -> np.ndarray:
+    """struct decoder_options (rtlsdr_ft8d.h:130-134) as a 1-element array."""
+    o = np.zeros(1, options_dtype)
+    o[0] = (dial_freq, rcall.encode(), rloc.encode())
+    return o
+
+
+def pskreporter_datagram(spots: np.ndarray, opt: np.ndarray, unixtime: int, sequence: int = 1, random_id: int = 0, app_version: str | None = None,
+                         cap: int = PSK_MAX_DATAGRAM):
+    """-> (datagram bytes, number of spots it carries); raises Ft8Error when `cap` is too small."""
+    spots = np.ascontiguousarray(spots, result_dtype)
+    out = np.zeros(cap, np.uint8)
+    used = C.c_uint32(0)
+    n = lib().ft8b200_pskreporter_datagram(_p(spots), C.c_uint32(spots.size), _p(opt), None if app_version is None else app_version.encode(),
+                                           C.c_uint32(unixtime), C.c_uint32(sequence), C.c_uint32(random_id), _p(out), C.c_size_t(cap), C.byref(used))
+    if n < 0:
+        raise Ft8Error("ft8b200_pskreporter_datagram failed (bad argument or buffer too small)")
+    return out[:n].tobytes(), used.value
+
+
+def pskreporter_batch(res: np.ndarray, nres: np.ndarray, opt: np.ndarray, unixtime, first_sequence: int = 1, random_id: int = 0,
+                      app_version: str | None = None):
+    """Records of a batch (fetch_results / Pipe.collect layout) -> list of datagrams (b"" for slots without spots)."""
+    res = np.ascontiguousarray(res, result_dtype)
+    n_slots, M = res.shape
+    nres = np.ascontiguousarray(nres, np.int32)
+    ut = np.ascontiguousarray(np.broadcast_to(np.asarray(unixtime, np.uint32), (n_slots,)))
+    out = np.zeros((n_slots, PSK_MAX_DATAGRAM), np.uint8)
+    lens = np.zeros(n_slots, np.int32)
+    k = lib().ft8b200_pskreporter_batch(_p(res), _p(nres), n_slots, M, _p(opt), None if app_version is None else app_version.encode(), _p(ut),
+                                        C.c_uint32(first_sequence), C.c_uint32(random_id), _p(out), C.c_size_t(PSK_MAX_DATAGRAM), _p(lens))
+    if k < 0:
+        raise Ft8Error("ft8b200_pskreporter_batch failed")
+    return [out[s, :lens[s]].tobytes() for s in range(n_slots)], k
+
+
+def webcluster_form(spot: np.ndarray, opt: np.ndarray) -> dict:
+    spot = np.ascontiguousarray(spot, result_dtype).reshape(1)
+    f = np.zeros(1, cluster_form_dtype)
+    if lib().ft8b200_webcluster_form(_p(spot), _p(opt), _p(f)) != 0:
+        raise Ft8Error("ft8b200_webcluster_form failed")
+    return {"_mycall": f[0]["mycall"], "_dxcall": f[0]["dxcall"], "_freq": f[0]["freq"], "_info": f[0]["info"]}
+
+
+def format_spots(spots: np.ndarray, dial_freq: int, unixtime: int) -> str:
+    spots = np.ascontiguousarray(spots, result_dtype)
+    need = lib().ft8b200_format_spots(_p(spots), C.c_uint32(spots.size), C.c_uint32(dial_freq), C.c_uint32(unixtime), None, C.c_size_t(0))
+    buf = C.create_string_buffer(need + 1)
+    lib().ft8b200_format_spots(_p(spots), C.c_uint32(spots.size), C.c_uint32(dial_freq), C.c_uint32(unixtime), buf, C.c_size_t(need + 1))
+    return buf.value.decode()
+
+
+def lib_app_version() -> str:
+    L = lib()
+    L.ft8b200_report_app_version.restype = C.c_char_p
+    return L.ft8b200_report_app_version().decode()

@@ -31,7 +31,40 @@ def slot_fixture(name, i_s, q_s, variant, store_input=True):
     print(name, "cands", len(r["cands"]), "n_results", r["n"], [m["text"].decode() for m, ok in zip(r["dec_msg"], r["dec_ok"]) if ok][:6])
 
 
+def report_fixture():
+    """Reporting formats from the reference's own postSpots()/webClusterSpots()/printSpots() (oracle/_ref/libref_report.so)."""
+    from oracle.pyoracle import ReferenceReport, result_dtype
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_report as T
+    ref = ReferenceReport()
+    rng = np.random.default_rng(2024)
+    spots, first, grams, lens, printed, ff, fi, meta = [], [0], np.zeros((8, 2048), np.uint8), [], [], [], [], []
+    for c in range(8):
+        n = [0, 1, 3, 7, 20, 50, 50, 12][c]
+        s = T.random_spots(rng, n)
+        if c == 6:
+            s[:] = (b"PJ4/K1ABC/QR", b"AA00aa", 1234, 30)   # maximum-length records: the 1200-byte cut
+        rcall, rloc, dial = T.STATIONS[c % len(T.STATIONS)]
+        ut = int(rng.integers(1, 2**32 - 1))
+        d = ref.post_spots(s, rcall, rloc, dial, ut)
+        grams[c, :len(d)] = np.frombuffer(d, np.uint8)
+        lens.append(len(d))
+        printed.append(ref.print_spots(s, dial, ut).encode())
+        for f in ref.webcluster(s, rcall, rloc, dial):
+            ff.append(f["_freq"]); fi.append(f["_info"])
+        meta.append((rcall.encode(), rloc.encode(), dial, ut, int.from_bytes(d[12:16], "big")))
+        spots.append(s); first.append(first[-1] + n)
+    np.savez_compressed(os.path.join(OUT, "report.npz"), spots=np.concatenate(spots).view(np.uint8), first=np.array(first, np.int32),
+                        rcall=np.array([m[0] for m in meta]), rloc=np.array([m[1] for m in meta]), dial=np.array([m[2] for m in meta], np.uint32),
+                        unixtime=np.array([m[3] for m in meta], np.uint32), random_id=np.array([m[4] for m in meta], np.uint32),
+                        datagrams=grams, datagram_len=np.array(lens, np.int32), printed=np.array(printed),
+                        form_freq=np.array(ff), form_info=np.array(fi), app_version=np.array(ref.app_version.encode()))
+    print("report.npz:", lens)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "report":
+        return report_fixture()
     # --- decimator: random bytes with forced 0x00 / 0xff (int8 wrap quirk), 10 super-blocks + ragged tail
     rng = np.random.default_rng(2024)
     nbytes = 12016 * 10 + 8 * 100
@@ -80,6 +113,7 @@ def main():
                         crc_test3=np.array([R.crc(bytes([0x11, 0, 0, 0, 0, 0x0E, 0x10, 0x04, 0x01, 0x00, 0, 0]), 76)]))
     assert p.hex() == "000000204dfcdc8a1408"  # rtlsdr_ft8d.c:921
     assert "".join(map(str, R.tones(p))) == "3140652000000001005477547106035036373140652547441342116056460065174427143140652"  # :922
+    report_fixture()
 
 
 if __name__ == "__main__":

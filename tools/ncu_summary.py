@@ -51,7 +51,13 @@ def read(path):
 
 def main():
     out = {}
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    argv = sys.argv[1:]
+    json_out = None
+    if "--json" in argv:
+        k = argv.index("--json")
+        json_out = argv[k + 1]
+        del argv[k:k + 2]
+    args = [a for a in argv if not a.startswith("--")]
     for path in args:
         d = read(path)
         name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
@@ -69,8 +75,8 @@ def main():
         for k, v in rec.items():
             if not k.endswith("_unit"):
                 print(f"   {k:22s} {v} {rec.get(k + '_unit', '')}")
-    if "--json" in sys.argv:
-        json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
+    if json_out:
+        json.dump(out, open(json_out, "w"), indent=1)
 
 if __name__ == "__main__":
     main()
