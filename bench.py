@@ -149,6 +149,18 @@ def _cpu_one_slot(idx: int):
     return int(orc.subsystem(i_s, q_s)["n"])
 
 
+def _cpu_synth_slot(idx: int):
+    """Slot `idx` of the bench batch into _CPU_SLOTS (shared memory), by the CPU twin of ft8b200_synth_raw."""
+    from oracle.pyoracle import Oracle, signal_dtype
+    orc = Oracle()
+    p = slot_params(idx)
+    sig = np.zeros(1, signal_dtype)
+    sig[0]["payload"] = np.frombuffer(orc.pack_std(*p["text"].split()), np.uint8)
+    sig[0]["f0_hz"], sig[0]["t0_sec"], sig[0]["amp"] = p["f_hz"], p["t0"], p["amp"]
+    _CPU_SLOTS[idx] = orc.synth_raw(sig, p["noise"], 0xF78, idx, RAW_SLOT_BYTES // 2)
+    return 0
+
+
 def cpu_run(n_slots: int, workers: int):
     """Seconds to push slots 0..n_slots-1 of _CPU_SLOTS through the CPU path with `workers` processes."""
     t0 = time.perf_counter()
@@ -162,6 +174,17 @@ def cpu_run(n_slots: int, workers: int):
 
 
 # --------------------------------------------------------------------------------------------- main
+_JSON_FD = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,6 +202,12 @@ def main():
     ap.add_argument("--cpu-slots", type=int, default=96, help="bounded CPU-baseline sample (slots)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line, the JSON: anything a library prints to fd 1 on the way (NCCL's version banner at
+    # communicator creation, for one) is sent to stderr, and the JSON line is written to the original stdout at the end
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -380,7 +409,7 @@ def main():
                                          "conditioning + ft8_subsystem (%.2f s)" % (n_cpu, B, secs),
                                "same_spot_counts_as_gpu": n_dec == gpu_n}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -393,14 +422,16 @@ def reference_arm(args, rank, world, config):
     global _CPU_SLOTS
     cores = os.cpu_count() or 1
     n = max(4 * cores, 16)  # a few slots per worker per step
+    # Inputs: the same synthetic slots as the CUDA arm, made by the synthesiser's bit-identical CPU twin (oracle/ft8_oracle_synth.c)
+    # in the worker processes -- nothing of libft8b200 and no GPU is involved anywhere in this arm.
     try:
-        import torch
-        dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
-        buf, _ = gen_batch(n, 0, dev)
-        _CPU_SLOTS = buf.cpu().numpy()
-        del buf
+        import multiprocessing as mp
+        shared = mp.RawArray("B", n * RAW_SLOT_BYTES)
+        _CPU_SLOTS = np.frombuffer(shared, np.uint8).reshape(n, RAW_SLOT_BYTES)
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_synth_slot, range(n), chunksize=1)
     except Exception as exc:  # pragma: no cover
-        print(json.dumps({"impl": "reference", "unavailable": f"input synthesis failed: {exc}"}))
+        emit({"impl": "reference", "unavailable": f"input synthesis failed: {exc}"})
         return 0
     for _ in range(min(args.warmup, 1)):
         cpu_run(min(n, cores), cores)
@@ -414,11 +445,11 @@ def reference_arm(args, rank, world, config):
     cfg["reference_sample"] = "%d slots per step over %d worker processes" % (n, cores)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "slots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-           "data": "synthetic", "config": cfg,
+           "data": "synthetic (same slots as the CUDA arm, made on the host by the synthesiser's bit-identical CPU twin)", "config": cfg,
            "cpu_baseline": {"value": value, "unit": "slots/s", "cores": cores, "kind": kind,
                             "sample": "%d slots per step, one forked process per slot on %d cores (the reference itself is single-threaded)" % (n, cores)},
            "e2e": {"value": value, "unit": "slots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
