@@ -252,7 +252,12 @@ def main():
     pipe.set_mode(serial=not args.overlap, decimator_variant=args.k1_variant)
     if args.back_sms > 0:
         # green contexts: disjoint SM sets for the HBM-bound decimator and the issue-bound back end (ft8b200_pipe_set_partition)
-        config["sm_partition"] = dict(zip(("front_sms", "back_sms"), pipe.set_partition(args.back_sms)))
+        try:
+            config["sm_partition"] = dict(zip(("front_sms", "back_sms"), pipe.set_partition(args.back_sms)))
+        except Exception as exc:  # a driver without green contexts: same kernels, consecutive batches back to back on the whole GPU
+            config["sm_partition"] = "unavailable (%s): running serial" % exc
+            config["executor"] = "ft8b200_pipe_t depth %d, %d batches of %d slots per step, serial" % (args.depth, args.chunks, args.slots // args.chunks)
+            args.back_sms = 0
     M = pipe.M
     gathered = torch.empty((world * Bc, M, 28), dtype=torch.uint8, device=device) if world > 1 else None
     gathered_n = torch.empty(world * Bc, dtype=torch.int32, device=device) if world > 1 else None
