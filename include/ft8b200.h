@@ -330,7 +330,10 @@ int ft8b200_pipe_stage_times(ft8b200_pipe_t *p, double *ms, int n, uint64_t *bat
 int ft8b200_pipe_timeline(ft8b200_pipe_t *p, float *out, int max_batches);
 uint64_t ft8b200_pipe_kernel_launches(ft8b200_pipe_t *p);
 
-/* Receiver streams for rtlsdr_callback(): persistent decimator state, double-buffered 15 s slots. */
+/* Receiver streams for rtlsdr_callback(): persistent decimator state, double-buffered 15 s slots.
+ * flip / count / fetch / decode accept s == NULL for the process-wide default stream, the one that
+ * rtlsdr_callback(..., ctx = NULL) feeds (the reference registers its callback with a NULL ctx, rtlsdr_ft8d.c:214);
+ * freeFFTW() destroys it together with the default context. */
 ft8b200_stream_t *ft8b200_stream_create(ft8b200_ctx_t *ctx);
 void ft8b200_stream_destroy(ft8b200_stream_t *s);
 /* what main() does every 15 s (rtlsdr_ft8d.c:1339-1354): close the current slot buffer, start the next */

@@ -19,6 +19,7 @@ using namespace ft8b200;
 namespace ft8b200 {
 ft8b200_ctx_t *default_ctx();
 void default_ctx_release();
+void default_stream_release();
 }
 
 namespace {
@@ -114,7 +115,7 @@ void default_ctx_release() {
 extern "C" {
 
 void initFFTW(void) { (void)default_ctx(); }
-void freeFFTW(void) { default_ctx_release(); }
+void freeFFTW(void) { default_stream_release(); default_ctx_release(); }
 
 void ft8_subsystem(float *iSamples, float *qSamples, uint32_t samples_len, struct decoder_results *decodes, int32_t *n_results) {
     (void)samples_len;  // the reference ignores it too (rtlsdr_ft8d.c:1393)

@@ -22,6 +22,7 @@ using namespace ft8b200;
 
 namespace ft8b200 {
 ft8b200_ctx_t *default_ctx();
+void default_stream_release();
 }
 
 namespace {
@@ -139,6 +140,17 @@ ft8b200_stream_t *default_stream() {
 
 }  // namespace
 
+namespace ft8b200 {
+// freeFFTW() tears the default context down: the default stream lives on it and must go first
+void default_stream_release() {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (g_default_stream) {
+        ft8b200_stream_destroy(g_default_stream);
+        g_default_stream = nullptr;
+    }
+}
+}  // namespace ft8b200
+
 extern "C" {
 
 ft8b200_stream_t *ft8b200_stream_create(ft8b200_ctx_t *ctx) {
@@ -189,8 +201,10 @@ void rtlsdr_callback(unsigned char *samples, uint32_t samples_count, void *ctx) 
     append(s, samples, samples_count);
 }
 
+// For the four calls below s == NULL means the process-wide default stream, the one rtlsdr_callback(..., ctx = NULL)
+// feeds -- which is how the reference's daemon registers its callback (rtlsdr_ft8d.c:214).
 uint32_t ft8b200_stream_count(ft8b200_stream_t *s) {
-    if (!s) return 0;
+    if (!s) s = default_stream();
     std::lock_guard<std::mutex> lk(s->mu);
     // outputs the reference would have stored so far = complete blocks received since the slot started
     const uint64_t pending = s->bytes_in / kBlockBytes - s->blocks_done;
@@ -199,7 +213,7 @@ uint32_t ft8b200_stream_count(ft8b200_stream_t *s) {
 }
 
 int ft8b200_stream_flip(ft8b200_stream_t *s) {
-    if (!s) return FT8B200_EINVAL;
+    if (!s) s = default_stream();
     std::lock_guard<std::mutex> lk(s->mu);
     pump(s);
     s->buffer_index ^= 1;
@@ -213,7 +227,8 @@ int ft8b200_stream_flip(ft8b200_stream_t *s) {
 }
 
 int ft8b200_stream_fetch(ft8b200_stream_t *s, float *h_i, float *h_q, uint32_t *n_valid) {
-    if (!s || !h_i || !h_q) return FT8B200_EINVAL;
+    if (!h_i || !h_q) return FT8B200_EINVAL;
+    if (!s) s = default_stream();
     std::lock_guard<std::mutex> lk(s->mu);
     const int prev = s->buffer_index ^ 1;
     CK(cudaMemcpyAsync(h_i, s->d_i[prev], sizeof(float) * kSlot, cudaMemcpyDeviceToHost, s->st));
@@ -224,7 +239,8 @@ int ft8b200_stream_fetch(ft8b200_stream_t *s, float *h_i, float *h_q, uint32_t *
 }
 
 int ft8b200_stream_decode(ft8b200_stream_t *s, struct decoder_results *h_results, int32_t *h_nresults) {
-    if (!s || !h_results || !h_nresults) return FT8B200_EINVAL;
+    if (!h_results || !h_nresults) return FT8B200_EINVAL;
+    if (!s) s = default_stream();
     int prev;
     {
         std::lock_guard<std::mutex> lk(s->mu);
