@@ -263,6 +263,15 @@ int ft8b200_set_protocol(ft8b200_ctx_t *ctx, int protocol);
  * consumer warps doing the arithmetic) which leaves most of each SM free for the back-end kernels of another batch.
  * Results are identical. */
 int ft8b200_set_decimator_variant(ft8b200_ctx_t *ctx, int variant);
+/* Which belief-propagation kernel ft8b200_decode and the process_* calls use (process-wide): 0 = node-centred (default: a lane
+ * owns a variable / a check row, Pade evaluations with the in-range division sequence inlined), 1 = edge-centred (a lane
+ * per edge).  Results are identical; 1 exists for comparison.  Also settable as FT8B200_DECODE_VARIANT=1 in the environment. */
+int ft8b200_set_decode_variant(int variant);
+/* Device self-check of variant 0's inlined fast_tanh / fast_atanh (ldpc.c:220-251) against the same expressions with the full
+ * IEEE division, over ALL 2^32 float bit patterns.  counts5[0] = tanh mismatches, [1] = atanh mismatches for |x| <= 2 or NaN
+ * (the argument is a product of tanh values), [2] = atanh mismatches elsewhere, [3], [4] = how many patterns took the full
+ * division (tanh, atanh).  [0..2] must be 0. */
+int ft8b200_selfcheck_pade(ft8b200_ctx_t *ctx, uint64_t *counts5);
 /* Run the context's work on caller-owned streams (cudaStream_t as void*): `front_stream` replaces the context's launching
  * stream, `back_stream` its back-end side stream, whose kernels size their persistent grids for `back_sm_count` SMs.
  * NULL restores the context's own stream.  Used by ft8b200_pipe_set_partition with green-context streams. */

@@ -109,6 +109,12 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def set_decode_variant(variant: int):
+    """0 = node-centred belief propagation (default), 1 = edge-centred; process-wide."""
+    if lib().ft8b200_set_decode_variant(int(variant)) != 0:
+        raise ValueError(lib().ft8b200_last_error().decode())
+
+
 class Ft8Error(RuntimeError):
     pass
 
@@ -343,6 +349,12 @@ class Context:
     def set_decimator_variant(self, variant: int):
         """0 = streaming cic_block_sums kernel; >= 1 = persistent bulk-copy (TMA) kernel, shape index 1..6."""
         self._chk(self.L.ft8b200_set_decimator_variant(C.c_void_p(self.h), int(variant)))
+
+    def selfcheck_pade(self):
+        """All 2^32 float patterns through variant 0's inlined tanh/atanh vs the full-division expressions: 5 counters."""
+        c = (C.c_uint64 * 5)()
+        self._chk(self.L.ft8b200_selfcheck_pade(C.c_void_p(self.h), c))
+        return [int(v) for v in c]
 
     def set_overlap(self, groups: int):
         self._chk(self.L.ft8b200_set_overlap(C.c_void_p(self.h), int(groups)))

@@ -563,6 +563,21 @@ int ft8b200_set_decimator_variant(ft8b200_ctx_t *ctx, int variant) {
     return 0;
 }
 
+int ft8b200_set_decode_variant(int variant) {
+    if (variant != 0 && variant != 1) return fail(FT8B200_EINVAL, "ft8b200_set_decode_variant: 0 (node-centred) or 1 (edge-centred)");
+    set_decode_variant(variant);
+    return 0;
+}
+
+int ft8b200_selfcheck_pade(ft8b200_ctx_t *ctx, uint64_t *counts5) {
+    if (!ctx || !counts5) return fail(FT8B200_EINVAL, "ft8b200_selfcheck_pade: bad argument");
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    cudaError_t e = run_pade_check(c, ctx->stream);
+    if (e != cudaSuccess) return fail(FT8B200_ECUDA, cudaGetErrorString(e));
+    for (int k = 0; k < 5; ++k) counts5[k] = c[k];
+    return 0;
+}
+
 void *ft8b200_front_event(ft8b200_ctx_t *ctx) { return ctx ? ctx->ev_front : nullptr; }
 
 // ms[0..5] = block sums, comb+FIR, waterfall, sync, decode, spots of the last process_* call, summed over its slot

@@ -61,6 +61,9 @@ cudaError_t launch_spots(int n_slots, int max_cand, int max_msgs, int min_score,
                          const uint8_t *d_ok, const message_t *d_msg, struct decoder_results *d_results, int32_t *d_nresults,
                          message_t *d_umsg, float *d_ufreq, int32_t *d_uscore, int32_t *d_ucand, int16_t *d_table, cudaStream_t st, int *launches);
 cudaError_t upload_ldpc_tables();
+void set_decode_variant(int v);  // 0 = node-centred belief propagation (default), 1 = edge-centred
+int decode_variant();
+cudaError_t run_pade_check(unsigned long long *h_counts5, cudaStream_t st);
 
 // host-side table builders (tables.cu)
 void build_window1024(float *w);

@@ -204,8 +204,56 @@ def check_slot_against_oracle(oracle, c, mag_np, cand, ncand, ok, stage, status,
     return o
 
 
+@pytest.fixture(params=[0, 1], ids=["bp_nodes", "bp_edges"])
+def bp_variant(request, pkg):
+    """Both belief-propagation kernels (ft8b200_set_decode_variant): node-centred (default) and edge-centred."""
+    pkg.set_decode_variant(request.param)
+    yield request.param
+    pkg.set_decode_variant(0)
+
+
+def test_inlined_pade_division_is_ieee_over_all_floats(ctx):
+    """The node-centred kernel inlines the in-range instruction sequence of div.rn.f32 into fast_tanh / fast_atanh
+    (ldpc.c:220-251).  Device sweep over all 2^32 float bit patterns against the same expressions with the full IEEE
+    division: not one result may differ (the full division itself is what the bit-exact edge-centred kernel uses)."""
+    tanh_bad, atanh_bad, atanh_far_bad, tanh_slow, atanh_slow = ctx.selfcheck_pade()
+    assert (tanh_bad, atanh_bad, atanh_far_bad) == (0, 0, 0)
+    assert 0 < tanh_slow < 2 ** 32 // 4 and 0 < atanh_slow < 2 ** 32  # the fallback exists and is not the common path
+
+
+def test_decode_degenerate_llrs(ctx, oracle, slots, bp_variant):
+    """Candidates placed by hand where the statistics degenerate: a flat waterfall (all LLRs 0 -> variance 0 -> scale inf ->
+    NaN LLRs, decode.c:295-314), a waterfall flat except one row, and candidates hanging over both time edges."""
+    flat = np.full(94208, 77, np.uint8)
+    one_row = flat.copy().reshape(92, 2, 2, 256)
+    one_row[40] = np.random.default_rng(4).integers(0, 256, size=(2, 2, 256), dtype=np.uint8)
+    real = oracle.waterfall(*slots[0])
+    mags = np.stack([flat, one_row.reshape(-1), real])
+    cands = np.zeros((3, ctx.K), cand_dtype)
+    picks = [(20, 0, 10, 0, 0), (20, -12, 100, 1, 1), (20, 23, 248, 1, 0), (20, 5, 0, 0, 1), (20, -7, 33, 0, 0), (20, 17, 200, 1, 1)]
+    for s in range(3):
+        for q, pk in enumerate(picks):
+            cands[s, q] = pk
+    ncand = np.full(3, len(picks), np.int32)
+    d_mag = torch.from_numpy(mags).to(dev())
+    d_cand = torch.from_numpy(cands.view(np.uint8).reshape(3, ctx.K, 8)).to(dev())
+    ok, stage, status, msg, plain, llr = ctx.decode(d_mag, d_cand, torch.from_numpy(ncand).to(dev()), want_plain=True, want_llr=True)
+    torch.cuda.synchronize()
+    g_st = [view(status[s], status_dtype) for s in range(3)]
+    saw_nan = False
+    for s in range(3):
+        for q in range(len(picks)):
+            d = oracle.decode(mags[s], cands[s, q])
+            gl = llr[s, q].cpu().numpy()
+            saw_nan |= bool(np.isnan(d["llr"]).any())
+            assert np.array_equal(np.isnan(gl), np.isnan(d["llr"])) and bits_equal(np.nan_to_num(gl), np.nan_to_num(d["llr"])), (s, q)
+            assert np.array_equal(plain[s, q].cpu().numpy(), d["plain"]), (s, q)
+            assert g_st[s][q]["ldpc_errors"] == d["status"]["ldpc_errors"] and int(ok[s, q]) == d["ok"], (s, q)
+    assert saw_nan
+
+
 @pytest.mark.parametrize("which", ["k120", "k500"])
-def test_sync_decode_spots_parity(ctx, ctx500, oracle, slots, which):
+def test_sync_decode_spots_parity(ctx, ctx500, oracle, slots, which, bp_variant):
     c = ctx if which == "k120" else ctx500
     mags = np.stack([oracle.waterfall(*s) for s in slots])
     rng = np.random.default_rng(3)
