@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <string>
+#include <mutex>
 #include <vector>
 
 using namespace ft8b200;
@@ -49,11 +50,25 @@ bool ends_with(const char *s, const char *suffix) {
     return a >= b && strcmp(s + a - b, suffix) == 0;
 }
 
+// Scratch device buffers of one call, from the device's stream-ordered pool: after the first call the pool holds the
+// memory (release threshold raised below), so a batch does not pay cudaMalloc/cudaFree -- which also synchronise the whole
+// device -- thirteen times over.
 struct DevFree {
+    cudaStream_t st;
     std::vector<void *> ptrs;
-    ~DevFree() { for (void *p : ptrs) cudaFree(p); }
+    explicit DevFree(cudaStream_t s) : st(s) {
+        static std::once_flag once[64];
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64)
+            std::call_once(once[dev], [dev] {
+                cudaMemPool_t pool;
+                unsigned long long keep = ~0ull;
+                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            });
+    }
+    ~DevFree() { for (void *p : ptrs) cudaFreeAsync(p, st); }
     template <class T> cudaError_t alloc(T **p, size_t bytes) {
-        cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -145,12 +160,12 @@ int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n,
         else { memset(&hi[(size_t)k * kSlot], 0, sizeof(float) * kSlot); memset(&hq[(size_t)k * kSlot], 0, sizeof(float) * kSlot); }
         if (h_samples) h_samples[k] = rec;
     }
-    DevFree pool;
+    cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
+    DevFree pool(st);
     float *d_i = nullptr, *d_q = nullptr, *d_peak = nullptr;
     const size_t bytes = (size_t)n * kSlot * sizeof(float);
     if (pool.alloc(&d_i, bytes) != cudaSuccess || pool.alloc(&d_q, bytes) != cudaSuccess || pool.alloc(&d_peak, sizeof(float) * n) != cudaSuccess)
         return FT8B200_ENOMEM;
-    cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
     if (cudaMemcpyAsync(d_i, hi.data(), bytes, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(d_q, hq.data(), bytes, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(d_peak, peak.data(), sizeof(float) * n, cudaMemcpyHostToDevice, st) != cudaSuccess)
@@ -182,7 +197,8 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
     const int num_bins = (int)(sample_rate * symbol_period / 2);
     const size_t bstride = (size_t)tosr * fosr * num_bins;
     const size_t mag_stride = ((size_t)max_blocks * bstride + 15) & ~(size_t)15;
-    DevFree pool;
+    cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
+    DevFree pool(st);
     uint8_t *d_mag = nullptr, *d_ok = nullptr, *d_stage = nullptr;
     candidate_t *d_cand = nullptr;
     int *d_ncand = nullptr;
@@ -212,7 +228,6 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
     std::vector<message_t> umsg(S * M);
     std::vector<int32_t> ucand(S * M), nres(S);
     std::vector<candidate_t> cand(S * K);
-    cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
     okc = cudaMemcpyAsync(umsg.data(), d_umsg, S * M * sizeof(message_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
           cudaMemcpyAsync(ucand.data(), d_ucand, S * M * sizeof(int32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
           cudaMemcpyAsync(nres.data(), d_nres, S * sizeof(int32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
@@ -253,12 +268,12 @@ int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n
     }
     for (int k = 0; k < n; ++k) h_count[k] = 0;
     if (max_n == 0) return 0;
-    DevFree pool;
+    cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
+    DevFree pool(st);
     int16_t *d_raw = nullptr;
     float *d_audio = nullptr;
     if (pool.alloc(&d_raw, (size_t)n * cap * sizeof(int16_t)) != cudaSuccess || pool.alloc(&d_audio, (size_t)n * cap * sizeof(float)) != cudaSuccess)
         return FT8B200_ENOMEM;
-    cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
     if (cudaMemcpyAsync(d_raw, raw.data(), (size_t)n * cap * sizeof(int16_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return FT8B200_ECUDA;
     const size_t total = (size_t)n * cap;
     s16_to_float_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_raw, d_audio, total);
