@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--e2e-slots", type=int, default=8, help="slots per step of the host-buffer (e2e) measurement")
     ap.add_argument("--chunks", type=int, default=4, help="executor batches per step: a step's slots are submitted to ft8b200_pipe_t in this many batches")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the pipelined executor")
-    ap.add_argument("--back-sms", type=int, default=40, help="SMs of the back-end partition (waterfall/sync/LDPC of batch n next to the decimator "
+    ap.add_argument("--back-sms", type=int, default=32, help="SMs of the back-end partition (waterfall/sync/LDPC of batch n next to the decimator "
                                                              "of batch n+1 on the other SMs); 0 = no partition, kernels of consecutive batches run serially")
     ap.add_argument("--overlap", action="store_true", help="(without a partition) let the back end of batch n time-share the GPU with the decimator of batch n+1")
     ap.add_argument("--k1-variant", type=int, default=0, help="0 = streaming cic_block_sums kernel, 1..6 = bulk-copy (TMA) variants")

@@ -334,8 +334,16 @@ int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_
     if (rc) return rc;
     if (!d_mag || !d_cand || !d_ncand || !d_ok || !d_stage || !d_status || !d_msg || n_slots < 1)
         return fail(FT8B200_EINVAL, "ft8b200_decode: bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = ctx->work_total.ensure(4 * sizeof(unsigned int)))) return rc;
+    unsigned int *pull = nullptr;
+    if (decode_variant() == 0 && (size_t)n_slots * ctx->cfg.max_candidates > 8u * 4u * (size_t)ctx->sm_count) {
+        // more candidates than resident warps: let the warps pull them (counter = word [1], see launch_decode)
+        pull = ctx->work_total.as<unsigned int>();
+        CU(cudaMemsetAsync(pull, 0, 4 * sizeof(unsigned int), pick(ctx, stream)));
+    }
     CU(launch_decode(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->protocol, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
-                     d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, nullptr, nullptr, ctx->sm_count, pick(ctx, stream), &ctx->launches));
+                     d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, nullptr, pull, ctx->sm_count, pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
 }
