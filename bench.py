@@ -223,7 +223,7 @@ def main():
                   ("SM partition: back end of batch n on >= %d SMs, decimator of batch n+1 on the others" % args.back_sms) if args.back_sms > 0 else
                   ("overlap (time-shared)" if args.overlap else "serial (kernels of consecutive batches do not share the GPU)")),
               "parallelism": "slots sharded across GPUs, no data-path collective; "
-              "spot records gathered with NCCL all_gather" if world > 1 else "single GPU"}
+              "spot records gathered with one NCCL all_gather per step" if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         return reference_arm(args, rank, world, config)
@@ -259,23 +259,36 @@ def main():
             config["executor"] = "ft8b200_pipe_t depth %d, %d batches of %d slots per step, serial" % (args.depth, args.chunks, args.slots // args.chunks)
             args.back_sms = 0
     M = pipe.M
-    gathered = torch.empty((world * Bc, M, 28), dtype=torch.uint8, device=device) if world > 1 else None
-    gathered_n = torch.empty(world * Bc, dtype=torch.int32, device=device) if world > 1 else None
-    gather_done = torch.cuda.Event()
+    # Multi-GPU: the spot records of a step's batches are staged on the device (a local copy, so a lane is free again as soon
+    # as its records are copied) and gathered to every rank with ONE NCCL all_gather per step; rank 0 reads them on the host.
+    rec_bytes = Bc * M * 28
+    if world > 1:
+        stage = torch.empty((args.chunks, rec_bytes + 4 * Bc), dtype=torch.uint8, device=device)  # per batch: records, then counts
+        gathered = torch.empty((world, args.chunks, rec_bytes + 4 * Bc), dtype=torch.uint8, device=device)
+        copied = torch.cuda.Event()
+    n_staged = [0]
 
     def collect():
-        """Oldest batch -> host records on rank 0 (multi-GPU: one NCCL all_gather of the fixed-size spot records)."""
+        """Oldest batch -> host records on rank 0 (multi-GPU: one NCCL all_gather of the fixed-size spot records per step)."""
         if world > 1 and os.environ.get("BENCH_NOGATHER"):
             return pipe.collect(Bc)   # diagnostic only: how fast would the ranks run without the collective
         if world > 1:
             res_dev, nres_dev = pipe.collect_device()
-            dist.all_gather_into_tensor(gathered, res_dev)   # spot records over NVLink
-            dist.all_gather_into_tensor(gathered_n, nres_dev)
-            gather_done.record()
-            pipe.depend_on(gather_done)   # the lane's buffers are rewritten only after the collective has read them
-            if rank == 0:
-                return gathered.cpu(), gathered_n.cpu()   # every batch's records reach the host on rank 0
-            return None
+            k = n_staged[0] % args.chunks
+            stage[k, :rec_bytes].view(Bc, M, 28).copy_(res_dev)
+            stage[k, rec_bytes:].view(torch.int32).copy_(nres_dev)
+            copied.record()
+            pipe.depend_on(copied)   # the lane's buffers are rewritten only after they have been copied out (ordered on the device)
+            n_staged[0] += 1
+            if n_staged[0] % args.chunks:
+                return None
+            dist.all_gather_into_tensor(gathered.view(-1), stage.view(-1))   # spot records over NVLink, once per step
+            if rank != 0:
+                return None
+            g = gathered.cpu().numpy()   # every step's records reach the host on rank 0
+            res = np.ascontiguousarray(g[:, :, :rec_bytes]).reshape(world * B, M, 28)
+            nres = np.ascontiguousarray(g[:, :, rec_bytes:]).view(np.int32).reshape(world * B)
+            return res, nres
         return pipe.collect(Bc)
 
     def run(steps):
@@ -289,9 +302,10 @@ def main():
                 pipe.submit(batch[c * Bc:(c + 1) * Bc], Bc)
         while pipe.in_flight():
             outs.append(collect())
+        if world > 1:
+            done = [o for o in outs if o is not None]
+            return done[-1] if done else None
         last = outs[-args.chunks:]
-        if last[0] is None:
-            return None
         return np.concatenate([np.asarray(o[0]) for o in last]), np.concatenate([np.asarray(o[1]) for o in last])
 
     out = run(args.warmup)
@@ -306,6 +320,8 @@ def main():
         n_good = sum(1 for s in range(B) if slot_ok(s))
     else:
         n_good = -1
+        if rank == 0 and out is not None:  # gathered records of every rank: slots that produced at least one message
+            config["decoded_slots_all_ranks"] = "%d of %d" % (int((out[1] >= 1).sum()), world * B)
 
     def barrier():
         if world > 1:
