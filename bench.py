@@ -266,7 +266,21 @@ def main():
         stage = torch.empty((args.chunks, rec_bytes + 4 * Bc), dtype=torch.uint8, device=device)  # per batch: records, then counts
         gathered = torch.empty((world, args.chunks, rec_bytes + 4 * Bc), dtype=torch.uint8, device=device)
         copied = torch.cuda.Event()
+        # rank 0 reads every step's gathered records into pinned host memory without blocking its submit loop
+        host_rec = [torch.empty(gathered.shape, dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
+        host_ev = [torch.cuda.Event(), torch.cuda.Event()]
     n_staged = [0]
+
+    def last_gathered():
+        """rank 0: records of the last gathered step, all ranks, in (rank, slot) order."""
+        if rank != 0 or n_staged[0] < args.chunks:
+            return None
+        i = (n_staged[0] // args.chunks - 1) % 2
+        host_ev[i].synchronize()
+        g = host_rec[i].numpy()
+        res = np.ascontiguousarray(g[:, :, :rec_bytes]).reshape(world * B, M, 28)
+        nres = np.ascontiguousarray(g[:, :, rec_bytes:]).view(np.int32).reshape(world * B)
+        return res, nres
 
     def collect():
         """Oldest batch -> host records on rank 0 (multi-GPU: one NCCL all_gather of the fixed-size spot records per step)."""
@@ -280,15 +294,14 @@ def main():
             copied.record()
             pipe.depend_on(copied)   # the lane's buffers are rewritten only after they have been copied out (ordered on the device)
             n_staged[0] += 1
-            if n_staged[0] % args.chunks:
-                return None
-            dist.all_gather_into_tensor(gathered.view(-1), stage.view(-1))   # spot records over NVLink, once per step
-            if rank != 0:
-                return None
-            g = gathered.cpu().numpy()   # every step's records reach the host on rank 0
-            res = np.ascontiguousarray(g[:, :, :rec_bytes]).reshape(world * B, M, 28)
-            nres = np.ascontiguousarray(g[:, :, rec_bytes:]).view(np.int32).reshape(world * B)
-            return res, nres
+            if n_staged[0] % args.chunks == 0:
+                dist.all_gather_into_tensor(gathered.view(-1), stage.view(-1))   # spot records over NVLink, once per step
+                if rank == 0:
+                    i = (n_staged[0] // args.chunks - 1) % 2
+                    host_ev[i].synchronize()   # the copy issued two steps ago (long finished) owns this buffer
+                    host_rec[i].copy_(gathered, non_blocking=True)
+                    host_ev[i].record()
+            return None
         return pipe.collect(Bc)
 
     def run(steps):
@@ -303,8 +316,7 @@ def main():
         while pipe.in_flight():
             outs.append(collect())
         if world > 1:
-            done = [o for o in outs if o is not None]
-            return done[-1] if done else None
+            return last_gathered()
         last = outs[-args.chunks:]
         return np.concatenate([np.asarray(o[0]) for o in last]), np.concatenate([np.asarray(o[1]) for o in last])
 
