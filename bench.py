@@ -177,6 +177,31 @@ def cpu_run(n_slots: int, workers: int):
 _JSON_FD = None
 
 
+def bind_to_gpu_numa(local: int):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the e2e measurement
+    (first touch) are local to the PCIe root the copies go through.  Returns a note for `config`, or None when it does not apply."""
+    if os.environ.get("BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "GPU %s on NUMA node %d: rank bound to its %d CPUs" % (bus, node, len(cpus))
+    except Exception as exc:
+        return "not bound (%s)" % type(exc).__name__
+
+
 def emit(obj):
     line = (json.dumps(obj) + "\n").encode()
     if _JSON_FD is None:
@@ -234,6 +259,9 @@ def main():
     pkg = load()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
+    if numa:
+        config["numa"] = numa
     if world > 1:
         # the all_gather of the spot records must not queue behind the decimator's 190k-CTA grid: high-priority NCCL stream
         opts = dist.ProcessGroupNCCL.Options()
