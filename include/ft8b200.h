@@ -394,6 +394,10 @@ typedef struct {
     float amp;            /* raw path: amplitude in LSB; float paths: linear amplitude */
 } ft8b200_signal_t;
 int ft8b200_pack77_std(const char *call_to, const char *call_de, const char *extra, uint8_t *payload10);
+/* replaces: pack77(), ft8_lib/ft8/pack.c:284-301 (what decoderSelfTest() and gen_ft8 call): a standard message when both call
+ * fields pack (pack77_1, :167-218: "CQ K1JT FN20QI" packs as FN20), else 13 characters of free text (packtext77, :220-282).
+ * Host code.  Returns 0 = standard message, 1 = free text, -1 = NULL argument (the reference returns 0 in both cases). */
+int ft8b200_pack77(const char *msg, uint8_t *payload10);
 /* n payloads (10 bytes each, host) -> n x 105 channel symbols (host; FT8 uses the first 79), computed on the device */
 int ft8b200_encode_tones(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, int protocol, uint8_t *h_tones);
 /* Slot s holds signals h_first[s] .. h_first[s+1]-1 (h_first has n_slots+1 entries).  Noise stream of slot s is selected by

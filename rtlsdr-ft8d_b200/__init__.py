@@ -41,6 +41,15 @@ def pack77_std(call_to: str, call_de: str, extra: str) -> bytes:
     return b.raw
 
 
+def pack77(msg: str):
+    """pack77() of ft8_lib (pack.c:284-301): message text -> (10-byte payload, kind) with kind 0 = standard, 1 = free text."""
+    b = C.create_string_buffer(10)
+    kind = lib().ft8b200_pack77(msg.encode(), b)
+    if kind < 0:
+        raise ValueError("ft8b200_pack77")
+    return b.raw, kind
+
+
 def make_signals(items):
     """items: iterable of (payload bytes, f0_hz, t0_sec, amp) -> signal_dtype array."""
     items = list(items)

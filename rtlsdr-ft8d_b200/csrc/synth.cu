@@ -323,6 +323,107 @@ int ft8b200_pack77_std(const char *call_to, const char *call_de, const char *ext
     return 0;
 }
 
+// ---- pack77(): message text -> 77-bit payload, the whole of ft8_lib/ft8/pack.c:284-301 -------------------------------
+// A standard message ("<call|DE|QRZ|CQ> <call> [grid | report | RRR | RR73 | 73]", pack77_1 :167-218) when both call fields
+// pack, otherwise 13 characters of free text (packtext77 :220-282).  The reference's quirks are kept because they decide
+// which bits go on the air: the third field is whatever follows the second blank ("FN20QI" packs as FN20; a field that is
+// neither a grid nor a keyword goes through dd_to_int() unchecked), special tokens need their trailing blank, the 3DA0 and
+// 3X prefix rewrites, and free text maps every character outside the 42-symbol alphabet (lower case included) to a blank.
+namespace {
+
+bool has_prefix(const char *s, const char *prefix) { return strncmp(s, prefix, strlen(prefix)) == 0; }
+bool digit(char c) { return c >= '0' && c <= '9'; }
+bool letter(char c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'); }
+int index_in(const char *alphabet, char c) {
+    if (!c) return -1;
+    const char *hit = strchr(alphabet, c);
+    return hit ? (int)(hit - alphabet) : -1;
+}
+
+// pack28(), pack.c:22-98: `field` points INTO the message, the field ends at the next blank or at the end of the string
+long field_to_n28(const char *field) {
+    if (has_prefix(field, "DE ")) return 0;
+    if (has_prefix(field, "QRZ ")) return 1;
+    if (has_prefix(field, "CQ ")) return 2;
+    int len = 0;
+    while (field[len] && field[len] != ' ') ++len;
+    auto at = [&](int k) { return k <= len ? field[k] : '\0'; };  // field[len] is the delimiter; nothing is read beyond it
+    char c6[6] = {' ', ' ', ' ', ' ', ' ', ' '};
+    if (has_prefix(field, "3DA0") && len <= 7) {          // Swaziland: 3DA0XYZ -> 3D0XYZ
+        memcpy(c6, "3D0", 3);
+        memcpy(c6 + 3, field + 4, (size_t)(len - 4));
+    } else if (has_prefix(field, "3X") && letter(at(2)) && len <= 7) {  // Guinea: 3XA0XYZ -> QA0XYZ
+        c6[0] = 'Q';
+        memcpy(c6 + 1, field + 2, (size_t)(len - 2));
+    } else if (digit(at(2)) && len <= 6) {
+        memcpy(c6, field, (size_t)len);
+    } else if (digit(at(1)) && len <= 5) {
+        memcpy(c6 + 1, field, (size_t)len);
+    }
+    static const char *const alphabets[6] = {" 0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ", "0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ", "0123456789",
+                                             " ABCDEFGHIJKLMNOPQRSTUVWXYZ", " ABCDEFGHIJKLMNOPQRSTUVWXYZ", " ABCDEFGHIJKLMNOPQRSTUVWXYZ"};
+    static const long radix[6] = {37, 36, 10, 27, 27, 27};
+    long n = 0;
+    for (int k = 0; k < 6; ++k) {
+        const int q = index_in(alphabets[k], c6[k]);
+        if (q < 0) return -1;
+        n = n * radix[k] + q;
+    }
+    return 2063592L + 4194304L + n;  // NTOKENS + MAX22 + n28
+}
+
+// dd_to_int(str, 3), text.c:103-131: optional sign, then digits while fewer than 3 characters have been consumed
+int report_value(const char *s) {
+    const bool neg = s[0] == '-';
+    int k = (neg || s[0] == '+') ? 1 : 0, v = 0;
+    for (; k < 3 && digit(s[k]); ++k) v = v * 10 + (s[k] - '0');
+    return neg ? -v : v;
+}
+
+// packgrid(), pack.c:122-164: `rest` = everything after the second blank, or NULL when there is none
+uint16_t third_field(const char *rest) {
+    if (!rest) return 32401;
+    if (!strcmp(rest, "RRR")) return 32402;
+    if (!strcmp(rest, "RR73")) return 32403;
+    if (!strcmp(rest, "73")) return 32404;
+    if (rest[0] >= 'A' && rest[0] <= 'R' && rest[1] >= 'A' && rest[1] <= 'R' && digit(rest[2]) && digit(rest[3]))
+        return (uint16_t)(((rest[0] - 'A') * 18 + (rest[1] - 'A')) * 100 + (rest[2] - '0') * 10 + (rest[3] - '0'));
+    if (rest[0] == 'R') return (uint16_t)((32400 + (uint16_t)(35 + report_value(rest + 1))) | 0x8000);
+    return (uint16_t)(32400 + (uint16_t)(35 + report_value(rest)));
+}
+
+}  // namespace
+
+int ft8b200_pack77(const char *msg, uint8_t *payload10) {
+    if (!msg || !payload10) return -1;
+    const char *blank1 = strchr(msg, ' ');
+    if (blank1) {
+        const long a = field_to_n28(msg), d = field_to_n28(blank1 + 1);
+        if (a >= 0 && d >= 0) {
+            const char *blank2 = strchr(blank1 + 1, ' ');
+            const uint32_t g = third_field(blank2 ? blank2 + 1 : nullptr);
+            const uint32_t a29 = (uint32_t)a << 1, d29 = (uint32_t)d << 1;  // ipa = ipb = 0
+            const uint32_t b[10] = {a29 >> 21, a29 >> 13, a29 >> 5, (a29 << 3) | (d29 >> 26), d29 >> 18, d29 >> 10, d29 >> 2, (d29 << 6) | (g >> 10), g >> 2,
+                                    (g << 6) | (1u << 3)};  // i3 = 1
+            for (int k = 0; k < 10; ++k) payload10[k] = (uint8_t)b[k];
+            return 0;
+        }
+    }
+    // free text, i3 = 0, n3 = 0: 13 base-42 digits as a 71-bit number, left-aligned in the first 72 bits
+    while (*msg == ' ') ++msg;
+    int len = (int)strlen(msg);
+    while (len > 0 && msg[len - 1] == ' ') --len;
+    unsigned __int128 v = 0;
+    for (int k = 0; k < 13; ++k) {
+        const int q = k < len ? index_in(" 0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ+-./?", msg[k]) : 0;
+        v = v * 42 + (unsigned)(q > 0 ? q : 0);
+    }
+    v <<= 1;
+    for (int k = 8; k >= 0; --k, v >>= 8) payload10[k] = (uint8_t)v;
+    payload10[9] = 0;
+    return 1;
+}
+
 // channel symbols of n payloads (10 bytes each) on the device: d_tones = n x 105 bytes (FT8 fills the first 79)
 int ft8b200_encode_tones(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, int protocol, uint8_t *h_tones) {
     if (!ctx || !h_payloads || !h_tones || n < 1 || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return FT8B200_EINVAL;

@@ -111,6 +111,22 @@ def test_wav_and_iq_readers_without_gpu(pkg, tmp_path):
     assert e.value.args[0] == -3
 
 
+def test_library_pack77_golden(pkg, oracle):
+    """ft8b200_pack77 against payloads the reference's pack77() produced for 400 message texts (tests/golden/pack77.npz);
+    standard ones agree with the restated field packer, free text with the restated text packer."""
+    g = golden("pack77")
+    kinds = []
+    for m, want in zip(g["msgs"], g["packed"]):
+        got, kind = pkg.pack77(str(m))
+        assert got == want.tobytes(), repr(str(m))
+        kinds.append(kind)
+        if kind == 1:
+            assert got == oracle.pack_text(str(m))
+    assert 100 < kinds.count(0) < 300
+    assert pkg.pack77("CQ K1JT FN20QI") == (bytes.fromhex("000000204dfcdc8a1408"), 0)   # rtlsdr_ft8d.c:919-923
+    assert pkg.pack77("CQ K1JT FN20")[0] == oracle.pack_std("CQ", "K1JT", "FN20")
+
+
 def test_pack77_std_matches_the_restated_packer(pkg, oracle):
     """ft8b200_pack77_std (host code of csrc/synth.cu) == the oracle's restatement of pack77 for standard messages
     (itself pinned to the reference), and rejects what the type-1 format cannot carry."""

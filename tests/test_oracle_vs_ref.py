@@ -132,6 +132,18 @@ def test_unpack77_fuzz(oracle):
         assert oracle.unpack77(bytes(a)) == ref.unpack77(bytes(a))
 
 
+def test_library_pack77_vs_reference(pkg):
+    """ft8b200_pack77 (host code of the library) against the reference's own pack77() (pack.c:284-301) on 20 000 message texts:
+    standard / free-text choice and every payload byte, quirks included ("FN20QI" packs as FN20, unchecked reports, 3DA0/3X)."""
+    ref = Reference("k120")
+    n_std = 0
+    for m in synth.pack77_fuzz_messages(23, 20000):
+        got, kind = pkg.pack77(m)
+        assert got == ref.pack77(m), repr(m)
+        n_std += kind == 0
+    assert 5000 < n_std < 15000
+
+
 def test_encoder_and_crc_vs_reference(oracle):
     ref = Reference("k120")
     rng = np.random.default_rng(8)

@@ -114,6 +114,9 @@ def main():
     assert p.hex() == "000000204dfcdc8a1408"  # rtlsdr_ft8d.c:921
     assert "".join(map(str, R.tones(p))) == "3140652000000001005477547106035036373140652547441342116056460065174427143140652"  # :922
     report_fixture()
+    # pack77(): message texts -> the reference's payloads (ft8_lib/ft8/pack.c:284-301)
+    msgs = synth.pack77_fuzz_messages(11, 400)
+    np.savez_compressed(os.path.join(OUT, "pack77.npz"), msgs=np.array(msgs), packed=np.stack([np.frombuffer(R.pack77(m), np.uint8) for m in msgs]))
 
 
 if __name__ == "__main__":

@@ -141,3 +141,49 @@ def audio_12k(signals, seed: int, noise_sigma: float = 0.05, n_samples: int = 18
                 x[a:b] += amp * np.cos(phase + 2.0 * np.pi * f * t[a - lo:b - lo])
             phase = (phase + 2.0 * np.pi * f * sym / fs) % (2.0 * np.pi)
     return x.astype(np.float32)
+
+
+def pack77_fuzz_messages(seed: int, n: int):
+    """Message texts for the pack77() parity tests: standard exchanges, special tokens, the 3DA0/3X prefix rewrites, reports
+    with and without sign/R, keywords, trailing junk, stray blanks, lower case, free text and empty strings."""
+    import random
+    rnd = random.Random(seed)
+    L, D = "ABCDEFGHIJKLMNOPQRSTUVWXYZ", "0123456789"
+
+    def call():
+        k = rnd.random()
+        if k < 0.5:
+            return rnd.choice(L) + rnd.choice(L + D) + rnd.choice(D) + "".join(rnd.choice(L) for _ in range(rnd.randint(0, 3)))
+        if k < 0.7:
+            return rnd.choice(L) + rnd.choice(D) + "".join(rnd.choice(L) for _ in range(rnd.randint(1, 3)))
+        if k < 0.75:
+            return "3DA0" + "".join(rnd.choice(L) for _ in range(rnd.randint(0, 4)))
+        if k < 0.8:
+            return "3X" + rnd.choice(L + D) + rnd.choice(D) + "".join(rnd.choice(L) for _ in range(rnd.randint(0, 4)))
+        if k < 0.9:
+            return rnd.choice(["DE", "QRZ", "CQ", "CQ_DX", "CQ 123", "<...>", "PJ4/K1ABC", "K1ABC/P", "W9XYZ/R"])
+        return "".join(rnd.choice(L + D + "/ ") for _ in range(rnd.randint(1, 9)))
+
+    def extra():
+        k = rnd.random()
+        if k < 0.3:
+            return rnd.choice(L[:18]) + rnd.choice(L[:18]) + rnd.choice(D) + rnd.choice(D) + rnd.choice(["", "QI", "xx", " 73"])
+        if k < 0.6:
+            return rnd.choice(["", "R"]) + rnd.choice(["+", "-", ""]) + "".join(rnd.choice(D) for _ in range(rnd.randint(0, 3)))
+        if k < 0.8:
+            return rnd.choice(["RRR", "RR73", "73", "RRR ", "R", "73 GL", "RR 73"])
+        return "".join(rnd.choice(L + D + "+-./? ") for _ in range(rnd.randint(0, 8)))
+
+    msgs = ["", " ", "CQ", "CQ ", "CQ K1JT", "CQ K1JT ", "CQ K1JT FN20", "CQ K1JT FN20QI", "CQ  K1JT FN20", " CQ K1JT FN20", "hello world",
+            "TNX BOB 73 GL", "K1", "K1 W2", "A", "AB", "3X", "3DA0", "3DA0 K1ABC FN20", "DE K1ABC -07", "QRZ W9XYZ R-15", "K1ABC W9XYZ R+",
+            "K1ABC W9XYZ -", "0123456789ABCDEFGHIJ", "+-./?", "a1bcd k1abc fn20"]
+    while len(msgs) < n:
+        k = rnd.random()
+        if k < 0.75:
+            m = call() + " " + call() + (" " + extra() if rnd.random() < 0.8 else "")
+        elif k < 0.9:
+            m = "".join(rnd.choice(L + D + "+-./? abc") for _ in range(rnd.randint(0, 16)))
+        else:
+            m = " " * rnd.randint(0, 2) + call() + " " * rnd.randint(1, 2) + call() + " " * rnd.randint(0, 2) + extra()
+        msgs.append(m)
+    return msgs[:n]
