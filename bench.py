@@ -289,10 +289,10 @@ def main():
     M = pipe.M
     # Multi-GPU: the spot records of a step's batches are staged on the device (a local copy, so a lane is free again as soon
     # as its records are copied) and gathered to every rank with ONE NCCL all_gather per step; rank 0 reads them on the host.
-    rec_bytes = Bc * M * 28
+    from tools.shard import stage_batch, stage_row_bytes, unpack_gathered
     if world > 1:
-        stage = torch.empty((args.chunks, rec_bytes + 4 * Bc), dtype=torch.uint8, device=device)  # per batch: records, then counts
-        gathered = torch.empty((world, args.chunks, rec_bytes + 4 * Bc), dtype=torch.uint8, device=device)
+        stage = torch.empty((args.chunks, stage_row_bytes(Bc, M)), dtype=torch.uint8, device=device)  # per batch: records, then counts
+        gathered = torch.empty((world, args.chunks, stage_row_bytes(Bc, M)), dtype=torch.uint8, device=device)
         copied = torch.cuda.Event()
         # rank 0 reads every step's gathered records into pinned host memory without blocking its submit loop
         host_rec = [torch.empty(gathered.shape, dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
@@ -305,10 +305,7 @@ def main():
             return None
         i = (n_staged[0] // args.chunks - 1) % 2
         host_ev[i].synchronize()
-        g = host_rec[i].numpy()
-        res = np.ascontiguousarray(g[:, :, :rec_bytes]).reshape(world * B, M, 28)
-        nres = np.ascontiguousarray(g[:, :, rec_bytes:]).view(np.int32).reshape(world * B)
-        return res, nres
+        return unpack_gathered(host_rec[i].numpy(), world, args.chunks, Bc, M)
 
     def collect():
         """Oldest batch -> host records on rank 0 (multi-GPU: one NCCL all_gather of the fixed-size spot records per step)."""
@@ -316,9 +313,7 @@ def main():
             return pipe.collect(Bc)   # diagnostic only: how fast would the ranks run without the collective
         if world > 1:
             res_dev, nres_dev = pipe.collect_device()
-            k = n_staged[0] % args.chunks
-            stage[k, :rec_bytes].view(Bc, M, 28).copy_(res_dev)
-            stage[k, rec_bytes:].view(torch.int32).copy_(nres_dev)
+            stage_batch(stage, n_staged[0] % args.chunks, res_dev, nres_dev, Bc, M)
             copied.record()
             pipe.depend_on(copied)   # the lane's buffers are rewritten only after they have been copied out (ordered on the device)
             n_staged[0] += 1

@@ -57,6 +57,54 @@ def _worker(rank, world, port, n_total, out_path):
     dist.destroy_process_group()
 
 
+def _step_worker(rank, world, port, chunks, bc, m, out_path):
+    """bench.py's multi-GPU record path on gloo: every batch's records are staged as soon as the batch is collected, ONE all_gather
+    per step moves the flat stage, rank 0 unpacks (rank, slot)-ordered records."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from tools.shard import stage_batch, stage_row_bytes, unpack_gathered
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    stage = torch.zeros((chunks, stage_row_bytes(bc, m)), dtype=torch.uint8)
+    gathered = torch.empty((world, chunks, stage_row_bytes(bc, m)), dtype=torch.uint8)
+    steps = []
+    for step in range(2):  # the stage is reused by the next step
+        for k in range(chunks):
+            slot0 = (rank * chunks + k) * bc   # global slot index of the batch's first slot
+            res = torch.zeros((bc, m, 28), dtype=torch.uint8)
+            nres = torch.zeros(bc, dtype=torch.int32)
+            for j in range(bc):
+                res[j, :, 0] = (slot0 + j + 7 * step) % 251
+                res[j, j % m, 27] = 200 + step
+                nres[j] = slot0 + j + 1000 * step
+            stage_batch(stage, k, res, nres, bc, m)
+        dist.all_gather_into_tensor(gathered.view(-1), stage.view(-1))
+        if rank == 0:
+            steps.append(unpack_gathered(gathered.numpy().copy(), world, chunks, bc, m))
+    if rank == 0:
+        np.savez(out_path, res0=steps[0][0], n0=steps[0][1], res1=steps[1][0], n1=steps[1][1])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_gather(tmp_path):
+    import torch.multiprocessing as mp
+    world, chunks, bc, m = 2, 3, 4, 5
+    out = str(tmp_path / "steps.npz")
+    mp.spawn(_step_worker, args=(world, _free_port(), chunks, bc, m, out), nprocs=world, join=True)
+    g = np.load(out)
+    total = world * chunks * bc
+    for step in range(2):
+        res, n = g[f"res{step}"], g[f"n{step}"]
+        assert res.shape == (total, m, 28) and n.shape == (total,)
+        assert n.tolist() == [s + 1000 * step for s in range(total)], "counts in (rank, slot) order"
+        for s in range(total):
+            assert (res[s, :, 0] == (s + 7 * step) % 251).all() and res[s, (s % bc) % m, 27] == 200 + step
+
+
 def test_shard_ranges_cover_everything_once():
     sys.path.insert(0, ROOT)
     from tools.shard import shard_range
