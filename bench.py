@@ -129,24 +129,33 @@ def cpu_kind():
     return "reference" if Reference.available("k120") else "port"
 
 
+_CPU_PHASE_S = {"decimator": 0.0, "decode": 0.0}   # seconds spent per phase by _cpu_one_slot in THIS process (single-thread baseline)
+
+
 def _cpu_one_slot(idx: int):
     """Raw slot -> spots on the CPU: rtlsdr_callback() in 65536-byte calls, decoder() conditioning, ft8_subsystem()."""
     from oracle.pyoracle import Oracle, Reference
     raw = _CPU_SLOTS[idx]
     orc = Oracle()
+    t0 = time.perf_counter()
     if cpu_kind() == "reference":
         ref = Reference("k120", fresh=True)  # private copy: the daemon's decimator state is function-static
         for o in range(0, raw.size, 65536):
             ref.callback(raw[o:o + 65536])
         i_s, q_s, n = ref.rx()
+        t1 = time.perf_counter()
         i_s, q_s, _ = orc.condition(i_s, q_s, n)  # decoder() itself is thread-bound in the daemon (rtlsdr_ft8d.c:221-285)
-        r = ref.subsystem(i_s, q_s)
-        return int(r["n"])
-    oi, oq = orc.decimate_slot(raw)
-    i_s = np.zeros(48000, np.float32); q_s = np.zeros(48000, np.float32)
-    i_s[:oi.size] = oi; q_s[:oq.size] = oq
-    i_s, q_s, _ = orc.condition(i_s, q_s, oi.size)
-    return int(orc.subsystem(i_s, q_s)["n"])
+        count = int(ref.subsystem(i_s, q_s)["n"])
+    else:
+        oi, oq = orc.decimate_slot(raw)
+        t1 = time.perf_counter()
+        i_s = np.zeros(48000, np.float32); q_s = np.zeros(48000, np.float32)
+        i_s[:oi.size] = oi; q_s[:oq.size] = oq
+        i_s, q_s, _ = orc.condition(i_s, q_s, oi.size)
+        count = int(orc.subsystem(i_s, q_s)["n"])
+    _CPU_PHASE_S["decimator"] += t1 - t0
+    _CPU_PHASE_S["decode"] += time.perf_counter() - t1
+    return count
 
 
 def _cpu_synth_slot(idx: int):
@@ -458,12 +467,16 @@ def main():
         global _CPU_SLOTS
         n_cpu = min(args.cpu_slots, B)
         _CPU_SLOTS = batch[:n_cpu].cpu().numpy()
+        _CPU_PHASE_S["decimator"] = _CPU_PHASE_S["decode"] = 0.0
         secs, n_dec = cpu_run(n_cpu, 1)
         gpu_n = [int(x) for x in nres[:n_cpu]]
         out["cpu_baseline"] = {"value": n_cpu / secs, "unit": "slots/s", "cores": 1, "kind": cpu_kind(),
                                "sample": "%d of the step's %d slots, single thread: rtlsdr_callback in 65536-byte calls + decoder() "
                                          "conditioning + ft8_subsystem (%.2f s)" % (n_cpu, B, secs),
-                               "same_spot_counts_as_gpu": n_dec == gpu_n}
+                               "same_spot_counts_as_gpu": n_dec == gpu_n,
+                               # the two halves of the path on one host thread
+                               "decimator_msps": n_cpu * (RAW_SLOT_BYTES // 2) / max(_CPU_PHASE_S["decimator"], 1e-9) / 1e6,
+                               "decode_slots_per_s": n_cpu / max(_CPU_PHASE_S["decode"], 1e-9)}
     if rank == 0:
         emit(out)
     if world > 1:
