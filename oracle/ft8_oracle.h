@@ -109,6 +109,7 @@ int orc_decode_waterfall(const orc_waterfall_t *wf, int max_candidates, int max_
 /* ---- encoder side (input synthesis only) ---- */
 int orc_pack_std(const char *call_to, const char *call_de, const char *extra, uint8_t *payload10);
 void orc_pack_text(const char *text, uint8_t *payload10);
+int orc_pack77(const char *msg, uint8_t *payload10); /* ref: pack77, pack.c:284-301; 0 = standard message, 1 = free text */
 void orc_encode_tones(const uint8_t *payload10, uint8_t *tones79);
 void orc_encode_tones_ft4(const uint8_t *payload10, uint8_t *tones105);
 void orc_encode174(const uint8_t *payload10, uint8_t *bits174);

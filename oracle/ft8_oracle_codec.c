@@ -570,6 +570,91 @@ void orc_pack_text(const char *text, uint8_t *b) { /* ref: packtext77, pack.c:23
     b[9] = 0;
 }
 
+/* ---- pack77(): whole message text -> payload.  ref: pack77, pack.c:284-301 = pack77_1 (:167-218) else packtext77 (:220-282) ---- */
+/* The fields are NOT separate strings in the reference: pack28() is handed a pointer into the message and looks at what follows. */
+static int begins(const char *s, const char *prefix) { return strncmp(s, prefix, strlen(prefix)) == 0; }
+
+static int32_t msg_pack28(const char *cs) { /* ref: pack28, pack.c:22-98 */
+    if (begins(cs, "DE ")) return 0;
+    if (begins(cs, "QRZ ")) return 1;
+    if (begins(cs, "CQ ")) return 2;
+    int length = 0;
+    while (cs[length] != ' ' && cs[length] != 0) ++length;
+    /* characters the reference tests beyond a short field: cs[length] is the delimiter, nothing further is ever decisive */
+    const char c1 = length >= 1 ? cs[1] : 0, c2 = length >= 2 ? cs[2] : 0;
+    char c6[6] = { ' ', ' ', ' ', ' ', ' ', ' ' };
+    if (begins(cs, "3DA0") && length <= 7) { /* :45-49 */
+        memcpy(c6, "3D0", 3);
+        memcpy(c6 + 3, cs + 4, (size_t)(length - 4));
+    } else if (begins(cs, "3X") && ((c2 >= 'A' && c2 <= 'Z') || (c2 >= 'a' && c2 <= 'z')) && length <= 7) { /* :50-55 */
+        memcpy(c6, "Q", 1);
+        memcpy(c6 + 1, cs + 2, (size_t)(length - 2));
+    } else if (c2 >= '0' && c2 <= '9' && length <= 6) { /* :58-62 */
+        memcpy(c6, cs, (size_t)length);
+    } else if (c1 >= '0' && c1 <= '9' && length <= 5) { /* :63-67 */
+        memcpy(c6 + 1, cs, (size_t)length);
+    }
+    const int i0 = index_of(" 0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ", c6[0]);
+    const int i1 = index_of("0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ", c6[1]);
+    const int i2 = index_of("0123456789", c6[2]);
+    const int i3 = index_of(" ABCDEFGHIJKLMNOPQRSTUVWXYZ", c6[3]);
+    const int i4 = index_of(" ABCDEFGHIJKLMNOPQRSTUVWXYZ", c6[4]);
+    const int i5 = index_of(" ABCDEFGHIJKLMNOPQRSTUVWXYZ", c6[5]);
+    if (i0 < 0 || i1 < 0 || i2 < 0 || i3 < 0 || i4 < 0 || i5 < 0) return -1;
+    int32_t n = i0;
+    n = n * 36 + i1; n = n * 10 + i2; n = n * 27 + i3; n = n * 27 + i4; n = n * 27 + i5;
+    return 2063592 + 4194304 + n;
+}
+
+static int msg_dd_to_int(const char *str, int length) { /* ref: dd_to_int, text.c:103-131 */
+    int result = 0, i, negative = 0;
+    if (str[0] == '-') { negative = 1; i = 1; }
+    else i = (str[0] == '+') ? 1 : 0;
+    while (i < length && str[i] != 0 && str[i] >= '0' && str[i] <= '9') { result = result * 10 + (str[i] - '0'); ++i; }
+    return negative ? -result : result;
+}
+
+static uint16_t msg_packgrid(const char *g) { /* ref: packgrid, pack.c:122-164; g = the text behind the second blank, or NULL */
+    if (g == 0) return 32400 + 1;
+    if (strcmp(g, "RRR") == 0) return 32400 + 2;
+    if (strcmp(g, "RR73") == 0) return 32400 + 3;
+    if (strcmp(g, "73") == 0) return 32400 + 4;
+    if (g[0] >= 'A' && g[0] <= 'R' && g[1] >= 'A' && g[1] <= 'R' && g[2] >= '0' && g[2] <= '9' && g[3] >= '0' && g[3] <= '9') {
+        uint16_t v = (uint16_t)(g[0] - 'A');
+        v = (uint16_t)(v * 18 + (g[1] - 'A'));
+        v = (uint16_t)(v * 10 + (g[2] - '0'));
+        v = (uint16_t)(v * 10 + (g[3] - '0'));
+        return v;
+    }
+    if (g[0] == 'R') {
+        const uint16_t irpt = (uint16_t)(35 + msg_dd_to_int(g + 1, 3));
+        return (uint16_t)((32400 + irpt) | 0x8000);
+    }
+    const uint16_t irpt = (uint16_t)(35 + msg_dd_to_int(g, 3));
+    return (uint16_t)(32400 + irpt);
+}
+
+int orc_pack77(const char *msg, uint8_t *b) { /* returns 0 = standard message, 1 = free text (the reference returns 0 for both) */
+    const char *s1 = strchr(msg, ' ');
+    if (s1 != 0) {
+        const int32_t a = msg_pack28(msg), d = msg_pack28(s1 + 1);
+        if (a >= 0 && d >= 0) {
+            const char *s2 = strchr(s1 + 1, ' ');
+            const uint16_t g = msg_packgrid(s2 ? s2 + 1 : 0);
+            const uint32_t n28a = (uint32_t)a << 1, n28b = (uint32_t)d << 1;
+            b[0] = (uint8_t)(n28a >> 21); b[1] = (uint8_t)(n28a >> 13); b[2] = (uint8_t)(n28a >> 5);
+            b[3] = (uint8_t)((uint8_t)(n28a << 3) | (uint8_t)(n28b >> 26));
+            b[4] = (uint8_t)(n28b >> 18); b[5] = (uint8_t)(n28b >> 10); b[6] = (uint8_t)(n28b >> 2);
+            b[7] = (uint8_t)((uint8_t)(n28b << 6) | (uint8_t)(g >> 10));
+            b[8] = (uint8_t)(g >> 2);
+            b[9] = (uint8_t)((uint8_t)(g << 6) | (1u << 3));
+            return 0;
+        }
+    }
+    orc_pack_text(msg, b);
+    return 1;
+}
+
 void orc_encode174(const uint8_t *payload, uint8_t *bits) {
     uint8_t a91[12];
     memcpy(a91, payload, 10);

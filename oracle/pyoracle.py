@@ -322,6 +322,12 @@ class Oracle:
         self.lib.orc_pack_text(text.encode(), b)
         return b.raw
 
+    def pack77(self, msg: str):
+        """pack77() restated (pack.c:284-301): (payload, kind) with kind 0 = standard message, 1 = free text."""
+        b = C.create_string_buffer(10)
+        kind = self.lib.orc_pack77(msg.encode(), b)
+        return b.raw, int(kind)
+
     def tones(self, payload: bytes) -> np.ndarray:
         t = np.zeros(79, np.uint8)
         self.lib.orc_encode_tones(payload, _ptr(t))

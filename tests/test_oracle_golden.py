@@ -6,6 +6,7 @@ import pytest
 
 from conftest import bits_equal, golden
 from oracle.pyoracle import cand_dtype
+from tools import synth
 
 
 def test_kat_pack_encode(oracle):
@@ -109,6 +110,16 @@ def test_wav_and_iq_readers_without_gpu(pkg, tmp_path):
     with pytest.raises(IOError) as e:
         pkg.load_wav(str(tmp_path / "nope.wav"))  # the reference would crash on fread(NULL); here -3
     assert e.value.args[0] == -3
+
+
+def test_library_pack77_vs_oracle(pkg, oracle):
+    """Runs anywhere: library packer and restated packer agree, payload and kind, on 20 000 message texts; the restatement
+    reproduces the committed reference payloads."""
+    for m in synth.pack77_fuzz_messages(37, 20000):
+        assert pkg.pack77(m) == oracle.pack77(m), repr(m)
+    g = golden("pack77")
+    for m, want in zip(g["msgs"], g["packed"]):
+        assert oracle.pack77(str(m))[0] == want.tobytes(), repr(str(m))
 
 
 def test_library_pack77_golden(pkg, oracle):

@@ -132,6 +132,13 @@ def test_unpack77_fuzz(oracle):
         assert oracle.unpack77(bytes(a)) == ref.unpack77(bytes(a))
 
 
+def test_oracle_pack77_vs_reference(oracle):
+    """The restated pack77() (oracle/ft8_oracle_codec.c) against the reference's on 20 000 message texts."""
+    ref = Reference("k120")
+    for m in synth.pack77_fuzz_messages(29, 20000):
+        assert oracle.pack77(m)[0] == ref.pack77(m), repr(m)
+
+
 def test_library_pack77_vs_reference(pkg):
     """ft8b200_pack77 (host code of the library) against the reference's own pack77() (pack.c:284-301) on 20 000 message texts:
     standard / free-text choice and every payload byte, quirks included ("FN20QI" packs as FN20, unchecked reports, 3DA0/3X)."""
