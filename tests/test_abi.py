@@ -75,11 +75,13 @@ def test_fails_loudly_without_a_gpu(pkg):
 def test_product_sources_do_not_touch_the_oracle():
     """The product path must not include, link or call anything under oracle/."""
     src = os.path.join(ROOT, "rtlsdr-ft8d_b200")
-    for dirpath, _, files in os.walk(src):
+    walk = list(os.walk(src)) + list(os.walk(os.path.join(ROOT, "host"))) + list(os.walk(os.path.join(ROOT, "include")))
+    walk.append((ROOT, [], ["ft8b200_loader.py"]))
+    for dirpath, _, files in walk:
         if "build" in dirpath:
             continue
         for f in files:
-            if f.endswith((".cu", ".cuh", ".h", ".py")) or f == "Makefile":
+            if f.endswith((".cu", ".cuh", ".h", ".c", ".py")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f)).read()
                 for line in text.splitlines():
                     code = line.split("//")[0]
