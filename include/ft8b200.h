@@ -31,9 +31,15 @@ extern "C" {
  * ABI types, byte-for-byte those of the reference
  * ---------------------------------------------------------------------------------------- */
 
+/* Included from the REFERENCE's own sources this header must not define what their headers already
+ * have: ft8_lib's constants.h / decode.h are recognised by their include guards; rtlsdr_ft8d.h uses #pragma once, so a
+ * translation unit that has included it defines FT8B200_WITH_RTLSDR_FT8D_H before including this header. */
+#ifndef _INCLUDE_CONSTANTS_H_
 /* replaces: ft8_lib/ft8/constants.h:6-10 */
 typedef enum { PROTO_FT4, PROTO_FT8 } ftx_protocol_t;
+#endif
 
+#ifndef _INCLUDE_DECODE_H_
 /* replaces: ft8_lib/ft8/decode.h:15-25 (40 bytes; mag @24, block_stride @32, protocol @36) */
 typedef struct {
     int max_blocks;
@@ -68,7 +74,9 @@ typedef struct {
     uint16_t crc_calculated;
     int unpack_status;
 } decode_status_t;
+#endif
 
+#ifndef FT8B200_WITH_RTLSDR_FT8D_H
 /* replaces: rtlsdr_ft8d.h:136-141 (28 bytes) */
 struct decoder_results {
     char call[13];
@@ -76,6 +84,7 @@ struct decoder_results {
     int32_t freq;
     int32_t snr;
 };
+#endif
 
 /* replaces: ft8_lib/decode_ft8.c:82-90 (defined inside the .c in the reference) */
 typedef struct {
@@ -114,24 +123,34 @@ typedef struct {
  * its state in function statics); otherwise ctx is a ft8b200_stream_t* from
  * ft8b200_stream_create(), which is how many receivers share one process.  Unlike the
  * reference the caller's buffer is NOT modified. */
+#ifndef FT8B200_WITH_RTLSDR_FT8D_H /* rtlsdr_ft8d.h:144 declares it itself -- `static` there: drop that word, the definition now lives here */
 void rtlsdr_callback(unsigned char *samples, uint32_t samples_count, void *ctx);
+#endif
 
 /* replaces: initFFTW()/freeFFTW(), rtlsdr_ft8d.c:314-347: creates / destroys the default
  * context (device tables, workspaces).  Every other entry point creates it on demand. */
+#ifndef FT8B200_WITH_RTLSDR_FT8D_H /* declared (without prototype) at rtlsdr_ft8d.h:155-156 */
 void initFFTW(void);
 void freeFFTW(void);
+#endif
 
 /* replaces: ft8_subsystem(), rtlsdr_ft8d.c:1387-1524.  48000 conditioned samples per rail;
  * samples_len is ignored exactly like the reference ignores it (:1393); decodes[] must hold
  * K_MAX_MESSAGES (50) records; *n_results counts ALL unique messages, CQ or not. */
+#ifndef FT8B200_WITH_RTLSDR_FT8D_H /* rtlsdr_ft8d.h:164 */
 void ft8_subsystem(float *iSamples, float *qSamples, uint32_t samples_len, struct decoder_results *decodes, int32_t *n_results);
+#endif
 
 /* replaces: ft8_find_sync(), ft8_lib/ft8/decode.h:63 / decode.c:173-234 */
+#ifndef _INCLUDE_DECODE_H_
 int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap[], int min_score);
+#endif
 
 /* replaces: ft8_decode(), ft8_lib/ft8/decode.h:72 / decode.c:316-376.  On early failure the
  * later fields of *status are left unwritten, as in the reference. */
+#ifndef _INCLUDE_DECODE_H_
 bool ft8_decode(const waterfall_t *power, const candidate_t *cand, message_t *message, int max_iterations, decode_status_t *status);
+#endif
 
 /* replaces: waterfall_init()/waterfall_free(), ft8_lib/decode_ft8.c:63-79 */
 void waterfall_init(waterfall_t *me, int max_blocks, int num_bins, int time_osr, int freq_osr);
@@ -420,11 +439,13 @@ int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t s
  * ---------------------------------------------------------------------------------------- */
 
 /* replaces: rtlsdr_ft8d.h:130-134 (24 bytes) -- dial frequency and identity of the receiving station */
+#ifndef FT8B200_WITH_RTLSDR_FT8D_H
 struct decoder_options {
     uint32_t freq;
     char rcall[13];
     char rloc[7];
 };
+#endif
 
 /* The four form fields webClusterSpots() posts for one spot (buffer sizes of rtlsdr_ft8d.c:599-602; longer values truncate) */
 typedef struct {
