@@ -54,7 +54,7 @@ def test_patched_daemon_builds_and_links_against_the_library(patched):
         assert sym in undef, sym + " must come from libft8b200.so"
     for sym in ("ft8_find_sync", "ft8_decode", "bp_decode", "unpack77", "fftwf_execute"):
         assert sym not in undef
-    run = subprocess.run([str(exe), "-t"], capture_output=True, text=True)
+    run = subprocess.run([str(exe), "-f", "2m", "-c", "A1XYZ", "-l", "AB12cd", "-t"], cwd=str(patched), capture_output=True, text=True)
     if cuda_device_present():
         assert run.returncode == 0 and "Self-test SUCCESS!" in run.stdout and "K1JT" in run.stdout
     else:
