@@ -198,6 +198,7 @@ void rtlsdr_callback(unsigned char *samples, uint32_t samples_count, void *ctx) 
         return;
     }
     std::lock_guard<std::mutex> lk(s->mu);
+    CK(cudaSetDevice(s->device));  // librtlsdr calls from its own thread, whose current device is 0 until told otherwise
     append(s, samples, samples_count);
 }
 
@@ -215,6 +216,7 @@ uint32_t ft8b200_stream_count(ft8b200_stream_t *s) {
 int ft8b200_stream_flip(ft8b200_stream_t *s) {
     if (!s) s = default_stream();
     std::lock_guard<std::mutex> lk(s->mu);
+    CK(cudaSetDevice(s->device));
     pump(s);
     s->buffer_index ^= 1;
     const int b = s->buffer_index;
@@ -230,6 +232,7 @@ int ft8b200_stream_fetch(ft8b200_stream_t *s, float *h_i, float *h_q, uint32_t *
     if (!h_i || !h_q) return FT8B200_EINVAL;
     if (!s) s = default_stream();
     std::lock_guard<std::mutex> lk(s->mu);
+    CK(cudaSetDevice(s->device));
     const int prev = s->buffer_index ^ 1;
     CK(cudaMemcpyAsync(h_i, s->d_i[prev], sizeof(float) * kSlot, cudaMemcpyDeviceToHost, s->st));
     CK(cudaMemcpyAsync(h_q, s->d_q[prev], sizeof(float) * kSlot, cudaMemcpyDeviceToHost, s->st));
