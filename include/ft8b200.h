@@ -291,6 +291,11 @@ int ft8b200_set_decode_variant(int variant);
  * (the argument is a product of tanh values), [2] = atanh mismatches elsewhere, [3], [4] = how many patterns took the full
  * division (tanh, atanh).  [0..2] must be 0. */
 int ft8b200_selfcheck_pade(ft8b200_ctx_t *ctx, uint64_t *counts5);
+/* Device self-check hook for the message unpacker (a13): n 77-bit payloads (10 bytes each, MSB first, host) through the
+ * kernel-side unpack77 (replaces: unpack77, ft8_lib/ft8/unpack.c:396-427 and everything under it), one thread each.
+ * h_text32: n x 32 chars (NUL-padded; empty when rejected), h_status: unpack77's return value (0, -1, -2).  Exists so that
+ * every message type and reject path can be fuzzed against the CPU checker without a waterfall in front of it. */
+int ft8b200_unpack77_batch(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, char *h_text32, int32_t *h_status);
 /* Run the context's work on caller-owned streams (cudaStream_t as void*): `front_stream` replaces the context's launching
  * stream, `back_stream` its back-end side stream, whose kernels size their persistent grids for `back_sm_count` SMs.
  * NULL restores the context's own stream.  Used by ft8b200_pipe_set_partition with green-context streams. */

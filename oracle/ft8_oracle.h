@@ -106,6 +106,10 @@ int orc_subsystem(const float *i_s, const float *q_s, int max_candidates, int ma
 int orc_decode_waterfall(const orc_waterfall_t *wf, int max_candidates, int max_messages, int min_score, int ldpc_iters,
                          orc_result_t *results, orc_slot_report_t *rep, orc_candidate_t *cand_out);
 
+/* the duplicate table + CQ filter alone over decoded candidates (rtlsdr_ft8d.c:1467-1522); rep may be NULL */
+int orc_spots(const orc_candidate_t *cand, const uint8_t *ok, const orc_message_t *msgs, int n_cand, int max_messages, int min_score,
+              int freq_osr, orc_result_t *results /* max_messages, caller-zeroed */, orc_slot_report_t *rep);
+
 /* ---- encoder side (input synthesis only) ---- */
 int orc_pack_std(const char *call_to, const char *call_de, const char *extra, uint8_t *payload10);
 void orc_pack_text(const char *text, uint8_t *payload10);

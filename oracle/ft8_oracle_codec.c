@@ -446,22 +446,20 @@ int orc_decode(const orc_waterfall_t *wf, const orc_candidate_t *c, int max_iter
  *   - strtok() returning NULL for an empty text would crash strncmp (:1509-1510); here it
  *     is treated as "not CQ".  A missing 2nd/3rd token prints as glibc's "(null)" (:1512-1514).
  * ====================================================================================== */
-int orc_decode_waterfall(const orc_waterfall_t *wf, int max_candidates, int max_messages, int min_score, int ldpc_iters,
-                         orc_result_t *results, orc_slot_report_t *rep, orc_candidate_t *cand_out) {
-    orc_candidate_t *cand = (orc_candidate_t *)malloc(sizeof(orc_candidate_t) * (size_t)max_candidates);
-    const int n_cand = orc_find_sync(wf, max_candidates, cand, min_score);
-    if (cand_out) memcpy(cand_out, cand, sizeof(orc_candidate_t) * (size_t)n_cand);
+/* The table + filter alone, over an already decoded candidate list (ok[k] != 0: msgs[k] holds candidate k's message):
+ * what ft8_subsystem() does after each successful ft8_decode(), rtlsdr_ft8d.c:1467-1522.  Callable with hand-made
+ * messages, which is how the edge cases (hash clashes, 2-token CQ, a full table) are pinned to the reference's own loop
+ * (oracle/ref_harness.c: ref_subsystem_scripted) and then asked of the CUDA spots kernel. */
+int orc_spots(const orc_candidate_t *cand, const uint8_t *ok, const orc_message_t *msgs, int n_cand, int max_messages, int min_score,
+              int freq_osr, orc_result_t *results, orc_slot_report_t *rep) {
     orc_message_t *table = (orc_message_t *)calloc((size_t)max_messages, sizeof(orc_message_t));
     uint8_t *used = (uint8_t *)calloc((size_t)max_messages, 1);
     int n_new = 0;
-    if (rep) { memset(rep, 0, sizeof(*rep)); rep->n_cand = n_cand; }
     for (int k = 0; k < n_cand; ++k) {
         const orc_candidate_t *c = &cand[k];
-        if (c->score < min_score) continue;
-        const float freq_hz = (c->freq_offset + (float)c->freq_sub / 2) * 6.25f;
-        orc_message_t msg;
-        orc_status_t st;
-        if (!orc_decode(wf, c, ldpc_iters, &msg, &st, NULL, NULL)) continue;
+        if (c->score < min_score || !ok[k]) continue;
+        const float freq_hz = (c->freq_offset + (float)c->freq_sub / freq_osr) * 6.25f;
+        const orc_message_t msg = msgs[k];
         int slot = msg.hash % max_messages, probes = 0, dup = 0, empty = 0;
         while (probes < max_messages) {
             if (!used[slot]) { empty = 1; break; }
@@ -474,7 +472,8 @@ int orc_decode_waterfall(const orc_waterfall_t *wf, int max_candidates, int max_
         used[slot] = 1;
         if (rep && n_new < 512) { rep->msgs[n_new] = msg; rep->freq_hz[n_new] = freq_hz; rep->score[n_new] = c->score; }
         char work[40];
-        strcpy(work, msg.text);
+        memset(work, 0, sizeof(work));
+        strncpy(work, msg.text, sizeof(msg.text));
         char *save = NULL;
         const char *tok = strtok_r(work, " ", &save);
         if (tok && strncmp(tok, "CQ", 2) == 0 && n_new < max_messages) {
@@ -488,7 +487,26 @@ int orc_decode_waterfall(const orc_waterfall_t *wf, int max_candidates, int max_
         ++n_new;
     }
     if (rep) rep->n_unique = n_new;
-    free(cand); free(table); free(used);
+    free(table); free(used);
+    return n_new;
+}
+
+int orc_decode_waterfall(const orc_waterfall_t *wf, int max_candidates, int max_messages, int min_score, int ldpc_iters,
+                         orc_result_t *results, orc_slot_report_t *rep, orc_candidate_t *cand_out) {
+    orc_candidate_t *cand = (orc_candidate_t *)malloc(sizeof(orc_candidate_t) * (size_t)max_candidates);
+    const int n_cand = orc_find_sync(wf, max_candidates, cand, min_score);
+    if (cand_out) memcpy(cand_out, cand, sizeof(orc_candidate_t) * (size_t)n_cand);
+    orc_message_t *msgs = (orc_message_t *)calloc((size_t)(n_cand > 0 ? n_cand : 1), sizeof(orc_message_t));
+    uint8_t *ok = (uint8_t *)calloc((size_t)(n_cand > 0 ? n_cand : 1), 1);
+    if (rep) memset(rep, 0, sizeof(*rep));
+    for (int k = 0; k < n_cand; ++k) {   /* ft8_decode() is a pure function of (waterfall, candidate): decoding first changes nothing */
+        orc_status_t st;
+        if (cand[k].score < min_score) continue;
+        ok[k] = (uint8_t)orc_decode(wf, &cand[k], ldpc_iters, &msgs[k], &st, NULL, NULL);
+    }
+    const int n_new = orc_spots(cand, ok, msgs, n_cand, max_messages, min_score, 2 /* K_FREQ_OSR, rtlsdr_ft8d.c:1470 */, results, rep);
+    if (rep) rep->n_cand = n_cand;
+    free(cand); free(msgs); free(ok);
     return n_new;
 }
 

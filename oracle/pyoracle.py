@@ -228,6 +228,18 @@ class Oracle:
         n = self.lib.orc_decode_waterfall(C.byref(wf), max_cand, max_msgs, min_score, iters, _ptr(res), C.byref(rep), _ptr(cands))
         return self._slot_dict(n, res, rep, cands, mag)
 
+    def spots(self, cands, ok, msgs, max_msgs=50, min_score=10, freq_osr=2):
+        """The duplicate table + CQ filter alone (rtlsdr_ft8d.c:1467-1522) over hand-made decode results."""
+        cands = np.ascontiguousarray(cands, cand_dtype)
+        ok = np.ascontiguousarray(ok, np.uint8)
+        msgs = np.ascontiguousarray(msgs, msg_dtype)
+        assert cands.size == ok.size == msgs.size
+        res = np.zeros(max_msgs, result_dtype)
+        rep = SlotReport()
+        n = self.lib.orc_spots(_ptr(cands), _ptr(ok), _ptr(msgs), cands.size, max_msgs, min_score, freq_osr, _ptr(res), C.byref(rep))
+        rep.n_cand = cands.size
+        return self._slot_dict(n, res, rep, cands, None)
+
     @staticmethod
     def _slot_dict(n, res, rep, cands, wf):
         k = min(rep.n_unique, 512)
@@ -411,6 +423,17 @@ class Reference:
         return dict(n=n, results=res, wf=t["wf"][:int(t["wf_bytes"])].copy(), cands=t["cand"][:nc].copy(),
                     dec_ok=t["dec_ok"][:nd].copy(), dec_status=t["dec_status"][:nd].copy(), dec_msg=t["dec_msg"][:nd].copy(),
                     llr=t["llr"][:nd].copy(), plain=t["plain"][:nd].copy(), bp_errors=t["bp_errors"][:nd].copy())
+
+    def subsystem_scripted(self, cands, ok, msgs):
+        """The reference's own candidate loop / table / CQ filter (rtlsdr_ft8d.c:1452-1523) over a hand-made candidate list and
+        hand-made ft8_decode() answers -> (n_results, decoder_results[K_MAX_MESSAGES])."""
+        cands = np.ascontiguousarray(cands, cand_dtype)
+        ok = np.ascontiguousarray(ok, np.int32)
+        msgs = np.ascontiguousarray(msgs, msg_dtype)
+        assert cands.size == ok.size == msgs.size <= min(self.kmax, self.TAP_MAX)
+        res = np.zeros(self.mmax, result_dtype)
+        n = self.lib.ref_subsystem_scripted(_ptr(cands), _ptr(ok), _ptr(msgs), cands.size, _ptr(res), self.mmax)
+        return int(n), res
 
     def find_sync(self, mag, max_cand=120, min_score=10, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, protocol=1):
         mag = np.ascontiguousarray(mag, np.uint8)

@@ -46,6 +46,18 @@ typedef struct {
 
 static ref_taps_t g_taps;
 
+/* Scripted mode: ft8_subsystem()'s own candidate loop / duplicate table / CQ filter (rtlsdr_ft8d.c:1452-1523) run over a
+ * HAND-MADE candidate list and hand-made decode results, so the a15 edge cases (hash clashes with different text, 2-token
+ * CQ messages, many unique messages) are answered by the reference's code itself.  While armed, the two taps below hand
+ * out the script instead of calling ft8_lib. */
+static struct {
+    int armed, n;
+    const candidate_t *heap_base;
+    candidate_t cand[TAP_MAX_CAND];
+    int32_t ok[TAP_MAX_CAND];
+    message_t msg[TAP_MAX_CAND];
+} g_script;
+
 void *ref_taps_ptr(void) { return &g_taps; }
 int ref_taps_size(void) { return (int)sizeof(g_taps); }
 void ref_taps_reset(void) { memset(&g_taps, 0, sizeof(g_taps)); }
@@ -58,6 +70,13 @@ int tap_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
     g_taps.wf_dims[0] = power->num_blocks; g_taps.wf_dims[1] = power->num_bins;
     g_taps.wf_dims[2] = power->time_osr;   g_taps.wf_dims[3] = power->freq_osr;
     g_taps.wf_dims[4] = power->block_stride; g_taps.wf_dims[5] = (int)power->protocol;
+    if (g_script.armed) {
+        int n = g_script.n < num_candidates ? g_script.n : num_candidates;
+        memcpy(heap, g_script.cand, sizeof(candidate_t) * (size_t)n);
+        g_script.heap_base = heap;
+        g_taps.n_cand = n;
+        return n;
+    }
     int n = ft8_find_sync(power, num_candidates, heap, min_score);
     g_taps.n_cand = n;
     for (int i = 0; i < n && i < TAP_MAX_CAND; ++i) g_taps.cand[i] = heap[i];
@@ -68,6 +87,14 @@ bool tap_decode(const waterfall_t *power, const candidate_t *cand, message_t *me
     int i = g_taps.n_decode_calls;
     memset(status, 0xA5, sizeof(*status));
     memset(message, 0, sizeof(*message));
+    if (g_script.armed) {
+        const long k = cand - g_script.heap_base;
+        g_taps.n_decode_calls = i + 1;
+        memset(status, 0, sizeof(*status));
+        if (k < 0 || k >= g_script.n || !g_script.ok[k]) { status->ldpc_errors = 1; return false; }
+        *message = g_script.msg[k];
+        return true;
+    }
     bool ok = ft8_decode(power, cand, message, max_iterations, status);
     if (i < TAP_MAX_CAND) {
         g_taps.dec_cand[i] = *cand;
@@ -127,6 +154,23 @@ int32_t ref_subsystem(float *i_samples, float *q_samples, struct decoder_results
     if (out_cap < cap) cap = out_cap;
     memcpy(out, dec_results, sizeof(struct decoder_results) * (size_t)cap);
     return n;
+}
+
+/* ft8_subsystem()'s candidate loop over a scripted candidate list (see g_script); the waterfall it computes from the
+ * silent input is ignored by the scripted taps */
+int32_t ref_subsystem_scripted(const candidate_t *cand, const int32_t *ok, const message_t *msg, int32_t n, struct decoder_results *out,
+                               int32_t out_cap) {
+    static float zeros_i[SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE], zeros_q[SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE];
+    if (n > TAP_MAX_CAND) n = TAP_MAX_CAND;
+    memset(&g_script, 0, sizeof(g_script));
+    memcpy(g_script.cand, cand, sizeof(candidate_t) * (size_t)n);
+    memcpy(g_script.ok, ok, sizeof(int32_t) * (size_t)n);
+    memcpy(g_script.msg, msg, sizeof(message_t) * (size_t)n);
+    g_script.n = n;
+    g_script.armed = 1;
+    const int32_t r = ref_subsystem(zeros_i, zeros_q, out, out_cap);
+    g_script.armed = 0;
+    return r;
 }
 
 int32_t ref_selftest(void) { ref_taps_reset(); return decoderSelfTest(); }

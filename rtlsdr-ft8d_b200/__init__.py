@@ -365,6 +365,15 @@ class Context:
         self._chk(self.L.ft8b200_selfcheck_pade(C.c_void_p(self.h), c))
         return [int(v) for v in c]
 
+    def unpack77_batch(self, payloads):
+        """n 77-bit payloads (uint8 [n, 10]) through the device unpacker -> (list of texts, int32 status[n])."""
+        payloads = np.ascontiguousarray(payloads, np.uint8).reshape(-1, 10)
+        n = payloads.shape[0]
+        text = np.zeros((n, 32), np.uint8)
+        status = np.zeros(n, np.int32)
+        self._chk(self.L.ft8b200_unpack77_batch(C.c_void_p(self.h), _p(payloads), n, _p(text), _p(status)))
+        return [bytes(t).split(b"\0")[0].decode("ascii", "replace") for t in text], status
+
     def set_overlap(self, groups: int):
         self._chk(self.L.ft8b200_set_overlap(C.c_void_p(self.h), int(groups)))
 

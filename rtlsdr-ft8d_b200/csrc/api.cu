@@ -586,6 +586,31 @@ int ft8b200_selfcheck_pade(ft8b200_ctx_t *ctx, uint64_t *counts5) {
     return 0;
 }
 
+int ft8b200_unpack77_batch(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, char *h_text32, int32_t *h_status) {
+    int rc = ctx_enter(ctx);
+    if (rc) return rc;
+    if (!h_payloads || !h_text32 || !h_status || n < 1) return fail(FT8B200_EINVAL, "ft8b200_unpack77_batch: bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    uint8_t *d_in = nullptr;
+    char *d_text = nullptr;
+    int32_t *d_st = nullptr;
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d_in), (size_t)n * 10, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&d_text), (size_t)n * 32, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&d_st), (size_t)n * sizeof(int32_t), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, h_payloads, (size_t)n * 10, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_unpack77_batch(d_in, n, d_text, d_st, st, &ctx->launches);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_text32, d_text, (size_t)n * 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_status, d_st, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (d_in) cudaFreeAsync(d_in, st);
+    if (d_text) cudaFreeAsync(d_text, st);
+    if (d_st) cudaFreeAsync(d_st, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    tally(ctx);
+    if (e != cudaSuccess) return cuda_fail(e, "ft8b200_unpack77_batch");
+    return 0;
+}
+
 void *ft8b200_front_event(ft8b200_ctx_t *ctx) { return ctx ? ctx->ev_front : nullptr; }
 
 // ms[0..5] = block sums, comb+FIR, waterfall, sync, decode, spots of the last process_* call, summed over its slot

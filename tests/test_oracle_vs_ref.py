@@ -132,6 +132,50 @@ def test_unpack77_fuzz(oracle):
         assert oracle.unpack77(bytes(a)) == ref.unpack77(bytes(a))
 
 
+def test_unpack77_stratified_vs_reference(oracle):
+    """tools/synth.py::payload_fuzz (the generator the GPU tests use for the device unpacker): every token class, flag, report
+    form and reject path -- oracle == reference on 60 000 payloads."""
+    ref = Reference("k120")
+    payloads, labels = synth.payload_fuzz(20261, 60_000)
+    for a, lab in zip(payloads, labels):
+        b = bytes(a) + b"\0\0"
+        rc_o, t_o = oracle.unpack77(b)
+        rc_r, t_r = ref.unpack77(b)
+        assert rc_o == rc_r and (rc_r < 0 or t_o == t_r), (lab, b.hex(), rc_o, t_o, rc_r, t_r)
+
+
+def test_spots_vs_reference_loop(oracle):
+    """The duplicate table / CQ filter restated in orc_spots() against the reference's OWN loop (ft8_subsystem, rtlsdr_ft8d.c:
+    1452-1523) fed hand-made candidates and ft8_decode() answers through the scripted taps of oracle/ref_harness.c: 2-token CQ
+    ("(null)" locator), "CQ DX ..." tokenisation, %.12s / %.6s truncation, hash clashes with different text, duplicates,
+    low-score and failed candidates, a table one short of full; plus 200 random scripts."""
+    from test_gpu_messages import spots_cases, _msg
+    ref = Reference("k120")
+    for name, c, okv, m, max_msgs, defined in spots_cases():
+        if not defined:
+            continue
+        n, res = ref.subsystem_scripted(c, okv, m)
+        o = oracle.spots(c, okv, m, max_msgs=max_msgs, min_score=10)
+        assert n == o["n"] and res.tobytes() == o["results"].tobytes(), name
+    rng = np.random.default_rng(5)
+    calls = ["K1JT", "W9XYZ", "PA0ABC", "PJ4/K1ABC", "DX", "TEST", "<...>", "3DA0XYZ/P"]
+    for _ in range(200):
+        k = int(rng.integers(1, 60))
+        c = np.zeros(k, cand_dtype)
+        c["score"] = np.sort(rng.integers(5, 40, k))[::-1]
+        c["freq_offset"] = rng.integers(0, 249, k); c["freq_sub"] = rng.integers(0, 2, k)
+        texts = ["%s %s %s" % (rng.choice(["CQ", "CQ", "QRZ", "K1ABC", "CQ DX"]), rng.choice(calls), rng.choice(["FN20", "RR73", "-15", ""])) for _ in range(k)]
+        texts = [t.strip() for t in texts]
+        m = np.array([_msg(t, int(rng.integers(0, 60))) for t in texts])   # few hash values: clashes are the rule
+        okv = (rng.random(k) < 0.8).astype(np.uint8)
+        live = {(t, int(h)) for t, h, o_, s_ in zip(texts, m["hash"], okv, c["score"]) if o_ and s_ >= 10}
+        if len(live) >= 50:
+            continue   # the reference never returns from a full table
+        n, res = ref.subsystem_scripted(c, okv, m)
+        o = oracle.spots(c, okv, m)
+        assert n == o["n"] and res.tobytes() == o["results"].tobytes(), texts
+
+
 def test_oracle_pack77_vs_reference(oracle):
     """The restated pack77() (oracle/ft8_oracle_codec.c) against the reference's on 20 000 message texts."""
     ref = Reference("k120")

@@ -187,3 +187,86 @@ def pack77_fuzz_messages(seed: int, n: int):
             m = " " * rnd.randint(0, 2) + call() + " " * rnd.randint(1, 2) + call() + " " * rnd.randint(0, 2) + extra()
         msgs.append(m)
     return msgs[:n]
+
+
+# ---- 77-bit payloads of every type unpack77() knows (and rejects), for fuzzing the device unpacker -------------------
+NTOK = 2063592          # unpack.c:12-13
+MAX22 = 4194304
+
+
+def bits_to_payload(fields) -> np.ndarray:
+    """fields: [(value, nbits), ...] MSB first, 77 bits in total -> 10 bytes (bits 77..79 zero)."""
+    v = 0
+    total = 0
+    for val, nb in fields:
+        assert 0 <= val < (1 << nb), (val, nb)
+        v = (v << nb) | int(val)
+        total += nb
+    assert total == 77, total
+    return np.frombuffer((v << 3).to_bytes(10, "big"), np.uint8).copy()
+
+
+def _n28_of_kind(rng, kind: str) -> int:
+    if kind == "token":
+        return int(rng.integers(0, 3))                       # DE, QRZ, CQ
+    if kind == "cq_nnn":
+        return int(rng.integers(3, 1003))                    # CQ 000 .. CQ 999
+    if kind == "cq_aaaa":
+        return int(rng.choice([1003, 1004, 1030, 1003 + 27 ** 3, 532443, int(rng.integers(1003, 532444))]))
+    if kind == "invalid":
+        return int(rng.choice([532444, NTOK - 1, int(rng.integers(532444, NTOK))]))    # unpack_callsign returns -1
+    if kind == "hashed":
+        return int(rng.choice([NTOK, NTOK + MAX22 - 1, int(rng.integers(NTOK, NTOK + MAX22))]))  # <...>
+    return int(rng.choice([NTOK + MAX22, (1 << 28) - 1, int(rng.integers(NTOK + MAX22, 1 << 28))]))  # a standard call sign
+
+
+def payload_fuzz(seed: int, n: int):
+    """n payloads cycling through every branch of unpack77 (unpack.c:18-427): free text (i3=0,n3=0), telemetry (n3=5), the
+    undefined n3, standard messages i3=1/2 with every token class for both call fields (DE/QRZ/CQ, CQ nnn, CQ aaaa, the
+    invalid gap, hashed calls, plain calls), /R and /P flags, grids, blank/RRR/RR73/73, signed reports with and without R,
+    non-standard calls (i3=4: every flip/rpt/cq), and i3 = 3, 5, 6, 7 (rejected).  -> (uint8[n, 10], [label, ...])."""
+    rng = np.random.default_rng(seed)
+    kinds = ["token", "cq_nnn", "cq_aaaa", "invalid", "hashed", "call"]
+    out = np.zeros((n, 10), np.uint8)
+    labels = []
+    for k in range(n):
+        sel = k % 16
+        if sel == 0:      # free text: 71 random bits (values beyond 42^13 still unpack), n3 = 0
+            out[k] = bits_to_payload([(int(rng.integers(0, 1 << 62)) | (int(rng.integers(0, 1 << 9)) << 62), 71), (0, 3), (0, 3)])
+            labels.append("free")
+        elif sel == 1:    # free text with few characters (leading blanks are trimmed), incl. the empty text
+            m = int(rng.integers(0, 42 ** int(rng.integers(0, 5))))
+            out[k] = bits_to_payload([(m, 71), (0, 3), (0, 3)])
+            labels.append("free_short")
+        elif sel == 2:
+            out[k] = bits_to_payload([(int(rng.integers(0, 1 << 62)) | (int(rng.integers(0, 1 << 9)) << 62), 71), (5, 3), (0, 3)])
+            labels.append("telemetry")
+        elif sel == 3:    # i3 = 0 with an n3 the reference does not unpack
+            out[k] = bits_to_payload([(int(rng.integers(0, 1 << 62)), 71), (int(rng.choice([1, 2, 3, 4, 6, 7])), 3), (0, 3)])
+            labels.append("n3_reject")
+        elif sel == 4:
+            out[k] = bits_to_payload([(int(rng.integers(0, 1 << 62)), 74), (int(rng.choice([3, 5, 6, 7])), 3)])
+            labels.append("i3_reject")
+        elif sel in (5, 6):   # non-standard call: 12-bit hash, 58-bit call, flip, rpt, cq
+            n58 = int(rng.integers(0, 1 << 58)) if sel == 5 else int(rng.integers(0, 38 ** int(rng.integers(1, 8))))
+            out[k] = bits_to_payload([(int(rng.integers(0, 1 << 12)), 12), (n58, 58), (int(rng.integers(0, 2)), 1), (int(rng.integers(0, 4)), 2),
+                                      (int(rng.integers(0, 2)), 1), (4, 3)])
+            labels.append("nonstd")
+        else:             # standard, i3 = 1 or 2
+            ka, kb = kinds[int(rng.integers(0, 6))], kinds[int(rng.integers(0, 6))]
+            if sel >= 12:     # mostly decodable ones
+                ka = kinds[int(rng.choice([0, 1, 2, 4, 5]))]
+                kb = kinds[int(rng.choice([4, 5, 5]))]
+            g_sel = int(rng.integers(0, 4))
+            if g_sel == 0:
+                g = int(rng.integers(0, 32401))
+            elif g_sel == 1:
+                g = 32400 + int(rng.integers(1, 5))          # blank, RRR, RR73, 73
+            elif g_sel == 2:
+                g = 32400 + 35 + int(rng.integers(-30, 31))  # reports -30 .. +30
+            else:
+                g = int(rng.integers(32405, 32768))          # every remaining value (reports beyond two digits print as int_to_dd prints them)
+            out[k] = bits_to_payload([(_n28_of_kind(rng, ka), 28), (int(rng.integers(0, 2)), 1), (_n28_of_kind(rng, kb), 28), (int(rng.integers(0, 2)), 1),
+                                      (int(rng.integers(0, 2)), 1), (g, 15), (int(rng.integers(1, 3)), 3)])
+            labels.append("std_%s_%s" % (ka, kb))
+    return out, labels
