@@ -188,20 +188,18 @@ ft8b200_ctx_t *ft8b200_create(const ft8b200_config_t *cfg_in) {
     okc = okc && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->stream = ctx->own_stream;
     // tables, built with the host libm exactly as the reference builds them
-    std::vector<float> win(kNfft), thr(257), fir(kFirTaps);
+    std::vector<float> win(kNfft), thr(257);
     std::vector<float2> tw(kNfft);
     build_window1024(win.data());
     build_twiddles(kNfft, tw.data());
     build_db_thresholds(thr.data());
-    build_fir(fir.data());
     okc = okc && cudaMalloc(&ctx->tb.window1024, kNfft * sizeof(float)) == cudaSuccess;
     okc = okc && cudaMalloc(&ctx->tb.twiddle1024, kNfft * sizeof(float2)) == cudaSuccess;
     okc = okc && cudaMalloc(&ctx->tb.db_thresholds, 257 * sizeof(float)) == cudaSuccess;
-    okc = okc && cudaMalloc(&ctx->tb.fir, kFirTaps * sizeof(float)) == cudaSuccess;
     okc = okc && cudaMemcpy(ctx->tb.window1024, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
     okc = okc && cudaMemcpy(ctx->tb.twiddle1024, tw.data(), kNfft * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
     okc = okc && cudaMemcpy(ctx->tb.db_thresholds, thr.data(), 257 * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
-    okc = okc && cudaMemcpy(ctx->tb.fir, fir.data(), kFirTaps * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    okc = okc && upload_fir_constants() == cudaSuccess;
     okc = okc && upload_ldpc_tables() == cudaSuccess;
     {
         std::vector<float> blob(waterfall_blob_floats());
@@ -229,7 +227,7 @@ void ft8b200_destroy(ft8b200_ctx_t *ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     for (cudaEvent_t e : ctx->ev_group) if (e) cudaEventDestroy(e);
-    cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.fir); cudaFree(ctx->tb.wf_blob);
+    cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.wf_blob);
     cudaFree(ctx->tb.mon_window); cudaFree(ctx->tb.mon_twiddle); cudaFree(ctx->tb.mon_super);
     DevBuf *bufs[] = {&ctx->raw, &ctx->sums, &ctx->si, &ctx->sq, &ctx->peak, &ctx->count, &ctx->mag, &ctx->cand, &ctx->ncand, &ctx->ok,
                       &ctx->stage, &ctx->status, &ctx->msg, &ctx->results, &ctx->nresults, &ctx->table, &ctx->scratch, &ctx->scores, &ctx->work, &ctx->work_total};
@@ -273,7 +271,7 @@ static int decimate_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t bytes_p
     CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_streams, st));
     BlockSums *s0 = ctx->sums.as<BlockSums>() + kHistBlocks;
     CU(launch_cic_block_sums(d_iq, stream_stride_bytes, n_streams, blocks, s0, sstride, ctx->k1_variant, ctx->sm_count, st, &ctx->launches));
-    CU(launch_cic_comb_fir(s0, sstride, blocks, 0, true, n_streams, ctx->tb.fir, d_i, d_q, d_count, d_peak, d_y2, st, &ctx->launches, segs,
+    CU(launch_cic_comb_fir(s0, sstride, blocks, 0, true, n_streams, d_i, d_q, d_count, d_peak, d_y2, st, &ctx->launches, segs,
                            (long long)(seg_bytes / 2)));
     tally(ctx);
     return 0;
@@ -310,8 +308,16 @@ int ft8b200_waterfall(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, co
     return 0;
 }
 
-int ft8b200_find_sync(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins, int time_osr,
-                      int freq_osr, candidate_t *d_cand, int *d_ncand, void *stream) {
+}  // extern "C"
+
+// find_sync / decode with an explicit protocol (the C entry points use the context's, ft8b200_set_protocol): what the whole-
+// recording calls of files.cu use, so that they neither change nor depend on the protocol selected for the stage-wise API
+namespace ft8b200 {
+int ctx_device(ft8b200_ctx_t *ctx) { return ctx ? ctx->cfg.device : -1; }
+int ctx_sm_count(ft8b200_ctx_t *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int find_sync_proto(ft8b200_ctx_t *ctx, int protocol, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins,
+                    int time_osr, int freq_osr, candidate_t *d_cand, int *d_ncand, void *stream) {
     int rc = ctx_enter(ctx);
     if (rc) return rc;
     if (!d_mag || !d_cand || !d_ncand || n_slots < 1 || num_blocks < 1 || num_bins < 8 || time_osr < 1 || freq_osr < 1)
@@ -320,16 +326,16 @@ int ft8b200_find_sync(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stri
     if (npos >= (1l << 20)) return fail(FT8B200_EINVAL, "ft8b200_find_sync: waterfall too large (position index exceeds 20 bits)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if ((rc = ensure_scratch(ctx, (int)npos, n_slots))) return rc;
-    CU(launch_find_sync(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->protocol, ctx->cfg.max_candidates, ctx->cfg.min_score,
+    CU(launch_find_sync(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, protocol, ctx->cfg.max_candidates, ctx->cfg.min_score,
                         d_cand, d_ncand, ctx->scores.as<int16_t>(), ctx->scratch.as<uint32_t>(), ctx->scratch_slots, nullptr, nullptr, ctx->sm_count,
                         pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
 }
 
-int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins, int time_osr,
-                   int freq_osr, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage, decode_status_t *d_status,
-                   message_t *d_msg, uint8_t *d_plain, float *d_llr, void *stream) {
+int decode_proto(ft8b200_ctx_t *ctx, int protocol, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins, int time_osr,
+                 int freq_osr, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage, decode_status_t *d_status,
+                 message_t *d_msg, uint8_t *d_plain, float *d_llr, void *stream) {
     int rc = ctx_enter(ctx);
     if (rc) return rc;
     if (!d_mag || !d_cand || !d_ncand || !d_ok || !d_stage || !d_status || !d_msg || n_slots < 1)
@@ -342,10 +348,27 @@ int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_
         pull = ctx->work_total.as<unsigned int>();
         CU(cudaMemsetAsync(pull, 0, 4 * sizeof(unsigned int), pick(ctx, stream)));
     }
-    CU(launch_decode(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, ctx->protocol, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
+    CU(launch_decode(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, protocol, ctx->cfg.max_candidates, ctx->cfg.ldpc_iterations,
                      d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, d_plain, d_llr, nullptr, pull, ctx->sm_count, pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
+}
+}  // namespace ft8b200
+
+extern "C" {
+
+int ft8b200_find_sync(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins, int time_osr,
+                      int freq_osr, candidate_t *d_cand, int *d_ncand, void *stream) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    return find_sync_proto(ctx, ctx->protocol, d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, d_cand, d_ncand, stream);
+}
+
+int ft8b200_decode(ft8b200_ctx_t *ctx, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins, int time_osr,
+                   int freq_osr, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage, decode_status_t *d_status,
+                   message_t *d_msg, uint8_t *d_plain, float *d_llr, void *stream) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    return decode_proto(ctx, ctx->protocol, d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, d_cand, d_ncand, d_ok, d_stage,
+                        d_status, d_msg, d_plain, d_llr, stream);
 }
 
 int ft8b200_spots(ft8b200_ctx_t *ctx, int n_slots, int freq_osr, const candidate_t *d_cand, const int *d_ncand, const uint8_t *d_ok,
@@ -484,7 +507,7 @@ static int process_raw_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t byte
             fst = back;
         }
         mark(ctx, 1, g, false, fst);
-        CU(launch_cic_comb_fir(sg, sstride, blocks, 0, true, n, ctx->tb.fir, ctx->si.as<float>() + (size_t)r0 * kSlot,
+        CU(launch_cic_comb_fir(sg, sstride, blocks, 0, true, n, ctx->si.as<float>() + (size_t)r0 * kSlot,
                                ctx->sq.as<float>() + (size_t)r0 * kSlot, ctx->count.as<uint32_t>() + r0, ctx->peak.as<float>() + r0, nullptr, fst,
                                &ctx->launches, segs, (long long)(seg_bytes / 2)));
         mark(ctx, 1, g, true, fst);
@@ -580,7 +603,8 @@ int ft8b200_set_decode_variant(int variant) {
 int ft8b200_selfcheck_pade(ft8b200_ctx_t *ctx, uint64_t *counts5) {
     if (!ctx || !counts5) return fail(FT8B200_EINVAL, "ft8b200_selfcheck_pade: bad argument");
     unsigned long long c[5] = {0, 0, 0, 0, 0};
-    cudaError_t e = run_pade_check(c, ctx->stream);
+    if (int rc = ctx_enter(ctx)) return rc;
+    cudaError_t e = run_pade_check(c, ctx->sm_count, ctx->stream);
     if (e != cudaSuccess) return fail(FT8B200_ECUDA, cudaGetErrorString(e));
     for (int k = 0; k < 5; ++k) counts5[k] = c[k];
     return 0;

@@ -25,7 +25,6 @@ struct DeviceTables {
     float *window1024;     // sinf((float)((M_PI/1024)*i))               rtlsdr_ft8d.c:331-334
     float2 *twiddle1024;   // ((float)cos, (float)sin)(-2*pi*k/1024)      kiss_fft.c:351-357
     float *db_thresholds;  // [257] smallest x with quantise(x) >= k       rtlsdr_ft8d.c:1416,1425-1427
-    float *fir;            // [57]                                          rtlsdr_ft8d.c:93-110
     float *wf_blob;        // the three tables above re-laid-out for waterfall1024_kernel (build_waterfall_tables)
     // monitor (12 kHz) tables, built lazily per nfft
     float *mon_window;     // fft_norm-free Hann, nfft floats
@@ -41,8 +40,9 @@ cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_byte
 cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq_first_block, size_t stream_stride_bytes, int n_streams, uint32_t phase0, int n_blocks,
                                           BlockSums *d_sums_first_block, size_t sums_stride, cudaStream_t st, int *launches);
 cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int n_blocks, int out_offset, bool zero_fill, int n_streams,
-                                const float *d_fir, float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st,
+                                float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st,
                                 int *launches, int segs = 1, long long seg_samples = 0);
+cudaError_t upload_fir_constants();  // once per device, synchronised (called by ft8b200_create / ft8b200_stream_create)
 cudaError_t launch_shift_history(BlockSums *d_sums_with_prefix, int n_blocks, cudaStream_t st, int *launches);
 cudaError_t launch_condition(float *d_i, float *d_q, const float *d_peak, int n_slots, cudaStream_t st, int *launches);
 cudaError_t launch_waterfall(const DeviceTables &t, const float *d_i, const float *d_q, const float *d_peak, int n_slots, uint8_t *d_mag,
@@ -64,7 +64,16 @@ cudaError_t launch_unpack77_batch(const uint8_t *d_payloads, int n, char *d_text
 cudaError_t upload_ldpc_tables();
 void set_decode_variant(int v);  // 0 = node-centred belief propagation (default), 1 = edge-centred
 int decode_variant();
-cudaError_t run_pade_check(unsigned long long *h_counts5, cudaStream_t st);
+cudaError_t run_pade_check(unsigned long long *h_counts5, int sm_count, cudaStream_t st);
+
+// api.cu: the context's device ordinal; find_sync / decode with an explicit protocol (independent of ft8b200_set_protocol)
+int ctx_device(ft8b200_ctx_t *ctx);
+int ctx_sm_count(ft8b200_ctx_t *ctx);
+int find_sync_proto(ft8b200_ctx_t *ctx, int protocol, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins,
+                    int time_osr, int freq_osr, candidate_t *d_cand, int *d_ncand, void *stream);
+int decode_proto(ft8b200_ctx_t *ctx, int protocol, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins, int time_osr,
+                 int freq_osr, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage, decode_status_t *d_status,
+                 message_t *d_msg, uint8_t *d_plain, float *d_llr, void *stream);
 
 // host-side table builders (tables.cu)
 void build_window1024(float *w);

@@ -22,6 +22,9 @@
 //   boundary are first attributed whole to the earlier block and corrected afterwards by 7 lanes.
 #include "common.cuh"
 
+#include <atomic>
+#include <mutex>
+
 namespace ft8b200 {
 
 namespace {
@@ -555,11 +558,9 @@ template <int kC, int kS>
 static cudaError_t launch_tma(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int supers, BlockSums *d_sums, size_t sums_stride,
                               int sm_count, unsigned int *counter, cudaStream_t st) {
     const int smem = kS * kStageBytes;
-    static bool attr_done = false;
-    if (!attr_done) {
+    {   // the opt-in is per device (and cheap): set it on whichever device is current, every time
         cudaError_t e = cudaFuncSetAttribute(cic_block_sums_tma_kernel<kC, kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const long total = (long)supers * n_streams;
     int grid = sm_count;
@@ -576,12 +577,12 @@ cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_byte
                                   size_t sums_stride, int variant, int sm_count, cudaStream_t st, int *launches) {
     const int supers = blocks_per_stream / 8;
     if (supers > 0 && variant >= 1 && (long)supers * n_streams < (1l << 31)) {
-        static unsigned int next_pair = 0;
+        static std::atomic<unsigned int> next_pair{0};  // contexts and lanes on any host thread draw from one pool
         int dev = 0;
         cudaGetDevice(&dev);
         unsigned int *pool = counter_pool(dev);
         if (!pool) return cudaErrorMemoryAllocation;
-        unsigned int *counter = pool + 2 * (next_pair++ % kCounterPairs);
+        unsigned int *counter = pool + 2 * (next_pair.fetch_add(1u) % kCounterPairs);
         cudaError_t e;
         switch (variant) {
         case 2: e = launch_tma<12, 8>(d_iq, stream_stride_bytes, n_streams, supers, d_sums, sums_stride, sm_count, counter, st); break;
@@ -619,29 +620,38 @@ cudaError_t launch_cic_block_sums_generic(const uint8_t *d_iq_first_block, size_
 }
 
 cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int n_blocks, int out_offset, bool zero_fill, int n_streams,
-                                const float *d_fir, float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st,
+                                float *d_i, float *d_q, uint32_t *d_count, float *d_peak, int32_t *d_y2, cudaStream_t st,
                                 int *launches, int segs, long long seg_samples) {
     int span = n_blocks;
     if (segs > 1) span = (int)(seg_samples / kDecim) + 2;  // outputs of one segment
     if (zero_fill && kSlot - out_offset > span) span = kSlot - out_offset;
     if (span <= 0) return cudaSuccess;
-    static bool fir_uploaded[64] = {};
-    int dev_id = 0;
-    cudaGetDevice(&dev_id);
-    if (dev_id >= 0 && dev_id < 64 && !fir_uploaded[dev_id]) {  // coefficients live in constant memory, once per device
-        float z[kFirTaps];
-        build_fir(z);
-        cudaError_t e = cudaMemcpyToSymbol(c_fir, z, sizeof(z));
-        if (e != cudaSuccess) return e;
-        fir_uploaded[dev_id] = true;
-    }
-    (void)d_fir;
     if (segs < 1) segs = 1;
     dim3 grid((span + kTile - 1) / kTile, n_streams * segs);
     cic_comb_fir_kernel<<<grid, kTileThreads, 0, st>>>(d_sums, sums_stride, n_blocks, out_offset, zero_fill ? 1 : 0, segs, seg_samples, d_i, d_q,
                                                        d_count, d_peak, d_y2);
     ++*launches;
     return cudaGetLastError();
+}
+
+// The 57 FIR coefficients live in constant memory: uploaded once per device when a context or stream is created on it
+// (ft8b200_create / ft8b200_stream_create), with a device synchronisation behind the copy -- never lazily next to the first
+// launch, where a pageable copy on the legacy stream would not be ordered against a non-blocking stream.
+cudaError_t upload_fir_constants() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return cudaSuccess;
+    float z[kFirTaps];
+    build_fir(z);
+    e = cudaMemcpyToSymbol(c_fir, z, sizeof(z));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
 }
 
 cudaError_t launch_shift_history(BlockSums *d_sums_with_prefix, int n_blocks, cudaStream_t st, int *launches) {

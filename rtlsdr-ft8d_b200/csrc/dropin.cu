@@ -28,10 +28,17 @@ ft8b200_ctx_t *g_ctx = nullptr;
 
 // The per-candidate ft8_decode() call pattern is hostile to a GPU, so ft8_find_sync() decodes all the
 // candidates it returns in the same visit and keeps the answers; ft8_decode() then only looks them up.
-// The cache is keyed by the waterfall CONTENT (64-bit hash of the host bytes + geometry), never by pointer.
+// The cache is keyed by the waterfall's geometry, its host pointer and a FINGERPRINT of its content: ft8_find_sync()
+// reads every byte anyway (it copies them to the device) and takes the fingerprint then; each of the up to K ft8_decode()
+// calls that follow re-takes it -- 1/16 of the bytes, in 64-byte pieces spread evenly over the buffer plus its last piece
+// (6 KB of the daemon's 94 KB, 22 KB of the 12 kHz monitor's 357 KB) instead of re-hashing the whole waterfall per
+// candidate.  A caller that rewrites the waterfall in place between the two calls (a new slot, another
+// monitor_process() block) changes those pieces or the geometry and gets a fresh decode; FT8B200_DROPIN_FULL_HASH=1 in
+// the environment hashes every byte on every call instead.
 struct DecodeCache {
     bool valid = false;
     uint64_t key = 0;
+    const uint8_t *host_ptr = nullptr;
     int iters = 0;
     int nb = 0, nbins = 0, tosr = 0, fosr = 0, proto = 1;
     std::vector<candidate_t> cand;
@@ -55,6 +62,18 @@ uint64_t hash_bytes(const uint8_t *p, size_t n) {
     uint64_t h = h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7) ^ (uint64_t)n;
     h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
     return h;
+}
+
+bool full_hash_mode() {
+    static const bool on = [] { const char *e = getenv("FT8B200_DROPIN_FULL_HASH"); return e && atoi(e) != 0; }();
+    return on;
+}
+// content fingerprint: every 16th 64-byte piece and the last one (or every byte in full-hash mode / for small buffers)
+uint64_t fingerprint(const uint8_t *p, size_t n) {
+    if (full_hash_mode() || n < 4096) return hash_bytes(p, n);
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
+    for (size_t o = 0; o + 64 <= n; o += 1024) h = (h ^ hash_bytes(p + o, 64)) * 0x100000001B3ull;
+    return (h ^ hash_bytes(p + n - 64, 64)) * 0x100000001B3ull;
 }
 
 struct Scratch {  // device buffers of the drop-in calls (separate from the batched workspaces)
@@ -140,6 +159,7 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
     }
     if (num_candidates <= 0) return 0;
     std::lock_guard<std::mutex> lk(g_mu);
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) die("ft8_find_sync (cudaSetDevice)");  // the decoder thread's current device may differ
     const size_t bytes = (size_t)power->num_blocks * power->block_stride;
     if (!ensure_scratch(bytes, (size_t)num_candidates)) die("ft8_find_sync (device allocation)");
     cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
@@ -158,12 +178,12 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
         scratch_npos = npos;
     }
     if (launch_find_sync(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, num_candidates, min_score,
-                         g_s.cand, g_s.ncand, scores, scratch, 1, nullptr, nullptr, 148, st, &launches) != cudaSuccess) die("ft8_find_sync (kernel)");
+                         g_s.cand, g_s.ncand, scores, scratch, 1, nullptr, nullptr, ctx_sm_count(ctx), st, &launches) != cudaSuccess) die("ft8_find_sync (kernel)");
     // decode everything now; ft8_decode() will look the answers up
     ft8b200_config_t cfg;
     ft8b200_default_config(&cfg);
     if (launch_decode(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, num_candidates, cfg.ldpc_iterations,
-                      g_s.cand, g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, 148, st, &launches) != cudaSuccess)
+                      g_s.cand, g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, ctx_sm_count(ctx), st, &launches) != cudaSuccess)
         die("ft8_find_sync (decode kernel)");
     int n = 0;
     g_cache.cand.resize((size_t)num_candidates); g_cache.ok.resize((size_t)num_candidates); g_cache.stage.resize((size_t)num_candidates);
@@ -178,7 +198,8 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
     if (!okc) die("ft8_find_sync (D2H)");
     g_cache.cand.resize((size_t)n); g_cache.ok.resize((size_t)n); g_cache.stage.resize((size_t)n);
     g_cache.status.resize((size_t)n); g_cache.msg.resize((size_t)n);
-    g_cache.key = hash_bytes(power->mag, bytes);
+    g_cache.key = fingerprint(power->mag, bytes);
+    g_cache.host_ptr = power->mag;
     g_cache.iters = cfg.ldpc_iterations;
     g_cache.nb = power->num_blocks; g_cache.nbins = power->num_bins; g_cache.tosr = power->time_osr; g_cache.fosr = power->freq_osr;
     g_cache.proto = (int)power->protocol;
@@ -201,10 +222,11 @@ bool ft8_decode(const waterfall_t *power, const candidate_t *cand, message_t *me
         abort();
     }
     std::lock_guard<std::mutex> lk(g_mu);
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) die("ft8_decode (cudaSetDevice)");
     const size_t bytes = (size_t)power->num_blocks * power->block_stride;
-    const uint64_t key = hash_bytes(power->mag, bytes);
-    if (g_cache.valid && g_cache.key == key && g_cache.iters == max_iterations && g_cache.nb == power->num_blocks &&
-        g_cache.nbins == power->num_bins && g_cache.tosr == power->time_osr && g_cache.fosr == power->freq_osr && g_cache.proto == (int)power->protocol) {
+    if (g_cache.valid && g_cache.host_ptr == power->mag && g_cache.iters == max_iterations && g_cache.nb == power->num_blocks &&
+        g_cache.nbins == power->num_bins && g_cache.tosr == power->time_osr && g_cache.fosr == power->freq_osr && g_cache.proto == (int)power->protocol &&
+        g_cache.key == fingerprint(power->mag, bytes)) {
         for (size_t k = 0; k < g_cache.cand.size(); ++k) {
             if (memcmp(&g_cache.cand[k], cand, sizeof(candidate_t)) == 0) {
                 write_status(status, g_cache.status[k], g_cache.stage[k]);
@@ -224,7 +246,7 @@ bool ft8_decode(const waterfall_t *power, const candidate_t *cand, message_t *me
                cudaMemcpyAsync(g_s.cand, cand, sizeof(candidate_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
                cudaMemcpyAsync(g_s.ncand, &one, sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess &&
                launch_decode(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, 1, max_iterations, g_s.cand,
-                             g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, 148, st, &launches) == cudaSuccess &&
+                             g_s.ncand, g_s.ok, g_s.stage, g_s.status, g_s.msg, nullptr, nullptr, nullptr, nullptr, ctx_sm_count(ctx), st, &launches) == cudaSuccess &&
                cudaMemcpyAsync(&okv, g_s.ok, 1, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                cudaMemcpyAsync(&stage, g_s.stage, 1, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                cudaMemcpyAsync(&s, g_s.status, sizeof(s), cudaMemcpyDeviceToHost, st) == cudaSuccess &&

@@ -152,6 +152,7 @@ int ft8b200_load_wav(float *signal, int *num_samples, int *sample_rate, const ch
 int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n, struct decoder_results *h_results, int32_t *h_nresults,
                             int32_t *h_samples) {
     if (!ctx || !paths || n < 1 || !h_results || !h_nresults) return FT8B200_EINVAL;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;  // the caller's current device may be another one
     std::vector<float> hi((size_t)n * kSlot), hq((size_t)n * kSlot), peak((size_t)n, 0.0f);
     for (int k = 0; k < n; ++k) {
         int rec = 0;
@@ -186,6 +187,7 @@ int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n,
 int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride, int n_samples, int n, int sample_rate, int protocol,
                          ft8b200_decoded_t *h_out, int32_t *h_count, int max_out_per_recording) {
     if (!ctx || !d_audio || n < 1 || !h_out || !h_count || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return FT8B200_EINVAL;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;
     ft8b200_config_t cfg;
     if (ft8b200_get_config(ctx, &cfg)) return FT8B200_EINVAL;
     const int K = cfg.max_candidates, M = cfg.max_messages;
@@ -219,11 +221,10 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
     if ((rc = ft8b200_monitor_waterfall(ctx, d_audio, stride, n_samples, n, sample_rate, tosr, fosr, protocol, d_mag, mag_stride, &nb, nullptr))) return rc;
     for (int k = 0; k < n; ++k) h_count[k] = 0;
     if (nb == 0) return 0;
-    ft8b200_set_protocol(ctx, protocol);
-    rc = ft8b200_find_sync(ctx, d_mag, mag_stride, n, nb, num_bins, tosr, fosr, d_cand, d_ncand, nullptr);
-    if (!rc) rc = ft8b200_decode(ctx, d_mag, mag_stride, n, nb, num_bins, tosr, fosr, d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, nullptr, nullptr, nullptr);
+    // explicit protocol: the one selected with ft8b200_set_protocol for the stage-wise API is neither used nor changed
+    rc = find_sync_proto(ctx, protocol, d_mag, mag_stride, n, nb, num_bins, tosr, fosr, d_cand, d_ncand, nullptr);
+    if (!rc) rc = decode_proto(ctx, protocol, d_mag, mag_stride, n, nb, num_bins, tosr, fosr, d_cand, d_ncand, d_ok, d_stage, d_status, d_msg, nullptr, nullptr, nullptr);
     if (!rc) rc = ft8b200_spots(ctx, n, fosr, d_cand, d_ncand, d_ok, d_msg, d_res, d_nres, d_umsg, d_ufreq, d_uscore, d_ucand, nullptr);
-    ft8b200_set_protocol(ctx, PROTO_FT8);
     if (rc) return rc;
     std::vector<message_t> umsg(S * M);
     std::vector<int32_t> ucand(S * M), nres(S);
@@ -253,6 +254,7 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
 int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n, int protocol, ft8b200_decoded_t *h_out, int32_t *h_count,
                              int max_out_per_recording, int32_t *h_status) {
     if (!ctx || !paths || n < 1 || !h_out || !h_count) return FT8B200_EINVAL;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;
     const int cap = 15 * 12000;  // decode_ft8.c:271-273: float signal[15 * sample_rate]
     std::vector<int16_t> raw((size_t)n * cap, 0);
     std::vector<int> ns((size_t)n, 0), status((size_t)n, 0);

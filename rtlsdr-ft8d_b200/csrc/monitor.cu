@@ -202,6 +202,7 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
 // ---- host-side plan / tables (same libm calls as kiss_fft / kiss_fftr / decode_ft8.c) ----------
 struct MonTables {
     int nfft = 0;
+    int device = 0;
     FftPlan plan = {};
     uint16_t *d_perm = nullptr;
     float2 *d_tw = nullptr, *d_super = nullptr;
@@ -255,12 +256,14 @@ bool build_plan(int n, FftPlan &plan, std::vector<uint16_t> &perm) {
 std::mutex g_mon_mu;
 std::vector<MonTables *> g_tables;
 
-MonTables *get_tables(int nfft) {
+// tables are device allocations: one set per (device, nfft); the caller has made `device` current
+MonTables *get_tables(int device, int nfft) {
     std::lock_guard<std::mutex> lk(g_mon_mu);
-    for (MonTables *t : g_tables) if (t->nfft == nfft) return t;
+    for (MonTables *t : g_tables) if (t->nfft == nfft && t->device == device) return t;
     if (nfft < 8 || (nfft & 1) || nfft / 2 > 65535) return nullptr;
     MonTables *t = new MonTables();
     t->nfft = nfft;
+    t->device = device;
     const int n = nfft / 2;
     std::vector<uint16_t> perm;
     if (!build_plan(n, t->plan, perm)) { delete t; return nullptr; }
@@ -290,15 +293,18 @@ MonTables *get_tables(int nfft) {
     return t;
 }
 
-float *g_thr = nullptr;  // device copy of the dB step thresholds (shared by all monitors)
-float *thresholds() {
+constexpr int kMaxDevices = 64;
+float *g_thr[kMaxDevices] = {};  // per device: copy of the dB step thresholds (shared by all monitors on that device)
+float *thresholds(int device) {
+    if (device < 0 || device >= kMaxDevices) return nullptr;
     std::lock_guard<std::mutex> lk(g_mon_mu);
-    if (!g_thr) {
+    if (!g_thr[device]) {
         float t[257];
         build_db_thresholds(t);
-        if (cudaMalloc(&g_thr, sizeof(t)) != cudaSuccess || cudaMemcpy(g_thr, t, sizeof(t), cudaMemcpyHostToDevice) != cudaSuccess) g_thr = nullptr;
+        if (cudaMalloc(&g_thr[device], sizeof(t)) != cudaSuccess || cudaMemcpy(g_thr[device], t, sizeof(t), cudaMemcpyHostToDevice) != cudaSuccess)
+            g_thr[device] = nullptr;
     }
-    return g_thr;
+    return g_thr[device];
 }
 
 cudaError_t launch_frames(const MonTables *t, const float *d_audio, size_t slot_stride, int n_samples, long first_start, int hop, int n_frames,
@@ -308,7 +314,7 @@ cudaError_t launch_frames(const MonTables *t, const float *d_audio, size_t slot_
     if (e != cudaSuccess) return e;
     dim3 grid(n_frames, n_slots);
     monitor_frames_kernel<<<grid, kMonThreads, smem, st>>>(d_audio, slot_stride, n_samples, first_start, hop, t->nfft, t->plan, t->d_perm, t->d_tw,
-                                                           t->d_super, t->d_wnorm, thresholds(), num_bins, freq_osr, d_mag, mag_slot_stride, d_xmax);
+                                                           t->d_super, t->d_wnorm, thresholds(t->device), num_bins, freq_osr, d_mag, mag_slot_stride, d_xmax);
     return cudaGetLastError();
 }
 
@@ -348,8 +354,10 @@ int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t s
     if (!ctx || !d_audio || !d_mag || n_slots < 1 || n_samples < 0 || time_osr < 1 || freq_osr < 1) return FT8B200_EINVAL;
     const MonGeom g = geometry(sample_rate, time_osr, freq_osr, protocol);
     if (g.block_size < 2 || g.subblock_size * time_osr != g.block_size) return FT8B200_EINVAL;
-    const MonTables *t = get_tables(g.nfft);
-    if (!t || !thresholds()) return FT8B200_EINVAL;
+    const int device = ctx_device(ctx);
+    if (cudaSetDevice(device) != cudaSuccess) return FT8B200_ECUDA;  // tables and launches belong to the context's device, not the caller's current one
+    const MonTables *t = get_tables(device, g.nfft);
+    if (!t || !thresholds(device)) return FT8B200_EINVAL;
     int nb = n_samples / g.block_size;
     if (nb > g.max_blocks) nb = g.max_blocks;
     if (num_blocks_out) *num_blocks_out = nb;
@@ -366,8 +374,10 @@ int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t s
 void monitor_init(monitor_t *me, const monitor_config_t *cfg) {
     ft8b200_ctx_t *ctx = default_ctx();
     const MonGeom g = geometry(cfg->sample_rate, cfg->time_osr, cfg->freq_osr, (int)cfg->protocol);
-    const MonTables *t = get_tables(g.nfft);
-    if (!t || !thresholds()) {
+    const int device = ctx_device(ctx);
+    if (cudaSetDevice(device) != cudaSuccess) die("monitor_init: cudaSetDevice");
+    const MonTables *t = get_tables(device, g.nfft);
+    if (!t || !thresholds(device)) {
         fprintf(stderr, "libft8b200: monitor_init: unsupported FFT size %d (radices 2,3,4,5 only)\n", g.nfft);
         abort();
     }
@@ -397,6 +407,7 @@ void monitor_init(monitor_t *me, const monitor_config_t *cfg) {
 void monitor_free(monitor_t *me) {
     MonitorDev *d = (MonitorDev *)me->fft_work;
     if (d) {
+        cudaSetDevice(d->tables->device);
         cudaStreamSynchronize(d->st);
         cudaFree(d->d_buf); cudaFree(d->d_mag); cudaFree(d->d_xmax); cudaFreeHost(d->h_buf);
         delete d;
@@ -415,6 +426,7 @@ void monitor_reset(monitor_t *me) {  // decode_ft8.c:220-224: last_frame is NOT 
 void monitor_process(monitor_t *me, const float *frame) {
     if (me->wf.num_blocks >= me->wf.max_blocks) return;  // silent no-op once full (decode_ft8.c:165-166)
     MonitorDev *d = (MonitorDev *)me->fft_work;
+    if (cudaSetDevice(d->tables->device) != cudaSuccess) die("monitor_process: cudaSetDevice");  // the caller's thread may have another device current
     const int nfft = me->nfft, sub = me->subblock_size, blk = me->block_size, tosr = me->wf.time_osr;
     const size_t nhist = (size_t)nfft - sub, nbuf = nhist + blk;
     memcpy(d->h_buf, me->last_frame + sub, sizeof(float) * nhist);

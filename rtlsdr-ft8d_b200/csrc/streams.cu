@@ -53,7 +53,6 @@ struct ft8b200_stream {
     uint64_t bytes_in = 0;              // bytes received so far
     uint64_t blocks_done = 0;           // blocks already reduced + filtered
     BlockSums *d_sums = nullptr;        // [kHistBlocks history][new blocks of this pump]
-    float *d_fir = nullptr;
     float *d_i[2] = {nullptr, nullptr}, *d_q[2] = {nullptr, nullptr};
     float *d_peak = nullptr;            // [2]
     uint32_t iq_index[2] = {0, 0};      // rx_state.iqIndex
@@ -87,7 +86,7 @@ void pump(ft8b200_stream_t *s) {
     if (b1 > a1)
         CK(launch_cic_block_sums_generic(ptr(a1), 0, 1, (uint32_t)((a1 * kDecim) & 3u), (int)(b1 - a1), out + (a1 - b0), 0, s->st, &s->launches));
     const int buf = s->buffer_index;
-    CK(launch_cic_comb_fir(out, 0, n_new, (int)s->iq_index[buf], false, 1, s->d_fir, s->d_i[buf], s->d_q[buf], nullptr, s->d_peak + buf, nullptr,
+    CK(launch_cic_comb_fir(out, 0, n_new, (int)s->iq_index[buf], false, 1, s->d_i[buf], s->d_q[buf], nullptr, s->d_peak + buf, nullptr,
                            s->st, &s->launches));
     CK(launch_shift_history(s->d_sums, n_new, s->st, &s->launches));
     const uint64_t idx = (uint64_t)s->iq_index[buf] + (uint64_t)n_new;
@@ -158,14 +157,12 @@ ft8b200_stream_t *ft8b200_stream_create(ft8b200_ctx_t *ctx) {
     ft8b200_stream_t *s = new ft8b200_stream();
     s->ctx = ctx;
     s->st = (cudaStream_t)ft8b200_cuda_stream(ctx);
-    CK(cudaGetDevice(&s->device));
+    s->device = ctx_device(ctx);   // the stream lives on its context's device, whatever the caller's current device is
+    CK(cudaSetDevice(s->device));
+    CK(upload_fir_constants());
     CK(cudaMalloc(&s->d_ring, kRingBytes + 16));
     CK(cudaMalloc(&s->d_sums, sizeof(BlockSums) * (size_t)(kHistBlocks + kMaxPumpBlocks)));
     CK(cudaMemsetAsync(s->d_sums, 0, sizeof(BlockSums) * kHistBlocks, s->st));  // zero filter state
-    CK(cudaMalloc(&s->d_fir, sizeof(float) * kFirTaps));
-    float fir[kFirTaps];
-    build_fir(fir);
-    CK(cudaMemcpy(s->d_fir, fir, sizeof(fir), cudaMemcpyHostToDevice));
     for (int b = 0; b < 2; ++b) {
         CK(cudaMalloc(&s->d_i[b], sizeof(float) * kSlot));
         CK(cudaMalloc(&s->d_q[b], sizeof(float) * kSlot));
@@ -183,8 +180,9 @@ ft8b200_stream_t *ft8b200_stream_create(ft8b200_ctx_t *ctx) {
 
 void ft8b200_stream_destroy(ft8b200_stream_t *s) {
     if (!s) return;
+    cudaSetDevice(s->device);
     cudaStreamSynchronize(s->st);
-    cudaFree(s->d_ring); cudaFree(s->d_sums); cudaFree(s->d_fir); cudaFree(s->d_peak);
+    cudaFree(s->d_ring); cudaFree(s->d_sums); cudaFree(s->d_peak);
     for (int b = 0; b < 2; ++b) { cudaFree(s->d_i[b]); cudaFree(s->d_q[b]); }
     for (int k = 0; k < kStage; ++k) { cudaFreeHost(s->h_stage[k]); cudaEventDestroy(s->ev[k]); }
     delete s;

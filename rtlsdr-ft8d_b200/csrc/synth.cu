@@ -432,6 +432,7 @@ int ft8b200_encode_tones(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, i
     memset(sig.data(), 0, sig.size() * sizeof(ft8b200_signal_t));
     for (int k = 0; k < n; ++k) { memcpy(sig[(size_t)k].payload, h_payloads + 10 * (size_t)k, 10); first[(size_t)k] = k; }
     first[(size_t)n] = n;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;  // tables (per device) and buffers belong to the context's device
     cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;
@@ -453,6 +454,7 @@ int ft8b200_synth_raw(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, con
     if (!ctx || !d_iq || !check_first(h_first, n_slots) || (bytes_per_slot & 1) || slot_stride_bytes < bytes_per_slot || (slot_stride_bytes & 15) ||
         (((size_t)d_iq) & 15))
         return FT8B200_EINVAL;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;
@@ -471,6 +473,7 @@ int ft8b200_synth_raw(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, con
 static int synth_float(ft8b200_ctx_t *ctx, int kind, int protocol, const ft8b200_signal_t *h_signals, const int *h_first, int n_slots,
                        float noise_sigma, uint64_t seed, int first_slot_index, float *d_i, float *d_q, size_t slot_stride, int n_samples, void *stream) {
     if (!ctx || !d_i || (kind == 1 && !d_q) || !check_first(h_first, n_slots) || n_samples < 1 || slot_stride < (size_t)n_samples) return FT8B200_EINVAL;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;

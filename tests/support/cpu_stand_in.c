@@ -10,6 +10,9 @@
 #include "ft8_oracle.h"
 #include "ft8b200.h"
 
+/* marker the no-oracle guard (tests/test_abi.py::test_product_sources_do_not_touch_the_oracle) rejects by name */
+const char ft8b200_cpu_stand_in_marker[] = "cpu_stand_in: oracle-backed test artefact, never the product";
+
 void initFFTW(void) {}
 void freeFFTW(void) {}
 

@@ -87,8 +87,20 @@ def test_product_sources_do_not_touch_the_oracle():
                     code = line.split("//")[0]
                     assert "#include" not in code or "oracle" not in code, (f, line)
                     assert "pyoracle" not in code and "libft8oracle" not in code and "libref_" not in code, (f, line)
-    ldd = subprocess.check_output(["ldd", os.path.join(src, "libft8b200.so")], text=True)
-    assert "oracle" not in ldd
+    so = os.path.join(src, "libft8b200.so")
+    ldd = subprocess.check_output(["ldd", so], text=True)
+    assert "oracle" not in ldd and "libft8oracle" not in ldd and "libref_" not in ldd
+    # ... nor be the oracle-backed CPU stand-in of tests/support/ (a test artefact that must never reach the product tree):
+    # the product exports its CUDA launch counter and carries sm_100a device code, the stand-in carries the oracle's symbols
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
+    assert " orc_" not in syms and "cpu_stand_in" not in syms, "an oracle-backed library sits where the product belongs"
+    assert b"cpu_stand_in" not in open(so, "rb").read()
+    elf_cubins = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True)
+    if elf_cubins.returncode == 0:
+        assert "sm_100a" in elf_cubins.stdout, "libft8b200.so carries no sm_100a device code"
+    for dirpath, _, files in os.walk(src):
+        for f in files:
+            assert f != "cpu_stand_in.c" and not f.startswith("libft8oracle"), os.path.join(dirpath, f)
 
 
 def test_bad_arguments_are_rejected_before_any_launch(pkg):
