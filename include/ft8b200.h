@@ -291,6 +291,11 @@ int ft8b200_set_decode_variant(int variant);
  * (the argument is a product of tanh values), [2] = atanh mismatches elsewhere, [3], [4] = how many patterns took the full
  * division (tanh, atanh).  [0..2] must be 0. */
 int ft8b200_selfcheck_pade(ft8b200_ctx_t *ctx, uint64_t *counts5);
+/* Device self-check of the waterfall kernel's dB quantiser (replaces: 10*log10f + (int)(2*db+240) + clamp, rtlsdr_ft8d.c:1416,1425-1427):
+ * every non-negative float bit pattern and every NaN through the kernel's straight-line form (MUFU.LG2 estimate, one load of the two
+ * host-computed step thresholds around it, two compares) against a search over all 256 thresholds.  counts3[0] = mismatches (must be 0),
+ * [1] = inputs whose estimate needed the +-1 correction, [2] = inputs whose estimate was off by more than one (must be 0). */
+int ft8b200_selfcheck_quantiser(ft8b200_ctx_t *ctx, uint64_t *counts3);
 /* Device self-check hook for the message unpacker (a13): n 77-bit payloads (10 bytes each, MSB first, host) through the
  * kernel-side unpack77 (replaces: unpack77, ft8_lib/ft8/unpack.c:396-427 and everything under it), one thread each.
  * h_text32: n x 32 chars (NUL-padded; empty when rejected), h_status: unpack77's return value (0, -1, -2).  Exists so that

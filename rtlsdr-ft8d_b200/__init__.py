@@ -18,7 +18,7 @@ import subprocess
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libft8b200.so")
+LIB_PATH = os.environ.get("FT8B200_LIB_PATH") or os.path.join(PKG_DIR, "libft8b200.so")  # override: A/B runs of an older build (tools/)
 
 N_SLOT = 48000
 WF_BYTES = 94208
@@ -363,6 +363,12 @@ class Context:
         """All 2^32 float patterns through variant 0's inlined tanh/atanh vs the full-division expressions: 5 counters."""
         c = (C.c_uint64 * 5)()
         self._chk(self.L.ft8b200_selfcheck_pade(C.c_void_p(self.h), c))
+        return [int(v) for v in c]
+
+    def selfcheck_quantiser(self):
+        """All float patterns the dB quantiser can see, straight-line kernel form vs threshold search: (mismatches, corrected, far)."""
+        c = (C.c_uint64 * 3)()
+        self._chk(self.L.ft8b200_selfcheck_quantiser(C.c_void_p(self.h), c))
         return [int(v) for v in c]
 
     def unpack77_batch(self, payloads):

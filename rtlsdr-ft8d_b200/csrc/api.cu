@@ -610,6 +610,16 @@ int ft8b200_selfcheck_pade(ft8b200_ctx_t *ctx, uint64_t *counts5) {
     return 0;
 }
 
+int ft8b200_selfcheck_quantiser(ft8b200_ctx_t *ctx, uint64_t *counts3) {
+    if (!ctx || !counts3) return fail(FT8B200_EINVAL, "ft8b200_selfcheck_quantiser: bad argument");
+    if (int rc = ctx_enter(ctx)) return rc;
+    unsigned long long c[3] = {0, 0, 0};
+    cudaError_t e = run_quantiser_check(ctx->tb.db_thresholds, c, ctx->sm_count, ctx->stream);
+    if (e != cudaSuccess) return fail(FT8B200_ECUDA, cudaGetErrorString(e));
+    for (int k = 0; k < 3; ++k) counts3[k] = c[k];
+    return 0;
+}
+
 int ft8b200_unpack77_batch(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, char *h_text32, int32_t *h_status) {
     int rc = ctx_enter(ctx);
     if (rc) return rc;

@@ -50,6 +50,7 @@ cudaError_t launch_waterfall(const DeviceTables &t, const float *d_i, const floa
 void build_waterfall_tables(const float *window, const float2 *tw, const float *thr257, float *blob);
 int waterfall_blob_floats();
 cudaError_t upload_waterfall_constants(const float *blob_host);
+cudaError_t run_quantiser_check(const float *d_thr257, unsigned long long *h_counts3, int sm_count, cudaStream_t st);
 cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
                              int protocol, int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_scratch,
                              int scratch_slots, uint32_t *d_work, unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches);

@@ -161,6 +161,20 @@ def test_waterfall_parity(ctx, oracle, slots):
         assert ndiff == 0, f"slot {s}: {ndiff} of 94208 cells differ (spec allows +-1 LSB on <= 9 cells; this build is exact)"
 
 
+def test_quantiser_is_exact_over_all_floats(ctx, oracle):
+    """The waterfall kernel's dB quantiser is straight-line code: log2 estimate, ONE load of the two step thresholds around it,
+    two compares.  That is exact iff the estimate is never off by more than one step; swept on the device over every
+    non-negative float bit pattern, +inf and all NaNs against a search over the 256 host-computed thresholds, which are
+    themselves the reference's log10f expression (tables.cu; oracle.quantize_db pins a sample of them here)."""
+    bad, corrected, far = ctx.selfcheck_quantiser()
+    assert bad == 0 and far == 0
+    assert 0 < corrected < 2 ** 31 // 50          # the +-1 correction exists and is rare
+    thr = oracle.db_thresholds()
+    for k in (1, 17, 128, 255):
+        below = np.nextafter(np.float32(thr[k]), np.float32(0))
+        assert oracle.quantize_db(float(thr[k])) == k and oracle.quantize_db(float(below)) == k - 1
+
+
 def test_waterfall_applies_decoder_conditioning(ctx, oracle):
     """Unconditioned samples + slot peak: the kernel applies decoder()'s 0.5/max scale on load (rtlsdr_ft8d.c:248-263)."""
     i_s, q_s = synth.slot_f32([std_sig()], 21)
@@ -281,6 +295,24 @@ def test_min_score_zero_and_small_k(pkg, oracle, slots):
     cand, ncand = c.find_sync(torch.from_numpy(mag[None]).to(dev()))
     o = oracle.find_sync(mag, max_cand=7, min_score=0)
     assert np.array_equal(view(cand[0], cand_dtype)[: int(ncand[0])], o)
+    c.close()
+
+
+@pytest.mark.parametrize("K", [1, 7, 120, 500])
+def test_every_position_survives(pkg, oracle, K):
+    """min_score below every possible score: all 35 856 positions reach the heap stage (the reference's loop then pushes K
+    and, for each later survivor, tests `score > heap[0].score`).  Random bytes, a narrow band of values (ties everywhere) and
+    a ramp whose scores grow along the loop order (evictions all the way): candidates identical in content and order."""
+    c = pkg.Context(0, max_candidates=K, max_messages=50, min_score=-1000)
+    rng = np.random.default_rng(100 + K)
+    mags = np.stack([rng.integers(0, 256, 94208, dtype=np.uint8), rng.integers(100, 104, 94208, dtype=np.uint8),
+                     np.clip(np.arange(94208) // 400 + rng.integers(0, 24, 94208), 0, 255).astype(np.uint8)])
+    cand, ncand = c.find_sync(torch.from_numpy(mags).to(dev()))
+    torch.cuda.synchronize()
+    for s in range(mags.shape[0]):
+        o = oracle.find_sync(mags[s], max_cand=K, min_score=-1000)
+        assert int(ncand[s]) == o.size == K
+        assert np.array_equal(view(cand[s], cand_dtype)[:K], o), (K, s)
     c.close()
 
 
