@@ -8,18 +8,24 @@ one 15 s slot = 36 M complex samples through the full CIC+FIR decimation and FT8
 A "step" is one pass of the whole hot path (decimate -> condition -> waterfall -> Costas sync/top-K ->
 LLR/LDPC/CRC/unpack -> spot table) over one batch of synthetic slots.  `value` times it with the batch already
 resident in HBM (the batch is larger than L2); `e2e` times the same path through the C-ABI call that takes HOST
-buffers (pinned), host->device copies and the device->host read of the spot records inside the timed region.
-`roofline` is for the dominant kernel (cic_block_sums, HBM-bound), timed live with CUDA events on the launching
-stream; `cpu_baseline` is the CPU checker (oracle/_ref = the unmodified reference when it was built, else the
-restatement) timed on this box's host cores on a bounded sample of the same batch.
-Prints ONE JSON line on rank 0.
+buffers (pinned), host->device copies, the device->host read of the spot records and -- on several GPUs -- the NCCL
+gather of the records inside the timed region.  `e2e_slots` is the same at the path's other boundary (the input of
+ft8_subsystem(): 3200 sps float slots from host memory).  `roofline` is for the dominant kernel (cic_block_sums,
+HBM-bound), timed live with CUDA events on the launching stream; `roofline_extra` times every kernel of the path in one
+serial, un-partitioned pass; `configs` carries the other BASELINE configurations (#1 as single-slot latency through the
+literal drop-in calls, #3 on both waterfall paths, #4 strong-scaled over the GPUs with the gather, #5 sharded by receiver
+stream), each with the CPU reference on a sample beside it and a parity flag; `cpu_baseline` is the CPU checker
+(oracle/_ref = the unmodified reference when it was built, else the restatement) timed on this box's host cores on a
+bounded sample of the headline batch.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -30,13 +36,17 @@ sys.path.insert(0, ROOT)
 
 RAW_SLOT_BYTES = 72_000_000
 ALGO_BYTES_PER_SLOT = 72_000_000 + 47_936 * 8  # 2 B/sample in + 8 B per output
+WF_BYTES_PER_SLOT = 384_000 + 94_208           # waterfall A reads the slot, writes the uint8 waterfall
+MON_BYTES_PER_SLOT = 720_000 + 357_120         # waterfall B (12 kHz monitor)
+COMB_BYTES_PER_SLOT = 47_936 * 16 + 384_000    # comb+FIR: block sums (int32x4 per block) in, two float rails out
+WF_FP32_PER_SLOT = 8.9e6                       # FP32 instructions (thread level) bit-exact kiss_fft arithmetic needs per slot
 METRIC = "FT8 15s-slots decoded/sec from raw 2.4 Msps uint8 IQ"
 
 
 # --------------------------------------------------------------------------------------------- inputs
 def slot_params(seed: int):
     """Deterministic message / frequency / time offset of synthetic slot `seed`."""
-    from tools import ft8enc, synth
+    from tools import synth
     rng = np.random.Generator(np.random.PCG64(0xF78 + seed))
     to, de, ex = synth.random_message(rng)
     if seed % 2 == 0:
@@ -60,6 +70,19 @@ def gen_batch(n_slots: int, first_seed: int, device, ctx=None):
     if own:
         ctx.close()
     return buf, [p["text"] for p in params]
+
+
+def slot_ok(text: str, res_row, n: int) -> bool:
+    """The slot's own message came back: CQ messages with their call sign in decoder_results; other messages only count
+    as a decode (rtlsdr_ft8d.c:1509-1520 writes records for CQ messages only)."""
+    if n < 1:
+        return False
+    to, de = text.split()[:2]
+    return to != "CQ" or any(r["call"] == de.encode() for r in res_row[:n])
+
+
+def count_ok(texts, res, nres) -> int:
+    return sum(1 for s in range(len(texts)) if slot_ok(texts[s], res[s], int(nres[s])))
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -182,7 +205,7 @@ def cpu_run(n_slots: int, workers: int):
     return time.perf_counter() - t0, out
 
 
-# --------------------------------------------------------------------------------------------- main
+# --------------------------------------------------------------------------------------------- helpers
 _JSON_FD = None
 
 
@@ -219,6 +242,143 @@ def emit(obj):
         os.write(_JSON_FD, line)
 
 
+class Env:
+    """What every part of the CUDA arm needs: torch, the harness package, rank/world, device, timing helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from ft8b200_loader import load
+        self.torch, self.dist, self.pkg, self.args = torch, dist, load(), args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa(self.local)
+        if self.world > 1:
+            # the all_gather of the spot records must not queue behind the decimator's 190k-CTA grid: high-priority NCCL stream
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            dist.init_process_group("nccl", device_id=self.device, pg_options=opts)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms: float) -> float:
+        if self.world == 1:
+            return float(ms)
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v: int) -> int:
+        if self.world == 1:
+            return int(v)
+        t = self.torch.tensor([v], dtype=self.torch.int64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def timed(self, fn, steps: int):
+        """barrier + sync | CUDA events around fn(steps) | barrier + sync -> ms, max over ranks."""
+        e0 = self.torch.cuda.Event(enable_timing=True); e1 = self.torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        t0 = time.time()
+        e0.record()
+        out = fn(steps)
+        e1.record()
+        self.barrier()
+        t1 = time.time()
+        return self.max_over_ranks(e0.elapsed_time(e1)), out, (t0, t1)
+
+    def gather_records(self, res_dev, nres_dev):
+        """ONE NCCL all_gather each for a batch's decoder_results (uint8[n, M, 28] device tensor) and counts (int32[n]);
+        -> (uint8[world*n, M, 28], int32[world*n]) device tensors (the local ones when there is one rank)."""
+        if self.world == 1:
+            return res_dev, nres_dev
+        g_res = self.torch.empty((self.world * res_dev.shape[0],) + tuple(res_dev.shape[1:]), dtype=res_dev.dtype, device=self.device)
+        g_n = self.torch.empty(self.world * nres_dev.shape[0], dtype=nres_dev.dtype, device=self.device)
+        self.dist.all_gather_into_tensor(g_res, res_dev.contiguous())
+        self.dist.all_gather_into_tensor(g_n, nres_dev.contiguous())
+        return g_res, g_n
+
+
+class StepGather:
+    """Multi-GPU: the spot records of a step's executor batches are staged on the device (a local copy, so a lane is free again
+    as soon as its records are copied) and gathered to every rank with ONE NCCL all_gather per step; rank 0 reads them on the
+    host through pinned double buffers without blocking its submit loop."""
+
+    def __init__(self, env: Env, pipe, chunks: int, bc: int):
+        from tools.shard import stage_row_bytes
+        torch = env.torch
+        self.env, self.pipe, self.chunks, self.bc, self.M = env, pipe, chunks, bc, pipe.M
+        row = stage_row_bytes(bc, pipe.M)
+        self.stage = torch.empty((chunks, row), dtype=torch.uint8, device=env.device)  # per batch: records, then counts
+        self.gathered = torch.empty((env.world, chunks, row), dtype=torch.uint8, device=env.device)
+        self.copied = torch.cuda.Event()
+        self.host_rec = [torch.empty(self.gathered.shape, dtype=torch.uint8).pin_memory() for _ in range(2)] if env.rank == 0 else None
+        self.host_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.n_staged = 0
+
+    def collect(self):
+        """Oldest batch in flight -> staged; after the step's last batch: all_gather + async read on rank 0."""
+        from tools.shard import stage_batch
+        res_dev, nres_dev = self.pipe.collect_device()
+        stage_batch(self.stage, self.n_staged % self.chunks, res_dev, nres_dev, self.bc, self.M)
+        self.copied.record()
+        self.pipe.depend_on(self.copied)   # the lane's buffers are rewritten only after they have been copied out (ordered on the device)
+        self.n_staged += 1
+        if self.n_staged % self.chunks == 0:
+            self.env.dist.all_gather_into_tensor(self.gathered.view(-1), self.stage.view(-1))   # spot records over NVLink, once per step
+            if self.env.rank == 0:
+                i = (self.n_staged // self.chunks - 1) % 2
+                self.host_ev[i].synchronize()   # the copy issued two steps ago (long finished) owns this buffer
+                self.host_rec[i].copy_(self.gathered, non_blocking=True)
+                self.host_ev[i].record()
+
+    def last(self):
+        """rank 0: records of the last gathered step, all ranks, in (rank, slot) order; None elsewhere."""
+        from tools.shard import unpack_gathered
+        if self.env.rank != 0 or self.n_staged < self.chunks:
+            return None
+        i = (self.n_staged // self.chunks - 1) % 2
+        self.host_ev[i].synchronize()
+        res, nres = unpack_gathered(self.host_rec[i].numpy(), self.env.world, self.chunks, self.bc, self.M)
+        from ft8b200_loader import load
+        return res.view(load().result_dtype).reshape(res.shape[0], self.M), nres
+
+
+def run_steps(env: Env, pipe, submit, steps: int, chunks: int, bc: int, gather: StepGather | None):
+    """`steps` passes, each `chunks` executor batches (submit(c) queues batch c); every batch's spot records are read back
+    (one rank) or staged + gathered (several).  Returns the last pass's records in slot order (gathered: rank 0 only)."""
+    outs = []
+
+    def collect():
+        if gather is not None:
+            gather.collect()
+        else:
+            outs.append(pipe.collect(bc))
+
+    for _ in range(steps):
+        for c in range(chunks):
+            if pipe.in_flight() == pipe.depth:
+                collect()
+            submit(c)
+    while pipe.in_flight():
+        collect()
+    if gather is not None:
+        return gather.last()
+    last = outs[-chunks:]
+    return np.concatenate([np.asarray(o[0]) for o in last]), np.concatenate([np.asarray(o[1]) for o in last])
+
+
+def records_equal(a, b) -> bool:
+    return bool(np.array_equal(np.asarray(a[1]), np.asarray(b[1])) and np.asarray(a[0]).tobytes() == np.asarray(b[0]).tobytes())
+
+
+# --------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,14 +386,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=512, help="15 s slots per GPU per step (36.9 GB of raw IQ per GPU at 512)")
-    ap.add_argument("--e2e-slots", type=int, default=8, help="slots per step of the host-buffer (e2e) measurement")
+    ap.add_argument("--e2e-slots", type=int, default=8, help="raw slots per step of the host-buffer (e2e) measurement")
     ap.add_argument("--chunks", type=int, default=4, help="executor batches per step: a step's slots are submitted to ft8b200_pipe_t in this many batches")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the pipelined executor")
-    ap.add_argument("--back-sms", type=int, default=32, help="SMs of the back-end partition (waterfall/sync/LDPC of batch n next to the decimator "
-                                                             "of batch n+1 on the other SMs); 0 = no partition, kernels of consecutive batches run serially")
+    ap.add_argument("--back-sms", type=int, default=-1, help="SMs of the back-end partition (waterfall/sync/LDPC of batch n next to the decimator of batch n+1 on the "
+                                                             "other SMs); -1 = measure 24/32/40 and both comb+FIR placements at start-up and keep the fastest "
+                                                             "(ft8b200_pipe_autotune); 0 = no partition, kernels of consecutive batches run serially")
     ap.add_argument("--overlap", action="store_true", help="(without a partition) let the back end of batch n time-share the GPU with the decimator of batch n+1")
     ap.add_argument("--k1-variant", type=int, default=0, help="0 = streaming cic_block_sums kernel, 1..6 = bulk-copy (TMA) variants")
     ap.add_argument("--cpu-slots", type=int, default=96, help="bounded CPU-baseline sample (slots)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (configs, e2e_slots, roofline_extra)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE line, the JSON: anything a library prints to fd 1 on the way (NCCL's version banner at
@@ -245,37 +407,23 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "BASELINE config #2 batched: %d x (one 15 s slot of raw 2.4 Msps uint8 RTL IQ, 36 M complex samples, one FT8 message "
                           "at 20 LSB over 30 LSB noise) per GPU per step -> CIC+FIR decimation -> decoder() conditioning -> waterfall -> "
                           "sync (K=120) -> LDPC/CRC/unpack -> spot table" % args.slots,
               "slots_per_gpu_per_step": args.slots, "input_bytes_per_step_per_gpu": args.slots * RAW_SLOT_BYTES,
               "l2": "inputs larger than L2 (%.1f GB per step per GPU vs 126 MB)" % (args.slots * RAW_SLOT_BYTES / 1e9),
               "max_candidates": 120, "max_messages": 50, "ldpc_iterations": 20,
-              "executor": "ft8b200_pipe_t depth %d, %d batches of %d slots per step, %s" % (
-                  args.depth, args.chunks, args.slots // max(args.chunks, 1),
-                  ("SM partition: back end of batch n on >= %d SMs, decimator of batch n+1 on the others" % args.back_sms) if args.back_sms > 0 else
-                  ("overlap (time-shared)" if args.overlap else "serial (kernels of consecutive batches do not share the GPU)")),
               "parallelism": "slots sharded across GPUs, no data-path collective; "
               "spot records gathered with one NCCL all_gather per step" if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         return reference_arm(args, rank, world, config)
 
-    import torch
-    import torch.distributed as dist
-    from ft8b200_loader import load
-    pkg = load()
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    numa = bind_to_gpu_numa(local)
-    if numa:
-        config["numa"] = numa
-    if world > 1:
-        # the all_gather of the spot records must not queue behind the decimator's 190k-CTA grid: high-priority NCCL stream
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
-        dist.init_process_group("nccl", device_id=device, pg_options=opts)
+    env = Env(args)
+    torch, dist, pkg = env.torch, env.dist, env.pkg
+    device, local = env.device, env.local
+    if env.numa:
+        config["numa"] = env.numa
 
     B = args.slots
     if args.chunks < 1 or B % args.chunks:
@@ -287,148 +435,93 @@ def main():
     # batches never share the GPU (each kernel is timed alone), only D2H of the records and host work overlap them.
     pipe = pkg.Pipe(local, args.depth)
     pipe.set_mode(serial=not args.overlap, decimator_variant=args.k1_variant)
-    if args.back_sms > 0:
+    mode_txt = "overlap (time-shared)" if args.overlap else "serial (kernels of consecutive batches do not share the GPU)"
+    if args.back_sms != 0:
         # green contexts: disjoint SM sets for the HBM-bound decimator and the issue-bound back end (ft8b200_pipe_set_partition)
         try:
-            config["sm_partition"] = dict(zip(("front_sms", "back_sms"), pipe.set_partition(args.back_sms)))
+            if args.back_sms < 0:
+                tuned = pipe.autotune(batch[:Bc], Bc, candidates=(24, 32, 40), batches=3 * args.depth + 3)
+                config["sm_partition"] = {"chosen_by": "ft8b200_pipe_autotune (ms per %d-slot batch at each point)" % Bc, **tuned}
+                mode_txt = "SM partition: back end of batch n on %d SMs (comb+FIR on the %s set), decimator of batch n+1 on the others" % (
+                    tuned["back_sms"], "front" if tuned["comb_front"] else "back")
+            else:
+                config["sm_partition"] = dict(zip(("front_sms", "back_sms"), pipe.set_partition(args.back_sms)))
+                mode_txt = "SM partition: back end of batch n on >= %d SMs, decimator of batch n+1 on the others" % args.back_sms
         except Exception as exc:  # a driver without green contexts: same kernels, consecutive batches back to back on the whole GPU
             config["sm_partition"] = "unavailable (%s): running serial" % exc
-            config["executor"] = "ft8b200_pipe_t depth %d, %d batches of %d slots per step, serial" % (args.depth, args.chunks, args.slots // args.chunks)
+            pipe.set_mode(serial=True, decimator_variant=args.k1_variant)
             args.back_sms = 0
+    config["executor"] = "ft8b200_pipe_t depth %d, %d batches of %d slots per step, %s" % (args.depth, args.chunks, Bc, mode_txt)
     M = pipe.M
-    # Multi-GPU: the spot records of a step's batches are staged on the device (a local copy, so a lane is free again as soon
-    # as its records are copied) and gathered to every rank with ONE NCCL all_gather per step; rank 0 reads them on the host.
-    from tools.shard import stage_batch, stage_row_bytes, unpack_gathered
+
+    gather = StepGather(env, pipe, args.chunks, Bc) if world > 1 and not os.environ.get("BENCH_NOGATHER") else None
+    submit_dev = lambda c: pipe.submit(batch[c * Bc:(c + 1) * Bc], Bc)
+    out = run_steps(env, pipe, submit_dev, args.warmup, args.chunks, Bc, gather)
+
+    # ---- correctness guard: every synthetic slot must decode to its own message -- on every rank, through both result paths
+    local_res, local_nres = run_steps(env, pipe, submit_dev, 1, args.chunks, Bc, None)   # this rank's records through the host-collect path
+    n_good_local = count_ok(texts, local_res, local_nres)
+    n_good = env.sum_over_ranks(n_good_local)
+    verify = {"slots_decoded_to_their_own_message": n_good, "of": world * B}
     if world > 1:
-        stage = torch.empty((args.chunks, stage_row_bytes(Bc, M)), dtype=torch.uint8, device=device)  # per batch: records, then counts
-        gathered = torch.empty((world, args.chunks, stage_row_bytes(Bc, M)), dtype=torch.uint8, device=device)
-        copied = torch.cuda.Event()
-        # rank 0 reads every step's gathered records into pinned host memory without blocking its submit loop
-        host_rec = [torch.empty(gathered.shape, dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
-        host_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    n_staged = [0]
-
-    def last_gathered():
-        """rank 0: records of the last gathered step, all ranks, in (rank, slot) order."""
-        if rank != 0 or n_staged[0] < args.chunks:
-            return None
-        i = (n_staged[0] // args.chunks - 1) % 2
-        host_ev[i].synchronize()
-        return unpack_gathered(host_rec[i].numpy(), world, args.chunks, Bc, M)
-
-    def collect():
-        """Oldest batch -> host records on rank 0 (multi-GPU: one NCCL all_gather of the fixed-size spot records per step)."""
-        if world > 1 and os.environ.get("BENCH_NOGATHER"):
-            return pipe.collect(Bc)   # diagnostic only: how fast would the ranks run without the collective
-        if world > 1:
-            res_dev, nres_dev = pipe.collect_device()
-            stage_batch(stage, n_staged[0] % args.chunks, res_dev, nres_dev, Bc, M)
-            copied.record()
-            pipe.depend_on(copied)   # the lane's buffers are rewritten only after they have been copied out (ordered on the device)
-            n_staged[0] += 1
-            if n_staged[0] % args.chunks == 0:
-                dist.all_gather_into_tensor(gathered.view(-1), stage.view(-1))   # spot records over NVLink, once per step
-                if rank == 0:
-                    i = (n_staged[0] // args.chunks - 1) % 2
-                    host_ev[i].synchronize()   # the copy issued two steps ago (long finished) owns this buffer
-                    host_rec[i].copy_(gathered, non_blocking=True)
-                    host_ev[i].record()
-            return None
-        return pipe.collect(Bc)
-
-    def run(steps):
-        """`steps` passes over the B resident slots, each submitted as args.chunks executor batches; every batch's spot
-        records are read back.  Returns the records of the last pass in slot order."""
-        outs = []
-        for _ in range(steps):
-            for c in range(args.chunks):
-                if pipe.in_flight() == pipe.depth:
-                    outs.append(collect())
-                pipe.submit(batch[c * Bc:(c + 1) * Bc], Bc)
-        while pipe.in_flight():
-            outs.append(collect())
-        if world > 1:
-            return last_gathered()
-        last = outs[-args.chunks:]
-        return np.concatenate([np.asarray(o[0]) for o in last]), np.concatenate([np.asarray(o[1]) for o in last])
-
-    out = run(args.warmup)
-    # correctness guard on the first batch: every synthetic slot must decode to its own message
-    if world == 1:
-        res, nres = out
-        def slot_ok(s):  # CQ messages must come back with their call sign; other messages only count as a decode (a15)
-            if nres[s] < 1:
-                return False
-            to, de = texts[s].split()[:2]
-            return to != "CQ" or any(r["call"] == de.encode() for r in res[s][:nres[s]])
-        n_good = sum(1 for s in range(B) if slot_ok(s))
-    else:
-        n_good = -1
-        if rank == 0 and out is not None:  # gathered records of every rank: slots that produced at least one message
-            config["decoded_slots_all_ranks"] = "%d of %d" % (int((out[1] >= 1).sum()), world * B)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        # rank 0 holds the gathered records of every rank (staged on the device, one all_gather per step): they must equal what each
+        # rank collects locally through ft8b200_pipe_collect, and every rank's slot must carry that rank's own message
+        t_res = torch.from_numpy(np.ascontiguousarray(local_res).view(np.uint8).reshape(B, M * 28)).to(device)
+        t_n = torch.from_numpy(np.ascontiguousarray(local_nres, np.int32)).to(device)
+        all_res, all_n = env.gather_records(t_res, t_n)
+        if rank == 0 and out is not None:
+            g_res, g_n = out
+            ref_res = all_res.cpu().numpy().view(pkg.result_dtype).reshape(world * B, M)
+            ref_n = all_n.cpu().numpy()
+            verify["gathered_records_equal_each_ranks_local_records"] = records_equal((g_res, g_n), (ref_res, ref_n))
+            all_texts = [slot_params(100_000 * r + s)["text"] for r in range(world) for s in range(B)]
+            verify["gathered_slots_decoded_to_their_own_message"] = count_ok(all_texts, g_res, g_n)
+    res, nres = local_res, local_nres
 
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
     pipe.set_profiling(True)
     launches0 = pipe.launches()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.time()
-    e0.record()
-    run(args.steps)
-    e1.record()
-    barrier()
-    t_wall1 = time.time()
-    ms = e0.elapsed_time(e1)
+    ms, _, (t_wall0, t_wall1) = env.timed(lambda k: run_steps(env, pipe, submit_dev, k, args.chunks, Bc, gather), args.steps)
     launches = pipe.launches() - launches0
     stage_acc, n_prof = pipe.stage_times()
     pipe.set_profiling(False)
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
     clocks = sampler.summary(t_wall0, t_wall1)
 
-    # ---- e2e: host buffers in, host results out, through the C-ABI calls that take HOST memory
+    # ---- e2e: host buffers in, host results out, through the C-ABI calls that take HOST memory; several GPUs: + the gather
     Be = min(args.e2e_slots, B)
     host = torch.empty((Be, RAW_SLOT_BYTES), dtype=torch.uint8, pin_memory=True)
     host.copy_(batch[:Be])
     host_np = host.numpy()
-
-    def run_host(steps):
-        out = None
-        for _ in range(steps):
-            if pipe.in_flight() == pipe.depth:
-                out = pipe.collect(Be)
-            pipe.submit_host(host_np, Be)
-        while pipe.in_flight():
-            out = pipe.collect(Be)
-        return out
-
-    run_host(args.warmup)
-    barrier()
-    e0.record()
-    r_e2e, n_e2e = run_host(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e2e], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+    gather_e = StepGather(env, pipe, 1, Be) if gather is not None else None
+    submit_host = lambda c: pipe.submit_host(host_np, Be)
+    run_steps(env, pipe, submit_host, args.warmup, 1, Be, gather_e)
+    ms_e2e, out_e2e, _ = env.timed(lambda k: run_steps(env, pipe, submit_host, k, 1, Be, gather_e), args.steps)
     sampler.stop()
+    if world == 1:
+        same_e2e = records_equal(out_e2e, (res[:Be], nres[:Be]))
+    else:
+        flag = 1
+        if rank == 0:
+            g_res, g_n = out_e2e
+            ref_res = all_res.cpu().numpy().view(pkg.result_dtype).reshape(world, B, M)[:, :Be].reshape(world * Be, M)
+            ref_n = all_n.cpu().numpy().reshape(world, B)[:, :Be].reshape(-1)
+            flag = int(records_equal((g_res, g_n), (ref_res, ref_n)))
+        same_e2e = bool(env.sum_over_ranks(flag) == world)
     e2e = {"value": world * Be * args.steps / (ms_e2e * 1e-3), "unit": "slots/s", "h2d_bytes_per_step": Be * RAW_SLOT_BYTES,
-           "d2h_bytes_per_step": Be * (M * 28 + 4), "slots_per_step": Be, "same_results_as_device_path": bool(world > 1 or (
-               np.array_equal(n_e2e, nres[:Be]) and r_e2e.tobytes() == res[:Be].tobytes())),
+           "d2h_bytes_per_step": Be * (M * 28 + 4) * (world if rank == 0 and world > 1 else 1), "slots_per_step": Be,
+           "same_results_as_device_path": same_e2e,
            "h2d_gbs": world * Be * RAW_SLOT_BYTES * args.steps / (ms_e2e * 1e-3) / 1e9,
-           "api": "ft8b200_pipe_submit_host / ft8b200_pipe_collect (pinned host IQ in, decoder_results out, %d batches in flight)" % pipe.depth}
+           "api": "ft8b200_pipe_submit_host / ft8b200_pipe_collect%s (pinned host IQ in, decoder_results out, %d batches in flight)" % (
+               "_device + one NCCL all_gather of the records per step, read on rank 0" if world > 1 else "", pipe.depth)}
+    try:
+        hc = json.load(open(os.path.join(ROOT, "profiles", "h2d_ceiling_r2.json")))
+        e2e["host_ceiling_gbs"] = hc.get("by_gpus", {}).get(str(world))
+        e2e["host_ceiling_source"] = "profiles/h2d_ceiling_r2.json (tools/h2d_probe.py: %s)" % hc.get("what", "")
+    except Exception:
+        pass
 
     # ---- roofline of the dominant kernel (cic_block_sums): algorithmic bytes / CUDA-event time
     peaks = {}
@@ -437,20 +530,20 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (measured, burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     n_prof = max(n_prof, 1)
     k1_ms = stage_acc.get("block_sums", 0.0) / n_prof
     k2_ms = stage_acc.get("comb_fir", 0.0) / n_prof
     achieved = Bc * ALGO_BYTES_PER_SLOT / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
     roofline = {"kernel": "cic_block_sums_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured, burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_source,
                 "algorithmic_bytes_per_launch": Bc * ALGO_BYTES_PER_SLOT, "slots_per_launch": Bc, "launch_ms": k1_ms,
                 "decimator_ms_incl_comb_fir": k1_ms + k2_ms,
                 "decimator_msps": Bc * 36.0 / ((k1_ms + k2_ms) * 1e-3) if k1_ms > 0 else None,
                 "timed": "CUDA events around every launch of the kernel inside the timed region (%d launches)" % n_prof,
                 "stage_ms_per_launch": {k: v / n_prof for k, v in stage_acc.items()},
                 "stage_note": "with an SM partition the back-end stages (comb_fir ... spots) run on the back-end SMs concurrently with the "
-                              "next batch's block sums: their times overlap it and do not add to the step" if args.back_sms > 0 else "stages run back to back"}
+                              "next batch's block sums: their times overlap it and do not add to the step" if args.back_sms != 0 else "stages run back to back"}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))  # one `ncu --set full` capture, per slot
         roofline["traffic"] = tr.get("dram_bytes_per_slot", 0) * Bc or None
@@ -461,11 +554,34 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": "slots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
            "data": "synthetic (generated on the device by ft8b200_synth_raw)", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-           "decoded_ok_slots_in_first_batch": n_good}
+           "decoded_ok_slots_in_first_batch": n_good_local, "verify": verify}
+
+    pipe.close()
+    if not args.no_configs:
+        from tools import bench_configs as bc
+        sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+        if rank == 0:
+            out["roofline_extra"] = bc.roofline_extra(env, batch, min(Bc, 128), peak, peak_source, sm_mhz)
+        env.barrier()
+        configs = {}
+        configs["c5_streams"] = bc.config5(env, batch, texts)
+        del batch, host
+        torch.cuda.empty_cache()
+        configs["c4_slots_sharded"], slots_host = bc.config4(env, args.steps)
+        out["e2e_slots"] = bc.e2e_slots(env, slots_host, args.steps, args.depth)
+        if world == 1:
+            configs["c3_daemon_k500"] = bc.config3_daemon(env)
+            configs["c3_monitor_12k"] = bc.config3_monitor(env)
+            configs["c1_single_slot_latency"] = bc.config1_latency(env)
+        out["configs"] = configs
+        # re-created for the CPU baseline sample below
+        batch = None
 
     if rank == 0 and world == 1:
         global _CPU_SLOTS
         n_cpu = min(args.cpu_slots, B)
+        if batch is None:
+            batch, _ = gen_batch(n_cpu, 0, device)
         _CPU_SLOTS = batch[:n_cpu].cpu().numpy()
         _CPU_PHASE_S["decimator"] = _CPU_PHASE_S["decode"] = 0.0
         secs, n_dec = cpu_run(n_cpu, 1)
@@ -511,6 +627,7 @@ def reference_arm(args, rank, world, config):
     value = n * args.steps / t
     kind = cpu_kind()
     cfg = dict(config)
+    cfg["executor"] = "n/a (CPU arm)"
     cfg["reference_sample"] = "%d slots per step over %d worker processes" % (n, cores)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "slots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",

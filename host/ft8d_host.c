@@ -12,6 +12,8 @@
  *   wav     [-ft4] F.wav ... ft8_lib's decode_ft8 main() (decode_ft8.c:226-409) through monitor_* / ft8_find_sync /
  *                            ft8_decode, printing the same lines
  *   batch                    B200-side extra: synthetic raw slots through the pipelined executor from host memory
+ *   latency SLOT.iq [RAW.u8 [F.wav]]   single-slot latency of the literal drop-in calls, one JSON line (BASELINE config #1; the
+ *                            reference publishes this as "decode burst per 15 s slot", README.md:153-157)
  *
  * Exit status: 0 = ran (selftest: and decoded the known answer), 1 = self-test failed / bad usage, 2 = library error.
  * Without a usable B200 the library reports why and the program stops: there is no CPU path behind these calls.
@@ -295,6 +297,102 @@ static int run_batch(int n_slots, int n_batches, int depth) {
     return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------- latency (config #1) */
+
+static double now_ms(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec;
+}
+static int cmp_double(const void *a, const void *b) { return (*(const double *)a > *(const double *)b) - (*(const double *)a < *(const double *)b); }
+static double median(double *v, int n) { qsort(v, (size_t)n, sizeof *v, cmp_double); return v[n / 2]; }
+
+/* One 15 s slot at a time through the reference's own entry points, wall-clock per call as the daemon's decoder thread sees it:
+ *   subsystem_ms   decoder()'s conditioning on the host (rtlsdr_ft8d.c:242-263) + ft8_subsystem(I, Q, 48000, spots, &n)
+ *   receive_ms     1099 x rtlsdr_callback(65536 bytes) of one raw 2.4 Msps slot + the 15 s flip + decoder() (stream_decode)
+ *   wav_ms         decode_ft8's main() flow: 93 x monitor_process + ft8_find_sync(120) + one ft8_decode per candidate */
+static int run_latency(const char *iq_path, const char *raw_path, const char *wav_path, int reps) {
+    static float rail_i[SLOT], rail_q[SLOT], ci[SLOT], cq[SLOT];
+    static struct decoder_results spots[MAX_MESSAGES];
+    double t[64];
+    if (reps < 3) reps = 3;
+    if (reps > 64) reps = 64;
+    float peak = 0.0f;
+    const int n_pairs = ft8b200_read_iq_file(iq_path, rail_i, rail_q, &peak);
+    if (n_pairs <= 0) { fprintf(stderr, "ft8d_host: cannot read %s\n", iq_path); return 1; }
+    initFFTW();
+    int32_t n = 0, n_sub = 0;
+    for (int r = 0; r < reps + 2; ++r) {   /* two untimed calls first (context creation, first launches) */
+        const double t0 = now_ms();
+        float max_sig = 1e-24f;            /* decoder(): zero tail is already there; peak-normalise to 0.5 */
+        for (int k = 0; k < SLOT; ++k) {
+            const float a = fabsf(rail_i[k]), b = fabsf(rail_q[k]);
+            if (a > max_sig) max_sig = a;
+            if (b > max_sig) max_sig = b;
+        }
+        const float scale = (float)(0.5 / (double)max_sig);
+        for (int k = 0; k < SLOT; ++k) { ci[k] = rail_i[k] * scale; cq[k] = rail_q[k] * scale; }
+        ft8_subsystem(ci, cq, SLOT, spots, &n);
+        if (r >= 2) t[r - 2] = now_ms() - t0;
+        n_sub = n;
+    }
+    const double subsystem_ms = median(t, reps);
+
+    double receive_ms = -1.0;
+    int32_t n_rx = -1;
+    if (raw_path && raw_path[0] && strcmp(raw_path, "-") != 0) {
+        FILE *f = fopen(raw_path, "rb");
+        unsigned char *raw = malloc(FT8B200_RAW_SLOT_BYTES);
+        if (!f || !raw || fread(raw, 1, FT8B200_RAW_SLOT_BYTES, f) != FT8B200_RAW_SLOT_BYTES) { fprintf(stderr, "ft8d_host: cannot read one raw slot from %s\n", raw_path); return 1; }
+        fclose(f);
+        const int rx_reps = reps < 5 ? reps : 5;
+        for (int r = 0; r < rx_reps + 1; ++r) {
+            const double t0 = now_ms();
+            for (size_t at = 0; at < FT8B200_RAW_SLOT_BYTES; at += 65536u) {
+                size_t len = FT8B200_RAW_SLOT_BYTES - at;
+                if (len > 65536u) len = 65536u;
+                rtlsdr_callback(raw + at, (uint32_t)(len - len % 8u), NULL);
+            }
+            if (ft8b200_stream_flip(NULL) != 0 || ft8b200_stream_decode(NULL, spots, &n) != 0) return fail("stream_decode");
+            if (r >= 1) t[r - 1] = now_ms() - t0;
+            n_rx = n;
+        }
+        receive_ms = median(t, rx_reps);
+        free(raw);
+    }
+
+    double wav_ms = -1.0;
+    int n_wav = -1;
+    if (wav_path && wav_path[0]) {
+        static float audio[15 * 12000];
+        int sample_rate = 12000, n_samples = 15 * 12000;
+        if (ft8b200_load_wav(audio, &n_samples, &sample_rate, wav_path) < 0) { fprintf(stderr, "ft8d_host: cannot read %s\n", wav_path); return 1; }
+        for (int r = 0; r < reps + 1; ++r) {
+            const double t0 = now_ms();
+            monitor_config_t mc = {100.0f, 3000.0f, sample_rate, 2, 2, PROTO_FT8};
+            monitor_t mon;
+            monitor_init(&mon, &mc);
+            for (int at = 0; at + mon.block_size <= n_samples; at += mon.block_size) monitor_process(&mon, audio + at);
+            candidate_t cand[MAX_CANDIDATES];
+            const int n_cand = ft8_find_sync(&mon.wf, MAX_CANDIDATES, cand, MIN_SCORE);
+            int ok = 0;
+            for (int c = 0; c < n_cand; ++c) {
+                message_t msg;
+                decode_status_t status;
+                ok += ft8_decode(&mon.wf, &cand[c], &msg, LDPC_ITERATIONS, &status) ? 1 : 0;
+            }
+            monitor_free(&mon);
+            if (r >= 1) t[r - 1] = now_ms() - t0;
+            n_wav = ok;
+        }
+        wav_ms = median(t, reps);
+    }
+    freeFFTW();
+    printf("{\"subsystem_ms\": %.4f, \"subsystem_results\": %d, \"receive_ms\": %.4f, \"receive_results\": %d, \"wav_ms\": %.4f, \"wav_decodes\": %d, \"reps\": %d}\n",
+           subsystem_ms, n_sub, receive_ms, n_rx, wav_ms, n_wav, reps);
+    return 0;
+}
+
 /* ---------------------------------------------------------------------------------------------- main */
 
 static int usage(void) {
@@ -302,7 +400,8 @@ static int usage(void) {
           "       ft8d_host [-f dial_hz] [-T unixtime] decode file.iq|file.c2 ...\n"
           "       ft8d_host [-f dial_hz] [-T unixtime] receive [-b bytes_per_callback] [-s] raw_iq.u8|-\n"
           "       ft8d_host wav [-ft4] file.wav ...\n"
-          "       ft8d_host batch [slots [batches [depth]]]\n",
+          "       ft8d_host batch [slots [batches [depth]]]\n"
+          "       ft8d_host latency slot.iq [raw_slot.u8|- [file.wav [reps]]]\n",
           stderr);
     return 1;
 }
@@ -330,6 +429,8 @@ int main(int argc, char **argv) {
         if (a >= argc || chunk < 8u || chunk % 8u) return usage();
         return run_receive(argv[a], chunk, own);
     }
+    if (strcmp(cmd, "latency") == 0)
+        return argc > a ? run_latency(argv[a], argc > a + 1 ? argv[a + 1] : NULL, argc > a + 2 ? argv[a + 2] : NULL, argc > a + 3 ? atoi(argv[a + 3]) : 15) : usage();
     if (strcmp(cmd, "batch") == 0) {
         const int slots = argc > a ? atoi(argv[a]) : 4, batches = argc > a + 1 ? atoi(argv[a + 1]) : 4, depth = argc > a + 2 ? atoi(argv[a + 2]) : 2;
         return slots > 0 && batches > 0 && depth > 0 ? run_batch(slots, batches, depth) : usage();

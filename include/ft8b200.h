@@ -305,6 +305,11 @@ int ft8b200_unpack77_batch(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n,
  * stream, `back_stream` its back-end side stream, whose kernels size their persistent grids for `back_sm_count` SMs.
  * NULL restores the context's own stream.  Used by ft8b200_pipe_set_partition with green-context streams. */
 int ft8b200_set_partition_streams(ft8b200_ctx_t *ctx, void *front_stream, void *back_stream, int back_sm_count);
+/* With partition streams set: 0 (default) = the comb+FIR pass runs on the back-end SM set with the rest of the back end,
+ * 1 = it stays on the front set directly behind cic_block_sums (it is a whole-GPU grid that takes 5x longer on a small back
+ * partition, but on the front set it queues ahead of the next batch's block sums).  Which is better depends on how the two
+ * sides balance: ft8b200_pipe_autotune measures it. */
+int ft8b200_set_comb_front(ft8b200_ctx_t *ctx, int on);
 void *ft8b200_front_event(ft8b200_ctx_t *ctx);
 /* device pointers to the last batch's outputs: results (n_slots x max_messages), counts (n_slots) */
 int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults);
@@ -345,12 +350,25 @@ int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant);
  * sizes actually provisioned come back through front_sms/back_sms, either may be NULL).  Implies FT8B200_PIPE_OVERLAP.
  * back_sms == 0 removes the partition.  Results are identical in every mode.  Needs depth >= 2 and no batch in flight. */
 int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms, int *back_sms_out);
+/* Chooses the partition by measurement: for every back_sms in `candidates` (0 = no partition, serial kernels) and both placements
+ * of the comb+FIR pass, `batches` batches of the caller's device-resident input (as for ft8b200_pipe_submit) are pushed through the
+ * executor and timed; the fastest setting is left in place and reported (best_back_sms, best_comb_front, ms per batch of each
+ * point in ms_out[2 * n_candidates], comb_front = 0 first; any of the three may be NULL).  The split that balances the HBM-bound
+ * front end against the issue-bound back end depends on the batch's candidate load and on the box; nothing in the results does. */
+int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots,
+                          const int *candidates, int n_candidates, int batches, int *best_back_sms, int *best_comb_front, float *ms_out);
 void ft8b200_pipe_destroy(ft8b200_pipe_t *p);
 const char *ft8b200_pipe_error(ft8b200_pipe_t *p);
 int ft8b200_pipe_depth(ft8b200_pipe_t *p);
 int ft8b200_pipe_in_flight(ft8b200_pipe_t *p);
 int ft8b200_pipe_submit(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots);
 int ft8b200_pipe_submit_host(ft8b200_pipe_t *p, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots);
+/* The same executor fed at the OTHER boundary of the path, the input of ft8_subsystem() (rtlsdr_ft8d.h:164): n_slots x 48000 float
+ * samples per rail at 3200 sps.  _host: conditioned samples in (pinned) host memory, copied H2D on the lane's stream; device form:
+ * d_peak == NULL for conditioned samples, else decoder()'s 0.5/peak scale is applied on load.  384 KB per slot instead of 72 MB:
+ * this is the call for hosts that decimate elsewhere (or replay .iq/.c2 recordings).  Use a pipe without an SM partition. */
+int ft8b200_pipe_submit_slots(ft8b200_pipe_t *p, const float *d_i, const float *d_q, const float *d_peak, int n_slots);
+int ft8b200_pipe_submit_slots_host(ft8b200_pipe_t *p, const float *h_i, const float *h_q, int n_slots);
 int ft8b200_pipe_collect(ft8b200_pipe_t *p, struct decoder_results *h_results, int32_t *h_nresults, int capacity_slots);
 /* same wait, but hands out the DEVICE buffers of the oldest batch (n_slots x max_messages records, n_slots counts) instead of
  * copying to the host -- for a collective on the records (NCCL all_gather).  They stay valid until that lane is submitted

@@ -435,6 +435,20 @@ class Reference:
         n = self.lib.ref_subsystem_scripted(_ptr(cands), _ptr(ok), _ptr(msgs), cands.size, _ptr(res), self.mmax)
         return int(n), res
 
+    def time_subsystem(self, i_s, q_s, reps=9):
+        """Wall-clock (ms per call, timed inside the C harness) of decoder()'s conditioning + ft8_subsystem on one slot."""
+        i_s = np.ascontiguousarray(i_s, np.float32); q_s = np.ascontiguousarray(q_s, np.float32)
+        ms = np.zeros(reps, np.float64)
+        n = self.lib.ref_time_subsystem(_ptr(i_s), _ptr(q_s), reps, _ptr(ms))
+        return ms, int(n)
+
+    def time_receive(self, raw):
+        """Wall-clock (ms) of one raw slot through rtlsdr_callback (65536-byte calls) + flip + conditioning + ft8_subsystem."""
+        buf = np.array(raw, np.uint8, copy=True)
+        ms = C.c_double(0)
+        n = self.lib.ref_time_receive(_ptr(buf), C.c_uint32(buf.size), C.byref(ms))
+        return float(ms.value), int(n)
+
     def find_sync(self, mag, max_cand=120, min_score=10, num_blocks=92, num_bins=256, time_osr=2, freq_osr=2, protocol=1):
         mag = np.ascontiguousarray(mag, np.uint8)
         heap = np.zeros(max_cand, cand_dtype)

@@ -173,6 +173,59 @@ int32_t ref_subsystem_scripted(const candidate_t *cand, const int32_t *ok, const
     return r;
 }
 
+/* ---- wall-clock of the reference's own single-slot flows (BASELINE config #1; what README.md:153-157 calls the "decode burst") ---- */
+#include <time.h>
+static double ref_now_ms(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec;
+}
+/* decoder()'s conditioning (rtlsdr_ft8d.c:242-263; the function itself is the body of a thread loop and cannot be called) */
+static void ref_condition(float *i_s, float *q_s, uint32_t n_valid) {
+    for (uint32_t k = n_valid; k < SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE; ++k) { i_s[k] = 0.0f; q_s[k] = 0.0f; }
+    float maxSig = 1e-24f;
+    for (uint32_t k = 0; k < SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE; ++k) {
+        const float a = fabsf(i_s[k]), b = fabsf(q_s[k]);
+        if (a > maxSig) maxSig = a;
+        if (b > maxSig) maxSig = b;
+    }
+    maxSig = 0.5 / maxSig;
+    for (uint32_t k = 0; k < SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE; ++k) { i_s[k] *= maxSig; q_s[k] *= maxSig; }
+}
+/* conditioning + ft8_subsystem on one slot, `reps` times: out_ms[r]; returns n_results of the last call */
+int32_t ref_time_subsystem(const float *i_samples, const float *q_samples, int reps, double *out_ms) {
+    static float ci[SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE], cq[SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE];
+    int32_t n = 0;
+    for (int r = 0; r < reps; ++r) {
+        const double t0 = ref_now_ms();
+        memcpy(ci, i_samples, sizeof(ci));
+        memcpy(cq, q_samples, sizeof(cq));
+        ref_condition(ci, cq, SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE);
+        memset(dec_results, 0, sizeof(dec_results));
+        ft8_subsystem(ci, cq, SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE, dec_results, &n);
+        out_ms[r] = ref_now_ms() - t0;
+    }
+    return n;
+}
+/* one raw 2.4 Msps slot: rtlsdr_callback() in 65536-byte calls, the 15 s flip, conditioning, ft8_subsystem; returns n_results.
+ * `raw` is modified in place by the reference's mixer (rtlsdr_ft8d.c:129-140). */
+int32_t ref_time_receive(unsigned char *raw, uint32_t nbytes, double *out_ms) {
+    const double t0 = ref_now_ms();
+    for (uint32_t at = 0; at < nbytes; at += 65536u) {
+        uint32_t len = nbytes - at;
+        if (len > 65536u) len = 65536u;
+        rtlsdr_callback(raw + at, len - len % 8u, NULL);
+    }
+    const uint32_t which = rx_state.bufferIndex, have = rx_state.iqIndex[which];
+    ref_rx_flip();
+    int32_t n = 0;
+    ref_condition(rx_state.iSamples[which], rx_state.qSamples[which], have);
+    memset(dec_results, 0, sizeof(dec_results));
+    ft8_subsystem(rx_state.iSamples[which], rx_state.qSamples[which], SIGNAL_LENGHT * SIGNAL_SAMPLE_RATE, dec_results, &n);
+    *out_ms = ref_now_ms() - t0;
+    return n;
+}
+
 int32_t ref_selftest(void) { ref_taps_reset(); return decoderSelfTest(); }
 
 /* ---- ft8_lib level entry points ------------------------------------------------ */

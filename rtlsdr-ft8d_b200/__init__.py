@@ -481,6 +481,18 @@ class Pipe:
         self._chk(self.L.ft8b200_pipe_set_partition(C.c_void_p(self.h), int(back_sms), C.byref(f), C.byref(b)))
         return f.value, b.value
 
+    def autotune(self, iq, n_slots: int, candidates=(24, 32, 40), batches: int = 12, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None):
+        """ft8b200_pipe_autotune: measure every (back_sms, comb+FIR placement) point on `iq`, keep the fastest.
+        -> dict(back_sms, comb_front, points={(back_sms, comb_front): ms_per_batch})."""
+        stride = bytes_per_stream if stride is None else stride
+        cand = (C.c_int * len(candidates))(*candidates)
+        ms = (C.c_float * (2 * len(candidates)))()
+        b, cf = C.c_int(0), C.c_int(0)
+        self._chk(self.L.ft8b200_pipe_autotune(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_slots, cand, len(candidates),
+                                               batches, C.byref(b), C.byref(cf), ms))
+        return {"back_sms": b.value, "comb_front": cf.value,
+                "points": {"%d/%s" % (s, "front" if k else "back"): float(ms[2 * i + k]) for i, s in enumerate(candidates) for k in (0, 1) if ms[2 * i + k] > 0}}
+
     def submit(self, iq, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None):
         """iq: device tensor (already complete on the device) -> queued on the next lane."""
         stride = bytes_per_stream if stride is None else stride
@@ -488,6 +500,14 @@ class Pipe:
 
     def submit_host(self, iq_host, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES):
         self._chk(self.L.ft8b200_pipe_submit_host(C.c_void_p(self.h), _p(iq_host), C.c_size_t(bytes_per_stream), n_slots))
+
+    def submit_slots(self, d_i, d_q, peak=None):
+        """Device tensors float32 [n, 48000] per rail (peak: unconditioned samples + their max per slot)."""
+        self._chk(self.L.ft8b200_pipe_submit_slots(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), d_i.shape[0]))
+
+    def submit_slots_host(self, h_i, h_q):
+        """Conditioned samples in (pinned) host memory: numpy float32 [n, 48000] per rail."""
+        self._chk(self.L.ft8b200_pipe_submit_slots_host(C.c_void_p(self.h), _p(h_i), _p(h_q), h_i.shape[0]))
 
     def collect(self, capacity_slots: int):
         res = np.zeros((capacity_slots, self.M), result_dtype)

@@ -72,6 +72,7 @@ struct ft8b200_ctx {
     int protocol = PROTO_FT8;              // what ft8b200_find_sync / ft8b200_decode score and demap (ft8b200_set_protocol)
     int k1_variant = 0;                    // 0 = streaming cic_block_sums kernel, >= 1 = persistent bulk-copy kernel (shape index)
     bool side_back = false;                // back end on the high-priority side stream even with a single group (pipe lanes)
+    bool comb_front = false;               // with an SM partition: comb+FIR stays on the front partition (ft8b200_set_comb_front)
     cudaEvent_t ev_front = nullptr;        // recorded on the launching stream right after the last process_raw's cic_block_sums
     cudaEvent_t ev_k1 = nullptr;
     cudaEvent_t ev[6][kMaxGroups][2] = {};
@@ -501,7 +502,7 @@ static int process_raw_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t byte
         // With an SM partition the comb+FIR pass belongs to the back end's SM set: it is a whole-GPU grid, and on the front
         // set its CTAs would queue ahead of the next batch's block sums (measured: the two then run back to back).
         cudaStream_t fst = st;
-        if (side && ctx->sm_back > 0) {
+        if (side && ctx->sm_back > 0 && !ctx->comb_front) {
             CU(cudaEventRecord(ctx->ev_group[g], st));
             CU(cudaStreamWaitEvent(back, ctx->ev_group[g], 0));
             fst = back;
@@ -568,6 +569,12 @@ int ft8b200_set_side_backend(ft8b200_ctx_t *ctx, int on) {
     if (!ctx) return fail(FT8B200_EINVAL, "null context");
     ctx->side_back = on != 0;
     if (!on) ctx->ev_front = nullptr;
+    return 0;
+}
+
+int ft8b200_set_comb_front(ft8b200_ctx_t *ctx, int on) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    ctx->comb_front = on != 0;
     return 0;
 }
 

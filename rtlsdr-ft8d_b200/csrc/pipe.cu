@@ -31,6 +31,8 @@ struct Lane {
     cudaStream_t st = nullptr;
     uint8_t *d_raw = nullptr;
     size_t raw_bytes = 0;
+    float *d_fi = nullptr, *d_fq = nullptr;   // host-submitted 3200 sps slots (ft8b200_pipe_submit_slots_host)
+    size_t f_slots = 0;
     struct decoder_results *h_res = nullptr;
     int32_t *h_n = nullptr;
     size_t res_slots = 0;
@@ -168,6 +170,48 @@ int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t b
     return 0;
 }
 
+// queue one batch of 3200 sps slots (BASELINE configs #1/#3/#4: the input of ft8_subsystem()) on the next free lane:
+// host samples are copied H2D on the lane's stream, then waterfall -> sync -> decode -> spots, records back through the
+// lane's pinned buffers.  d_peak != NULL: the samples are unconditioned, decoder()'s 0.5/peak scale is applied on load.
+int submit_slots(ft8b200_pipe_t *p, const float *h_i, const float *h_q, const float *d_i, const float *d_q, const float *d_peak, int n_slots) {
+    if (!p) return FT8B200_EINVAL;
+    if (!((h_i && h_q) || (d_i && d_q)) || n_slots < 1) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_submit_slots: bad argument");
+    if (p->count == (int)p->lanes.size()) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_submit_slots: every lane is in flight, collect first");
+    PCU(cudaSetDevice(p->cfg.device));
+    Lane &l = p->lanes[(p->head + p->count) % p->lanes.size()];
+    int rc = lane_results(p, l, n_slots);
+    if (rc) return rc;
+    if (h_i) {
+        if ((size_t)n_slots > l.f_slots) {
+            if (l.d_fi) cudaFree(l.d_fi);
+            if (l.d_fq) cudaFree(l.d_fq);
+            l.d_fi = l.d_fq = nullptr; l.f_slots = 0;
+            PCU(cudaMalloc(&l.d_fi, (size_t)n_slots * ft8b200::kSlot * sizeof(float)));
+            PCU(cudaMalloc(&l.d_fq, (size_t)n_slots * ft8b200::kSlot * sizeof(float)));
+            l.f_slots = (size_t)n_slots;
+        }
+        const size_t bytes = (size_t)n_slots * ft8b200::kSlot * sizeof(float);
+        PCU(cudaMemcpyAsync(l.d_fi, h_i, bytes, cudaMemcpyHostToDevice, l.st));
+        PCU(cudaMemcpyAsync(l.d_fq, h_q, bytes, cudaMemcpyHostToDevice, l.st));
+        d_i = l.d_fi; d_q = l.d_fq; d_peak = nullptr;
+    }
+    if (p->dependency) {
+        PCU(cudaStreamWaitEvent(l.st, p->dependency, 0));
+        p->dependency = nullptr;
+    }
+    // there is no HBM-bound front end to keep apart here: in SERIAL mode batches follow each other, otherwise the lanes'
+    // streams simply run side by side (copies of batch n+1 under the kernels of batch n)
+    if (p->mode == FT8B200_PIPE_SERIAL && p->prev_done) PCU(cudaStreamWaitEvent(l.st, p->prev_done, 0));
+    if ((rc = ft8b200_process_conditioned(l.ctx, d_i, d_q, d_peak, n_slots, nullptr))) return pfail(p, rc, ft8b200_last_error());
+    p->prev_front = nullptr;
+    if ((rc = ft8b200_fetch_results_async(l.ctx, n_slots, l.h_res, l.h_n, nullptr))) return pfail(p, rc, ft8b200_last_error());
+    PCU(cudaEventRecord(l.done, l.st));
+    p->prev_done = l.done;
+    l.n_slots = n_slots;
+    ++p->count;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -275,6 +319,67 @@ int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_o
     return 0;
 }
 
+int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots,
+                          const int *candidates, int n_candidates, int batches, int *best_back_sms, int *best_comb_front, float *ms_out) {
+    if (!p || !d_iq || !candidates || n_candidates < 1 || n_slots < 1) return FT8B200_EINVAL;
+    if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_autotune: batches in flight");
+    if (batches < (int)p->lanes.size() + 2) batches = (int)p->lanes.size() + 2;
+    PCU(cudaSetDevice(p->cfg.device));
+    std::vector<struct decoder_results> res((size_t)n_slots * p->cfg.max_messages);
+    std::vector<int32_t> cnt((size_t)n_slots);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    PCU(cudaEventCreate(&e0));
+    PCU(cudaEventCreate(&e1));
+    float best = -1.0f;
+    int best_sms = 0, best_comb = 0, rc = 0;
+    auto apply = [&](int sms, int comb) -> int {
+        int r = ft8b200_pipe_set_partition(p, sms, nullptr, nullptr);
+        if (r) return r;
+        if (sms == 0 && (r = ft8b200_pipe_set_mode(p, FT8B200_PIPE_SERIAL, -1))) return r;
+        for (Lane &l : p->lanes) ft8b200_set_comb_front(l.ctx, comb);
+        return 0;
+    };
+    for (int c = 0; c < n_candidates && !rc; ++c) {
+        for (int comb = 0; comb < 2 && !rc; ++comb) {
+            float ms = -1.0f;
+            if (candidates[c] == 0 && comb == 1) { if (ms_out) ms_out[2 * c + 1] = -1.0f; continue; }  // no partition: the placement means nothing
+            if (apply(candidates[c], comb) != 0) { if (ms_out) ms_out[2 * c + comb] = -1.0f; continue; }   // e.g. a split the driver refuses
+            for (int pass = 0; pass < 2 && !rc; ++pass) {  // pass 0 warms the lanes' workspaces up
+                int submitted = 0, collected = 0;
+                const int n = pass == 0 ? (int)p->lanes.size() : batches;
+                if (pass == 1) PCU(cudaEventRecord(e0, p->lanes[0].st));
+                while (collected < n && !rc) {
+                    while (submitted < n && p->count < (int)p->lanes.size() && !rc) {
+                        rc = submit(p, nullptr, d_iq, bytes_per_stream, stream_stride_bytes, n_slots);
+                        ++submitted;
+                    }
+                    if (rc) break;
+                    const int got = ft8b200_pipe_collect(p, res.data(), cnt.data(), n_slots);
+                    if (got < 0) rc = got;
+                    ++collected;
+                }
+                if (pass == 1 && !rc) {
+                    // every batch has been collected (host-synchronised), so an event recorded now closes the interval
+                    PCU(cudaEventRecord(e1, p->lanes[0].st));
+                    PCU(cudaEventSynchronize(e1));
+                    PCU(cudaEventElapsedTime(&ms, e0, e1));
+                    ms /= (float)batches;
+                }
+            }
+            if (ms_out) ms_out[2 * c + comb] = ms;
+            if (!rc && ms > 0.0f && (best < 0.0f || ms < best)) { best = ms; best_sms = candidates[c]; best_comb = comb; }
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    if (best < 0.0f) return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_autotune: no candidate could be measured");
+    if ((rc = apply(best_sms, best_comb))) return rc;
+    if (best_back_sms) *best_back_sms = best_sms;
+    if (best_comb_front) *best_comb_front = best_comb;
+    return 0;
+}
+
 void ft8b200_pipe_destroy(ft8b200_pipe_t *p) {
     if (!p) return;
     cudaSetDevice(p->cfg.device);
@@ -284,6 +389,8 @@ void ft8b200_pipe_destroy(ft8b200_pipe_t *p) {
         if (l.ctx) ft8b200_destroy(l.ctx);
         if (l.done) cudaEventDestroy(l.done);
         if (l.d_raw) cudaFree(l.d_raw);
+        if (l.d_fi) cudaFree(l.d_fi);
+        if (l.d_fq) cudaFree(l.d_fq);
         if (l.h_res) cudaFreeHost(l.h_res);
         if (l.h_n) cudaFreeHost(l.h_n);
     }
@@ -301,6 +408,14 @@ int ft8b200_pipe_submit(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per
 
 int ft8b200_pipe_submit_host(ft8b200_pipe_t *p, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots) {
     return submit(p, h_iq, nullptr, bytes_per_stream, bytes_per_stream, n_slots);
+}
+
+int ft8b200_pipe_submit_slots(ft8b200_pipe_t *p, const float *d_i, const float *d_q, const float *d_peak, int n_slots) {
+    return submit_slots(p, nullptr, nullptr, d_i, d_q, d_peak, n_slots);
+}
+
+int ft8b200_pipe_submit_slots_host(ft8b200_pipe_t *p, const float *h_i, const float *h_q, int n_slots) {
+    return submit_slots(p, h_i, h_q, nullptr, nullptr, nullptr, n_slots);
 }
 
 static int pop(ft8b200_pipe_t *p, struct decoder_results *h_results, int32_t *h_nresults, int capacity_slots, struct decoder_results **d_results,
