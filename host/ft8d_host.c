@@ -12,6 +12,10 @@
  *   wav     [-ft4] F.wav ... ft8_lib's decode_ft8 main() (decode_ft8.c:226-409) through monitor_* / ft8_find_sync /
  *                            ft8_decode, printing the same lines
  *   batch                    B200-side extra: synthetic raw slots through the pipelined executor from host memory
+ *   cluster [-n devices] [streams [slots_per_stream]]   B200-side extra: BASELINE config #5 in miniature over every visible GPU from this
+ *                            one process: receiver streams made on their own device, sharded by stream, decoded-spot records
+ *                            gathered with NCCL (ft8b200_cluster_t); prints one line per (stream, slot) -- the same lines whatever
+ *                            the number of devices
  *   latency SLOT.iq [RAW.u8 [F.wav]]   single-slot latency of the literal drop-in calls, one JSON line (BASELINE config #1; the
  *                            reference publishes this as "decode burst per 15 s slot", README.md:153-157)
  *
@@ -297,6 +301,82 @@ static int run_batch(int n_slots, int n_batches, int depth) {
     return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------- cluster (config #5) */
+
+/* Stream s, slot g carries "CQ <call(s, g)> <grid>" at its own frequency; everything is derived from the GLOBAL stream index, so the
+ * bytes -- and therefore the spots -- do not depend on which device a stream lands on. */
+static void cluster_call(int stream, int slot, char *call7, char *grid5) {
+    const unsigned k = (unsigned)(stream * 8 + slot);
+    call7[0] = 'K'; call7[1] = (char)('0' + k % 10u); call7[2] = (char)('A' + (k / 10u) % 26u); call7[3] = (char)('A' + (k / 260u) % 26u);
+    call7[4] = (char)('A' + (k * 7u) % 26u); call7[5] = 0;
+    grid5[0] = (char)('A' + (k * 5u) % 18u); grid5[1] = (char)('A' + (k * 11u) % 18u); grid5[2] = (char)('0' + k % 10u); grid5[3] = (char)('0' + (k / 3u) % 10u);
+    grid5[4] = 0;
+}
+
+static int run_cluster(int n_devices, int n_streams, int slots_per_stream) {
+    ft8b200_config_t cfg;
+    ft8b200_default_config(&cfg);
+    ft8b200_cluster_t *cl = ft8b200_cluster_create(&cfg, n_devices, 2);
+    if (!cl) return fail("cluster_create");
+    const int nd = ft8b200_cluster_devices(cl);
+    const size_t slot_bytes = FT8B200_RAW_SLOT_BYTES, stream_bytes = slot_bytes * (size_t)slots_per_stream;
+    uint8_t *d_iq[64] = {0};
+    int counts[64] = {0};
+    if (nd > 64) return 1;
+    for (int d = 0; d < nd; ++d) {
+        int first = 0, count = 0;
+        ft8b200_cluster_shard(cl, n_streams, d, &first, &count);
+        counts[d] = count;
+        if (!count) continue;
+        ft8b200_ctx_t *ctx = ft8b200_cluster_ctx(cl, d);
+        const int rows = count * slots_per_stream;
+        d_iq[d] = ft8b200_device_malloc(ctx, stream_bytes * (size_t)count);
+        ft8b200_signal_t *sig = calloc((size_t)rows, sizeof *sig);
+        int *firsts = calloc((size_t)rows + 1, sizeof *firsts);
+        if (!d_iq[d] || !sig || !firsts) { fprintf(stderr, "ft8d_host: out of memory\n"); return 2; }
+        for (int r = 0; r < rows; ++r) {
+            const int stream = first + r / slots_per_stream, slot = r % slots_per_stream;
+            char call[8], grid[8];
+            cluster_call(stream, slot, call, grid);
+            if (ft8b200_pack77_std("CQ", call, grid, sig[r].payload) != 0) { fprintf(stderr, "ft8d_host: cannot pack CQ %s %s\n", call, grid); return 1; }
+            sig[r].f0_hz = 300.0f + 37.0f * (float)((stream * 8 + slot) % 29);
+            sig[r].t0_sec = 0.5f;
+            sig[r].amp = 20.0f;
+            firsts[r + 1] = r + 1;
+        }
+        /* rows of one stream are consecutive in memory: the stream is one continuous recording of slots_per_stream slots */
+        if (ft8b200_synth_raw(ctx, sig, firsts, rows, 30.0f, 0xC5u, first * slots_per_stream, d_iq[d], slot_bytes, slot_bytes, NULL) != 0) return fail("synth_raw");
+        free(sig); free(firsts);
+    }
+    const int total = n_streams * slots_per_stream;
+    struct decoder_results *spots = calloc((size_t)total * MAX_MESSAGES, sizeof *spots);
+    int32_t *n_spots = calloc((size_t)total, sizeof *n_spots);
+    if (!spots || !n_spots) return 2;
+    if (ft8b200_cluster_submit_streams(cl, (const uint8_t *const *)d_iq, stream_bytes, stream_bytes, counts, slots_per_stream, slot_bytes) != 0 ||
+        ft8b200_cluster_collect(cl, spots, n_spots, total) != total) {
+        fprintf(stderr, "ft8d_host: cluster: %s\n", ft8b200_cluster_error(cl));
+        return 2;
+    }
+    int good = 0;
+    for (int r = 0; r < total; ++r) {
+        char call[8], grid[8];
+        cluster_call(r / slots_per_stream, r % slots_per_stream, call, grid);
+        const struct decoder_results *s = spots + (size_t)r * MAX_MESSAGES;
+        printf("stream %d slot %d: %d message(s)", r / slots_per_stream, r % slots_per_stream, n_spots[r]);
+        for (int k = 0; k < n_spots[r] && k < MAX_MESSAGES; ++k)
+            if (s[k].call[0]) printf("  %s %s %d Hz", s[k].call, s[k].loc, s[k].freq);
+        putchar('\n');
+        for (int k = 0; k < n_spots[r] && k < MAX_MESSAGES; ++k)
+            if (strcmp(s[k].call, call) == 0 && strcmp(s[k].loc, grid) == 0) { ++good; break; }
+    }
+    fprintf(stderr, "%d devices, %d of %d slots decoded to their own message, %llu NCCL gather(s) (NCCL %d), %llu kernel launches\n", nd, good, total,
+            (unsigned long long)ft8b200_cluster_gathers(cl), ft8b200_cluster_nccl_version(cl), (unsigned long long)ft8b200_cluster_kernel_launches(cl));
+    for (int d = 0; d < nd; ++d) if (d_iq[d]) ft8b200_device_free(ft8b200_cluster_ctx(cl, d), d_iq[d]);
+    ft8b200_cluster_destroy(cl);
+    free(spots); free(n_spots);
+    return good == total ? 0 : 1;
+}
+
 /* ---------------------------------------------------------------------------------------------- latency (config #1) */
 
 static double now_ms(void) {
@@ -401,6 +481,7 @@ static int usage(void) {
           "       ft8d_host [-f dial_hz] [-T unixtime] receive [-b bytes_per_callback] [-s] raw_iq.u8|-\n"
           "       ft8d_host wav [-ft4] file.wav ...\n"
           "       ft8d_host batch [slots [batches [depth]]]\n"
+          "       ft8d_host cluster [-n devices] [streams [slots_per_stream]]\n"
           "       ft8d_host latency slot.iq [raw_slot.u8|- [file.wav [reps]]]\n",
           stderr);
     return 1;
@@ -428,6 +509,12 @@ int main(int argc, char **argv) {
         }
         if (a >= argc || chunk < 8u || chunk % 8u) return usage();
         return run_receive(argv[a], chunk, own);
+    }
+    if (strcmp(cmd, "cluster") == 0) {
+        int nd = 0;
+        if (a + 1 < argc && strcmp(argv[a], "-n") == 0) { nd = atoi(argv[a + 1]); a += 2; }
+        const int streams = argc > a ? atoi(argv[a]) : 4, spp = argc > a + 1 ? atoi(argv[a + 1]) : 2;
+        return streams > 0 && spp > 0 && spp <= 8 ? run_cluster(nd, streams, spp) : usage();
     }
     if (strcmp(cmd, "latency") == 0)
         return argc > a ? run_latency(argv[a], argc > a + 1 ? argv[a + 1] : NULL, argc > a + 2 ? argv[a + 2] : NULL, argc > a + 3 ? atoi(argv[a + 3]) : 15) : usage();

@@ -363,6 +363,10 @@ int ft8b200_pipe_depth(ft8b200_pipe_t *p);
 int ft8b200_pipe_in_flight(ft8b200_pipe_t *p);
 int ft8b200_pipe_submit(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots);
 int ft8b200_pipe_submit_host(ft8b200_pipe_t *p, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots);
+/* continuous receiver streams cut into consecutive slots (BASELINE config #5, see ft8b200_process_raw_streams): the batch has
+ * n_streams * slots_per_stream result rows */
+int ft8b200_pipe_submit_streams(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams,
+                                int slots_per_stream, size_t bytes_per_slot);
 /* The same executor fed at the OTHER boundary of the path, the input of ft8_subsystem() (rtlsdr_ft8d.h:164): n_slots x 48000 float
  * samples per rail at 3200 sps.  _host: conditioned samples in (pinned) host memory, copied H2D on the lane's stream; device form:
  * d_peak == NULL for conditioned samples, else decoder()'s 0.5/peak scale is applied on load.  384 KB per slot instead of 72 MB:
@@ -385,6 +389,40 @@ int ft8b200_pipe_stage_times(ft8b200_pipe_t *p, double *ms, int n, uint64_t *bat
  * returns how many batches were written.  Shows what actually overlapped. */
 int ft8b200_pipe_timeline(ft8b200_pipe_t *p, float *out, int max_batches);
 uint64_t ft8b200_pipe_kernel_launches(ft8b200_pipe_t *p);
+
+/* ---- every GPU of one box from ONE process (csrc/cluster.cu) --------------------------------------------------------------------
+ * The path shards by independent slot or receiver stream (no data-path collective); a cluster owns one ft8b200_pipe_t per device
+ * and the only exchange is the one BASELINE.json names: the decoded-spot records of a step are gathered with one grouped
+ * ncclAllGather over NVLink on a side stream per device, device 0's copy is read to the host and handed out in (device, slot)
+ * order.  NCCL is loaded at run time (libnccl.so.2); with a single device none is needed, with several and no NCCL the cluster
+ * cannot be created.  A step = one batch per device; up to `depth` steps may be in flight before the oldest is collected. */
+typedef struct ft8b200_cluster ft8b200_cluster_t;
+/* n_devices <= 0: all visible devices (ordinals 0..n-1).  NULL on failure (reason on stderr and in ft8b200_last_error()). */
+ft8b200_cluster_t *ft8b200_cluster_create(const ft8b200_config_t *cfg, int n_devices, int depth);
+void ft8b200_cluster_destroy(ft8b200_cluster_t *c);
+const char *ft8b200_cluster_error(ft8b200_cluster_t *c);
+int ft8b200_cluster_devices(ft8b200_cluster_t *c);
+int ft8b200_cluster_in_flight(ft8b200_cluster_t *c);
+/* device `device_index`'s executor, and a utility context on that device (ft8b200_synth_*, ft8b200_device_malloc) */
+ft8b200_pipe_t *ft8b200_cluster_pipe(ft8b200_cluster_t *c, int device_index);
+ft8b200_ctx_t *ft8b200_cluster_ctx(ft8b200_cluster_t *c, int device_index);
+/* contiguous block of n_items (slots or streams) that device `device_index` owns: blocks of ceil(n / devices) */
+int ft8b200_cluster_shard(ft8b200_cluster_t *c, int n_items, int device_index, int *first, int *count);
+/* One step from device-resident input: d_iq[d] on device d holds n_per_device[d] slots (0 = that device sits the step out). */
+int ft8b200_cluster_submit(ft8b200_cluster_t *c, const uint8_t *const *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, const int *n_slots_per_device);
+/* ... or n_streams_per_device[d] continuous receiver streams cut into slots_per_stream consecutive slots (BASELINE config #5) */
+int ft8b200_cluster_submit_streams(ft8b200_cluster_t *c, const uint8_t *const *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes,
+                                   const int *n_streams_per_device, int slots_per_stream, size_t bytes_per_slot);
+/* One step from (pinned) host memory: n_slots independent slots, sharded in contiguous blocks (ft8b200_cluster_shard) */
+int ft8b200_cluster_submit_host(ft8b200_cluster_t *c, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots);
+/* Oldest step: records of all devices in (device, slot) order; returns the number of slots (>= 0) or an error (< 0). */
+int ft8b200_cluster_collect(ft8b200_cluster_t *c, struct decoder_results *h_results, int32_t *h_nresults, int capacity_slots);
+uint64_t ft8b200_cluster_gathers(ft8b200_cluster_t *c);          /* NCCL all-gathers issued so far */
+int ft8b200_cluster_nccl_version(ft8b200_cluster_t *c);          /* e.g. 22809; 0 for a single-device cluster */
+uint64_t ft8b200_cluster_kernel_launches(ft8b200_cluster_t *c);
+/* device memory on the context's device for callers without the CUDA headers (the C host program); NULL on failure */
+void *ft8b200_device_malloc(ft8b200_ctx_t *ctx, size_t bytes);
+void ft8b200_device_free(ft8b200_ctx_t *ctx, void *p);
 
 /* Receiver streams for rtlsdr_callback(): persistent decimator state, double-buffered 15 s slots.
  * flip / count / fetch / decode accept s == NULL for the process-wide default stream, the one that

@@ -161,10 +161,18 @@ class Context:
         self.K = max_candidates
         self.M = max_messages
 
+    @classmethod
+    def borrow(cls, handle: int, device: int, max_candidates: int = 120, max_messages: int = 50):
+        """A non-owning view of a context created elsewhere (ft8b200_cluster_ctx): close() leaves it alone."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.h, self.device, self.K, self.M, self.borrowed = handle, device, max_candidates, max_messages, True
+        return self
+
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "borrowed", False):
             self.L.ft8b200_destroy(C.c_void_p(self.h))
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -540,6 +548,80 @@ class Pipe:
 
     def launches(self) -> int:
         return int(self.L.ft8b200_pipe_kernel_launches(C.c_void_p(self.h)))
+
+
+class Cluster:
+    """ft8b200_cluster_t: every visible GPU from ONE process, spot records gathered with NCCL (see include/ft8b200.h)."""
+
+    def __init__(self, n_devices: int = 0, depth: int = 2, max_candidates: int = 120, max_messages: int = 50, min_score: int = 10, ldpc_iterations: int = 20):
+        self.L = L = lib()
+        L.ft8b200_cluster_create.restype = C.c_void_p
+        L.ft8b200_cluster_error.restype = C.c_char_p
+        L.ft8b200_cluster_ctx.restype = C.c_void_p
+        L.ft8b200_cluster_pipe.restype = C.c_void_p
+        L.ft8b200_cluster_gathers.restype = C.c_uint64
+        L.ft8b200_cluster_kernel_launches.restype = C.c_uint64
+        self.cfg = Config(0, 1, max_candidates, max_messages, min_score, ldpc_iterations)
+        self.h = L.ft8b200_cluster_create(C.byref(self.cfg), n_devices, depth)
+        if not self.h:
+            raise Ft8Error(L.ft8b200_last_error().decode() or "ft8b200_cluster_create failed (see stderr)")
+        self.n = L.ft8b200_cluster_devices(C.c_void_p(self.h))
+        self.depth, self.K, self.M = depth, max_candidates, max_messages
+
+    def close(self):
+        if self.h:
+            self.L.ft8b200_cluster_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise Ft8Error(f"ft8b200 cluster error {rc}: {self.L.ft8b200_cluster_error(C.c_void_p(self.h)).decode()}")
+        return rc
+
+    def ctx(self, d: int) -> "Context":
+        return Context.borrow(self.L.ft8b200_cluster_ctx(C.c_void_p(self.h), d), d, self.K, self.M)
+
+    def shard(self, n_items: int, d: int):
+        a, b = C.c_int(0), C.c_int(0)
+        self._chk(self.L.ft8b200_cluster_shard(C.c_void_p(self.h), n_items, d, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def in_flight(self) -> int:
+        return self.L.ft8b200_cluster_in_flight(C.c_void_p(self.h))
+
+    def submit(self, tensors, counts, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None, slots_per_stream: int = 1, bytes_per_slot: int = RAW_SLOT_BYTES):
+        """tensors[d]: uint8 device tensor on device d (or None when counts[d] == 0)."""
+        stride = bytes_per_stream if stride is None else stride
+        ptrs = (C.c_void_p * self.n)(*[(t.data_ptr() if t is not None else 0) for t in tensors])
+        cnt = (C.c_int * self.n)(*counts)
+        if slots_per_stream > 1:
+            self._chk(self.L.ft8b200_cluster_submit_streams(C.c_void_p(self.h), ptrs, C.c_size_t(bytes_per_stream), C.c_size_t(stride), cnt, slots_per_stream, C.c_size_t(bytes_per_slot)))
+        else:
+            self._chk(self.L.ft8b200_cluster_submit(C.c_void_p(self.h), ptrs, C.c_size_t(bytes_per_stream), C.c_size_t(stride), cnt))
+
+    def submit_host(self, iq_host, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES):
+        self._chk(self.L.ft8b200_cluster_submit_host(C.c_void_p(self.h), _p(iq_host), C.c_size_t(bytes_per_stream), n_slots))
+
+    def collect(self, capacity_slots: int):
+        res = np.zeros((capacity_slots, self.M), result_dtype)
+        nres = np.zeros(capacity_slots, np.int32)
+        n = self._chk(self.L.ft8b200_cluster_collect(C.c_void_p(self.h), _p(res), _p(nres), capacity_slots))
+        return res[:n], nres[:n]
+
+    def gathers(self) -> int:
+        return int(self.L.ft8b200_cluster_gathers(C.c_void_p(self.h)))
+
+    def nccl_version(self) -> int:
+        return int(self.L.ft8b200_cluster_nccl_version(C.c_void_p(self.h)))
+
+    def launches(self) -> int:
+        return int(self.L.ft8b200_cluster_kernel_launches(C.c_void_p(self.h)))
 
 
 class Stream:

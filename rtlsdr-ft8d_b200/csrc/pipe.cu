@@ -127,14 +127,17 @@ int lane_results(ft8b200_pipe_t *p, Lane &l, int n_slots) {
     return 0;
 }
 
-// queue one batch on the next free lane; `h_iq` (host) or `d_iq` (device) holds the raw IQ
-int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t bytes_per_stream, size_t stride, int n_slots) {
+// queue one batch on the next free lane; `h_iq` (host) or `d_iq` (device) holds the raw IQ.  segs > 1: the n_slots streams are
+// continuous receivers cut into `segs` consecutive slots of seg_bytes each (ft8b200_process_raw_streams): n_slots * segs result rows
+int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t bytes_per_stream, size_t stride, int n_slots, int segs = 1,
+           size_t seg_bytes = 0) {
     if (!p) return FT8B200_EINVAL;
-    if ((!h_iq && !d_iq) || n_slots < 1 || (bytes_per_stream & 7)) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_submit: bad argument");
+    if ((!h_iq && !d_iq) || n_slots < 1 || (bytes_per_stream & 7) || segs < 1) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_submit: bad argument");
+    const int n_rows = n_slots * segs;
     if (p->count == (int)p->lanes.size()) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_submit: every lane is in flight, collect first");
     PCU(cudaSetDevice(p->cfg.device));
     Lane &l = p->lanes[(p->head + p->count) % p->lanes.size()];
-    int rc = lane_results(p, l, n_slots);
+    int rc = lane_results(p, l, n_rows);
     if (rc) return rc;
     if (h_iq) {
         stride = (bytes_per_stream + 15) & ~(size_t)15;
@@ -160,12 +163,14 @@ int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t b
         // kernels of consecutive batches never share the GPU; only copies and host work overlap them
         PCU(cudaStreamWaitEvent(l.st, p->prev_done, 0));
     }
-    if ((rc = ft8b200_process_raw(l.ctx, d_iq, bytes_per_stream, stride, n_slots, nullptr))) return pfail(p, rc, ft8b200_last_error());
+    rc = segs > 1 ? ft8b200_process_raw_streams(l.ctx, d_iq, bytes_per_stream, stride, n_slots, segs, seg_bytes, nullptr)
+                  : ft8b200_process_raw(l.ctx, d_iq, bytes_per_stream, stride, n_slots, nullptr);
+    if (rc) return pfail(p, rc, ft8b200_last_error());
     p->prev_front = reinterpret_cast<cudaEvent_t>(ft8b200_front_event(l.ctx));
-    if ((rc = ft8b200_fetch_results_async(l.ctx, n_slots, l.h_res, l.h_n, nullptr))) return pfail(p, rc, ft8b200_last_error());
+    if ((rc = ft8b200_fetch_results_async(l.ctx, n_rows, l.h_res, l.h_n, nullptr))) return pfail(p, rc, ft8b200_last_error());
     PCU(cudaEventRecord(l.done, l.st));
     p->prev_done = l.done;
-    l.n_slots = n_slots;
+    l.n_slots = n_rows;
     ++p->count;
     return 0;
 }
@@ -408,6 +413,11 @@ int ft8b200_pipe_submit(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per
 
 int ft8b200_pipe_submit_host(ft8b200_pipe_t *p, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots) {
     return submit(p, h_iq, nullptr, bytes_per_stream, bytes_per_stream, n_slots);
+}
+
+int ft8b200_pipe_submit_streams(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_streams,
+                                int slots_per_stream, size_t bytes_per_slot) {
+    return submit(p, nullptr, d_iq, bytes_per_stream, stream_stride_bytes, n_streams, slots_per_stream, bytes_per_slot);
 }
 
 int ft8b200_pipe_submit_slots(ft8b200_pipe_t *p, const float *d_i, const float *d_q, const float *d_peak, int n_slots) {
