@@ -395,6 +395,8 @@ def main():
     ap.add_argument("--overlap", action="store_true", help="(without a partition) let the back end of batch n time-share the GPU with the decimator of batch n+1")
     ap.add_argument("--k1-variant", type=int, default=0, help="0 = streaming cic_block_sums kernel, 1..6 = bulk-copy (TMA) variants")
     ap.add_argument("--cpu-slots", type=int, default=96, help="bounded CPU-baseline sample (slots)")
+    ap.add_argument("--cluster", action="store_true", help="single-process arm: all --gpus devices driven from THIS process through ft8b200_cluster_t "
+                                                          "(records gathered by the library's own NCCL all-gather); not launched under torchrun")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (configs, e2e_slots, roofline_extra)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -418,6 +420,8 @@ def main():
 
     if args.impl == "reference":
         return reference_arm(args, rank, world, config)
+    if args.cluster:
+        return cluster_arm(args, config)
 
     env = Env(args)
     torch, dist, pkg = env.torch, env.dist, env.pkg
@@ -597,6 +601,74 @@ def main():
         emit(out)
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def cluster_arm(args, config):
+    """The library's own multi-GPU plane: ONE process, ft8b200_cluster_t over args.gpus devices (one executor per device, spot records
+    of every step gathered with the library's grouped ncclAllGather and read on the host).  Same workload and step as the headline;
+    torch only allocates nothing here -- the inputs are made by each device's context.  Timed on the host clock between
+    synchronisations of every device (one process drives all of them, so there is no per-rank clock to take the maximum of)."""
+    import torch
+    from ft8b200_loader import load
+    pkg = load()
+    B, Bc = args.slots, args.slots // args.chunks
+    cl = pkg.Cluster(args.gpus, args.depth)
+    n = cl.n
+    bufs, texts = [], []
+    for d in range(n):
+        b, t = gen_batch(B, 100_000 * d, torch.device("cuda", d), cl.ctx(d))
+        bufs.append(b); texts += t
+    part = []
+    for d in range(n):
+        p = cl.pipe(d)
+        p.set_mode(serial=True)
+        try:
+            part.append(p.autotune(bufs[d][:Bc], Bc, candidates=(24, 32, 40), batches=3 * args.depth + 3) if args.back_sms < 0 else
+                        (dict(zip(("front_sms", "back_sms"), p.set_partition(args.back_sms))) if args.back_sms > 0 else "serial"))
+        except Exception as exc:
+            part.append("unavailable (%s)" % exc)
+
+    def sync_all():
+        for d in range(n):
+            torch.cuda.synchronize(d)
+
+    def run(steps):
+        outs = []
+        for _ in range(steps):
+            for c in range(args.chunks):
+                if cl.in_flight() == cl.depth:
+                    outs.append(cl.collect(n * Bc))
+                cl.submit([bufs[d][c * Bc:(c + 1) * Bc] for d in range(n)], [Bc] * n)
+        while cl.in_flight():
+            outs.append(cl.collect(n * Bc))
+        return outs[-args.chunks:]
+
+    last = run(args.warmup)
+    # records of a step come back chunk by chunk, each in (device, slot) order
+    n_good = 0
+    for c, (res, nres) in enumerate(last):
+        for d in range(n):
+            for k in range(Bc):
+                n_good += slot_ok(texts[d * B + c * Bc + k], res[d * Bc + k], int(nres[d * Bc + k]))
+    launches0 = cl.launches()
+    gathers0 = cl.gathers()
+    sync_all()
+    t0 = time.perf_counter()
+    run(args.steps)
+    sync_all()
+    secs = time.perf_counter() - t0
+    cfg = dict(config)
+    cfg["parallelism"] = "ONE process, ft8b200_cluster_t: %d devices, slots sharded by device, records gathered by the library (grouped ncclAllGather, NCCL %d)" % (n, cl.nccl_version())
+    cfg["executor"] = "one ft8b200_pipe_t of depth %d per device, %d batches of %d slots per device per step" % (args.depth, args.chunks, Bc)
+    cfg["sm_partition"] = part
+    out = {"impl": "cluster", "metric": METRIC, "value": n * B * args.steps / secs, "unit": "slots/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
+           "data": "synthetic (generated on each device by ft8b200_synth_raw)", "config": cfg, "gpu_launches": int(cl.launches() - launches0),
+           "nccl_gathers": int(cl.gathers() - gathers0), "verify": {"slots_decoded_to_their_own_message": int(n_good), "of": n * B},
+           "timed": "host clock between synchronisations of all devices"}
+    cl.close()
+    emit(out)
     return 0
 
 

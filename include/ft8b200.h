@@ -473,7 +473,8 @@ int ft8b200_get_config(ft8b200_ctx_t *ctx, ft8b200_config_t *cfg);
  * (32-bit phase accumulators, table cosine, counter-hash noise) so that a CPU twin reproduces it bit for bit. */
 typedef struct {
     uint8_t payload[10];  /* 77-bit message, MSB first (ft8b200_pack77_std or any packer) */
-    uint8_t reserved[2];
+    uint8_t reserved[2];  /* [0]: 0 = plain FSK as decoderSelfTest() sends it (rtlsdr_ft8d.c:937-955), 1 = GFSK as gen_ft8 does (gen_ft8.c:28-102:
+                           *      Gaussian-smoothed frequency, BT 2 (FT8) / 1 (FT4), extended end symbols, raised-cosine ramps); [1]: 0 */
     float f0_hz;          /* frequency of tone 0 as the decoder will see it */
     float t0_sec;         /* start of symbol 0 */
     float amp;            /* raw path: amplitude in LSB; float paths: linear amplitude */

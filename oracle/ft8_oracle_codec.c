@@ -473,7 +473,7 @@ int orc_spots(const orc_candidate_t *cand, const uint8_t *ok, const orc_message_
         if (rep && n_new < 512) { rep->msgs[n_new] = msg; rep->freq_hz[n_new] = freq_hz; rep->score[n_new] = c->score; }
         char work[40];
         memset(work, 0, sizeof(work));
-        strncpy(work, msg.text, sizeof(msg.text));
+        memcpy(work, msg.text, sizeof(msg.text));   /* 25 bytes, NUL-terminated by the zero fill */
         char *save = NULL;
         const char *tok = strtok_r(work, " ", &save);
         if (tok && strncmp(tok, "CQ", 2) == 0 && n_new < max_messages) {

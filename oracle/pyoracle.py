@@ -570,6 +570,32 @@ class ReferenceMonitor:
         return sig[:n.value].copy(), sr.value
 
 
+class ReferenceGen:
+    """ft8_lib's gen_ft8.c (gfsk_pulse / synth_gfsk), unmodified (oracle/_ref/libref_gen.so)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libref_gen.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_gen.so"))
+
+    def pulse(self, n_spsym: int, bt: float) -> np.ndarray:
+        out = np.zeros(3 * n_spsym, np.float32)
+        self.lib.refgen_pulse(n_spsym, C.c_float(bt), _ptr(out))
+        return out
+
+    def synth_gfsk(self, tones: np.ndarray, f0: float, bt: float, symbol_period: float, rate: int) -> np.ndarray:
+        tones = np.ascontiguousarray(tones, np.uint8)
+        n_spsym = int(0.5 + rate * symbol_period)
+        out = np.zeros(tones.size * n_spsym, np.float32)
+        self.lib.refgen_synth(_ptr(tones), tones.size, C.c_float(f0), C.c_float(bt), C.c_float(symbol_period), rate, _ptr(out))
+        return out
+
+
 class ReferenceReport:
     """The reference daemon's own reporting functions (postSpots / webClusterSpots / printSpots) with network, clock and stdout
     captured (oracle/_ref/libref_report.so, see ref_report_harness.c for the two lines edited in a temp copy)."""

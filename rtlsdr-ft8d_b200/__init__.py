@@ -50,10 +50,12 @@ def pack77(msg: str):
     return b.raw, kind
 
 
-def make_signals(items):
-    """items: iterable of (payload bytes, f0_hz, t0_sec, amp) -> signal_dtype array."""
+def make_signals(items, gfsk: bool = False):
+    """items: iterable of (payload bytes, f0_hz, t0_sec, amp) -> signal_dtype array.  gfsk: Gaussian-smoothed frequency, extended end
+    symbols and ramps as gen_ft8 sends them (gen_ft8.c:28-102) instead of the self-test's plain FSK."""
     items = list(items)
     out = np.zeros(len(items), signal_dtype)
+    out["reserved"][:, 0] = 1 if gfsk else 0
     for k, (payload, f0, t0, amp) in enumerate(items):
         out[k]["payload"] = np.frombuffer(payload, np.uint8)
         out[k]["f0_hz"], out[k]["t0_sec"], out[k]["amp"] = f0, t0, amp
@@ -450,10 +452,21 @@ class Pipe:
         self.depth = depth
         self.M = max_messages
 
+    @classmethod
+    def borrow(cls, handle: int, device: int, depth: int, max_messages: int = 50):
+        """A non-owning view of a pipe created elsewhere (ft8b200_cluster_pipe)."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.L.ft8b200_pipe_error.restype = C.c_char_p
+        self.L.ft8b200_pipe_kernel_launches.restype = C.c_uint64
+        self.cfg = Config(device, 1, 120, max_messages, 10, 20)
+        self.h, self.depth, self.M, self.borrowed = handle, depth, max_messages, True
+        return self
+
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "borrowed", False):
             self.L.ft8b200_pipe_destroy(C.c_void_p(self.h))
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -586,6 +599,9 @@ class Cluster:
 
     def ctx(self, d: int) -> "Context":
         return Context.borrow(self.L.ft8b200_cluster_ctx(C.c_void_p(self.h), d), d, self.K, self.M)
+
+    def pipe(self, d: int) -> "Pipe":
+        return Pipe.borrow(self.L.ft8b200_cluster_pipe(C.c_void_p(self.h), d), d, self.depth, self.M)
 
     def shard(self, n_items: int, d: int):
         a, b = C.c_int(0), C.c_int(0)

@@ -2,12 +2,20 @@
 // Replaces monitor_init/process/reset/free and the kiss_fftr loop, /root/reference/ft8_lib/decode_ft8.c:35-39,
 // 111-224, ft8_lib/fft/kiss_fftr.c:22-115, ft8_lib/fft/kiss_fft.c:15-382.
 //
-// One CTA per analysis frame.  A frame of nfft real samples (3840 for FT8 at 12 kHz) is transformed the way
-// kiss_fftr does it -- as an nfft/2-point complex FFT of the even/odd-packed signal followed by the split
-// step with "super twiddles" -- and the complex FFT follows kiss_fft's own decomposition (radix 4 first, then
-// 2, 3, 5; 1920 = 4*4*4*2*3*5) with its butterflies' exact operation order, so spectra and waterfall bytes are
-// bit-identical to the CPU path.  The stage list, the input permutation and all twiddles are built on the host
-// (same libm calls as kiss_fft) and read from global memory; data lives in shared memory between stages.
+// A frame of nfft real samples (3840 for FT8 at 12 kHz) is transformed the way kiss_fftr does it -- as an nfft/2-point complex
+// FFT of the even/odd-packed signal followed by the split step with "super twiddles" -- and the complex FFT follows kiss_fft's own
+// decomposition (radix 4 first, then 2, 3, 5; 1920 = 4*4*4*2*3*5) with its butterflies' exact operation order, so spectra and
+// waterfall bytes are bit-identical to the CPU path.  The stage list, the input permutation and all twiddles are built on the host
+// (same libm calls as kiss_fft).
+//
+// Execution shape (round 2): PERSISTENT CTAs walking contiguous ranges of (recording, frame) items.  Once per CTA lifetime the
+// tables go to shared memory: the twiddles RE-LAID-OUT PER STAGE (tw[q k fstride] for k < m contiguous: the strided reads of the
+// plain table were 16- to 32-way bank conflicts from shared memory and one sector per lane from global), the super twiddles and
+// the quantiser's threshold pairs.  Per frame the windowed samples are written straight to their permuted place (inverse
+// permutation table), the data is one float2 array (64-bit accesses), the butterfly index split b -> (group, k) is a multiply-high
+// by a per-stage constant, and the quantiser is the straight-line form of waterfall.cu (ft8b200_selfcheck_quantiser).  The
+// round-1 kernel (one CTA per frame, tables and twiddles from global memory, separate re/im arrays, runtime division per butterfly)
+// took 9.4 us per 15 s recording; see profiles/ for the captures of both.
 #include "common.cuh"
 
 #include <math.h>
@@ -33,6 +41,10 @@ struct FftPlan {
     int n;            // complex FFT length (nfft / 2)
     int nstages;
     int radix[kMaxStages], m[kMaxStages], fstride[kMaxStages];  // in EXECUTION order (innermost recursion first)
+    unsigned int magic[kMaxStages];   // ceil(2^32 / m): b / m == __umulhi(b, magic) for b < 65536 (0: m == 1)
+    int tw_off[kMaxStages];           // float2 offset of the stage's compact twiddles: (q - 1) * m + k -> tw[q k fstride], q = 1..radix-1
+    float2 c1[kMaxStages], c2[kMaxStages];  // radix 3: c1 = tw[fstride m]; radix 5: c1 = tw[fstride m], c2 = tw[2 fstride m]
+    int tw_total;
 };
 
 struct cpx { float r, i; };
@@ -46,156 +58,175 @@ __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return cpx{__fadd_rn(a.r, b.
 __device__ __forceinline__ cpx csub(cpx a, cpx b) { return cpx{__fsub_rn(a.r, b.r), __fsub_rn(a.i, b.i)}; }
 // x * .5 evaluated in double then rounded to float (HALF_OF, _kiss_fft_guts.h): an exact halving
 __device__ __forceinline__ float half_of(float x) { return __fmul_rn(x, 0.5f); }
+__device__ __forceinline__ cpx ld(const float2 *z, int i) { const float2 v = z[i]; return cpx{v.x, v.y}; }
+__device__ __forceinline__ void st(float2 *z, int i, cpx v) { z[i] = make_float2(v.r, v.i); }
 
-__device__ __forceinline__ int quantise(float x, const float *__restrict__ thr) {
-    int k = (int)(6.0206f * __log2f(x) + 240.0f);
+// straight-line quantiser: estimate, the two thresholds around it in one 64-bit load, two compares (exactness: waterfall.cu)
+__device__ __forceinline__ int quantise(float x, const float2 *__restrict__ thr2) {
+    int k = (int)__fmaf_rn(6.0206f, __log2f(x), 240.0f);
     k = k < 0 ? 0 : (k > 255 ? 255 : k);
-    while (k > 0 && x < thr[k]) --k;
-    while (k < 255 && x >= thr[k + 1]) ++k;
-    return k;
+    const float2 lh = thr2[k];
+    return k + (x >= lh.y ? 1 : 0) - (x < lh.x ? 1 : 0);
 }
 
-// dynamic smem: re[n], im[n], thr[257]
+// dynamic smem: z float2[n] | stage twiddles float2[tw_total] | super twiddles float2[n/2 + 1] | thr2 float2[256] | out u8[2 n]
 __global__ void __launch_bounds__(kMonThreads)
 monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n_samples, long first_start, int hop, int nfft, FftPlan plan,
-                      const uint16_t *__restrict__ perm, const float2 *__restrict__ tw, const float2 *__restrict__ super_tw,
-                      const float *__restrict__ wnorm, const float *__restrict__ thr_g, int num_bins, int freq_osr, uint8_t *__restrict__ mag,
-                      size_t mag_slot_stride, unsigned int *__restrict__ xmax_bits) {
-    extern __shared__ float smem[];
-    const int n = plan.n;
-    float *re = smem, *im = smem + n, *thr = smem + 2 * n;
-    const int t = threadIdx.x, frame = blockIdx.x, slot = blockIdx.y;
-    const float *x = audio + (size_t)slot * slot_stride;
-    const long start = first_start + (long)frame * hop;
-    for (int k = t; k < 257; k += kMonThreads) thr[k] = thr_g[k];
-    // windowed, normalised frame, packed (even, odd) -> complex, stored in kiss_fft's permuted leaf order
-    for (int o = t; o < n; o += kMonThreads) {
-        const int src = perm[o];
-        const long p0 = start + 2 * src, p1 = p0 + 1;
-        const float a = (p0 >= 0 && p0 < n_samples) ? x[p0] : 0.0f;
-        const float b = (p1 >= 0 && p1 < n_samples) ? x[p1] : 0.0f;
-        re[o] = __fmul_rn(wnorm[2 * src], a);      // (fft_norm * window[pos]) * last_frame[pos], decode_ft8.c:191
-        im[o] = __fmul_rn(wnorm[2 * src + 1], b);
-    }
-    __syncthreads();
-    for (int s = 0; s < plan.nstages; ++s) {
-        const int p = plan.radix[s], m = plan.m[s], fs = plan.fstride[s];
-        const int nbf = n / p;  // butterflies in this stage
-        for (int b = t; b < nbf; b += kMonThreads) {
-            const int g = b / m, k = b - g * m;
-            const int i0 = g * p * m + k;
-            if (p == 4) {  // kf_bfly4, kiss_fft.c:38-84
-                cpx f0{re[i0], im[i0]}, f1{re[i0 + m], im[i0 + m]}, f2{re[i0 + 2 * m], im[i0 + 2 * m]}, f3{re[i0 + 3 * m], im[i0 + 3 * m]};
-                const cpx a = cmul(f1, tw[k * fs]);
-                const cpx bb = cmul(f2, tw[2 * k * fs]);
-                const cpx c = cmul(f3, tw[3 * k * fs]);
-                const cpx d5 = csub(f0, bb);
-                f0 = cadd(f0, bb);
-                const cpx s3 = cadd(a, c), s4 = csub(a, c);
-                f2 = csub(f0, s3);
-                f0 = cadd(f0, s3);
-                re[i0] = f0.r; im[i0] = f0.i;
-                re[i0 + 2 * m] = f2.r; im[i0 + 2 * m] = f2.i;
-                re[i0 + m] = __fadd_rn(d5.r, s4.i); im[i0 + m] = __fsub_rn(d5.i, s4.r);
-                re[i0 + 3 * m] = __fsub_rn(d5.r, s4.i); im[i0 + 3 * m] = __fadd_rn(d5.i, s4.r);
-            } else if (p == 2) {  // kf_bfly2, kiss_fft.c:15-36
-                cpx f0{re[i0], im[i0]}, f1{re[i0 + m], im[i0 + m]};
-                const cpx tt = cmul(f1, tw[k * fs]);
-                f1 = csub(f0, tt);
-                f0 = cadd(f0, tt);
-                re[i0] = f0.r; im[i0] = f0.i;
-                re[i0 + m] = f1.r; im[i0 + m] = f1.i;
-            } else if (p == 3) {  // kf_bfly3, kiss_fft.c:86-128
-                const float2 e3 = tw[fs * m];
-                cpx f0{re[i0], im[i0]}, f1{re[i0 + m], im[i0 + m]}, f2{re[i0 + 2 * m], im[i0 + 2 * m]};
-                const cpx s1 = cmul(f1, tw[k * fs]);
-                const cpx s2 = cmul(f2, tw[2 * k * fs]);
-                const cpx s3 = cadd(s1, s2);
-                cpx s0 = csub(s1, s2);
-                f1.r = __fsub_rn(f0.r, half_of(s3.r));
-                f1.i = __fsub_rn(f0.i, half_of(s3.i));
-                s0.r = __fmul_rn(s0.r, e3.y);
-                s0.i = __fmul_rn(s0.i, e3.y);
-                f0 = cadd(f0, s3);
-                f2.r = __fadd_rn(f1.r, s0.i);
-                f2.i = __fsub_rn(f1.i, s0.r);
-                f1.r = __fsub_rn(f1.r, s0.i);
-                f1.i = __fadd_rn(f1.i, s0.r);
-                re[i0] = f0.r; im[i0] = f0.i;
-                re[i0 + m] = f1.r; im[i0 + m] = f1.i;
-                re[i0 + 2 * m] = f2.r; im[i0 + 2 * m] = f2.i;
-            } else {  // p == 5: kf_bfly5, kiss_fft.c:130-190
-                const float2 ya = tw[fs * m], yb = tw[fs * 2 * m];
-                const cpx s0{re[i0], im[i0]};
-                cpx f1{re[i0 + m], im[i0 + m]}, f2{re[i0 + 2 * m], im[i0 + 2 * m]}, f3{re[i0 + 3 * m], im[i0 + 3 * m]}, f4{re[i0 + 4 * m], im[i0 + 4 * m]};
-                const cpx s1 = cmul(f1, tw[k * fs]);
-                const cpx s2 = cmul(f2, tw[2 * k * fs]);
-                const cpx s3 = cmul(f3, tw[3 * k * fs]);
-                const cpx s4 = cmul(f4, tw[4 * k * fs]);
-                const cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
-                re[i0] = __fadd_rn(s0.r, __fadd_rn(s7.r, s8.r));
-                im[i0] = __fadd_rn(s0.i, __fadd_rn(s7.i, s8.i));
-                cpx s5, s6, s11, s12;
-                s5.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, ya.x)), __fmul_rn(s8.r, yb.x));
-                s5.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, ya.x)), __fmul_rn(s8.i, yb.x));
-                s6.r = __fadd_rn(__fmul_rn(s10.i, ya.y), __fmul_rn(s9.i, yb.y));
-                s6.i = __fsub_rn(-__fmul_rn(s10.r, ya.y), __fmul_rn(s9.r, yb.y));
-                f1 = csub(s5, s6);
-                f4 = cadd(s5, s6);
-                s11.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, yb.x)), __fmul_rn(s8.r, ya.x));
-                s11.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, yb.x)), __fmul_rn(s8.i, ya.x));
-                s12.r = __fadd_rn(-__fmul_rn(s10.i, yb.y), __fmul_rn(s9.i, ya.y));
-                s12.i = __fsub_rn(__fmul_rn(s10.r, yb.y), __fmul_rn(s9.r, ya.y));
-                f2 = cadd(s11, s12);
-                f3 = csub(s11, s12);
-                re[i0 + m] = f1.r; im[i0 + m] = f1.i;
-                re[i0 + 2 * m] = f2.r; im[i0 + 2 * m] = f2.i;
-                re[i0 + 3 * m] = f3.r; im[i0 + 3 * m] = f3.i;
-                re[i0 + 4 * m] = f4.r; im[i0 + 4 * m] = f4.i;
-            }
+                      const uint16_t *__restrict__ inv_perm, const float2 *__restrict__ tw_stage, const float2 *__restrict__ super_tw,
+                      const float *__restrict__ wnorm, const float *__restrict__ thr_g, int num_bins, int freq_osr, int n_frames, int total_items,
+                      uint8_t *__restrict__ mag, size_t mag_slot_stride, unsigned int *__restrict__ xmax_bits) {
+    extern __shared__ __align__(16) float2 smem2[];
+    const int n = plan.n, t = threadIdx.x;
+    float2 *z = smem2, *tws = z + n, *sup = tws + plan.tw_total, *thr2 = sup + (n / 2 + 1);
+    uint8_t *outb = reinterpret_cast<uint8_t *>(thr2 + 256);
+    const int it_begin = (int)((long long)blockIdx.x * total_items / gridDim.x), it_end = (int)((long long)(blockIdx.x + 1) * total_items / gridDim.x);
+    if (it_begin >= it_end) return;
+    for (int k = t; k < plan.tw_total; k += kMonThreads) tws[k] = tw_stage[k];
+    for (int k = t; k < n / 2 + 1; k += kMonThreads) sup[k] = super_tw[k];
+    for (int k = t; k < 256; k += kMonThreads) thr2[k] = make_float2(thr_g[k], thr_g[k + 1]);
+    const int wanted = num_bins * freq_osr;  // bins 0 .. wanted-1 are stored (wanted <= n)
+
+    for (int item = it_begin; item < it_end; ++item) {
+        const int slot = item / n_frames, frame = item - slot * n_frames;
+        const float *x = audio + (size_t)slot * slot_stride;
+        const long start = first_start + (long)frame * hop;
+        __syncthreads();  // tables loaded / the previous frame's bytes have left outb and z
+        // windowed, normalised frame, packed (even, odd) -> complex, written to kiss_fft's permuted leaf place
+        for (int src = t; src < n; src += kMonThreads) {
+            const long p0 = start + 2 * src, p1 = p0 + 1;
+            const float a = (p0 >= 0 && p0 < n_samples) ? x[p0] : 0.0f;
+            const float b = (p1 >= 0 && p1 < n_samples) ? x[p1] : 0.0f;
+            const float2 w = *reinterpret_cast<const float2 *>(wnorm + 2 * src);
+            z[inv_perm[src]] = make_float2(__fmul_rn(w.x, a), __fmul_rn(w.y, b));   // (fft_norm * window[pos]) * last_frame[pos], decode_ft8.c:191
         }
         __syncthreads();
-    }
-    // real-FFT split (kiss_fftr.c:80-113) fused with |X|^2 -> dB -> uint8 (decode_ft8.c:196-213)
-    const int wanted = num_bins * freq_osr;  // bins 0 .. wanted-1 are stored (wanted <= n)
-    uint8_t *out = mag + (size_t)slot * mag_slot_stride + (size_t)frame * wanted;
-    float xmax = 0.0f;
-    for (int k = t; k <= n / 2; k += kMonThreads) {
-        cpx lo, hi;  // bins k and n-k
-        bool have_hi = false;
-        if (k == 0) {
-            lo.r = __fadd_rn(re[0], im[0]);
-            lo.i = 0.0f;
-        } else {
-            const cpx fpk{re[k], im[k]};
-            const cpx fpnk{re[n - k], -im[n - k]};
-            const cpx f1 = cadd(fpk, fpnk), f2 = csub(fpk, fpnk);
-            const cpx tt = cmul(f2, super_tw[k - 1]);
-            lo.r = half_of(__fadd_rn(f1.r, tt.r));
-            lo.i = half_of(__fadd_rn(f1.i, tt.i));
-            hi.r = half_of(__fsub_rn(f1.r, tt.r));
-            hi.i = half_of(__fsub_rn(tt.i, f1.i));
-            have_hi = true;
-            if (k == n - k) lo = hi;  // the loop's last iteration writes freqdata[k] then freqdata[ncfft-k]: the latter wins
+        for (int s = 0; s < plan.nstages; ++s) {
+            const int p = plan.radix[s], m = plan.m[s];
+            const unsigned int magic = plan.magic[s];
+            const float2 *tq = tws + plan.tw_off[s];
+            const int nbf = n / p;  // butterflies in this stage
+            for (int b = t; b < nbf; b += kMonThreads) {
+                const int g = magic ? (int)__umulhi((unsigned int)b, magic) : b, k = b - g * m;
+                const int i0 = g * p * m + k;
+                if (p == 4) {  // kf_bfly4, kiss_fft.c:38-84
+                    cpx f0 = ld(z, i0), f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m), f3 = ld(z, i0 + 3 * m);
+                    const cpx a = cmul(f1, tq[k]);
+                    const cpx bb = cmul(f2, tq[m + k]);
+                    const cpx c = cmul(f3, tq[2 * m + k]);
+                    const cpx d5 = csub(f0, bb);
+                    f0 = cadd(f0, bb);
+                    const cpx s3 = cadd(a, c), s4 = csub(a, c);
+                    f2 = csub(f0, s3);
+                    f0 = cadd(f0, s3);
+                    st(z, i0, f0);
+                    st(z, i0 + 2 * m, f2);
+                    st(z, i0 + m, cpx{__fadd_rn(d5.r, s4.i), __fsub_rn(d5.i, s4.r)});
+                    st(z, i0 + 3 * m, cpx{__fsub_rn(d5.r, s4.i), __fadd_rn(d5.i, s4.r)});
+                } else if (p == 2) {  // kf_bfly2, kiss_fft.c:15-36
+                    cpx f0 = ld(z, i0), f1 = ld(z, i0 + m);
+                    const cpx tt = cmul(f1, tq[k]);
+                    f1 = csub(f0, tt);
+                    f0 = cadd(f0, tt);
+                    st(z, i0, f0);
+                    st(z, i0 + m, f1);
+                } else if (p == 3) {  // kf_bfly3, kiss_fft.c:86-128
+                    const float2 e3 = plan.c1[s];
+                    cpx f0 = ld(z, i0), f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m);
+                    const cpx s1 = cmul(f1, tq[k]);
+                    const cpx s2 = cmul(f2, tq[m + k]);
+                    const cpx s3 = cadd(s1, s2);
+                    cpx s0 = csub(s1, s2);
+                    f1.r = __fsub_rn(f0.r, half_of(s3.r));
+                    f1.i = __fsub_rn(f0.i, half_of(s3.i));
+                    s0.r = __fmul_rn(s0.r, e3.y);
+                    s0.i = __fmul_rn(s0.i, e3.y);
+                    f0 = cadd(f0, s3);
+                    f2.r = __fadd_rn(f1.r, s0.i);
+                    f2.i = __fsub_rn(f1.i, s0.r);
+                    f1.r = __fsub_rn(f1.r, s0.i);
+                    f1.i = __fadd_rn(f1.i, s0.r);
+                    st(z, i0, f0);
+                    st(z, i0 + m, f1);
+                    st(z, i0 + 2 * m, f2);
+                } else {  // p == 5: kf_bfly5, kiss_fft.c:130-190
+                    const float2 ya = plan.c1[s], yb = plan.c2[s];
+                    const cpx s0 = ld(z, i0);
+                    cpx f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m), f3 = ld(z, i0 + 3 * m), f4 = ld(z, i0 + 4 * m);
+                    const cpx s1 = cmul(f1, tq[k]);
+                    const cpx s2 = cmul(f2, tq[m + k]);
+                    const cpx s3 = cmul(f3, tq[2 * m + k]);
+                    const cpx s4 = cmul(f4, tq[3 * m + k]);
+                    const cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
+                    st(z, i0, cpx{__fadd_rn(s0.r, __fadd_rn(s7.r, s8.r)), __fadd_rn(s0.i, __fadd_rn(s7.i, s8.i))});
+                    cpx s5, s6, s11, s12;
+                    s5.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, ya.x)), __fmul_rn(s8.r, yb.x));
+                    s5.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, ya.x)), __fmul_rn(s8.i, yb.x));
+                    s6.r = __fadd_rn(__fmul_rn(s10.i, ya.y), __fmul_rn(s9.i, yb.y));
+                    s6.i = __fsub_rn(-__fmul_rn(s10.r, ya.y), __fmul_rn(s9.r, yb.y));
+                    f1 = csub(s5, s6);
+                    f4 = cadd(s5, s6);
+                    s11.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, yb.x)), __fmul_rn(s8.r, ya.x));
+                    s11.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, yb.x)), __fmul_rn(s8.i, ya.x));
+                    s12.r = __fadd_rn(-__fmul_rn(s10.i, yb.y), __fmul_rn(s9.i, ya.y));
+                    s12.i = __fsub_rn(__fmul_rn(s10.r, yb.y), __fmul_rn(s9.r, ya.y));
+                    f2 = cadd(s11, s12);
+                    f3 = csub(s11, s12);
+                    st(z, i0 + m, f1);
+                    st(z, i0 + 2 * m, f2);
+                    st(z, i0 + 3 * m, f3);
+                    st(z, i0 + 4 * m, f4);
+                }
+            }
+            __syncthreads();
         }
-        if (k < wanted) {
-            const float m2 = __fadd_rn(__fmul_rn(lo.i, lo.i), __fmul_rn(lo.r, lo.r));
-            const float xv = __fadd_rn(1E-12f, m2);
-            xmax = fmaxf(xmax, xv);
-            out[(k % freq_osr) * num_bins + k / freq_osr] = (uint8_t)quantise(xv, thr);
+        // real-FFT split (kiss_fftr.c:80-113) fused with |X|^2 -> dB -> uint8 (decode_ft8.c:196-213)
+        float xmax = 0.0f;
+        for (int k = t; k <= n / 2; k += kMonThreads) {
+            cpx lo, hi;  // bins k and n-k
+            bool have_hi = false;
+            if (k == 0) {
+                const float2 z0 = z[0];
+                lo.r = __fadd_rn(z0.x, z0.y);
+                lo.i = 0.0f;
+            } else {
+                const cpx fpk = ld(z, k);
+                const float2 zn = z[n - k];
+                const cpx fpnk{zn.x, -zn.y};
+                const cpx f1 = cadd(fpk, fpnk), f2 = csub(fpk, fpnk);
+                const cpx tt = cmul(f2, sup[k - 1]);
+                lo.r = half_of(__fadd_rn(f1.r, tt.r));
+                lo.i = half_of(__fadd_rn(f1.i, tt.i));
+                hi.r = half_of(__fsub_rn(f1.r, tt.r));
+                hi.i = half_of(__fsub_rn(tt.i, f1.i));
+                have_hi = true;
+                if (k == n - k) lo = hi;  // the loop's last iteration writes freqdata[k] then freqdata[ncfft-k]: the latter wins
+            }
+            if (k < wanted) {
+                const float m2 = __fadd_rn(__fmul_rn(lo.i, lo.i), __fmul_rn(lo.r, lo.r));
+                const float xv = __fadd_rn(1E-12f, m2);
+                xmax = fmaxf(xmax, xv);
+                outb[(k % freq_osr) * num_bins + k / freq_osr] = (uint8_t)quantise(xv, thr2);
+            }
+            const int kh = n - k;
+            if (have_hi && kh != k && kh < wanted) {
+                const float m2 = __fadd_rn(__fmul_rn(hi.i, hi.i), __fmul_rn(hi.r, hi.r));
+                const float xv = __fadd_rn(1E-12f, m2);
+                xmax = fmaxf(xmax, xv);
+                outb[(kh % freq_osr) * num_bins + kh / freq_osr] = (uint8_t)quantise(xv, thr2);
+            }
         }
-        const int kh = n - k;
-        if (have_hi && kh != k && kh < wanted) {
-            const float m2 = __fadd_rn(__fmul_rn(hi.i, hi.i), __fmul_rn(hi.r, hi.r));
-            const float xv = __fadd_rn(1E-12f, m2);
-            xmax = fmaxf(xmax, xv);
-            out[(kh % freq_osr) * num_bins + kh / freq_osr] = (uint8_t)quantise(xv, thr);
-        }
-    }
-    if (xmax_bits) {
+        if (xmax_bits) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-        if ((t & 31) == 0) atomicMax(xmax_bits + slot, __float_as_uint(xmax));
+            for (int o = 16; o > 0; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            if ((t & 31) == 0) atomicMax(xmax_bits + slot, __float_as_uint(xmax));
+        }
+        __syncthreads();
+        uint8_t *out = mag + (size_t)slot * mag_slot_stride + (size_t)frame * wanted;
+        if (((((size_t)out) | (size_t)wanted) & 15) == 0) {
+            for (int k = t; k < wanted / 16; k += kMonThreads) reinterpret_cast<uint4 *>(out)[k] = reinterpret_cast<const uint4 *>(outb)[k];
+        } else {
+            for (int k = t; k < wanted; k += kMonThreads) out[k] = outb[k];
+        }
     }
 }
 
@@ -269,6 +300,22 @@ MonTables *get_tables(int device, int nfft) {
     if (!build_plan(n, t->plan, perm)) { delete t; return nullptr; }
     std::vector<float2> tw((size_t)n), sup((size_t)(n / 2 + 1));
     build_twiddles(n, tw.data());
+    // per-stage compact twiddles tw[q k fstride] (q = 1..radix-1, k < m), the radix-3/5 constants, the division constants,
+    // and the INVERSE of the leaf permutation (the kernel scatters input sample pair `src` to its permuted place)
+    std::vector<float2> tws;
+    for (int s2 = 0; s2 < t->plan.nstages; ++s2) {
+        const int p = t->plan.radix[s2], m = t->plan.m[s2], fs = t->plan.fstride[s2];
+        t->plan.tw_off[s2] = (int)tws.size();
+        for (int q = 1; q < p; ++q)
+            for (int k = 0; k < m; ++k) tws.push_back(tw[(size_t)(q * k * fs)]);
+        t->plan.magic[s2] = m > 1 ? (unsigned int)((0x100000000ull + (unsigned long long)m - 1) / (unsigned long long)m) : 0u;
+        t->plan.c1[s2] = tw[(size_t)(fs * m) % (size_t)n];
+        t->plan.c2[s2] = tw[(size_t)(2 * fs * m) % (size_t)n];
+    }
+    t->plan.tw_total = (int)tws.size();
+    std::vector<uint16_t> inv((size_t)n);
+    for (int o = 0; o < n; ++o) inv[perm[(size_t)o]] = (uint16_t)o;
+    perm.swap(inv);
     for (int k = 0; k < n / 2; ++k) {  // kiss_fftr_alloc, kiss_fftr.c:50-56
         const double phase = -3.14159265358979323846264338327 * ((double)(k + 1) / n + .5);
         sup[(size_t)k].x = (float)cos(phase);
@@ -282,10 +329,10 @@ MonTables *get_tables(int device, int nfft) {
         t->window[(size_t)i] = x * x;
         wn[(size_t)i] = t->fft_norm * t->window[(size_t)i];
     }
-    bool ok = cudaMalloc(&t->d_perm, sizeof(uint16_t) * n) == cudaSuccess && cudaMalloc(&t->d_tw, sizeof(float2) * n) == cudaSuccess &&
+    bool ok = cudaMalloc(&t->d_perm, sizeof(uint16_t) * n) == cudaSuccess && cudaMalloc(&t->d_tw, sizeof(float2) * (tws.size() + 1)) == cudaSuccess &&
               cudaMalloc(&t->d_super, sizeof(float2) * (n / 2 + 1)) == cudaSuccess && cudaMalloc(&t->d_wnorm, sizeof(float) * nfft) == cudaSuccess &&
               cudaMemcpy(t->d_perm, perm.data(), sizeof(uint16_t) * n, cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(t->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(t->d_tw, tws.data(), sizeof(float2) * tws.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(t->d_super, sup.data(), sizeof(float2) * (n / 2 + 1), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(t->d_wnorm, wn.data(), sizeof(float) * nfft, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) { delete t; return nullptr; }
@@ -309,12 +356,21 @@ float *thresholds(int device) {
 
 cudaError_t launch_frames(const MonTables *t, const float *d_audio, size_t slot_stride, int n_samples, long first_start, int hop, int n_frames,
                           int n_slots, int num_bins, int freq_osr, uint8_t *d_mag, size_t mag_slot_stride, unsigned int *d_xmax, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (2 * (size_t)t->plan.n + 257);
+    const int n = t->plan.n;
+    // z | stage twiddles | super twiddles | threshold pairs | one frame's bytes (see monitor_frames_kernel)
+    const size_t smem = sizeof(float2) * ((size_t)n + (size_t)t->plan.tw_total + (size_t)(n / 2 + 1) + 256) + (((size_t)2 * n + 15) & ~(size_t)15);
     cudaError_t e = cudaFuncSetAttribute(monitor_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid(n_frames, n_slots);
-    monitor_frames_kernel<<<grid, kMonThreads, smem, st>>>(d_audio, slot_stride, n_samples, first_start, hop, t->nfft, t->plan, t->d_perm, t->d_tw,
-                                                           t->d_super, t->d_wnorm, thresholds(t->device), num_bins, freq_osr, d_mag, mag_slot_stride, d_xmax);
+    int sms = 0, per_sm = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, monitor_frames_kernel, kMonThreads, smem)) != cudaSuccess) return e;
+    const long total = (long)n_frames * n_slots;
+    long grid = (long)sms * (per_sm > 0 ? per_sm : 1);   // persistent: every CTA walks a contiguous range of (recording, frame) items
+    if (grid > total) grid = total;
+    if (total >= (1l << 31)) return cudaErrorInvalidValue;
+    monitor_frames_kernel<<<(unsigned)grid, kMonThreads, smem, st>>>(d_audio, slot_stride, n_samples, first_start, hop, t->nfft, t->plan, t->d_perm, t->d_tw,
+                                                                      t->d_super, t->d_wnorm, thresholds(t->device), num_bins, freq_osr, n_frames, (int)total,
+                                                                      d_mag, mag_slot_stride, d_xmax);
     return cudaGetLastError();
 }
 

@@ -13,12 +13,21 @@
 // accumulator per signal (frequency words computed once on the host in double), a host-built cosine table, and noise from a
 // counter hash (splitmix64 of seed/slot/sample index; sum of uniform bytes ~ Gaussian).  oracle/ft8_oracle_synth.c is its
 // CPU twin; tests assert the two produce identical bytes / float bit patterns, and that the signals decode.
+//
+// GFSK (ft8b200_signal_t.reserved[0] = 1; gen_ft8.c:28-102): the frequency of symbol i is smoothed by the Gaussian pulse of
+// gfsk_pulse() (three symbols long, BT = 2 for FT8, 1 for FT4), the first and last symbol are extended by a copy of themselves,
+// and the first and last eighth of a symbol are ramped by a raised cosine.  The reference integrates the smoothed frequency
+// sample by sample (phi += dphi[k]); here the pulse is an INTEGER table q[j] = round(pulse[j] * tone-spacing word) with prefix
+// sums P[m], so that the phase of any sample is a closed form of at most three table entries --
+//     phase(s L + j) = pstart[s] + j fw0 + t[s+1] P[j] + t[s] (P[j+L] - P[L]) + t[s-1] (P[j+2L] - P[2L]),   t[-1] = t[0], t[n] = t[n-1]
+// -- every thread computes its own samples, and the CPU twin reproduces the waveform bit for bit.
 #include "common.cuh"
 #include "ft8_tables.h"
 
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 using namespace ft8b200;
@@ -37,7 +46,16 @@ struct SigDev {
     int32_t n_sym;           // 79 (FT8) or 105 (FT4)
     uint8_t payload[10];
     uint8_t ft4;
+    uint8_t gfsk;            // 0 = plain FSK (decoderSelfTest, rtlsdr_ft8d.c:937-955), 1 = GFSK (gen_ft8.c:49-102)
     uint8_t tones[kMaxSym];
+};
+
+// integer GFSK pulse of one layout (symbol length L): prefix sums P[0..3L], the raised-cosine ramp of L/8 samples
+struct GfskDev {
+    const uint32_t *P;
+    const float *env_f;      // (1 - cosf(2 pi i / (2 n_ramp))) / 2
+    const int32_t *env_q15;  // the same * 32768, rounded
+    uint32_t p1, p2, p3;     // P[L], P[2L], P[3L]
 };
 
 __constant__ uint8_t c_gen[kLdpcM][12];   // the protocol tables of ft8_tables.h, uploaded by ensure_tables()
@@ -64,7 +82,7 @@ __device__ uint32_t crc14_dev(const uint8_t *msg, int num_bits) {  // ftx_comput
 }
 
 // one thread per signal: channel symbols + per-symbol start phases
-__global__ void synth_prepare_kernel(SigDev *sigs, int n, int sym_len) {
+__global__ void synth_prepare_kernel(SigDev *sigs, int n, int sym_len, GfskDev gf) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     SigDev &s = sigs[t];
@@ -109,25 +127,40 @@ __global__ void synth_prepare_kernel(SigDev *sigs, int n, int sym_len) {
     uint32_t ph = 0;
     for (int i = 0; i < s.n_sym; ++i) {
         s.pstart[i] = ph;
-        ph += (uint32_t)sym_len * s.fw[s.tones[i]];
+        if (s.gfsk) {  // a symbol's worth of: tone 0, the tail of the previous pulse, the middle of this one, the head of the next
+            const uint32_t tp = s.tones[i > 0 ? i - 1 : 0], tc = s.tones[i], tn = s.tones[i + 1 < s.n_sym ? i + 1 : i];
+            ph += (uint32_t)sym_len * s.fw[0] + tn * gf.p1 + tc * (gf.p2 - gf.p1) + tp * (gf.p3 - gf.p2);
+        } else {
+            ph += (uint32_t)sym_len * s.fw[s.tones[i]];
+        }
     }
 }
 
-// phase of signal `s` at sample n, or false when the signal is silent there
+// phase of signal `s` at sample n, or false when the signal is silent there; ramp = index into the GFSK envelope table or -1
 template <int kSymLen>
-__device__ __forceinline__ bool phase_at(const SigDev &s, long long n, uint32_t &ph) {
+__device__ __forceinline__ bool phase_at(const SigDev &s, long long n, const GfskDev &gf, uint32_t &ph, int &ramp) {
     const long long rel = n - s.s0;
-    if (rel < 0 || rel >= (long long)s.n_sym * kSymLen) return false;
+    const long long total = (long long)s.n_sym * kSymLen;
+    if (rel < 0 || rel >= total) return false;
     const int k = (int)(rel / kSymLen);
     const uint32_t j = (uint32_t)(rel - (long long)k * kSymLen);
-    ph = s.pstart[k] + j * s.fw[s.tones[k]];
+    ramp = -1;
+    if (s.gfsk) {
+        const uint32_t tp = s.tones[k > 0 ? k - 1 : 0], tc = s.tones[k], tn = s.tones[k + 1 < s.n_sym ? k + 1 : k];
+        ph = s.pstart[k] + j * s.fw[0] + tn * gf.P[j] + tc * (gf.P[j + kSymLen] - gf.p1) + tp * (gf.P[j + 2 * kSymLen] - gf.p2);
+        constexpr int kRamp = kSymLen / 8;
+        if (rel < kRamp) ramp = (int)rel;
+        else if (rel >= total - kRamp) ramp = (int)(total - 1 - rel);
+    } else {
+        ph = s.pstart[k] + j * s.fw[s.tones[k]];
+    }
     return true;
 }
 
 // raw RTL bytes: 8 complex samples (16 bytes) per thread
 __global__ void __launch_bounds__(256)
-synth_raw_kernel(const SigDev *__restrict__ sigs, const int *__restrict__ first, int noise_q8, uint64_t seed, int slot0, uint8_t *__restrict__ out,
-                 size_t slot_stride, long long n_samples) {
+synth_raw_kernel(const SigDev *__restrict__ sigs, const int *__restrict__ first, GfskDev gf, int noise_q8, uint64_t seed, int slot0,
+                 uint8_t *__restrict__ out, size_t slot_stride, long long n_samples) {
     const int slot = blockIdx.y;
     const long long n0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (n0 >= n_samples) return;
@@ -140,9 +173,11 @@ synth_raw_kernel(const SigDev *__restrict__ sigs, const int *__restrict__ first,
         int vi = 0, vq = 0;
         for (int g = a; g < b; ++g) {
             uint32_t ph;
-            if (!phase_at<384000>(sigs[g], n, ph)) continue;
+            int ramp;
+            if (!phase_at<384000>(sigs[g], n, gf, ph, ramp)) continue;
             const int idx = (int)(ph >> (32 - kLutBits));
-            const int amp = sigs[g].amp_q8;
+            int amp = sigs[g].amp_q8;
+            if (ramp >= 0) amp = (int)(((long long)amp * gf.env_q15[ramp] + 16384) >> 15);
             vi += (amp * (int)g_lut_q14[idx] + (1 << 21)) >> 22;                          // amp * cos
             vq += (amp * (int)g_lut_q14[(idx - kLut / 4) & (kLut - 1)] + (1 << 21)) >> 22;  // amp * sin
         }
@@ -169,7 +204,7 @@ synth_raw_kernel(const SigDev *__restrict__ sigs, const int *__restrict__ first,
 // float paths: complex baseband (kComplex) or real audio; one sample per thread
 template <int kSymLen, bool kComplex>
 __global__ void __launch_bounds__(256)
-synth_float_kernel(const SigDev *__restrict__ sigs, const int *__restrict__ first, float noise_scale, uint64_t seed, int slot0,
+synth_float_kernel(const SigDev *__restrict__ sigs, const int *__restrict__ first, GfskDev gf, float noise_scale, uint64_t seed, int slot0,
                    float *__restrict__ out_i, float *__restrict__ out_q, size_t slot_stride, int n_samples) {
     const int slot = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,10 +220,12 @@ synth_float_kernel(const SigDev *__restrict__ sigs, const int *__restrict__ firs
     }
     for (int g = first[slot]; g < first[slot + 1]; ++g) {
         uint32_t ph;
-        if (!phase_at<kSymLen>(sigs[g], (long long)n, ph)) continue;
+        int ramp;
+        if (!phase_at<kSymLen>(sigs[g], (long long)n, gf, ph, ramp)) continue;
         const int idx = (int)(ph >> (32 - kLutBits));
-        vi = __fadd_rn(vi, __fmul_rn(sigs[g].amp, g_lut_f[idx]));
-        if (kComplex) vq = __fadd_rn(vq, __fmul_rn(sigs[g].amp, g_lut_f[(idx - kLut / 4) & (kLut - 1)]));
+        const float amp = ramp >= 0 ? __fmul_rn(sigs[g].amp, gf.env_f[ramp]) : sigs[g].amp;
+        vi = __fadd_rn(vi, __fmul_rn(amp, g_lut_f[idx]));
+        if (kComplex) vq = __fadd_rn(vq, __fmul_rn(amp, g_lut_f[(idx - kLut / 4) & (kLut - 1)]));
     }
     out_i[(size_t)slot * slot_stride + n] = vi;
     if (kComplex) out_q[(size_t)slot * slot_stride + n] = vq;
@@ -219,6 +256,31 @@ cudaError_t ensure_tables() {
     return e;
 }
 
+// The integer GFSK pulse of one layout, per device.  pulse[j] is gfsk_pulse()'s own float expression (gen_ft8.c:28-38, erff of the
+// host libm); q[j] = round(pulse[j] * step) with step = the tone spacing as a phase word; P = prefix sums (wrapping uint32).
+struct GfskTab { uint32_t *d_P = nullptr; float *d_env_f = nullptr; int32_t *d_env_q = nullptr; uint32_t p1 = 0, p2 = 0, p3 = 0; bool ready = false; };
+GfskTab g_gfsk[64][4];  // [device][layout: 0 raw, 1 3200 sps, 2 12 kHz FT8, 3 12 kHz FT4]
+
+void build_gfsk_host(int L, float bt, uint32_t step, std::vector<uint32_t> &P, std::vector<float> &env_f, std::vector<int32_t> &env_q) {
+    P.assign((size_t)3 * L + 1, 0u);
+    uint32_t acc = 0;
+    for (int j = 0; j < 3 * L; ++j) {
+        const float t = j / (float)L - 1.5f;
+        const float arg1 = 5.336446f * bt * (t + 0.5f), arg2 = 5.336446f * bt * (t - 0.5f);   // GFSK_CONST_K, gen_ft8.c:19
+        const float pulse = (erff(arg1) - erff(arg2)) / 2;
+        P[(size_t)j] = acc;
+        acc += (uint32_t)llround((double)pulse * (double)step);
+    }
+    P[(size_t)3 * L] = acc;
+    const int n_ramp = L / 8;
+    env_f.resize((size_t)n_ramp);
+    env_q.resize((size_t)n_ramp);
+    for (int i = 0; i < n_ramp; ++i) {
+        env_f[(size_t)i] = (1 - cosf(2 * (float)M_PI * i / (2 * n_ramp))) / 2;   // gen_ft8.c:96-101
+        env_q[(size_t)i] = (int32_t)lround((double)env_f[(size_t)i] * 32768.0);
+    }
+}
+
 struct Layout { double fs; int sym_len; double tone_hz; double f_shift; };
 Layout layout_of(int kind, int protocol) {
     if (kind == 0) return {2400000.0, 384000, 6.25, -600000.0};                  // raw bytes (FT8 only)
@@ -226,12 +288,49 @@ Layout layout_of(int kind, int protocol) {
     return protocol == PROTO_FT4 ? Layout{12000.0, 576, 1.0 / 0.048, 0.0} : Layout{12000.0, 1920, 6.25, 0.0};  // 12 kHz audio
 }
 
+// the GFSK tables of a layout on the current device (built and uploaded on first use; empty descriptor on failure)
+std::mutex g_gfsk_mu;
+GfskDev gfsk_tables(int kind, int protocol) {
+    GfskDev out = {nullptr, nullptr, nullptr, 0, 0, 0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return out;
+    const int slot = kind == 0 ? 0 : (kind == 1 ? 1 : (protocol == PROTO_FT4 ? 3 : 2));
+    std::lock_guard<std::mutex> lk(g_gfsk_mu);
+    GfskTab &t = g_gfsk[dev][slot];
+    if (!t.ready) {
+        const Layout L = layout_of(kind, protocol);
+        const uint32_t step = (uint32_t)llround(L.tone_hz / L.fs * 4294967296.0);
+        std::vector<uint32_t> P;
+        std::vector<float> ef;
+        std::vector<int32_t> eq;
+        build_gfsk_host(L.sym_len, (kind == 2 && protocol == PROTO_FT4) ? 1.0f : 2.0f, step, P, ef, eq);   // FT8_SYMBOL_BT / FT4_SYMBOL_BT, gen_ft8.c:16-17
+        const bool ok = cudaMalloc(&t.d_P, P.size() * sizeof(uint32_t)) == cudaSuccess && cudaMalloc(&t.d_env_f, ef.size() * sizeof(float)) == cudaSuccess &&
+                        cudaMalloc(&t.d_env_q, eq.size() * sizeof(int32_t)) == cudaSuccess &&
+                        cudaMemcpy(t.d_P, P.data(), P.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess &&
+                        cudaMemcpy(t.d_env_f, ef.data(), ef.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+                        cudaMemcpy(t.d_env_q, eq.data(), eq.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) return out;
+        t.p1 = P[(size_t)L.sym_len]; t.p2 = P[(size_t)2 * L.sym_len]; t.p3 = P[(size_t)3 * L.sym_len];
+        t.ready = true;
+    }
+    out.P = t.d_P; out.env_f = t.d_env_f; out.env_q15 = t.d_env_q; out.p1 = t.p1; out.p2 = t.p2; out.p3 = t.p3;
+    return out;
+}
+
 // host descriptors -> device descriptors (frequency words in double, once per signal), then the prepare kernel
 int upload_signals(const ft8b200_signal_t *h_signals, const int *h_first, int n_slots, int kind, int protocol, SigDev **d_sigs, int **d_first,
-                   cudaStream_t st) {
+                   GfskDev *gf_out, cudaStream_t st) {
     if (!h_signals && h_first[n_slots] > 0) return FT8B200_EINVAL;
     const int n = h_first[n_slots];
     const Layout L = layout_of(kind, protocol);
+    bool any_gfsk = false;
+    for (int g = 0; g < n; ++g) any_gfsk = any_gfsk || h_signals[g].reserved[0] != 0;
+    GfskDev gf = {nullptr, nullptr, nullptr, 0, 0, 0};
+    if (any_gfsk) {
+        gf = gfsk_tables(kind, protocol);
+        if (!gf.P) return FT8B200_ENOMEM;
+    }
+    if (gf_out) *gf_out = gf;
     std::vector<SigDev> host((size_t)(n > 0 ? n : 1));
     memset(host.data(), 0, host.size() * sizeof(SigDev));
     for (int g = 0; g < n; ++g) {
@@ -246,6 +345,7 @@ int upload_signals(const ft8b200_signal_t *h_signals, const int *h_first, int n_
         d.amp_q8 = (int32_t)lround((double)s.amp * 256.0);
         memcpy(d.payload, s.payload, 10);
         d.ft4 = (kind == 2 && protocol == PROTO_FT4) ? 1 : 0;
+        d.gfsk = s.reserved[0] != 0 ? 1 : 0;
     }
     if (cudaMalloc(d_sigs, host.size() * sizeof(SigDev)) != cudaSuccess) return FT8B200_ENOMEM;
     if (cudaMalloc(d_first, sizeof(int) * (size_t)(n_slots + 1)) != cudaSuccess) { cudaFree(*d_sigs); return FT8B200_ENOMEM; }
@@ -253,7 +353,7 @@ int upload_signals(const ft8b200_signal_t *h_signals, const int *h_first, int n_
               cudaMemcpyAsync(*d_sigs, host.data(), host.size() * sizeof(SigDev), cudaMemcpyHostToDevice, st) == cudaSuccess &&
               cudaMemcpyAsync(*d_first, h_first, sizeof(int) * (size_t)(n_slots + 1), cudaMemcpyHostToDevice, st) == cudaSuccess;
     if (ok && n > 0) {
-        synth_prepare_kernel<<<(n + 127) / 128, 128, 0, st>>>(*d_sigs, n, L.sym_len);
+        synth_prepare_kernel<<<(n + 127) / 128, 128, 0, st>>>(*d_sigs, n, L.sym_len, gf);
         ok = cudaGetLastError() == cudaSuccess;
     }
     // the pageable host vector must outlive the async copies
@@ -436,7 +536,7 @@ int ft8b200_encode_tones(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, i
     cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;
-    int rc = upload_signals(sig.data(), first.data(), n, 2, protocol, &d_sigs, &d_first, st);
+    int rc = upload_signals(sig.data(), first.data(), n, 2, protocol, &d_sigs, &d_first, nullptr, st);
     if (rc) return rc;
     std::vector<SigDev> back((size_t)n);
     const bool ok = cudaMemcpy(back.data(), d_sigs, sizeof(SigDev) * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess;
@@ -458,12 +558,13 @@ int ft8b200_synth_raw(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, con
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;
-    int rc = upload_signals(h_signals, h_first, n_slots, 0, PROTO_FT8, &d_sigs, &d_first, st);
+    GfskDev gf;
+    int rc = upload_signals(h_signals, h_first, n_slots, 0, PROTO_FT8, &d_sigs, &d_first, &gf, st);
     if (rc) return rc;
     const long long n_samples = (long long)(bytes_per_slot / 2);
     const int noise_q8 = (int)lround((double)noise_lsb * 65536.0 / 147.79715829474123);  // sigma of a sum of 4 uniform bytes
     dim3 grid((unsigned)((n_samples + 8 * 256 - 1) / (8 * 256)), (unsigned)n_slots);
-    synth_raw_kernel<<<grid, 256, 0, st>>>(d_sigs, d_first, noise_q8, seed, first_slot_index, d_iq, slot_stride_bytes, n_samples);
+    synth_raw_kernel<<<grid, 256, 0, st>>>(d_sigs, d_first, gf, noise_q8, seed, first_slot_index, d_iq, slot_stride_bytes, n_samples);
     const bool ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
     cudaFree(d_sigs); cudaFree(d_first);
     return ok ? 0 : FT8B200_ECUDA;
@@ -477,13 +578,14 @@ static int synth_float(ft8b200_ctx_t *ctx, int kind, int protocol, const ft8b200
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;
-    int rc = upload_signals(h_signals, h_first, n_slots, kind, protocol, &d_sigs, &d_first, st);
+    GfskDev gf;
+    int rc = upload_signals(h_signals, h_first, n_slots, kind, protocol, &d_sigs, &d_first, &gf, st);
     if (rc) return rc;
     const float scale = (float)((double)noise_sigma / 209.02153956946134);  // sigma of a sum of 8 uniform bytes
     dim3 grid((unsigned)((n_samples + 255) / 256), (unsigned)n_slots);
-    if (kind == 1) synth_float_kernel<512, true><<<grid, 256, 0, st>>>(d_sigs, d_first, scale, seed, first_slot_index, d_i, d_q, slot_stride, n_samples);
-    else if (protocol == PROTO_FT4) synth_float_kernel<576, false><<<grid, 256, 0, st>>>(d_sigs, d_first, scale, seed, first_slot_index, d_i, nullptr, slot_stride, n_samples);
-    else synth_float_kernel<1920, false><<<grid, 256, 0, st>>>(d_sigs, d_first, scale, seed, first_slot_index, d_i, nullptr, slot_stride, n_samples);
+    if (kind == 1) synth_float_kernel<512, true><<<grid, 256, 0, st>>>(d_sigs, d_first, gf, scale, seed, first_slot_index, d_i, d_q, slot_stride, n_samples);
+    else if (protocol == PROTO_FT4) synth_float_kernel<576, false><<<grid, 256, 0, st>>>(d_sigs, d_first, gf, scale, seed, first_slot_index, d_i, nullptr, slot_stride, n_samples);
+    else synth_float_kernel<1920, false><<<grid, 256, 0, st>>>(d_sigs, d_first, gf, scale, seed, first_slot_index, d_i, nullptr, slot_stride, n_samples);
     const bool ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
     cudaFree(d_sigs); cudaFree(d_first);
     return ok ? 0 : FT8B200_ECUDA;

@@ -984,3 +984,65 @@ def test_synth_full_raw_slots_decode(pkg, ctx):
     res, n = ctx.fetch_results(4)
     for k in range(4):
         assert n[k] >= 1 and res[k][0]["call"].decode() == texts[k].split()[1] and res[k][0]["loc"] == b"FN20"
+
+
+# ------------------------------------------------------------------------------------------- GFSK (gen_ft8.c:28-102)
+def _gfsk_signals(pkg, rng, n, f_lo, f_hi, t_lo, t_hi, amp_lo, amp_hi):
+    items, texts = [], []
+    for _ in range(n):
+        to, de, ex = synth.random_message(rng)
+        items.append((pkg.pack77_std(to, de, ex), float(rng.uniform(f_lo, f_hi)), float(rng.uniform(t_lo, t_hi)), float(rng.uniform(amp_lo, amp_hi))))
+        texts.append(f"{to} {de} {ex}")
+    return pkg.make_signals(items, gfsk=True), texts
+
+
+def test_gfsk_synth_matches_cpu_twin(pkg, ctx, oracle):
+    """GFSK mode of the synthesiser (Gaussian-smoothed frequency from an integer pulse table, extended end symbols, raised-cosine
+    ramps) == its CPU twin bit for bit in all three output forms and both protocols; the twin is compared with the reference's own
+    synth_gfsk() in tests/test_oracle_vs_ref.py.  Mixed FSK / GFSK signals in one slot are allowed."""
+    rng = np.random.default_rng(61)
+    n_samp = 3 * 384_000 + 5000                      # raw bytes: the ramp, three symbols and their pulse overlaps
+    g, _ = _gfsk_signals(pkg, rng, 2, 300.0, 1300.0, -0.02, 0.01, 20.0, 35.0)
+    g[1]["reserved"][0] = 0                          # one plain-FSK signal next to a GFSK one
+    raw = ctx.synth_raw(g, [0, 2], 30.0, 5, first_slot_index=3, bytes_per_slot=2 * n_samp).cpu().numpy()
+    assert np.array_equal(raw[0, :2 * n_samp], oracle.synth_raw(g, 30.0, 5, 3, n_samp))
+    g, texts = _gfsk_signals(pkg, rng, 5, 100.0, 1400.0, 0.2, 1.5, 0.25, 0.4)
+    d_i, d_q = ctx.synth_slots(g, [0, 5], 1.0, 8)
+    wi, wq = oracle.synth_float(1, False, g, 1.0, 8, 0, 48000)
+    assert bits_equal(d_i[0].cpu().numpy(), wi) and bits_equal(d_q[0].cpu().numpy(), wq)
+    peak = torch.maximum(d_i.abs().amax(1), d_q.abs().amax(1))
+    ctx.process_conditioned(d_i, d_q, peak)
+    res, n = ctx.fetch_results(1)
+    o = oracle.subsystem(*oracle.condition(wi, wq, 48000)[:2])
+    assert n[0] == o["n"] >= 4 and res[0].tobytes() == o["results"].tobytes()
+    for proto, n_samp in ((1, 180_000), (0, 90_000)):
+        g, texts = _gfsk_signals(pkg, rng, 3, 300.0, 2500.0, 0.3, 1.0, 0.08, 0.12)
+        d_a = ctx.synth_audio(g, [0, 3], proto, 0.05, 11, n_samples=n_samp)
+        wa, _ = oracle.synth_float(2, proto == 0, g, 0.05, 11, 0, n_samp)
+        assert bits_equal(d_a[0].cpu().numpy(), wa)
+        lines = [pkg.format_decoded(r) for r in pkg.decode_audio(ctx, d_a, 12000, proto)[0]]
+        assert lines == oracle.decode_ft8_lines(wa, 12000, protocol=proto)
+        assert {l.split("~  ")[1] for l in lines} == set(texts)
+
+
+def test_crowded_band_gfsk_parity(pkg, ctx500, oracle):
+    """BASELINE config #3 with on-air-shaped signals: 60 overlapping GFSK messages over 50-1500 Hz at -24..+5 dB, K = 500 / 200
+    messages: decoder_results identical to the oracle's ft8_subsystem on the twin's samples, for two slots."""
+    def amp(snr_db):
+        return float(np.sqrt(2.0 * (2500.0 / 3200.0) * 10.0 ** (snr_db / 10.0)))
+    sigs, firsts = [], [0]
+    for s in range(2):
+        g, _ = _gfsk_signals(pkg, np.random.default_rng(900 + s), 60, 50.0, 1500.0, -0.5, 1.5, amp(-24.0), amp(5.0))
+        sigs.append(g); firsts.append(firsts[-1] + g.size)
+    d_i, d_q = ctx500.synth_slots(np.concatenate(sigs), firsts, 1.0, 17)
+    peak = torch.maximum(d_i.abs().amax(1), d_q.abs().amax(1))
+    ctx500.process_conditioned(d_i, d_q, peak)
+    res, n = ctx500.fetch_results(2)
+    total = 0
+    for s in range(2):
+        wi, wq = oracle.synth_float(1, False, sigs[s], 1.0, 17, s, 48000)
+        assert bits_equal(d_i[s].cpu().numpy(), wi) and bits_equal(d_q[s].cpu().numpy(), wq)
+        o = oracle.subsystem(*oracle.condition(wi, wq, 48000)[:2], max_cand=500, max_msgs=200)
+        assert n[s] == o["n"] and res[s].tobytes() == o["results"].tobytes()
+        total += int(n[s])
+    assert total >= 20

@@ -176,6 +176,35 @@ def test_spots_vs_reference_loop(oracle):
         assert n == o["n"] and res.tobytes() == o["results"].tobytes(), texts
 
 
+def test_gfsk_twin_vs_reference_synth_gfsk(oracle):
+    """The synthesiser's GFSK mode (integer pulse table, closed-form phase; oracle/ft8_oracle_synth.c is the bit-identical twin
+    of csrc/synth.cu) against ft8_lib's own synth_gfsk() (gen_ft8.c:49-102) at the same sample rate: the quadrature rail of the
+    complex 3200 sps waveform is sin(phase), which is what the reference emits -- same smoothed frequency, same extended end
+    symbols, same ramps, to within the 4096-entry phase table and the reference's float phase accumulator."""
+    from oracle.pyoracle import ReferenceGen, signal_dtype
+    if not ReferenceGen.available():
+        pytest.skip("oracle/_ref/libref_gen.so not built")
+    gen = ReferenceGen()
+    for k, msg in enumerate([("CQ", "K1JT", "FN20"), ("K1ABC", "W9XYZ", "RR73")]):
+        sig = np.zeros(1, signal_dtype)
+        sig[0]["payload"] = np.frombuffer(oracle.pack_std(*msg), np.uint8)
+        sig[0]["reserved"][0] = 1
+        sig[0]["f0_hz"], sig[0]["t0_sec"], sig[0]["amp"] = 400.0 + 311.0 * k, 0.0, 1.0
+        wi, wq = oracle.synth_float(1, False, sig, 0.0, 1, 0, 79 * 512)
+        ref = gen.synth_gfsk(oracle.tones(sig[0]["payload"].tobytes()), float(sig[0]["f0_hz"]), 2.0, 0.16, 3200)
+        assert ref.size == wq.size == 79 * 512
+        err = np.abs(wq.astype(np.float64) - ref.astype(np.float64))
+        assert err.max() < 0.02 and np.sqrt((err ** 2).mean()) < 0.005, (err.max(), np.sqrt((err ** 2).mean()))
+        assert abs(wi[0]) < 1e-6 and abs(wi[10]) < 0.07          # ramped start: the envelope reaches 1 only after 64 samples (0.059 at sample 10)
+        # plain FSK of the same message differs (phase discontinuities in frequency at every symbol boundary)
+        sig[0]["reserved"][0] = 0
+        _, fq = oracle.synth_float(1, False, sig, 0.0, 1, 0, 79 * 512)
+        assert np.abs(fq.astype(np.float64) - ref).max() > 0.5
+    # FT4 / 12 kHz: BT = 1, 576 samples per symbol; the real-audio rail is cos(phase): compare instantaneous frequency instead
+    p8, p4 = gen.pulse(512, 2.0), gen.pulse(576, 1.0)
+    assert abs(float(p8.sum()) - 512.0) < 0.5 and abs(float(p4.sum()) - 576.0) < 0.5   # a pulse integrates to one symbol of deviation
+
+
 def test_oracle_pack77_vs_reference(oracle):
     """The restated pack77() (oracle/ft8_oracle_codec.c) against the reference's on 20 000 message texts."""
     ref = Reference("k120")

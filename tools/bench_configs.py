@@ -21,21 +21,21 @@ def _amp_for_snr(snr_db: float, sigma: float) -> float:
     return float(np.sqrt(2.0 * sigma * sigma * (2500.0 / 3200.0) * 10.0 ** (snr_db / 10.0)))
 
 
-def _signals(pkg, rng, n, f_lo, f_hi, t_lo, t_hi, amp_lo, amp_hi):
+def _signals(pkg, rng, n, f_lo, f_hi, t_lo, t_hi, amp_lo, amp_hi, gfsk=False):
     from tools import synth
     items, texts = [], []
     for _ in range(n):
         to, de, ex = synth.random_message(rng)
         items.append((pkg.pack77_std(to, de, ex), float(rng.uniform(f_lo, f_hi)), float(rng.uniform(t_lo, t_hi)), float(rng.uniform(amp_lo, amp_hi))))
         texts.append(f"{to} {de} {ex}")
-    return pkg.make_signals(items), texts
+    return pkg.make_signals(items, gfsk=gfsk), texts
 
 
-def _batch_signals(pkg, seeds, per_slot, *args):
+def _batch_signals(pkg, seeds, per_slot, *args, gfsk=False):
     """One independent generator per slot (seed = global slot index), so that shards made on different GPUs equal one big batch."""
     sigs, texts = [], []
     for seed in seeds:
-        s, t = _signals(pkg, np.random.default_rng(seed), per_slot, *args)
+        s, t = _signals(pkg, np.random.default_rng(seed), per_slot, *args, gfsk=gfsk)
         sigs.append(s); texts.append(t)
     first = np.concatenate([[0], np.cumsum([s.size for s in sigs])]).astype(np.int32)
     return np.concatenate(sigs), first, texts
@@ -296,7 +296,7 @@ def config3_daemon(env):
     torch, pkg = env.torch, env.pkg
     ctx = pkg.Context(env.local, max_candidates=500, max_messages=200)
     N3 = 1024
-    sig, first, _ = _batch_signals(pkg, range(N3), 60, 50.0, 1500.0, -0.5, 1.5, _amp_for_snr(-24.0, 1.0), _amp_for_snr(5.0, 1.0))
+    sig, first, _ = _batch_signals(pkg, range(N3), 60, 50.0, 1500.0, -0.5, 1.5, _amp_for_snr(-24.0, 1.0), _amp_for_snr(5.0, 1.0), gfsk=True)
     d_i, d_q = ctx.synth_slots(sig, first, 1.0, 9)
     peak = torch.maximum(d_i.abs().amax(1), d_q.abs().amax(1))
     ctx.condition(d_i, d_q, peak)
@@ -317,7 +317,7 @@ def config3_daemon(env):
         same &= int(nres[s]) == o_["n"] and res[s].tobytes() == o_["results"].tobytes()
     cpu_s = (time.perf_counter() - t0) / k_cpu
     ctx.close()
-    return {"workload": "BASELINE config #3 on the daemon path (0-1600 Hz): 1024 slots x 60 overlapping signals, -24..+5 dB, random DT/frequency, K = 500 / 200 messages",
+    return {"workload": "BASELINE config #3 on the daemon path (0-1600 Hz): 1024 slots x 60 overlapping GFSK signals (gen_ft8's shaping), -24..+5 dB, random DT/frequency, K = 500 / 200 messages",
             "slots_per_s": N3 / (ms * 1e-3), "ms": ms, "mean_unique_messages_per_slot": float(nres.mean()), "cpu_slots_per_s_1thread": 1.0 / cpu_s,
             "cpu_kind": kind, "cpu_sample": "%d slots through ft8_subsystem() built with K_MAX_CANDIDATES 500 / K_MAX_MESSAGES 200" % k_cpu, "parity": bool(same)}
 
@@ -327,7 +327,7 @@ def config3_monitor(env):
     torch, pkg = env.torch, env.pkg
     ctx = pkg.Context(env.local)
     NB = 512
-    sig, first, _ = _batch_signals(pkg, range(NB), 60, 200.0, 3000.0, 0.0, 1.5, 0.02, 0.5)
+    sig, first, _ = _batch_signals(pkg, range(NB), 60, 200.0, 3000.0, 0.0, 1.5, 0.02, 0.5, gfsk=True)
     aud = ctx.synth_audio(sig, first, 1, 0.05, 13)
     run = lambda: pkg.decode_audio(ctx, aud, 12000, 1)
     t = []
@@ -346,7 +346,7 @@ def config3_monitor(env):
         same &= [pkg.format_decoded(r) for r in lines[s]] == want
     cpu_s = (time.perf_counter() - t0) / k_cpu
     ctx.close()
-    return {"workload": "BASELINE config #3 on the 12 kHz monitor path (200-3000 Hz): 512 recordings x 60 overlapping signals, decode_ft8's main() per recording",
+    return {"workload": "BASELINE config #3 on the 12 kHz monitor path (200-3000 Hz): 512 recordings x 60 overlapping GFSK signals, decode_ft8's main() per recording",
             "slots_per_s": NB / sec, "ms": sec * 1e3, "mean_decodes_per_slot": float(np.mean([len(l) for l in lines])), "cpu_slots_per_s_1thread": 1.0 / cpu_s,
             "cpu_kind": "port (oracle restatement of decode_ft8's main(), pinned to the reference's own main() on its 60 recordings)",
             "cpu_sample": "%d recordings" % k_cpu, "parity": bool(same)}
