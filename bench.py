@@ -549,7 +549,7 @@ def main():
                 "stage_note": "with an SM partition the back-end stages (comb_fir ... spots) run on the back-end SMs concurrently with the "
                               "next batch's block sums: their times overlap it and do not add to the step" if args.back_sms != 0 else "stages run back to back"}
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))  # one `ncu --set full` capture, per slot
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))  # one `ncu --set full` capture, per slot
         roofline["traffic"] = tr.get("dram_bytes_per_slot", 0) * Bc or None
         roofline["traffic_source"] = tr.get("source")
     except Exception:

@@ -161,6 +161,15 @@ void monitor_init(monitor_t *me, const monitor_config_t *cfg);
 void monitor_process(monitor_t *me, const float *frame);
 void monitor_reset(monitor_t *me);
 void monitor_free(monitor_t *me);
+/* B200-side extension of the monitor: DEFERRED mode.  monitor_process() as the reference defines it is a copy-launch-copy-
+ * synchronise round trip per 160 ms block (93 per recording).  With ft8b200_monitor_set_deferred(me, 1) -- or FT8B200_MONITOR_DEFERRED=1
+ * in the environment at monitor_init() -- it only appends the block on the host; all pending blocks are transformed in ONE launch when
+ * the waterfall is needed: ft8_find_sync() / ft8_decode() on me->wf do it themselves, as do monitor_reset(), monitor_free() and
+ * ft8b200_monitor_flush() (returns the number of blocks transformed).  The only observable difference: between a monitor_process()
+ * and the next flush, me->wf.mag and me->max_mag do not yet include the appended blocks (me->wf.num_blocks does).  decode_ft8's
+ * main() reads max_mag once, after its loop (decode_ft8.c:301): a flush there keeps its output identical. */
+int ft8b200_monitor_set_deferred(monitor_t *me, int on);
+int ft8b200_monitor_flush(monitor_t *me);
 
 /* ------------------------------------------------------------------------------------------
  * (2) batched entry points (device pointers unless the name says _host)

@@ -704,6 +704,14 @@ class Monitor:
     def reset(self):
         self.L.monitor_reset(C.byref(self.me))
 
+    def set_deferred(self, on: bool):
+        """ft8b200_monitor_set_deferred: process() only appends; the pending blocks are transformed at find_sync/decode/flush."""
+        if self.L.ft8b200_monitor_set_deferred(C.byref(self.me), int(on)) != 0:
+            raise Ft8Error("ft8b200_monitor_set_deferred")
+
+    def flush(self) -> int:
+        return self.L.ft8b200_monitor_flush(C.byref(self.me))
+
     def mag(self) -> np.ndarray:
         n = self.me.wf.num_blocks * self.me.wf.block_stride
         return np.ctypeslib.as_array(C.cast(self.me.wf.mag, C.POINTER(C.c_uint8)), shape=(n,)).copy()

@@ -20,6 +20,7 @@ namespace ft8b200 {
 ft8b200_ctx_t *default_ctx();
 void default_ctx_release();
 void default_stream_release();
+void monitor_flush_for_mag(const uint8_t *mag);
 }
 
 namespace {
@@ -158,6 +159,7 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
         abort();
     }
     if (num_candidates <= 0) return 0;
+    monitor_flush_for_mag(power->mag);   // a deferred monitor (ft8b200_monitor_set_deferred) transforms its pending blocks now
     std::lock_guard<std::mutex> lk(g_mu);
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) die("ft8_find_sync (cudaSetDevice)");  // the decoder thread's current device may differ
     const size_t bytes = (size_t)power->num_blocks * power->block_stride;
@@ -221,6 +223,7 @@ bool ft8_decode(const waterfall_t *power, const candidate_t *cand, message_t *me
         fprintf(stderr, "libft8b200: ft8_decode: unknown protocol %d\n", (int)power->protocol);
         abort();
     }
+    monitor_flush_for_mag(power->mag);
     std::lock_guard<std::mutex> lk(g_mu);
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) die("ft8_decode (cudaSetDevice)");
     const size_t bytes = (size_t)power->num_blocks * power->block_stride;

@@ -240,6 +240,8 @@ struct MonTables {
     float *d_wnorm = nullptr;
     std::vector<float> window;  // Hann, host copy
     float fft_norm = 0;
+    size_t smem = 0;            // launch shape of monitor_frames_kernel for these tables, worked out once
+    long max_grid = 0;
 };
 
 bool build_plan(int n, FftPlan &plan, std::vector<uint16_t> &perm) {
@@ -357,15 +359,22 @@ float *thresholds(int device) {
 cudaError_t launch_frames(const MonTables *t, const float *d_audio, size_t slot_stride, int n_samples, long first_start, int hop, int n_frames,
                           int n_slots, int num_bins, int freq_osr, uint8_t *d_mag, size_t mag_slot_stride, unsigned int *d_xmax, cudaStream_t st) {
     const int n = t->plan.n;
-    // z | stage twiddles | super twiddles | threshold pairs | one frame's bytes (see monitor_frames_kernel)
-    const size_t smem = sizeof(float2) * ((size_t)n + (size_t)t->plan.tw_total + (size_t)(n / 2 + 1) + 256) + (((size_t)2 * n + 15) & ~(size_t)15);
-    cudaError_t e = cudaFuncSetAttribute(monitor_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int sms = 0, per_sm = 0;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, monitor_frames_kernel, kMonThreads, smem)) != cudaSuccess) return e;
+    cudaError_t e;
+    if (t->max_grid == 0) {  // once per (device, nfft): monitor_process() launches this 93 times per recording
+        // z | stage twiddles | super twiddles | threshold pairs | one frame's bytes (see monitor_frames_kernel)
+        const size_t need = sizeof(float2) * ((size_t)n + (size_t)t->plan.tw_total + (size_t)(n / 2 + 1) + 256) + (((size_t)2 * n + 15) & ~(size_t)15);
+        int sms = 0, per_sm = 0;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, monitor_frames_kernel, kMonThreads, need)) != cudaSuccess) return e;
+        MonTables *mt = const_cast<MonTables *>(t);
+        mt->smem = need;
+        mt->max_grid = (long)sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const size_t smem = t->smem;
+    // the opt-in is per FUNCTION, not per table set: another geometry (FT4's 1152-point frames) may have lowered it since
+    if ((e = cudaFuncSetAttribute(monitor_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const long total = (long)n_frames * n_slots;
-    long grid = (long)sms * (per_sm > 0 ? per_sm : 1);   // persistent: every CTA walks a contiguous range of (recording, frame) items
+    long grid = t->max_grid;   // persistent: every CTA walks a contiguous range of (recording, frame) items
     if (grid > total) grid = total;
     if (total >= (1l << 31)) return cudaErrorInvalidValue;
     monitor_frames_kernel<<<(unsigned)grid, kMonThreads, smem, st>>>(d_audio, slot_stride, n_samples, first_start, hop, t->nfft, t->plan, t->d_perm, t->d_tw,
@@ -389,12 +398,22 @@ MonGeom geometry(int sample_rate, int time_osr, int freq_osr, int protocol) {
 
 struct MonitorDev {  // hangs off monitor_t.fft_work
     const MonTables *tables;
-    float *d_buf;          // nfft - subblock + block_size floats: history + the new block
-    uint8_t *d_mag;        // one block's worth of bytes
+    float *d_buf;          // history (nfft - subblock floats) + up to max_blocks new blocks
+    uint8_t *d_mag;        // up to max_blocks blocks' worth of bytes
     unsigned int *d_xmax;
-    float *h_buf;          // pinned
+    float *h_buf;          // pinned, same shape as d_buf
     cudaStream_t st;
+    // deferred mode (ft8b200_monitor_set_deferred): monitor_process() only appends the block to h_buf; the frames are transformed in
+    // ONE launch when the waterfall is needed -- ft8_find_sync / ft8_decode on this monitor's wf, ft8b200_monitor_flush,
+    // monitor_reset, monitor_free -- instead of a copy-launch-copy-synchronise round trip per 160 ms block
+    bool deferred;
+    int pending;           // blocks appended since the last flush
+    int max_blocks;
 };
+
+// monitors in deferred mode, by the host address of their waterfall bytes (what ft8_find_sync / ft8_decode are handed)
+std::mutex g_deferred_mu;
+std::vector<monitor_t *> g_deferred;
 
 void die(const char *what) {
     fprintf(stderr, "libft8b200: monitor: %s (%s)\n", what, cudaGetErrorString(cudaGetLastError()));
@@ -402,6 +421,19 @@ void die(const char *what) {
 }
 
 }  // namespace
+
+namespace ft8b200 {
+// ft8_find_sync / ft8_decode (dropin.cu) call this with the waterfall they were handed: a deferred monitor that owns those
+// bytes transforms its pending blocks first
+void monitor_flush_for_mag(const uint8_t *mag) {
+    monitor_t *hit = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_deferred_mu);
+        for (monitor_t *m : g_deferred) if (m->wf.mag == mag) { hit = m; break; }
+    }
+    if (hit) ft8b200_monitor_flush(hit);
+}
+}  // namespace ft8b200
 
 extern "C" {
 
@@ -452,16 +484,42 @@ void monitor_init(monitor_t *me, const monitor_config_t *cfg) {
     MonitorDev *d = new MonitorDev();
     d->tables = t;
     d->st = (cudaStream_t)ft8b200_cuda_stream(ctx);
-    const size_t nbuf = (size_t)g.nfft - g.subblock_size + g.block_size;
-    if (cudaMalloc(&d->d_buf, sizeof(float) * nbuf) != cudaSuccess || cudaMalloc(&d->d_mag, (size_t)me->wf.block_stride) != cudaSuccess ||
+    d->deferred = false;
+    d->pending = 0;
+    d->max_blocks = g.max_blocks;
+    const size_t nbuf = (size_t)g.nfft - g.subblock_size + (size_t)g.block_size * (size_t)g.max_blocks;
+    if (cudaMalloc(&d->d_buf, sizeof(float) * nbuf) != cudaSuccess || cudaMalloc(&d->d_mag, (size_t)me->wf.block_stride * (size_t)g.max_blocks) != cudaSuccess ||
         cudaMalloc(&d->d_xmax, sizeof(unsigned int)) != cudaSuccess || cudaHostAlloc(&d->h_buf, sizeof(float) * nbuf, cudaHostAllocDefault) != cudaSuccess)
         die("monitor_init: allocation failed");
     me->fft_work = d;
     me->fft_cfg = nullptr;
+    const char *env = getenv("FT8B200_MONITOR_DEFERRED");
+    if (env && atoi(env) != 0) ft8b200_monitor_set_deferred(me, 1);
+}
+
+// transform the `blocks` blocks that sit behind the history in h_buf, write their bytes to wf.mag from block `first_block` on
+static void run_blocks(monitor_t *me, MonitorDev *d, int first_block, int blocks) {
+    const int nfft = me->nfft, sub = me->subblock_size, blk = me->block_size, tosr = me->wf.time_osr;
+    const size_t nhist = (size_t)nfft - sub, nbuf = nhist + (size_t)blk * blocks;
+    const size_t off = (size_t)first_block * me->wf.block_stride, bytes = (size_t)blocks * me->wf.block_stride;
+    unsigned int xbits = 0;
+    bool ok = cudaMemcpyAsync(d->d_buf, d->h_buf, sizeof(float) * nbuf, cudaMemcpyHostToDevice, d->st) == cudaSuccess &&
+              cudaMemsetAsync(d->d_xmax, 0, sizeof(unsigned int), d->st) == cudaSuccess &&
+              launch_frames(d->tables, d->d_buf, 0, (int)nbuf, 0, sub, tosr * blocks, 1, me->wf.num_bins, me->wf.freq_osr, d->d_mag, 0, d->d_xmax, d->st) == cudaSuccess &&
+              cudaMemcpyAsync(me->wf.mag + off, d->d_mag, bytes, cudaMemcpyDeviceToHost, d->st) == cudaSuccess &&
+              cudaMemcpyAsync(&xbits, d->d_xmax, sizeof(xbits), cudaMemcpyDeviceToHost, d->st) == cudaSuccess && cudaStreamSynchronize(d->st) == cudaSuccess;
+    if (!ok) die("monitor_process failed");
+    // host copy of the sliding frame, as the reference keeps it (decode_ft8.c:178-186): the last nfft samples seen
+    memcpy(me->last_frame, d->h_buf + nbuf - (size_t)nfft, sizeof(float) * (size_t)nfft);
+    float xmax;
+    memcpy(&xmax, &xbits, 4);
+    const float db = 10.0f * log10f(xmax);  // max over the blocks of 10*log10f(x): log10f is monotone, so this is their max dB
+    if (db > me->max_mag) me->max_mag = db;
 }
 
 void monitor_free(monitor_t *me) {
     MonitorDev *d = (MonitorDev *)me->fft_work;
+    if (d && d->deferred) ft8b200_monitor_set_deferred(me, 0);  // flushes and leaves the registry
     if (d) {
         cudaSetDevice(d->tables->device);
         cudaStreamSynchronize(d->st);
@@ -475,6 +533,7 @@ void monitor_free(monitor_t *me) {
 }
 
 void monitor_reset(monitor_t *me) {  // decode_ft8.c:220-224: last_frame is NOT cleared
+    ft8b200_monitor_flush(me);       // deferred blocks still shape last_frame (and max_mag is reset below, after them)
     me->wf.num_blocks = 0;
     me->max_mag = 0;
 }
@@ -482,26 +541,45 @@ void monitor_reset(monitor_t *me) {  // decode_ft8.c:220-224: last_frame is NOT 
 void monitor_process(monitor_t *me, const float *frame) {
     if (me->wf.num_blocks >= me->wf.max_blocks) return;  // silent no-op once full (decode_ft8.c:165-166)
     MonitorDev *d = (MonitorDev *)me->fft_work;
+    const int nfft = me->nfft, sub = me->subblock_size, blk = me->block_size;
+    const size_t nhist = (size_t)nfft - sub;
+    if (d->deferred) {  // append only; the device work happens at the flush
+        if (d->pending == 0) memcpy(d->h_buf, me->last_frame + sub, sizeof(float) * nhist);
+        memcpy(d->h_buf + nhist + (size_t)d->pending * blk, frame, sizeof(float) * (size_t)blk);
+        ++d->pending;
+        ++me->wf.num_blocks;
+        return;
+    }
     if (cudaSetDevice(d->tables->device) != cudaSuccess) die("monitor_process: cudaSetDevice");  // the caller's thread may have another device current
-    const int nfft = me->nfft, sub = me->subblock_size, blk = me->block_size, tosr = me->wf.time_osr;
-    const size_t nhist = (size_t)nfft - sub, nbuf = nhist + blk;
     memcpy(d->h_buf, me->last_frame + sub, sizeof(float) * nhist);
     memcpy(d->h_buf + nhist, frame, sizeof(float) * (size_t)blk);
-    const size_t off = (size_t)me->wf.num_blocks * me->wf.block_stride;
-    unsigned int xbits = 0;
-    bool ok = cudaMemcpyAsync(d->d_buf, d->h_buf, sizeof(float) * nbuf, cudaMemcpyHostToDevice, d->st) == cudaSuccess &&
-              cudaMemsetAsync(d->d_xmax, 0, sizeof(unsigned int), d->st) == cudaSuccess &&
-              launch_frames(d->tables, d->d_buf, 0, (int)nbuf, 0, sub, tosr, 1, me->wf.num_bins, me->wf.freq_osr, d->d_mag, 0, d->d_xmax, d->st) == cudaSuccess &&
-              cudaMemcpyAsync(me->wf.mag + off, d->d_mag, (size_t)me->wf.block_stride, cudaMemcpyDeviceToHost, d->st) == cudaSuccess &&
-              cudaMemcpyAsync(&xbits, d->d_xmax, sizeof(xbits), cudaMemcpyDeviceToHost, d->st) == cudaSuccess && cudaStreamSynchronize(d->st) == cudaSuccess;
-    if (!ok) die("monitor_process failed");
-    // host copy of the sliding frame, as the reference keeps it (decode_ft8.c:178-186)
-    memcpy(me->last_frame, d->h_buf + (size_t)(tosr - 1) * sub, sizeof(float) * (size_t)nfft);
-    float xmax;
-    memcpy(&xmax, &xbits, 4);
-    const float db = 10.0f * log10f(xmax);  // max over the block of 10*log10f(x): log10f is monotone, so this is the block's max dB
-    if (db > me->max_mag) me->max_mag = db;
+    run_blocks(me, d, me->wf.num_blocks, 1);
     ++me->wf.num_blocks;
+}
+
+// Deferred mode: see MonitorDev.  What a caller must know: between a monitor_process() and the next flush, wf.mag and max_mag do
+// not yet reflect the appended blocks (wf.num_blocks does).  ft8_find_sync() and ft8_decode() flush by themselves.
+int ft8b200_monitor_flush(monitor_t *me) {
+    MonitorDev *d = me ? (MonitorDev *)me->fft_work : nullptr;
+    if (!d) return FT8B200_EINVAL;
+    if (d->pending == 0) return 0;
+    if (cudaSetDevice(d->tables->device) != cudaSuccess) die("ft8b200_monitor_flush: cudaSetDevice");
+    const int blocks = d->pending;
+    d->pending = 0;
+    run_blocks(me, d, me->wf.num_blocks - blocks, blocks);
+    return blocks;
+}
+
+int ft8b200_monitor_set_deferred(monitor_t *me, int on) {
+    MonitorDev *d = me ? (MonitorDev *)me->fft_work : nullptr;
+    if (!d) return FT8B200_EINVAL;
+    if (!on) ft8b200_monitor_flush(me);
+    std::lock_guard<std::mutex> lk(g_deferred_mu);
+    for (size_t k = 0; k < g_deferred.size(); ++k)
+        if (g_deferred[k] == me) { g_deferred.erase(g_deferred.begin() + (long)k); break; }
+    if (on) g_deferred.push_back(me);
+    d->deferred = on != 0;
+    return 0;
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@ namespace ft8b200 {
 namespace {
 
 constexpr int kSyncThreads = 256;  // small CTAs: the heap replay is one thread's latency, so many slots should be resident per SM
+constexpr int kSurvSmem = 1024;    // survivors of a slot mirrored in shared memory for the serial replay (4 KB)
 
 struct Geo { int nb, nbins, tosr, fosr, stride, nfo, npos; };
 
@@ -276,8 +277,13 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
 // time_offset, freq_offset) is decoded after the sort by all threads, off the serial path.
 __global__ void __launch_bounds__(kSyncThreads)
 sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, int max_cand, int min_score, candidate_t *__restrict__ cand_out,
-                   int *__restrict__ ncand_out, uint32_t *__restrict__ scratch_all, uint32_t *__restrict__ work, unsigned int *__restrict__ work_total) {
+                   int *__restrict__ ncand_out, uint32_t *__restrict__ scratch_all, uint32_t *__restrict__ work, unsigned int *__restrict__ work_total,
+                   int mask_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *gmask = smem + (((size_t)max_cand * 4 + 15) & ~(size_t)15);   // one pass mask per group of 8 positions (mask_bytes > 0)
+    // the first kSurvSmem survivors are ALSO kept in shared memory: the replay below is one thread reading them one after the other,
+    // and from the global scratch list each read was an L2 round trip on the kernel's critical path
+    uint32_t *surv = reinterpret_cast<uint32_t *>(gmask + (((size_t)(mask_bytes > 0 ? mask_bytes : 0) + 15) & ~(size_t)15));
     __shared__ int s_warp_cnt[2][32];
     __shared__ int s_total, s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -288,31 +294,99 @@ sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, i
         const int16_t *scores = scores_all + (size_t)slot * g.npos;
         // Ordered compaction with ONE block barrier: warp w owns the contiguous positions [w*span, (w+1)*span); it counts
         // its survivors, the warp totals are prefix-summed, then it writes its survivors at its offset (position order ==
-        // the reference's loop order).  Scores are re-read in the second sweep (L1/L2 hits).
+        // the reference's loop order).  Scores are re-read in the second sweep (L1/L2 hits).  A lane reads EIGHT consecutive
+        // scores per step (one 128-bit load) when the slot's score array allows it: the sweeps are chains of dependent L2
+        // loads, and with one score per lane and step they were the kernel's whole duration (37 of its 42 us at 15 survivors).
         constexpr int kSelWarps = kSyncThreads / 32;
-        const int span = ((g.npos + kSelWarps - 1) / kSelWarps + 31) / 32 * 32;  // positions per warp, multiple of 32
-        const int w0 = warp * span;
-        int mine = 0;
+        int running, n_pass;
+        if (mask_bytes > 0 && (g.npos & 7) == 0 && (((size_t)scores) & 15) == 0) {
+            // One sweep over the scores (loads batched six deep) leaves a pass mask per group in shared memory; the second pass reads
+            // the masks and fetches scores only for the few groups that hold a survivor.
+            const int n8 = g.npos >> 3;                                            // groups of 8 positions
+            const int span8 = (n8 + kSelWarps - 1) / kSelWarps;                    // groups per warp
+            const int g0 = warp * span8, g1 = (g0 + span8 < n8) ? g0 + span8 : n8;
+            const uint4 *sv = reinterpret_cast<const uint4 *>(scores);
+            auto pass_mask = [&](const uint4 v) -> unsigned {                      // bit j: score j of the group passes
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                unsigned m = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((int)(short)(w[j] & 0xffffu) >= min_score) m |= 1u << (2 * j);
+                    if ((int)(short)(w[j] >> 16) >= min_score) m |= 2u << (2 * j);
+                }
+                return m;
+            };
+            int mine = 0;
+            for (int qb = g0 + lane; qb < g1; qb += 32 * 6) {
+                uint4 v[6];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) v[u] = (qb + 32 * u < g1) ? __ldg(sv + qb + 32 * u) : make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+#pragma unroll
+                for (int u = 0; u < 6; ++u) {
+                    if (qb + 32 * u < g1) {
+                        const unsigned m = pass_mask(v[u]);
+                        gmask[qb + 32 * u] = (uint8_t)m;
+                        mine += __popc(m);
+                    }
+                }
+            }
+            mine = __reduce_add_sync(0xffffffffu, mine);
+            if (lane == 0) s_warp_cnt[0][warp] = mine;
+            __syncthreads();
+            const int cnt = lane < kSelWarps ? s_warp_cnt[0][lane] : 0;
+            running = __reduce_add_sync(0xffffffffu, lane < warp ? cnt : 0);
+            n_pass = __reduce_add_sync(0xffffffffu, cnt);
+            if (mine > 0) {                                                        // warp-uniform: most warps hold no survivor at all
+                for (int qb = g0; qb < g1; qb += 32) {                             // warp-uniform trip count
+                    const int q = qb + lane;
+                    unsigned m = q < g1 ? gmask[q] : 0u;
+                    if (__ballot_sync(0xffffffffu, m != 0) == 0) continue;
+                    const int c = __popc(m);
+                    int incl = c;                                                  // inclusive prefix over the lanes: lane order == position order
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+                    int at = running + incl - c;
+                    while (m) {
+                        const int j = __ffs((int)m) - 1;
+                        m &= m - 1;
+                        const int p = 8 * q + j;
+                        const uint32_t ent = ((uint32_t)p << 12) | ((uint32_t)(int)scores[p] & 0xfffu);
+                        if (at < kSurvSmem) surv[at] = ent;
+                        scratch[at++] = ent;
+                    }
+                    running += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+        } else {
+            const int span = ((g.npos + kSelWarps - 1) / kSelWarps + 31) / 32 * 32;  // positions per warp, multiple of 32
+            const int w0 = warp * span;
+            int mine = 0;
 #pragma unroll 4
-        for (int o = 0; o < span; o += 32) {
-            const int p = w0 + o + lane;
-            const bool pass = p < g.npos && scores[p] >= min_score;
-            mine += __popc(__ballot_sync(0xffffffffu, pass));
-        }
-        if (lane == 0) s_warp_cnt[0][warp] = mine;
-        __syncthreads();
-        const int cnt = lane < kSelWarps ? s_warp_cnt[0][lane] : 0;
-        int running = __reduce_add_sync(0xffffffffu, lane < warp ? cnt : 0);
-        const int n_pass = __reduce_add_sync(0xffffffffu, cnt);
+            for (int o = 0; o < span; o += 32) {
+                const int p = w0 + o + lane;
+                const bool pass = p < g.npos && scores[p] >= min_score;
+                mine += __popc(__ballot_sync(0xffffffffu, pass));
+            }
+            if (lane == 0) s_warp_cnt[0][warp] = mine;
+            __syncthreads();
+            const int cnt = lane < kSelWarps ? s_warp_cnt[0][lane] : 0;
+            running = __reduce_add_sync(0xffffffffu, lane < warp ? cnt : 0);
+            n_pass = __reduce_add_sync(0xffffffffu, cnt);
 #pragma unroll 4
-        for (int o = 0; o < span; o += 32) {
-            const int p = w0 + o + lane;
-            int score = 0;
-            bool pass = false;
-            if (p < g.npos) { score = scores[p]; pass = score >= min_score; }
-            const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-            if (pass) scratch[running + __popc(ballot & ((1u << lane) - 1u))] = ((uint32_t)p << 12) | ((uint32_t)score & 0xfffu);
-            running += __popc(ballot);
+            for (int o = 0; o < span; o += 32) {
+                const int p = w0 + o + lane;
+                int score = 0;
+                bool pass = false;
+                if (p < g.npos) { score = scores[p]; pass = score >= min_score; }
+                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    const int at = running + __popc(ballot & ((1u << lane) - 1u));
+                    const uint32_t ent = ((uint32_t)p << 12) | ((uint32_t)score & 0xfffu);
+                    if (at < kSurvSmem) surv[at] = ent;
+                    scratch[at] = ent;
+                }
+                running += __popc(ballot);
+            }
         }
         __syncthreads();
 
@@ -321,7 +395,7 @@ sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, i
             // (a) room in the heap: every survivor is pushed (one thread; nothing to skip)
             const int n_fill = n_pass < max_cand ? n_pass : max_cand;
             if (lane == 0)
-                for (; n < n_fill; ++n) sift_up(heap, n + 1, scratch[n]);
+                for (; n < n_fill; ++n) sift_up(heap, n + 1, n < kSurvSmem ? surv[n] : scratch[n]);
             n = n_fill;
             // (b) heap full: 32 survivors per step against the root score, which only ever rises
             if (n_pass > max_cand) {
@@ -329,7 +403,7 @@ sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, i
                 int root = ent_score(heap[0]);
                 for (int base = max_cand; base < n_pass; base += 32) {
                     const int e = base + lane;
-                    const uint32_t v = e < n_pass ? scratch[e] : 0u;
+                    const uint32_t v = e < n_pass ? (e < kSurvSmem ? surv[e] : scratch[e]) : 0u;
                     const int sc = ent_score(v);
                     unsigned todo = __ballot_sync(0xffffffffu, e < n_pass && sc > root);
                     while (todo) {
@@ -432,8 +506,13 @@ cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slo
         if (e != cudaSuccess) return e;
     }
     const int sgrid = n_slots < scratch_slots ? n_slots : scratch_slots;
-    sync_select_kernel<<<sgrid, kSyncThreads, (size_t)max_cand * 4, st>>>(d_scores, n_slots, g, max_cand, min_score, d_cand, d_ncand, d_scratch,
-                                                                          d_work, d_work_total);
+    // heap words + (when they fit under the default 48 KB) one pass-mask byte per group of 8 positions
+    const size_t heap_bytes = ((size_t)max_cand * 4 + 15) & ~(size_t)15;
+    int mask_bytes = (g.npos & 7) == 0 ? g.npos >> 3 : 0;
+    const size_t surv_bytes = (size_t)kSurvSmem * sizeof(uint32_t);
+    if (heap_bytes + (size_t)mask_bytes + 16 + surv_bytes > 48 * 1024) mask_bytes = 0;
+    sync_select_kernel<<<sgrid, kSyncThreads, heap_bytes + (((size_t)mask_bytes + 15) & ~(size_t)15) + surv_bytes, st>>>(d_scores, n_slots, g, max_cand, min_score, d_cand, d_ncand, d_scratch,
+                                                                                    d_work, d_work_total, mask_bytes);
     ++*launches;
     return cudaGetLastError();
 }

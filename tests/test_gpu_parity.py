@@ -506,6 +506,50 @@ def test_monitor_dropin_and_decode(pkg, oracle, audio):
     mon.close()
 
 
+def test_monitor_deferred_mode(pkg, oracle, audio):
+    """ft8b200_monitor_set_deferred: monitor_process() only appends, ONE launch transforms the pending blocks when the waterfall is
+    needed (ft8_find_sync / ft8_decode / flush / reset / free).  Same bytes, max_mag, last_frame, candidates and messages as the
+    block-by-block mode, also when the two modes are mixed and across a reset."""
+    strict, lazy = pkg.Monitor(12000, 2, 2, 1), pkg.Monitor(12000, 2, 2, 1)
+    lazy.set_deferred(True)
+    blocks = [audio[o:o + 1920] for o in range(0, audio.size - 1920 + 1, 1920)]
+    for b in blocks[:40]:
+        strict.process(b); lazy.process(b)
+    assert lazy.me.wf.num_blocks == strict.me.wf.num_blocks == 40
+    assert lazy.flush() == 40 and lazy.flush() == 0
+    assert np.array_equal(lazy.mag(), strict.mag()) and np.float32(lazy.me.max_mag) == np.float32(strict.me.max_mag)
+    lazy.set_deferred(False)
+    for b in blocks[40:50]:
+        strict.process(b); lazy.process(b)          # block by block again
+    lazy.set_deferred(True)
+    for b in blocks[50:]:
+        strict.process(b); lazy.process(b)
+    lazy.process(blocks[0]); strict.process(blocks[0])   # 94th block: ignored in both modes
+    heap_l = lazy.find_sync(120, 10)                # flushes by itself
+    heap_s = strict.find_sync(120, 10)
+    assert np.array_equal(heap_l, heap_s) and np.array_equal(lazy.mag(), strict.mag()) and lazy.me.wf.num_blocks == 93
+    assert np.float32(lazy.me.max_mag) == np.float32(strict.me.max_mag)
+    lf_l = np.ctypeslib.as_array(__import__("ctypes").cast(lazy.me.last_frame, __import__("ctypes").POINTER(__import__("ctypes").c_float)), shape=(3840,))
+    lf_s = np.ctypeslib.as_array(__import__("ctypes").cast(strict.me.last_frame, __import__("ctypes").POINTER(__import__("ctypes").c_float)), shape=(3840,))
+    assert np.array_equal(lf_l, lf_s)
+    ref, _, _ = oracle.monitor_waterfall(audio)
+    assert np.array_equal(lazy.mag(), ref)
+    for cd in heap_s[:10]:
+        a, b = lazy.decode(cd, 20), strict.decode(cd, 20)
+        assert a[0] == b[0] and a[1].tobytes() == b[1].tobytes() and a[2].tobytes() == b[2].tobytes()
+    # reset with blocks pending: they still shape the history; then the next recording
+    lazy.reset(); strict.reset()
+    for b in blocks[:5]:
+        strict.process(b); lazy.process(b)
+    lazy.reset(); strict.reset()
+    for b in blocks[5:9]:
+        strict.process(b); lazy.process(b)
+    lazy.flush()
+    assert np.array_equal(lazy.mag(), strict.mag()) and lazy.me.wf.num_blocks == 4
+    lazy.process(blocks[9])                         # freed with a block pending
+    lazy.close(); strict.close()
+
+
 def test_grouped_overlap_gives_identical_results(ctx, raw_slot):
     """Large raw batches are split into slot groups whose back end overlaps the next group's decimator on a side
     stream; that must not change a single byte, and every slot must equal its stand-alone result."""

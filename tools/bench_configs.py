@@ -122,7 +122,7 @@ def roofline_extra(env, batch, n_slots, hbm_peak, peak_source, sm_mhz):
     out.append(hbm("monitor_frames_kernel", ms, bench.MON_BYTES_PER_SLOT, n_mon, "3840-point real FFT per frame with kiss_fftr's arithmetic: FP32-issue bound like the daemon waterfall"))
     mag, nb = ctx.monitor_waterfall(aud)
     ms = _ev_ms(torch, lambda: ctx.find_sync(mag, num_blocks=nb, num_bins=960), 10)
-    out.append(issue("sync_score_kernel<0,true,false> + sync_select_kernel (960 bins)", ms, n_mon, "sync960"))
+    out.append(issue("sync_score_ft8_kernel + sync_select_kernel at the 12 kHz geometry (960 bins, 137 232 positions)", ms, n_mon, "sync960"))
     del aud, mag
     ctx.close()
     return out
@@ -365,7 +365,8 @@ def config1_latency(env):
     measured inside the C host program (host/ft8d_host.c `latency`), next to the reference's own functions timed inside the C
     harness on the same inputs and host (the reference publishes this as "decode burst": 18 ms on an i7-5820K, README.md:153-157).
       subsystem: decoder()'s conditioning + ft8_subsystem(I, Q)          receive: 1099 x rtlsdr_callback(65536 B) + flip + decoder()
-      wav:       decode_ft8's main(): 93 x monitor_process + ft8_find_sync(120) + one ft8_decode per candidate"""
+      wav:       decode_ft8's main(): 93 x monitor_process + ft8_find_sync(120) + one ft8_decode per candidate
+      wav_deferred: the same calls with ft8b200_monitor_set_deferred (monitor_process appends, ft8_find_sync transforms all blocks at once)"""
     import bench
     torch, pkg = env.torch, env.pkg
     host_bin = os.path.join(ROOT, "host", "ft8d_host")
@@ -418,7 +419,7 @@ def config1_latency(env):
             o_ = orc.subsystem(*orc.condition(i_s, q_s, 48000)[:2])
             cpu["subsystem_ms"], cpu["subsystem_results"] = (time.perf_counter() - t0) * 1e3, int(o_["n"])
     out = {"workload": "BASELINE config #1: single 15 s slot, one message at -10 dB, through the literal drop-in calls (wall-clock per call, median)",
-           "gpu_ms": {k: gpu[k] for k in ("subsystem_ms", "receive_ms", "wav_ms")}, "cpu_ms": {k: v for k, v in cpu.items() if k.endswith("_ms")},
+           "gpu_ms": {k: gpu[k] for k in ("subsystem_ms", "receive_ms", "wav_ms", "wav_deferred_ms") if k in gpu}, "cpu_ms": {k: v for k, v in cpu.items() if k.endswith("_ms")},
            "cpu_kind": kind, "measured_by": "host/ft8d_host.c `latency` (C, clock_gettime around the calls) vs oracle/ref_harness.c ref_time_* on the same host",
            "parity": bool(gpu.get("subsystem_results") == cpu.get("subsystem_results") and (cpu.get("receive_results") is None or gpu.get("receive_results") == cpu.get("receive_results"))),
            "results": {"gpu": {k: gpu[k] for k in gpu if k.endswith("results") or k.endswith("decodes")}, "cpu": {k: v for k, v in cpu.items() if not k.endswith("_ms")}},

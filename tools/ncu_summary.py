@@ -10,9 +10,10 @@ KEYS = [
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct2"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
-    ("sm__inst_executed.sum", "warp_insts"),
+    ("smsp__inst_executed.sum", "warp_insts"),
+    ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue_active_elapsed_pct"),
     ("sm__inst_executed.avg.per_cycle_active", "ipc_active"),
-    ("sm__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
     ("sm__instruction_throughput.avg.pct_of_peak_sustained_active", "inst_tp_pct"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
     ("launch__registers_per_thread", "regs"),
@@ -59,8 +60,17 @@ def main():
         del argv[k:k + 2]
     args = [a for a in argv if not a.startswith("--")]
     for path in args:
-        d = read(path)
+        try:
+            d = read(path)
+        except IndexError:
+            print(f"== {path}: no kernel captured (skipped)")
+            continue
         name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
+        head, lt, targs = name.partition("<unnamed>::")      # ft8b200::<unnamed>::kernel<args> -> kernel<args>
+        name = targs if lt else name.split("::")[-1]
+        for tag in ("_12k_", "_ft4_"):   # the same kernel captured at another geometry keeps its own entry
+            if tag in path:
+                name += tag.rstrip("_")
         rec = {}
         for key, short in KEYS:
             if key in d:
