@@ -14,6 +14,7 @@ timeout 600 $TR --nproc-per-node 8 --master-port 29700 bench.py --gpus 8 --steps
 timeout 600 python bench.py --gpus 8 --cluster --steps 10 --warmup 3 > gpurun_out/bench_r2_cluster8.json 2> gpurun_out/bench_r2_cluster8.err; echo cluster8 rc=$?
 python - <<'PY'
 import json
+for f in ("bench_r2_8gpu", "bench_r2_cluster8"):
     try:
         d = json.load(open("gpurun_out/%s.json" % f))
         print(f, d["value"], d.get("verify"), (d.get("e2e") or {}).get("value"), (d.get("e2e_slots") or {}).get("value"))
