@@ -320,6 +320,9 @@ int ft8b200_set_partition_streams(ft8b200_ctx_t *ctx, void *front_stream, void *
  * sides balance: ft8b200_pipe_autotune measures it. */
 int ft8b200_set_comb_front(ft8b200_ctx_t *ctx, int on);
 void *ft8b200_front_event(ft8b200_ctx_t *ctx);
+/* One-shot: the cic_block_sums kernel of the NEXT ft8b200_process_raw* call on this context starts only after `cuda_event` (a
+ * cudaEvent_t) has completed; the call's buffer initialisation ahead of it does not wait.  What ft8b200_pipe_t chains its lanes with. */
+int ft8b200_set_front_wait(ft8b200_ctx_t *ctx, void *cuda_event);
 /* device pointers to the last batch's outputs: results (n_slots x max_messages), counts (n_slots) */
 int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults);
 int ft8b200_fetch_results(ft8b200_ctx_t *ctx, int n_slots, struct decoder_results *h_results, int32_t *h_nresults, void *stream);

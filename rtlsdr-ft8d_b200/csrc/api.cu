@@ -73,6 +73,7 @@ struct ft8b200_ctx {
     int k1_variant = 0;                    // 0 = streaming cic_block_sums kernel, >= 1 = persistent bulk-copy kernel (shape index)
     bool side_back = false;                // back end on the high-priority side stream even with a single group (pipe lanes)
     bool comb_front = false;               // with an SM partition: comb+FIR stays on the front partition (ft8b200_set_comb_front)
+    cudaEvent_t front_wait = nullptr;      // one-shot: the next process_raw's block sums wait for it (ft8b200_set_front_wait), its memsets do not
     cudaEvent_t ev_front = nullptr;        // recorded on the launching stream right after the last process_raw's cic_block_sums
     cudaEvent_t ev_k1 = nullptr;
     cudaEvent_t ev[6][kMaxGroups][2] = {};
@@ -486,6 +487,10 @@ static int process_raw_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t byte
     clear_marks(ctx);
     CU(cudaMemsetAsync(ctx->peak.p, 0, sizeof(float) * n_rows, st));
     CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_slots, st));  // fresh filter state
+    if (ctx->front_wait) {  // the executor's chain: the previous batch's block sums must have finished -- the two memsets above need not wait for that
+        CU(cudaStreamWaitEvent(st, ctx->front_wait, 0));
+        ctx->front_wait = nullptr;
+    }
     for (int g = 0, s0 = 0; s0 < n_slots; ++g, s0 += per) {
         const int n = (n_slots - s0) < per ? (n_slots - s0) : per;
         const int r0 = s0 * segs, nr = n * segs;
@@ -569,6 +574,12 @@ int ft8b200_set_side_backend(ft8b200_ctx_t *ctx, int on) {
     if (!ctx) return fail(FT8B200_EINVAL, "null context");
     ctx->side_back = on != 0;
     if (!on) ctx->ev_front = nullptr;
+    return 0;
+}
+
+int ft8b200_set_front_wait(ft8b200_ctx_t *ctx, void *cuda_event) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    ctx->front_wait = reinterpret_cast<cudaEvent_t>(cuda_event);
     return 0;
 }
 

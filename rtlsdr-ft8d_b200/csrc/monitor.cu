@@ -69,14 +69,123 @@ __device__ __forceinline__ int quantise(float x, const float2 *__restrict__ thr2
     return k + (x >= lh.y ? 1 : 0) - (x < lh.x ? 1 : 0);
 }
 
+// one butterfly of radix P on z[i0 + q m], q < P, with the stage's compact twiddles tq[(q - 1) m + k]
+template <int P>
+__device__ __forceinline__ void butterfly(float2 *z, const float2 *tq, int i0, int m, int k, float2 c1, float2 c2) {
+    if (P == 4) {  // kf_bfly4, kiss_fft.c:38-84
+        cpx f0 = ld(z, i0), f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m), f3 = ld(z, i0 + 3 * m);
+        const cpx a = cmul(f1, tq[k]);
+        const cpx bb = cmul(f2, tq[m + k]);
+        const cpx c = cmul(f3, tq[2 * m + k]);
+        const cpx d5 = csub(f0, bb);
+        f0 = cadd(f0, bb);
+        const cpx s3 = cadd(a, c), s4 = csub(a, c);
+        f2 = csub(f0, s3);
+        f0 = cadd(f0, s3);
+        st(z, i0, f0);
+        st(z, i0 + 2 * m, f2);
+        st(z, i0 + m, cpx{__fadd_rn(d5.r, s4.i), __fsub_rn(d5.i, s4.r)});
+        st(z, i0 + 3 * m, cpx{__fsub_rn(d5.r, s4.i), __fadd_rn(d5.i, s4.r)});
+    } else if (P == 2) {  // kf_bfly2, kiss_fft.c:15-36
+        cpx f0 = ld(z, i0), f1 = ld(z, i0 + m);
+        const cpx tt = cmul(f1, tq[k]);
+        f1 = csub(f0, tt);
+        f0 = cadd(f0, tt);
+        st(z, i0, f0);
+        st(z, i0 + m, f1);
+    } else if (P == 3) {  // kf_bfly3, kiss_fft.c:86-128
+        const float2 e3 = c1;
+        cpx f0 = ld(z, i0), f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m);
+        const cpx s1 = cmul(f1, tq[k]);
+        const cpx s2 = cmul(f2, tq[m + k]);
+        const cpx s3 = cadd(s1, s2);
+        cpx s0 = csub(s1, s2);
+        f1.r = __fsub_rn(f0.r, half_of(s3.r));
+        f1.i = __fsub_rn(f0.i, half_of(s3.i));
+        s0.r = __fmul_rn(s0.r, e3.y);
+        s0.i = __fmul_rn(s0.i, e3.y);
+        f0 = cadd(f0, s3);
+        f2.r = __fadd_rn(f1.r, s0.i);
+        f2.i = __fsub_rn(f1.i, s0.r);
+        f1.r = __fsub_rn(f1.r, s0.i);
+        f1.i = __fadd_rn(f1.i, s0.r);
+        st(z, i0, f0);
+        st(z, i0 + m, f1);
+        st(z, i0 + 2 * m, f2);
+    } else {  // P == 5: kf_bfly5, kiss_fft.c:130-190
+        const float2 ya = c1, yb = c2;
+        const cpx s0 = ld(z, i0);
+        cpx f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m), f3 = ld(z, i0 + 3 * m), f4 = ld(z, i0 + 4 * m);
+        const cpx s1 = cmul(f1, tq[k]);
+        const cpx s2 = cmul(f2, tq[m + k]);
+        const cpx s3 = cmul(f3, tq[2 * m + k]);
+        const cpx s4 = cmul(f4, tq[3 * m + k]);
+        const cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
+        st(z, i0, cpx{__fadd_rn(s0.r, __fadd_rn(s7.r, s8.r)), __fadd_rn(s0.i, __fadd_rn(s7.i, s8.i))});
+        cpx s5, s6, s11, s12;
+        s5.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, ya.x)), __fmul_rn(s8.r, yb.x));
+        s5.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, ya.x)), __fmul_rn(s8.i, yb.x));
+        s6.r = __fadd_rn(__fmul_rn(s10.i, ya.y), __fmul_rn(s9.i, yb.y));
+        s6.i = __fsub_rn(-__fmul_rn(s10.r, ya.y), __fmul_rn(s9.r, yb.y));
+        f1 = csub(s5, s6);
+        f4 = cadd(s5, s6);
+        s11.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, yb.x)), __fmul_rn(s8.r, ya.x));
+        s11.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, yb.x)), __fmul_rn(s8.i, ya.x));
+        s12.r = __fadd_rn(-__fmul_rn(s10.i, yb.y), __fmul_rn(s9.i, ya.y));
+        s12.i = __fsub_rn(__fmul_rn(s10.r, yb.y), __fmul_rn(s9.r, ya.y));
+        f2 = cadd(s11, s12);
+        f3 = csub(s11, s12);
+        st(z, i0 + m, f1);
+        st(z, i0 + 2 * m, f2);
+        st(z, i0 + 3 * m, f3);
+        st(z, i0 + 4 * m, f4);
+    }
+}
+
+// Compile-time stage lists of the two geometries in use (kf_factor's decomposition, execution order = innermost recursion first):
+// FT8 at 12 kHz: 3840-point frames -> 1920 = 5 * 3 * 2 * 4 * 4 * 4;  FT4 at 12 kHz: 1152-point frames -> 576 = 3 * 3 * 4 * 4 * 4.
+// The launcher uses them only when the host-built plan (build_plan) is identical; any other size runs the generic stage loop.
+template <int N> struct StaticPlan { static constexpr int ns = 0; };
+template <> struct StaticPlan<1920> {
+    static constexpr int ns = 6;
+    __host__ __device__ static constexpr int radix(int s) { constexpr int r[6] = {5, 3, 2, 4, 4, 4}; return r[s]; }
+    __host__ __device__ static constexpr int m(int s) { constexpr int v[6] = {1, 5, 15, 30, 120, 480}; return v[s]; }
+};
+template <> struct StaticPlan<576> {
+    static constexpr int ns = 5;
+    __host__ __device__ static constexpr int radix(int s) { constexpr int r[5] = {3, 3, 4, 4, 4}; return r[s]; }
+    __host__ __device__ static constexpr int m(int s) { constexpr int v[5] = {1, 3, 9, 36, 144}; return v[s]; }
+};
+template <int N> __host__ __device__ constexpr int static_tw_off(int s) { return s == 0 ? 0 : static_tw_off<N>(s - 1) + (StaticPlan<N>::radix(s - 1) - 1) * StaticPlan<N>::m(s - 1); }
+
+template <int N, int S>
+__device__ __forceinline__ void static_stages(float2 *z, const float2 *tws, const FftPlan &plan, int t) {
+    if constexpr (S < StaticPlan<N>::ns) {
+        constexpr int p = StaticPlan<N>::radix(S), m = StaticPlan<N>::m(S), nbf = N / p;
+        const float2 *tq = tws + static_tw_off<N>(S);
+#pragma unroll
+        for (int b0 = 0; b0 < nbf; b0 += kMonThreads) {
+            const int b = b0 + t;
+            if (b0 + kMonThreads <= nbf || b < nbf) {
+                const int g = b / m, k = b - g * m;   // m is a compile-time constant: multiply + shift
+                butterfly<p>(z, tq, g * p * m + k, m, k, plan.c1[S], plan.c2[S]);
+            }
+        }
+        __syncthreads();
+        static_stages<N, S + 1>(z, tws, plan, t);
+    }
+}
+
 // dynamic smem: z float2[n] | stage twiddles float2[tw_total] | super twiddles float2[n/2 + 1] | thr2 float2[256] | out u8[2 n]
+// kN = 0: generic stage loop from the run-time plan; kN = 1920 / 576: the stage loop unrolled at compile time (StaticPlan)
+template <int kN>
 __global__ void __launch_bounds__(kMonThreads)
 monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n_samples, long first_start, int hop, int nfft, FftPlan plan,
                       const uint16_t *__restrict__ inv_perm, const float2 *__restrict__ tw_stage, const float2 *__restrict__ super_tw,
                       const float *__restrict__ wnorm, const float *__restrict__ thr_g, int num_bins, int freq_osr, int n_frames, int total_items,
                       uint8_t *__restrict__ mag, size_t mag_slot_stride, unsigned int *__restrict__ xmax_bits) {
     extern __shared__ __align__(16) float2 smem2[];
-    const int n = plan.n, t = threadIdx.x;
+    const int n = kN > 0 ? kN : plan.n, t = threadIdx.x;
     float2 *z = smem2, *tws = z + n, *sup = tws + plan.tw_total, *thr2 = sup + (n / 2 + 1);
     uint8_t *outb = reinterpret_cast<uint8_t *>(thr2 + 256);
     const int it_begin = (int)((long long)blockIdx.x * total_items / gridDim.x), it_end = (int)((long long)(blockIdx.x + 1) * total_items / gridDim.x);
@@ -100,84 +209,24 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
             z[inv_perm[src]] = make_float2(__fmul_rn(w.x, a), __fmul_rn(w.y, b));   // (fft_norm * window[pos]) * last_frame[pos], decode_ft8.c:191
         }
         __syncthreads();
-        for (int s = 0; s < plan.nstages; ++s) {
-            const int p = plan.radix[s], m = plan.m[s];
-            const unsigned int magic = plan.magic[s];
-            const float2 *tq = tws + plan.tw_off[s];
-            const int nbf = n / p;  // butterflies in this stage
-            for (int b = t; b < nbf; b += kMonThreads) {
-                const int g = magic ? (int)__umulhi((unsigned int)b, magic) : b, k = b - g * m;
-                const int i0 = g * p * m + k;
-                if (p == 4) {  // kf_bfly4, kiss_fft.c:38-84
-                    cpx f0 = ld(z, i0), f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m), f3 = ld(z, i0 + 3 * m);
-                    const cpx a = cmul(f1, tq[k]);
-                    const cpx bb = cmul(f2, tq[m + k]);
-                    const cpx c = cmul(f3, tq[2 * m + k]);
-                    const cpx d5 = csub(f0, bb);
-                    f0 = cadd(f0, bb);
-                    const cpx s3 = cadd(a, c), s4 = csub(a, c);
-                    f2 = csub(f0, s3);
-                    f0 = cadd(f0, s3);
-                    st(z, i0, f0);
-                    st(z, i0 + 2 * m, f2);
-                    st(z, i0 + m, cpx{__fadd_rn(d5.r, s4.i), __fsub_rn(d5.i, s4.r)});
-                    st(z, i0 + 3 * m, cpx{__fsub_rn(d5.r, s4.i), __fadd_rn(d5.i, s4.r)});
-                } else if (p == 2) {  // kf_bfly2, kiss_fft.c:15-36
-                    cpx f0 = ld(z, i0), f1 = ld(z, i0 + m);
-                    const cpx tt = cmul(f1, tq[k]);
-                    f1 = csub(f0, tt);
-                    f0 = cadd(f0, tt);
-                    st(z, i0, f0);
-                    st(z, i0 + m, f1);
-                } else if (p == 3) {  // kf_bfly3, kiss_fft.c:86-128
-                    const float2 e3 = plan.c1[s];
-                    cpx f0 = ld(z, i0), f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m);
-                    const cpx s1 = cmul(f1, tq[k]);
-                    const cpx s2 = cmul(f2, tq[m + k]);
-                    const cpx s3 = cadd(s1, s2);
-                    cpx s0 = csub(s1, s2);
-                    f1.r = __fsub_rn(f0.r, half_of(s3.r));
-                    f1.i = __fsub_rn(f0.i, half_of(s3.i));
-                    s0.r = __fmul_rn(s0.r, e3.y);
-                    s0.i = __fmul_rn(s0.i, e3.y);
-                    f0 = cadd(f0, s3);
-                    f2.r = __fadd_rn(f1.r, s0.i);
-                    f2.i = __fsub_rn(f1.i, s0.r);
-                    f1.r = __fsub_rn(f1.r, s0.i);
-                    f1.i = __fadd_rn(f1.i, s0.r);
-                    st(z, i0, f0);
-                    st(z, i0 + m, f1);
-                    st(z, i0 + 2 * m, f2);
-                } else {  // p == 5: kf_bfly5, kiss_fft.c:130-190
-                    const float2 ya = plan.c1[s], yb = plan.c2[s];
-                    const cpx s0 = ld(z, i0);
-                    cpx f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m), f3 = ld(z, i0 + 3 * m), f4 = ld(z, i0 + 4 * m);
-                    const cpx s1 = cmul(f1, tq[k]);
-                    const cpx s2 = cmul(f2, tq[m + k]);
-                    const cpx s3 = cmul(f3, tq[2 * m + k]);
-                    const cpx s4 = cmul(f4, tq[3 * m + k]);
-                    const cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
-                    st(z, i0, cpx{__fadd_rn(s0.r, __fadd_rn(s7.r, s8.r)), __fadd_rn(s0.i, __fadd_rn(s7.i, s8.i))});
-                    cpx s5, s6, s11, s12;
-                    s5.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, ya.x)), __fmul_rn(s8.r, yb.x));
-                    s5.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, ya.x)), __fmul_rn(s8.i, yb.x));
-                    s6.r = __fadd_rn(__fmul_rn(s10.i, ya.y), __fmul_rn(s9.i, yb.y));
-                    s6.i = __fsub_rn(-__fmul_rn(s10.r, ya.y), __fmul_rn(s9.r, yb.y));
-                    f1 = csub(s5, s6);
-                    f4 = cadd(s5, s6);
-                    s11.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, yb.x)), __fmul_rn(s8.r, ya.x));
-                    s11.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, yb.x)), __fmul_rn(s8.i, ya.x));
-                    s12.r = __fadd_rn(-__fmul_rn(s10.i, yb.y), __fmul_rn(s9.i, ya.y));
-                    s12.i = __fsub_rn(__fmul_rn(s10.r, yb.y), __fmul_rn(s9.r, ya.y));
-                    f2 = cadd(s11, s12);
-                    f3 = csub(s11, s12);
-                    st(z, i0 + m, f1);
-                    st(z, i0 + 2 * m, f2);
-                    st(z, i0 + 3 * m, f3);
-                    st(z, i0 + 4 * m, f4);
+        if constexpr (kN > 0) {
+            static_stages<kN, 0>(z, tws, plan, t);
+        } else {
+            for (int s = 0; s < plan.nstages; ++s) {
+                const int p = plan.radix[s], m = plan.m[s];
+                const unsigned int magic = plan.magic[s];
+                const float2 *tq = tws + plan.tw_off[s];
+                const int nbf = n / p;  // butterflies in this stage
+                for (int b = t; b < nbf; b += kMonThreads) {
+                    const int g = magic ? (int)__umulhi((unsigned int)b, magic) : b, k = b - g * m;
+                    const int i0 = g * p * m + k;
+                    if (p == 4) butterfly<4>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    else if (p == 2) butterfly<2>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    else if (p == 3) butterfly<3>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    else butterfly<5>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
         // real-FFT split (kiss_fftr.c:80-113) fused with |X|^2 -> dB -> uint8 (decode_ft8.c:196-213)
         float xmax = 0.0f;
@@ -360,24 +409,35 @@ cudaError_t launch_frames(const MonTables *t, const float *d_audio, size_t slot_
                           int n_slots, int num_bins, int freq_osr, uint8_t *d_mag, size_t mag_slot_stride, unsigned int *d_xmax, cudaStream_t st) {
     const int n = t->plan.n;
     cudaError_t e;
+    // compile-time stage list when the host-built plan is exactly the one StaticPlan spells out
+    auto matches = [&](auto tag) {
+        using SP = decltype(tag);
+        if (SP::ns == 0 || t->plan.nstages != SP::ns) return false;
+        for (int s2 = 0; s2 < SP::ns; ++s2) if (t->plan.radix[s2] != SP::radix(s2) || t->plan.m[s2] != SP::m(s2)) return false;
+        return true;
+    };
+    auto kern = monitor_frames_kernel<0>;
+    if (n == 1920 && matches(StaticPlan<1920>{})) kern = monitor_frames_kernel<1920>;
+    else if (n == 576 && matches(StaticPlan<576>{})) kern = monitor_frames_kernel<576>;
     if (t->max_grid == 0) {  // once per (device, nfft): monitor_process() launches this 93 times per recording
         // z | stage twiddles | super twiddles | threshold pairs | one frame's bytes (see monitor_frames_kernel)
         const size_t need = sizeof(float2) * ((size_t)n + (size_t)t->plan.tw_total + (size_t)(n / 2 + 1) + 256) + (((size_t)2 * n + 15) & ~(size_t)15);
         int sms = 0, per_sm = 0;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, monitor_frames_kernel, kMonThreads, need)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMonThreads, need)) != cudaSuccess) return e;
         MonTables *mt = const_cast<MonTables *>(t);
         mt->smem = need;
         mt->max_grid = (long)sms * (per_sm > 0 ? per_sm : 1);
     }
     const size_t smem = t->smem;
-    // the opt-in is per FUNCTION, not per table set: another geometry (FT4's 1152-point frames) may have lowered it since
-    if ((e = cudaFuncSetAttribute(monitor_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    // the opt-in is per FUNCTION, not per table set: another geometry may have lowered it since
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const long total = (long)n_frames * n_slots;
     long grid = t->max_grid;   // persistent: every CTA walks a contiguous range of (recording, frame) items
     if (grid > total) grid = total;
     if (total >= (1l << 31)) return cudaErrorInvalidValue;
-    monitor_frames_kernel<<<(unsigned)grid, kMonThreads, smem, st>>>(d_audio, slot_stride, n_samples, first_start, hop, t->nfft, t->plan, t->d_perm, t->d_tw,
+    kern<<<(unsigned)grid, kMonThreads, smem, st>>>(d_audio, slot_stride, n_samples, first_start, hop, t->nfft, t->plan, t->d_perm, t->d_tw,
                                                                       t->d_super, t->d_wnorm, thresholds(t->device), num_bins, freq_osr, n_frames, (int)total,
                                                                       d_mag, mag_slot_stride, d_xmax);
     return cudaGetLastError();

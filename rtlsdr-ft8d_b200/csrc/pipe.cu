@@ -157,8 +157,9 @@ int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t b
         p->dependency = nullptr;
     }
     if (p->mode == FT8B200_PIPE_OVERLAP) {
-        // front ends are serialised across lanes: this batch's decimator starts when the previous batch's has finished
-        if (p->prev_front) PCU(cudaStreamWaitEvent(l.st, p->prev_front, 0));
+        // front ends are serialised across lanes: this batch's decimator starts when the previous batch's has finished (the wait is
+        // placed by the context right in front of its block-sum kernel, behind the memsets that prepare the batch's buffers)
+        if (p->prev_front) ft8b200_set_front_wait(l.ctx, p->prev_front);
     } else if (p->prev_done) {
         // kernels of consecutive batches never share the GPU; only copies and host work overlap them
         PCU(cudaStreamWaitEvent(l.st, p->prev_done, 0));
