@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #include <cuda.h>  // types and prototypes only: the driver entry points are resolved through cudaGetDriverEntryPoint, libcuda is not linked
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -159,6 +160,8 @@ int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t b
     if (p->mode == FT8B200_PIPE_OVERLAP) {
         // front ends are serialised across lanes: this batch's decimator starts when the previous batch's has finished (the wait is
         // placed by the context right in front of its block-sum kernel, behind the memsets that prepare the batch's buffers)
+        // (measured in round 2: without the chain consecutive block-sum kernels fill each other's tails and the step gains 0.8 %, but
+        // their per-launch times then overlap and no longer say what the kernel achieves -- kept chained)
         if (p->prev_front) ft8b200_set_front_wait(l.ctx, p->prev_front);
     } else if (p->prev_done) {
         // kernels of consecutive batches never share the GPU; only copies and host work overlap them
