@@ -63,9 +63,7 @@ struct ft8b200_ctx {
     uint64_t launches_total = 0;
     int sm_count = 0;
     // workspaces (grown on demand)
-    DevBuf raw, sums, si, sq, peak, count, mag, cand, ncand, ok, stage, status, msg, results, nresults, table, scratch, scores, work, work_total;
-    int scratch_slots = 0;
-    int scratch_npos = 0;
+    DevBuf raw, sums, si, sq, peak, count, mag, cand, ncand, ok, stage, status, msg, results, nresults, table, lists, scores, work, work_total;
     // optional per-stage timing of the last process_* call (CUDA events on the launching stream)
     bool profiling = false;
     int overlap = 0;                       // number of slot groups ft8b200_process_raw pipelines (0/1 = off)
@@ -117,22 +115,11 @@ int ensure_slot_buffers(ft8b200_ctx_t *ctx, int n_slots) {
 }
 
 int ensure_scratch(ft8b200_ctx_t *ctx, int npos, int n_slots) {
-    // one compaction list per resident CTA of the sync kernel (it loops over slots)
-    int want = ctx->sm_count * 6;  // 256-thread CTAs, 6 resident per SM
-    if (want > n_slots) want = n_slots;
-    if (want < 1) want = 1;
     int rc0 = ctx->scores.ensure((size_t)n_slots * npos * sizeof(int16_t));
     if (rc0) return rc0;
+    if ((rc0 = ctx->lists.ensure(find_sync_list_bytes(n_slots)))) return rc0;   // survivor lists, score kernel -> selection
     if ((rc0 = ctx->work.ensure((size_t)n_slots * ctx->cfg.max_candidates * sizeof(uint32_t)))) return rc0;
     if ((rc0 = ctx->work_total.ensure(4 * sizeof(unsigned int)))) return rc0;
-    if (npos > ctx->scratch_npos || want > ctx->scratch_slots) {
-        const int slots = want > ctx->scratch_slots ? want : ctx->scratch_slots;
-        const int np = npos > ctx->scratch_npos ? npos : ctx->scratch_npos;
-        int rc = ctx->scratch.ensure((size_t)slots * np * sizeof(uint32_t));
-        if (rc) return rc;
-        ctx->scratch_slots = slots;
-        ctx->scratch_npos = np;
-    }
     return 0;
 }
 
@@ -232,7 +219,7 @@ void ft8b200_destroy(ft8b200_ctx_t *ctx) {
     cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.wf_blob);
     cudaFree(ctx->tb.mon_window); cudaFree(ctx->tb.mon_twiddle); cudaFree(ctx->tb.mon_super);
     DevBuf *bufs[] = {&ctx->raw, &ctx->sums, &ctx->si, &ctx->sq, &ctx->peak, &ctx->count, &ctx->mag, &ctx->cand, &ctx->ncand, &ctx->ok,
-                      &ctx->stage, &ctx->status, &ctx->msg, &ctx->results, &ctx->nresults, &ctx->table, &ctx->scratch, &ctx->scores, &ctx->work, &ctx->work_total};
+                      &ctx->stage, &ctx->status, &ctx->msg, &ctx->results, &ctx->nresults, &ctx->table, &ctx->lists, &ctx->scores, &ctx->work, &ctx->work_total};
     for (DevBuf *b : bufs) b->release();
     delete ctx;
 }
@@ -329,7 +316,7 @@ int find_sync_proto(ft8b200_ctx_t *ctx, int protocol, const uint8_t *d_mag, size
     std::lock_guard<std::mutex> lk(ctx->mu);
     if ((rc = ensure_scratch(ctx, (int)npos, n_slots))) return rc;
     CU(launch_find_sync(d_mag, slot_stride_bytes, n_slots, num_blocks, num_bins, time_osr, freq_osr, protocol, ctx->cfg.max_candidates, ctx->cfg.min_score,
-                        d_cand, d_ncand, ctx->scores.as<int16_t>(), ctx->scratch.as<uint32_t>(), ctx->scratch_slots, nullptr, nullptr, ctx->sm_count,
+                        d_cand, d_ncand, ctx->scores.as<int16_t>(), ctx->lists.as<uint32_t>(), nullptr, nullptr, ctx->sm_count,
                         pick(ctx, stream), &ctx->launches));
     tally(ctx);
     return 0;
@@ -415,7 +402,7 @@ static int run_back_end(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, 
     mark(ctx, 2, group, true, st);
     mark(ctx, 3, group, false, st);
     CU(launch_find_sync(mag, kWfBytes, n, 92, 256, 2, 2, PROTO_FT8, ctx->cfg.max_candidates, ctx->cfg.min_score, cand, ncand, ctx->scores.as<int16_t>(),
-                        ctx->scratch.as<uint32_t>(), ctx->scratch_slots, ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), sms,
+                        ctx->lists.as<uint32_t>(), ctx->work.as<uint32_t>(), ctx->work_total.as<unsigned int>(), sms,
                         st, &ctx->launches));
     mark(ctx, 3, group, true, st);
     mark(ctx, 4, group, false, st);

@@ -51,9 +51,11 @@ void build_waterfall_tables(const float *window, const float2 *tw, const float *
 int waterfall_blob_floats();
 cudaError_t upload_waterfall_constants(const float *blob_host);
 cudaError_t run_quantiser_check(const float *d_thr257, unsigned long long *h_counts3, int sm_count, cudaStream_t st);
+constexpr int kListCap = 1024;               // survivor words per slot handed from the score kernels to the selection (4 KB)
+size_t find_sync_list_bytes(int n_slots);    // size of `d_lists`: per-slot counters + survivor lists
 cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
-                             int protocol, int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_scratch,
-                             int scratch_slots, uint32_t *d_work, unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches);
+                             int protocol, int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_lists,
+                             uint32_t *d_work, unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches);
 cudaError_t launch_decode(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
                           int protocol, int max_cand, int max_iters, const candidate_t *d_cand, const int *d_ncand, uint8_t *d_ok, uint8_t *d_stage,
                           decode_status_t *d_status, message_t *d_msg, uint8_t *d_plain, float *d_llr, const uint32_t *d_work,

@@ -31,7 +31,6 @@ namespace {
 
 constexpr int kChunksPerSuper = 751;          // 16-byte chunks per super-block
 constexpr int kSuperBytes = 12016;            // 8 * 751 * 2
-constexpr int kIters = 24;                    // ceil(751 / 32)
 constexpr uint32_t kOnes = 0x01010101u;
 // sample index (0..7 inside the chunk) of each byte of the regrouped words
 constexpr uint32_t kW_IP = 0x07040300u;  // I rail, plain   : samples 0,3,4,7  (bytes I0,Q3,I4,Q7)

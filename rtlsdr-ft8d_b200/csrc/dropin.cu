@@ -169,18 +169,17 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
     // a private context view with the caller's K / min_score
     int launches = 0;
     const int npos = power->time_osr * power->freq_osr * 36 * (power->num_bins - 7);
-    static uint32_t *scratch = nullptr;
+    static uint32_t *lists = nullptr;   // survivor list of the one slot (score kernel -> selection)
     static int16_t *scores = nullptr;
     static int scratch_npos = 0;
+    if (!lists && cudaMalloc(&lists, find_sync_list_bytes(1)) != cudaSuccess) die("ft8_find_sync (scratch)");
     if (npos > scratch_npos) {
-        cudaFree(scratch);
         cudaFree(scores);
-        if (cudaMalloc(&scratch, (size_t)npos * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&scores, (size_t)npos * sizeof(int16_t)) != cudaSuccess)
-            die("ft8_find_sync (scratch)");
+        if (cudaMalloc(&scores, (size_t)npos * sizeof(int16_t)) != cudaSuccess) die("ft8_find_sync (scratch)");
         scratch_npos = npos;
     }
     if (launch_find_sync(g_s.mag, bytes, 1, power->num_blocks, power->num_bins, power->time_osr, power->freq_osr, (int)power->protocol, num_candidates, min_score,
-                         g_s.cand, g_s.ncand, scores, scratch, 1, nullptr, nullptr, ctx_sm_count(ctx), st, &launches) != cudaSuccess) die("ft8_find_sync (kernel)");
+                         g_s.cand, g_s.ncand, scores, lists, nullptr, nullptr, ctx_sm_count(ctx), st, &launches) != cudaSuccess) die("ft8_find_sync (kernel)");
     // decode everything now; ft8_decode() will look the answers up
     ft8b200_config_t cfg;
     ft8b200_default_config(&cfg);

@@ -2,22 +2,21 @@
 // Replaces ft8_find_sync() / ft8_sync_score() / heapify_*(), /root/reference/ft8_lib/ft8/decode.c:35-108,
 // 173-234, 388-435.
 //
-// Two kernels.  sync_score_kernel: a few CTAs per slot, each stages the slot's waterfall (94 KB for the daemon
-// geometry) in shared memory and scores its share of the tosr*fosr*36*(bins-7) positions; scores are stored in the
-// reference's loop order (time_sub, freq_sub, time_offset, freq_offset).  sync_select_kernel: one CTA per slot
-// compacts the positions with score >= min_score IN THAT ORDER (ballot + prefix) and one thread replays the
-// reference's min-heap insertions and the final heap sort over the survivors only.  The replay is what makes the
-// retained set at the cut score and the order among equal scores identical to the reference (they depend on heap
-// history).  The surviving candidates are also appended to a flat work list for the decode kernel.
+// The score kernels (a few CTAs per slot) stage their part of the slot's waterfall in shared memory, score their share of the
+// tosr*fosr*36*(bins-7) positions, store the scores in the reference's loop order (time_sub, freq_sub, time_offset,
+// freq_offset) and append every position with score >= min_score to the slot's survivor list.  sync_select_kernel (one small
+// CTA per slot) sorts the survivors back into loop order and one thread replays the reference's min-heap insertions and the
+// final heap sort over them.  The replay is what makes the retained set at the cut score and the order among equal scores
+// identical to the reference (they depend on heap history).  The surviving candidates are also appended to a flat work list
+// for the decode kernel.
 #include "common.cuh"
 
 namespace ft8b200 {
 namespace {
 
-constexpr int kSyncThreads = 256;  // small CTAs: the heap replay is one thread's latency, so many slots should be resident per SM
-constexpr int kSurvSmem = 1024;    // survivors of a slot mirrored in shared memory for the serial replay (4 KB)
+constexpr int kSyncThreads = 128;  // small CTAs: the heap replay is one thread's latency, so many slots should be resident per SM
 
-struct Geo { int nb, nbins, tosr, fosr, stride, nfo, npos; };
+struct Geo { int nb, nbins, tosr, fosr, stride, nfo, npos; uint32_t nfo_magic, fosr_magic; };  // x / d == umulhi(x, magic) for x < 2^20, d < 2^12
 
 // A heap entry is the survivor word itself: (position << 12) | (score & 0xfff) -- position = index in the reference's loop
 // order (< 2^20), score sign-extended from 12 bits.  Comparisons look at the score only, exactly like the reference's
@@ -60,6 +59,246 @@ __device__ __forceinline__ void sift_up(uint32_t *h, int n, uint32_t x) {
     h[cur] = x;
 }
 
+// The exact top-K selection of one slot (ref: ft8_find_sync, decode.c:173-234).
+//
+// The reference visits the positions in loop order and keeps a min-heap of the best K: push while there is room; once the heap
+// is full a position enters only if its score is STRICTLY above the root's, evicting the root; a final heap sort orders the
+// result.  Which positions are retained at the cut score, and the order among equal scores, depend on that history, so the
+// pushes/evictions are replayed by one thread exactly as the reference performs them -- but ONLY those: a position that fails
+// `score >= min_score` (or, with a full heap, `score > root`) is a no-op in the reference and is skipped wholesale here.
+//
+// Survivors come from the score kernels themselves: every position with score >= min_score is appended (warp-aggregated
+// atomicAdd) to the slot's list as (position << 12) | score.  The list is unordered, but positions are distinct, so sorting the
+// 32-bit words ascending restores the reference's visiting order (bitonic sort in shared memory).  A slot with more than
+// kListCap survivors (min_score <= 0 on noise: every other position) takes the scan path instead: warp 0 walks the score array
+// in position order, 256 positions per step, and tests them against `min_score` (heap not full) or the root (full) -- still no
+// serial step for a position that does nothing.  Neither path needs a scratch list in global memory.
+//
+// Tried and measured in round 2, not kept: running the selection as the TAIL of the score kernel (the last CTA of a slot to
+// finish, found with one atomic counter per slot, selects for that slot).  It saves a launch, but a tail holds a score CTA's
+// 73 KB of shared memory while one thread replays the heap: equal at 128 slots (57.5 vs 57.3 us for the stage), 12 % slower at
+// 4096 (1.261 vs 1.123 ms), where the separate kernel keeps 16 small CTAs per SM in flight and their serial parts overlap.
+struct SelArgs {
+    uint32_t *lists;          // [n_slots][kListCap] survivor words
+    int *count;               // [n_slots] survivors appended (may exceed kListCap: overflow -> scan path)
+    int max_cand, min_score;
+    candidate_t *cand_out;    // [n_slots][max_cand]
+    int *ncand_out;           // [n_slots]
+    uint32_t *work;           // flat decode work list (may be null)
+    unsigned int *work_total; // its counter
+};
+
+__device__ __forceinline__ uint32_t survivor_word(int pos, int score) { return ((uint32_t)pos << 12) | ((uint32_t)score & 0xfffu); }
+
+// Called by all 32 lanes of a warp (converged).  `s_over` is a per-CTA flag in shared memory: once a CTA has seen the slot's
+// count pass kListCap it stops issuing atomics (the count only has to END above the cap for the selection to take the scan path).
+__device__ __forceinline__ void emit_survivor(const SelArgs &sa, int slot, bool pass, uint32_t word, volatile int *s_over) {
+    const unsigned b = __ballot_sync(0xffffffffu, pass);
+    if (b == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)b) - 1, n = __popc(b);
+    int base = 0;
+    if (lane == leader) {
+        base = *s_over ? kListCap : atomicAdd(sa.count + slot, n);
+        if (base + n > kListCap) *s_over = 1;
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) {
+        const int at = base + __popc(b & ((1u << lane) - 1u));
+        if (at < kListCap) sa.lists[(size_t)slot * kListCap + at] = word;
+    }
+}
+
+// ref: the pop + push of a full heap, decode.c:203-216 (last element to the root, sift down, newcomer appended, sift up)
+__device__ __forceinline__ void heap_replace_root(uint32_t *heap, int max_cand, uint32_t word) {
+    heap[0] = heap[max_cand - 1];
+    sift_down(heap, max_cand - 1);
+    sift_up(heap, max_cand, word);
+}
+
+// `dyn` = at least max_cand*4 (16-byte aligned up) + kListCap*4 bytes of shared memory, free for this call.  All kThreads threads
+// of the CTA call it.  Scores and list words come from the score kernel: read through L2 (__ldcg), they are used once.
+template <int kThreads>
+__device__ void select_slot(const int16_t *__restrict__ scores, const Geo &g, const SelArgs &sa, int slot, uint8_t *dyn) {
+    __shared__ int s_total, s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int max_cand = sa.max_cand, min_score = sa.min_score;
+    uint32_t *heap = reinterpret_cast<uint32_t *>(dyn);
+    uint32_t *surv = reinterpret_cast<uint32_t *>(dyn + (((size_t)max_cand * 4 + 15) & ~(size_t)15));
+    // warp 0 fetches the first 32 list words together with the count (one L2 round trip instead of two for the usual slot)
+    const uint32_t first = warp == 0 ? __ldcg(sa.lists + (size_t)slot * kListCap + lane) : 0u;
+    const int n_list = __ldcg(sa.count + slot);
+    const bool listed = n_list <= kListCap, small = n_list <= 32;
+
+    if (listed && !small) {
+        // the slot's survivors, sorted by position (= by word: positions are distinct and sit in the high bits)
+        int m = 64;
+        while (m < n_list) m <<= 1;
+        for (int i = tid; i < m; i += kThreads) surv[i] = i < n_list ? __ldcg(sa.lists + (size_t)slot * kListCap + i) : 0xffffffffu;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < m; i += kThreads) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint32_t a = surv[i], b = surv[ixj];
+                        if (((i & k) == 0) ? (a > b) : (a < b)) { surv[i] = b; surv[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+    }
+
+    if (warp == 0) {
+        int n = 0;
+        if (small) {  // the usual slot (a few signals): sorted in registers, no block barrier before the replay
+            uint32_t v = lane < n_list ? first : 0xffffffffu;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+                    const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+                    v = keep_min ? (v < o ? v : o) : (v > o ? v : o);
+                }
+            surv[lane] = v;
+            __syncwarp();
+        }
+        if (max_cand > 0 && listed) {
+            // (a) room in the heap: every survivor is pushed (one thread; nothing to skip)
+            const int n_fill = n_list < max_cand ? n_list : max_cand;
+            if (lane == 0)
+                for (int e = 0; e < n_fill; ++e) sift_up(heap, e + 1, surv[e]);
+            n = n_fill;
+            // (b) heap full: 32 survivors per step against the root score, which only ever rises
+            if (n_list > max_cand) {
+                __syncwarp();
+                int root = ent_score(heap[0]);
+                for (int base = max_cand; base < n_list; base += 32) {
+                    const int e = base + lane;
+                    const uint32_t v = e < n_list ? surv[e] : 0u;
+                    const int sc = ent_score(v);
+                    unsigned todo = __ballot_sync(0xffffffffu, e < n_list && sc > root);
+                    while (todo) {
+                        const int src = __ffs((int)todo) - 1;
+                        const uint32_t vv = __shfl_sync(0xffffffffu, v, src);
+                        if (lane == 0) {
+                            heap_replace_root(heap, max_cand, vv);
+                            root = ent_score(heap[0]);
+                        }
+                        root = __shfl_sync(0xffffffffu, root, 0);
+                        todo &= ~((2u << src) - 1u);                                   // lanes up to src are settled
+                        todo &= __ballot_sync(0xffffffffu, e < n_list && sc > root);   // the others face the new root
+                    }
+                }
+            }
+        } else if (max_cand > 0) {
+            // scan path: 8 consecutive positions per lane and step (256 per warp step), four steps of loads in flight;
+            // `need` = the score a position must reach to act: min_score while the heap has room, root + 1 once it is full
+            const bool vec = (g.npos & 7) == 0 && (((size_t)scores) & 15) == 0;
+            auto load8 = [&](int base) -> uint4 {   // eight int16 scores, packed as they lie in memory
+                const int p0 = base + 8 * lane;
+                if (p0 >= g.npos) return make_uint4(0u, 0u, 0u, 0u);
+                if (vec) return __ldcg(reinterpret_cast<const uint4 *>(scores + p0));
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (p0 + j < g.npos) w[j >> 1] |= ((uint32_t)(uint16_t)__ldcg(scores + p0 + j)) << (16 * (j & 1));
+                return make_uint4(w[0], w[1], w[2], w[3]);
+            };
+            int need = min_score;
+            uint4 ring[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ring[u] = load8(256 * u);
+            for (int base0 = 0; base0 < g.npos; base0 += 1024) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int base = base0 + 256 * u;
+                    if (base >= g.npos) break;
+                    const uint4 raw = ring[u];
+                    ring[u] = load8(base + 1024);
+                    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+                    int cur[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { cur[2 * j] = (int)(short)(w[j] & 0xffffu); cur[2 * j + 1] = (int)(short)(w[j] >> 16); }
+                    const int left = g.npos - (base + 8 * lane);                   // positions of this lane inside the slot
+                    const unsigned valid = left >= 8 ? 0xffu : (left > 0 ? (1u << left) - 1u : 0u);
+                    unsigned m = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) m |= (cur[j] >= need ? 1u : 0u) << j;
+                    m &= valid;
+                    unsigned lanes = __ballot_sync(0xffffffffu, m != 0);
+                    while (lanes) {
+                        const int src = __ffs((int)lanes) - 1;
+                        const int j = __ffs((int)__shfl_sync(0xffffffffu, m, src)) - 1;
+                        int mine = 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) mine = q == j ? cur[q] : mine;
+                        const int sc = __shfl_sync(0xffffffffu, mine, src);
+                        if (lane == 0) {
+                            const uint32_t word = survivor_word(base + 8 * src + j, sc);
+                            if (n < max_cand) sift_up(heap, n + 1, word);
+                            else heap_replace_root(heap, max_cand, word);
+                        }
+                        if (n < max_cand) ++n;
+                        if (n == max_cand) {
+                            int root = lane == 0 ? ent_score(heap[0]) : 0;
+                            root = __shfl_sync(0xffffffffu, root, 0);
+                            need = root + 1;                                          // strictly above the root
+                        }
+                        if (lane == src) m &= ~((2u << j) - 1u);                      // this lane's positions up to j are settled
+                        unsigned still = 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) still |= (cur[q] >= need ? 1u : 0u) << q;
+                        m &= still;
+                        lanes = __ballot_sync(0xffffffffu, m != 0);
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            for (int rest = n; rest > 1;) {  // heap sort -> descending score (decode.c:219-231)
+                const uint32_t t = heap[rest - 1]; heap[rest - 1] = heap[0]; heap[0] = t;
+                --rest;
+                sift_down(heap, rest);
+            }
+            s_total = n;
+            sa.ncand_out[slot] = n;
+            s_base = (sa.work && n > 0) ? (int)atomicAdd(sa.work_total, (unsigned int)n) : 0;
+        }
+    }
+    __syncthreads();
+    {
+        // position -> (time_sub, freq_sub, time_offset, freq_offset), by all threads, off the serial path
+        const int n = s_total;
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(sa.cand_out + (size_t)slot * max_cand);
+        for (int k = tid; k < max_cand; k += kThreads) {
+            unsigned long long c = 0ull;
+            if (k < n) {  // candidate_t as one 64-bit word: score | time_offset<<16 | freq_offset<<32 | time_sub<<48 | freq_sub<<56
+                const uint32_t v = heap[k];
+                const int score = ent_score(v), p = (int)(v >> 12);
+                int q = g.nfo_magic ? (int)__umulhi((uint32_t)p, g.nfo_magic) : p;   // p / nfo (exact: p < 2^20, nfo < 2^12; magic 0 = divide by 1)
+                const int fo = p - q * g.nfo;
+                const int q36 = q / 36;
+                const int to = q - 36 * q36 - 12;
+                const int ts = g.fosr_magic ? (int)__umulhi((uint32_t)q36, g.fosr_magic) : q36, fs = q36 - ts * g.fosr;
+                c = ((unsigned long long)(uint16_t)(short)score) | ((unsigned long long)(uint16_t)(short)to << 16) |
+                    ((unsigned long long)(uint16_t)(short)fo << 32) | ((unsigned long long)(uint8_t)ts << 48) | ((unsigned long long)(uint8_t)fs << 56);
+            }
+            dst[k] = c;
+        }
+        if (sa.work)
+            for (int k = tid; k < n; k += kThreads) sa.work[s_base + k] = (uint32_t)slot * (uint32_t)max_cand + (uint32_t)k;
+    }
+    __syncthreads();
+}
+
+// One CTA per slot (looping over slots).
+__global__ void __launch_bounds__(kSyncThreads, 8)
+sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, SelArgs sa) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) select_slot<kSyncThreads>(scores_all + (size_t)slot * g.npos, g, sa, slot, smem);
+}
+
 // Phase 1: score every position.  For a fixed (time_sub, freq_sub) every byte a score touches lies in ONE sub-plane of
 // the waterfall: mag[((row*tosr + ts)*fosr + fs)*nbins + bin] for row < nb, bin < nbins (nb x nbins bytes: 23.5 KB for
 // the daemon geometry, 89 KB for the 12 kHz monitor).  grid = (planes * splits, slots): a CTA stages its plane compactly
@@ -100,9 +339,13 @@ __device__ __forceinline__ int sync_score_plane(const uint8_t *__restrict__ plan
 
 template <int kBins, bool kStage, bool kFt4>
 __global__ void __launch_bounds__(kScoreThreads)
-sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int splits, int to_per_cta, int16_t *__restrict__ scores_all) {
+sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int splits, int to_per_cta, int16_t *__restrict__ scores_all,
+                  SelArgs sa) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_over;
     const int tid = threadIdx.x;
+    if (tid == 0) s_over = 0;
+    if (!kStage) __syncthreads();
     const int slot = blockIdx.y;
     const int plane_id = blockIdx.x / splits, split = blockIdx.x - plane_id * splits;  // plane_id = ts*fosr + fs
     const int nbins = kBins > 0 ? kBins : g.nbins;
@@ -136,11 +379,17 @@ sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g
         plane = gplane;
         pitch = g.stride;
     }
-    int16_t *scores = scores_all + (size_t)slot * g.npos + (size_t)plane_id * 36 * g.nfo;
+    const int pos0 = plane_id * 36 * g.nfo;
+    int16_t *scores = scores_all + (size_t)slot * g.npos + pos0;
     for (int to = to0; to < to1; ++to) {
-        for (int fo = tid; fo < g.nfo; fo += kScoreThreads) {
-            const int sc = kStage ? sync_score_plane<kBins, kFt4>(plane, g.nb, pitch, to, fo) : sync_score_plane<0, kFt4>(plane, g.nb, pitch, to, fo);
-            scores[(to + 12) * g.nfo + fo] = (int16_t)sc;  // stored as int16_t in candidate_t
+        for (int f0 = 0; f0 < g.nfo; f0 += kScoreThreads) {   // CTA-uniform trip count: emit_survivor() is a whole-warp call
+            const int fo = f0 + tid;
+            int sc = 0;
+            if (fo < g.nfo) {
+                sc = kStage ? sync_score_plane<kBins, kFt4>(plane, g.nb, pitch, to, fo) : sync_score_plane<0, kFt4>(plane, g.nb, pitch, to, fo);
+                scores[(to + 12) * g.nfo + fo] = (int16_t)sc;  // stored as int16_t in candidate_t
+            }
+            emit_survivor(sa, slot, fo < g.nfo && sc >= sa.min_score, survivor_word(pos0 + (to + 12) * g.nfo + fo, sc), &s_over);
         }
     }
 }
@@ -168,10 +417,12 @@ __host__ __device__ constexpr int fast_rows(int nb) { return kPadBefore + (nb > 
 __device__ __forceinline__ uint32_t diff2(uint32_t p2, uint32_t n2) { return p2 + 0x01000100u - n2; }
 
 __global__ void __launch_bounds__(kScoreThreads)
-sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int tiles, int16_t *__restrict__ scores_all) {
+sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int tiles, int16_t *__restrict__ scores_all, SelArgs sa) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_magic[36];
+    __shared__ int s_over;
     const int tid = threadIdx.x, slot = blockIdx.y;
+    if (tid == 0) s_over = 0;
     const int plane_id = blockIdx.x / tiles, tile = blockIdx.x - plane_id * tiles;
     const int fo0 = tile * kTileF;
     const int nb = g.nb, nbins = g.nbins;
@@ -242,8 +493,9 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
     }
     __syncthreads();
     const int fl = tid & (kTileF - 1), fo = fo0 + fl;
-    if (fo >= g.nfo) return;
-    int16_t *scores = scores_all + (size_t)slot * g.npos + (size_t)plane_id * 36 * g.nfo;
+    const bool valid = fo < g.nfo;   // the other threads of the last tile still score (cells inside the tile) but store nothing
+    const int pos0 = plane_id * 36 * g.nfo;
+    int16_t *scores = scores_all + (size_t)slot * g.npos + pos0;
     constexpr int kCostas8[7] = {3, 1, 4, 0, 6, 5, 2};
     for (int ti = tid / kTileF; ti < 36; ti += kScoreThreads / kTileF) {  // warp-uniform time offset to = ti - 12: padded row = ti + 36 grp + k
         const uint16_t *b0 = w0 + ti * kTilePitch + fl, *bm = b0 + plane_elems, *b3 = bm + plane_elems, *b6 = b3 + plane_elems;
@@ -262,212 +514,34 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
             const uint32_t mag_q = __umulhi((uint32_t)(score < 0 ? -score : score), magic);
             score = score < 0 ? -(int)mag_q : (int)mag_q;
         }
-        scores[ti * g.nfo + fo] = (int16_t)score;
-    }
-}
-
-// Phase 2: one CTA per slot (looping over slots): ordered compaction of the positions with score >= min_score, then the
-// exact heap replay, then the candidates are appended to the decode work list.
-//
-// The replay is the reference's loop (decode.c:198-231): push while the heap has room; once it is full a survivor enters
-// only if its score is STRICTLY above the root's, evicting the root.  A survivor that fails that test is a no-op in the
-// reference, so warp 0 tests 32 survivors at a time against the current root score and skips the failures wholesale: the
-// serial work is the pushes/evictions that really happen (about K (1 + ln(survivors / K)) on noise), not one step per
-// survivor -- 35 856 of them with min_score = 0, 137 232 on the 12 kHz waterfall.  Position -> (time_sub, freq_sub,
-// time_offset, freq_offset) is decoded after the sort by all threads, off the serial path.
-__global__ void __launch_bounds__(kSyncThreads)
-sync_select_kernel(const int16_t *__restrict__ scores_all, int n_slots, Geo g, int max_cand, int min_score, candidate_t *__restrict__ cand_out,
-                   int *__restrict__ ncand_out, uint32_t *__restrict__ scratch_all, uint32_t *__restrict__ work, unsigned int *__restrict__ work_total,
-                   int mask_bytes) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *gmask = smem + (((size_t)max_cand * 4 + 15) & ~(size_t)15);   // one pass mask per group of 8 positions (mask_bytes > 0)
-    // the first kSurvSmem survivors are ALSO kept in shared memory: the replay below is one thread reading them one after the other,
-    // and from the global scratch list each read was an L2 round trip on the kernel's critical path
-    uint32_t *surv = reinterpret_cast<uint32_t *>(gmask + (((size_t)(mask_bytes > 0 ? mask_bytes : 0) + 15) & ~(size_t)15));
-    __shared__ int s_warp_cnt[2][32];
-    __shared__ int s_total, s_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t *heap = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *scratch = scratch_all + (size_t)blockIdx.x * g.npos;
-
-    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-        const int16_t *scores = scores_all + (size_t)slot * g.npos;
-        // Ordered compaction with ONE block barrier: warp w owns the contiguous positions [w*span, (w+1)*span); it counts
-        // its survivors, the warp totals are prefix-summed, then it writes its survivors at its offset (position order ==
-        // the reference's loop order).  Scores are re-read in the second sweep (L1/L2 hits).  A lane reads EIGHT consecutive
-        // scores per step (one 128-bit load) when the slot's score array allows it: the sweeps are chains of dependent L2
-        // loads, and with one score per lane and step they were the kernel's whole duration (37 of its 42 us at 15 survivors).
-        constexpr int kSelWarps = kSyncThreads / 32;
-        int running, n_pass;
-        if (mask_bytes > 0 && (g.npos & 7) == 0 && (((size_t)scores) & 15) == 0) {
-            // One sweep over the scores (loads batched six deep) leaves a pass mask per group in shared memory; the second pass reads
-            // the masks and fetches scores only for the few groups that hold a survivor.
-            const int n8 = g.npos >> 3;                                            // groups of 8 positions
-            const int span8 = (n8 + kSelWarps - 1) / kSelWarps;                    // groups per warp
-            const int g0 = warp * span8, g1 = (g0 + span8 < n8) ? g0 + span8 : n8;
-            const uint4 *sv = reinterpret_cast<const uint4 *>(scores);
-            auto pass_mask = [&](const uint4 v) -> unsigned {                      // bit j: score j of the group passes
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                unsigned m = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if ((int)(short)(w[j] & 0xffffu) >= min_score) m |= 1u << (2 * j);
-                    if ((int)(short)(w[j] >> 16) >= min_score) m |= 2u << (2 * j);
-                }
-                return m;
-            };
-            int mine = 0;
-            for (int qb = g0 + lane; qb < g1; qb += 32 * 6) {
-                uint4 v[6];
-#pragma unroll
-                for (int u = 0; u < 6; ++u) v[u] = (qb + 32 * u < g1) ? __ldg(sv + qb + 32 * u) : make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
-#pragma unroll
-                for (int u = 0; u < 6; ++u) {
-                    if (qb + 32 * u < g1) {
-                        const unsigned m = pass_mask(v[u]);
-                        gmask[qb + 32 * u] = (uint8_t)m;
-                        mine += __popc(m);
-                    }
-                }
-            }
-            mine = __reduce_add_sync(0xffffffffu, mine);
-            if (lane == 0) s_warp_cnt[0][warp] = mine;
-            __syncthreads();
-            const int cnt = lane < kSelWarps ? s_warp_cnt[0][lane] : 0;
-            running = __reduce_add_sync(0xffffffffu, lane < warp ? cnt : 0);
-            n_pass = __reduce_add_sync(0xffffffffu, cnt);
-            if (mine > 0) {                                                        // warp-uniform: most warps hold no survivor at all
-                for (int qb = g0; qb < g1; qb += 32) {                             // warp-uniform trip count
-                    const int q = qb + lane;
-                    unsigned m = q < g1 ? gmask[q] : 0u;
-                    if (__ballot_sync(0xffffffffu, m != 0) == 0) continue;
-                    const int c = __popc(m);
-                    int incl = c;                                                  // inclusive prefix over the lanes: lane order == position order
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
-                    int at = running + incl - c;
-                    while (m) {
-                        const int j = __ffs((int)m) - 1;
-                        m &= m - 1;
-                        const int p = 8 * q + j;
-                        const uint32_t ent = ((uint32_t)p << 12) | ((uint32_t)(int)scores[p] & 0xfffu);
-                        if (at < kSurvSmem) surv[at] = ent;
-                        scratch[at++] = ent;
-                    }
-                    running += __shfl_sync(0xffffffffu, incl, 31);
-                }
-            }
-        } else {
-            const int span = ((g.npos + kSelWarps - 1) / kSelWarps + 31) / 32 * 32;  // positions per warp, multiple of 32
-            const int w0 = warp * span;
-            int mine = 0;
-#pragma unroll 4
-            for (int o = 0; o < span; o += 32) {
-                const int p = w0 + o + lane;
-                const bool pass = p < g.npos && scores[p] >= min_score;
-                mine += __popc(__ballot_sync(0xffffffffu, pass));
-            }
-            if (lane == 0) s_warp_cnt[0][warp] = mine;
-            __syncthreads();
-            const int cnt = lane < kSelWarps ? s_warp_cnt[0][lane] : 0;
-            running = __reduce_add_sync(0xffffffffu, lane < warp ? cnt : 0);
-            n_pass = __reduce_add_sync(0xffffffffu, cnt);
-#pragma unroll 4
-            for (int o = 0; o < span; o += 32) {
-                const int p = w0 + o + lane;
-                int score = 0;
-                bool pass = false;
-                if (p < g.npos) { score = scores[p]; pass = score >= min_score; }
-                const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-                if (pass) {
-                    const int at = running + __popc(ballot & ((1u << lane) - 1u));
-                    const uint32_t ent = ((uint32_t)p << 12) | ((uint32_t)score & 0xfffu);
-                    if (at < kSurvSmem) surv[at] = ent;
-                    scratch[at] = ent;
-                }
-                running += __popc(ballot);
-            }
-        }
-        __syncthreads();
-
-        if (warp == 0) {
-            int n = 0;
-            // (a) room in the heap: every survivor is pushed (one thread; nothing to skip)
-            const int n_fill = n_pass < max_cand ? n_pass : max_cand;
-            if (lane == 0)
-                for (; n < n_fill; ++n) sift_up(heap, n + 1, n < kSurvSmem ? surv[n] : scratch[n]);
-            n = n_fill;
-            // (b) heap full: 32 survivors per step against the root score, which only ever rises
-            if (n_pass > max_cand) {
-                __syncwarp();
-                int root = ent_score(heap[0]);
-                for (int base = max_cand; base < n_pass; base += 32) {
-                    const int e = base + lane;
-                    const uint32_t v = e < n_pass ? (e < kSurvSmem ? surv[e] : scratch[e]) : 0u;
-                    const int sc = ent_score(v);
-                    unsigned todo = __ballot_sync(0xffffffffu, e < n_pass && sc > root);
-                    while (todo) {
-                        const int src = __ffs((int)todo) - 1;
-                        const uint32_t vv = __shfl_sync(0xffffffffu, v, src);
-                        if (lane == 0) {  // pop the root (last element to the root, sift down), push the newcomer (decode.c:203-216)
-                            heap[0] = heap[max_cand - 1];
-                            sift_down(heap, max_cand - 1);
-                            sift_up(heap, max_cand, vv);
-                            root = ent_score(heap[0]);
-                        }
-                        root = __shfl_sync(0xffffffffu, root, 0);
-                        todo &= ~((2u << src) - 1u);                                   // lanes up to src are settled
-                        todo &= __ballot_sync(0xffffffffu, e < n_pass && sc > root);   // the others face the new root
-                    }
-                }
-            }
-            if (lane == 0) {
-                for (int rest = n; rest > 1;) {  // heap sort -> descending score (decode.c:219-231)
-                    const uint32_t t = heap[rest - 1]; heap[rest - 1] = heap[0]; heap[0] = t;
-                    --rest;
-                    sift_down(heap, rest);
-                }
-                s_total = n;
-                ncand_out[slot] = n;
-                s_base = (work && n > 0) ? (int)atomicAdd(work_total, (unsigned int)n) : 0;
-            }
-        }
-        __syncthreads();
-        {
-            const int n = s_total;
-            unsigned long long *dst = reinterpret_cast<unsigned long long *>(cand_out + (size_t)slot * max_cand);
-            for (int k = tid; k < max_cand; k += kSyncThreads) {
-                unsigned long long c = 0ull;
-                if (k < n) {  // candidate_t as one 64-bit word: score | time_offset<<16 | freq_offset<<32 | time_sub<<48 | freq_sub<<56
-                    const uint32_t v = heap[k];
-                    const int score = ent_score(v), p = (int)(v >> 12);
-                    const int fo = p % g.nfo;
-                    int q = p / g.nfo;
-                    const int to = q % 36 - 12;
-                    q /= 36;
-                    const int fs = q % g.fosr, ts = q / g.fosr;
-                    c = ((unsigned long long)(uint16_t)(short)score) | ((unsigned long long)(uint16_t)(short)to << 16) |
-                        ((unsigned long long)(uint16_t)(short)fo << 32) | ((unsigned long long)(uint8_t)ts << 48) | ((unsigned long long)(uint8_t)fs << 56);
-                }
-                dst[k] = c;
-            }
-            if (work)
-                for (int k = tid; k < n; k += kSyncThreads) work[s_base + k] = (uint32_t)slot * (uint32_t)max_cand + (uint32_t)k;
-        }
-        __syncthreads();
+        if (valid) scores[ti * g.nfo + fo] = (int16_t)score;
+        emit_survivor(sa, slot, valid && score >= sa.min_score, survivor_word(pos0 + ti * g.nfo + fo, score), &s_over);
     }
 }
 
 }  // namespace
 
+size_t find_sync_list_bytes(int n_slots) { return ((size_t)n_slots + (size_t)n_slots * kListCap) * sizeof(uint32_t); }
+
 cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slots, int num_blocks, int num_bins, int time_osr, int freq_osr,
-                             int protocol, int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_scratch,
-                             int scratch_slots, uint32_t *d_work, unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches) {
+                             int protocol, int max_cand, int min_score, candidate_t *d_cand, int *d_ncand, int16_t *d_scores, uint32_t *d_lists,
+                             uint32_t *d_work, unsigned int *d_work_total, int sm_count, cudaStream_t st, int *launches) {
     Geo g;
     g.nb = num_blocks; g.nbins = num_bins; g.tosr = time_osr; g.fosr = freq_osr;
     g.stride = time_osr * freq_osr * num_bins;
     g.nfo = num_bins - 7;
     g.npos = time_osr * freq_osr * 36 * g.nfo;
+    if (g.nfo < 1 || g.nfo >= 4096 || freq_osr >= 4096 || g.npos >= (1 << 20)) return cudaErrorInvalidValue;
+    g.nfo_magic = g.nfo > 1 ? 0xffffffffu / (uint32_t)g.nfo + 1u : 0u;   // 0: division by 1
+    g.fosr_magic = freq_osr > 1 ? 0xffffffffu / (uint32_t)freq_osr + 1u : 0u;
+    SelArgs sa;
+    sa.count = reinterpret_cast<int *>(d_lists);                  // layout: count[n_slots] | words[n_slots][kListCap]
+    sa.lists = d_lists + n_slots;
+    sa.max_cand = max_cand; sa.min_score = min_score;
+    sa.cand_out = d_cand; sa.ncand_out = d_ncand;
+    sa.work = d_work; sa.work_total = d_work_total;
+    cudaError_t e = cudaMemsetAsync(sa.count, 0, (size_t)n_slots * sizeof(int), st);
+    if (e != cudaSuccess) return e;
     // one CTA per (slot, sub-plane, share of the 36 time offsets); enough CTAs to fill the machine for small batches
     const int planes = time_osr * freq_osr;
     int splits = (4 * sm_count + n_slots * planes - 1) / (n_slots * planes);
@@ -482,37 +556,34 @@ cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slo
     if (!ft4 && fast_smem <= 96 * 1024 && (((size_t)d_mag | slot_stride | (size_t)g.stride | (size_t)g.nbins) & 3) == 0) {
         // FT8 fast path: derived int16 planes per (plane, tile of 64 frequency offsets)
         const int tiles = (g.nfo + kTileF - 1) / kTileF;
-        cudaError_t e = cudaFuncSetAttribute(sync_score_ft8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        e = cudaFuncSetAttribute(sync_score_ft8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         if (e != cudaSuccess) return e;
-        sync_score_ft8_kernel<<<dim3(planes * tiles, n_slots), kScoreThreads, fast_smem, st>>>(d_mag, slot_stride, g, tiles, d_scores);
+        sync_score_ft8_kernel<<<dim3(planes * tiles, n_slots), kScoreThreads, fast_smem, st>>>(d_mag, slot_stride, g, tiles, d_scores, sa);
     } else if (staged <= 200 * 1024) {
         if (g.nbins == 256 && !ft4) {
-            sync_score_kernel<256, true, false><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
+            sync_score_kernel<256, true, false><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores, sa);
         } else {
             auto kern = ft4 ? sync_score_kernel<0, true, true> : sync_score_kernel<0, true, false>;
-            if (staged > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
-                if (e != cudaSuccess) return e;
-            }
-            kern<<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
+            if (staged > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged)) != cudaSuccess) return e;
+            kern<<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores, sa);
         }
     } else {
         auto kern = ft4 ? sync_score_kernel<0, false, true> : sync_score_kernel<0, false, false>;
-        kern<<<grid, kScoreThreads, 0, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores);
+        kern<<<grid, kScoreThreads, 0, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores, sa);
     }
     ++*launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (d_work_total) {
-        cudaError_t e = cudaMemsetAsync(d_work_total, 0, 4 * sizeof(unsigned int), st);  // [0] items, [1] next item (decode_kernel)
+        e = cudaMemsetAsync(d_work_total, 0, 4 * sizeof(unsigned int), st);  // [0] items, [1] next item (decode_kernel)
         if (e != cudaSuccess) return e;
     }
-    const int sgrid = n_slots < scratch_slots ? n_slots : scratch_slots;
-    // heap words + (when they fit under the default 48 KB) one pass-mask byte per group of 8 positions
-    const size_t heap_bytes = ((size_t)max_cand * 4 + 15) & ~(size_t)15;
-    int mask_bytes = (g.npos & 7) == 0 ? g.npos >> 3 : 0;
-    const size_t surv_bytes = (size_t)kSurvSmem * sizeof(uint32_t);
-    if (heap_bytes + (size_t)mask_bytes + 16 + surv_bytes > 48 * 1024) mask_bytes = 0;
-    sync_select_kernel<<<sgrid, kSyncThreads, heap_bytes + (((size_t)mask_bytes + 15) & ~(size_t)15) + surv_bytes, st>>>(d_scores, n_slots, g, max_cand, min_score, d_cand, d_ncand, d_scratch,
-                                                                                    d_work, d_work_total, mask_bytes);
+    // the selection's shared memory: heap + survivors
+    const size_t sel_smem = (((size_t)max_cand * 4 + 15) & ~(size_t)15) + (size_t)kListCap * sizeof(uint32_t);
+    if (sel_smem > 200 * 1024) return cudaErrorInvalidValue;
+    int sgrid = sm_count * 12;  // 128-thread CTAs looping over the slots
+    if (sgrid > n_slots) sgrid = n_slots;
+    if (sel_smem > 48 * 1024 && (e = cudaFuncSetAttribute(sync_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem)) != cudaSuccess) return e;
+    sync_select_kernel<<<sgrid, kSyncThreads, sel_smem, st>>>(d_scores, n_slots, g, sa);
     ++*launches;
     return cudaGetLastError();
 }

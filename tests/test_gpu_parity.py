@@ -316,6 +316,58 @@ def test_every_position_survives(pkg, oracle, K):
     c.close()
 
 
+@pytest.mark.parametrize("geometry", ["ft8_3200", "ft8_12k", "ft4", "odd", "narrow"])
+def test_selection_paths(pkg, oracle, slots, geometry):
+    """The candidate selection on both of its paths.  The score kernels hand every position with
+    score >= min_score to the selection as an unordered list of at most 1024 words per slot (sorted back into the reference's
+    loop order); a slot with more survivors is scanned in position order instead.  Thresholds are chosen per waterfall so that
+    survivor counts fall on either side of 32 (sorted in registers by one warp), of K and of 1024 (and all positions at once);
+    slots of both kinds share a launch."""
+    rng = np.random.default_rng(77)
+    if geometry == "ft8_3200":
+        dims, proto, cells = dict(num_blocks=92, num_bins=256, time_osr=2, freq_osr=2), 1, 94208
+    elif geometry == "ft8_12k":
+        dims, proto, cells = dict(num_blocks=93, num_bins=960, time_osr=2, freq_osr=2), 1, 93 * 4 * 960
+    elif geometry == "ft4":
+        dims, proto, cells = dict(num_blocks=156, num_bins=288, time_osr=2, freq_osr=2), 0, 156 * 4 * 288
+    elif geometry == "odd":      # 7668 positions: not a multiple of 8 (scalar loads in the scan path), freq_osr 3, unaligned rows
+        dims, proto, cells = dict(num_blocks=60, num_bins=78, time_osr=1, freq_osr=3), 1, 60 * 3 * 78
+    else:                        # one frequency offset per sub-plane, no oversampling
+        dims, proto, cells = dict(num_blocks=95, num_bins=8, time_osr=1, freq_osr=1), 1, 95 * 8
+    npos = dims["time_osr"] * dims["freq_osr"] * 36 * (dims["num_bins"] - 7)
+    mags = [rng.integers(0, 256, cells, dtype=np.uint8), rng.integers(100, 104, cells, dtype=np.uint8), np.zeros(cells, np.uint8),
+            np.clip(np.arange(cells) // max(cells // 230, 1) + rng.integers(0, 24, cells), 0, 255).astype(np.uint8)]
+    if geometry == "ft8_3200":
+        mags.append(oracle.waterfall(*slots[0]))
+    mags = np.stack(mags)
+
+    every = [oracle.find_sync(m, max_cand=npos, min_score=-1000, protocol=proto, **dims)["score"] for m in mags]   # all scores of a slot
+
+    def survivors(s, t):
+        return int((every[s] >= t).sum())
+
+    # thresholds around the list capacity on the noise waterfall, plus fixed ones
+    counts = {t: survivors(0, t) for t in range(1, 200)}
+    below = max((t for t in counts if counts[t] <= 1024), key=lambda t: counts[t])
+    above = min((t for t in counts if counts[t] > 1024), key=lambda t: counts[t], default=None)
+    few = max((t for t in counts if 0 < counts[t] <= 32), key=lambda t: counts[t], default=None)
+    assert npos <= 1024 or counts[below] <= 1024 < counts[above]
+    thresholds = [t for t in (few, below, above, 10, 1, 0, -1000) if t is not None]
+    d_mag = torch.from_numpy(mags).to(dev())
+    for K in (1, 50, 120, 1500):
+        for t in thresholds:
+            c = pkg.Context(0, max_candidates=K, max_messages=50, min_score=t)
+            c.set_protocol(proto)
+            cand, ncand = c.find_sync(d_mag, **dims)
+            torch.cuda.synchronize()
+            g = view(cand, cand_dtype)
+            for s in range(mags.shape[0]):
+                o = oracle.find_sync(mags[s], max_cand=K, min_score=t, protocol=proto, **dims)
+                assert int(ncand[s]) == o.size, (geometry, K, t, s)
+                assert g[s, : o.size].tobytes() == o.tobytes(), (geometry, K, t, s, survivors(s, t))
+            c.close()
+
+
 @pytest.mark.parametrize("name,src", [("slot_single", "slot_single"), ("slot_crowded_k500", "slot_crowded_k500"), ("slot_crowded_k120", "slot_crowded_k500")])
 def test_golden_slots_on_gpu(ctx, ctx500, name, src):
     """The committed outputs of the UNMODIFIED reference, stage by stage, without the oracle in between."""
