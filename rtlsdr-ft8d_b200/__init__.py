@@ -519,6 +519,14 @@ class Pipe:
         stride = bytes_per_stream if stride is None else stride
         self._chk(self.L.ft8b200_pipe_submit(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_slots))
 
+    def submit_streams(self, iq, n_streams: int, slots_per_stream: int, bytes_per_slot: int = RAW_SLOT_BYTES, stride: int | None = None):
+        """iq: device tensor of n_streams receiver streams, each slots_per_stream consecutive slots (decimator state carried through
+        the slot boundaries) -> one batch of n_streams * slots_per_stream slots, records in (stream, slot) order."""
+        bytes_per_stream = slots_per_stream * bytes_per_slot
+        stride = bytes_per_stream if stride is None else stride
+        self._chk(self.L.ft8b200_pipe_submit_streams(C.c_void_p(self.h), _p(iq), C.c_size_t(bytes_per_stream), C.c_size_t(stride), n_streams,
+                                                     slots_per_stream, C.c_size_t(bytes_per_slot)))
+
     def submit_host(self, iq_host, n_slots: int, bytes_per_stream: int = RAW_SLOT_BYTES):
         self._chk(self.L.ft8b200_pipe_submit_host(C.c_void_p(self.h), _p(iq_host), C.c_size_t(bytes_per_stream), n_slots))
 

@@ -408,7 +408,8 @@ sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g
 // grid = (planes * tiles, slots); a tile is kTileF frequency offsets (all 36 time offsets, all rows).
 constexpr int kTileF = 64;
 constexpr int kTilePitch = kTileF + 8;   // 16-bit elements per derived row (71 needed: fo .. fo + 6), 18 groups of 4
-constexpr int kRawPitch = kTileF + 16;   // raw bytes per row: columns fo0 - 4 .. fo0 + 75, whole aligned words
+constexpr int kRawPitch = kTileF + 32;   // raw bytes per row: columns fo0 - 16 .. fo0 + 79, whole 16-byte chunks of the waterfall row
+constexpr int kRawLead = 16;             // columns staged before fo0 (4 are needed; 16 keeps the chunks aligned)
 constexpr int kPadBefore = 12;           // time offsets start at -12
 constexpr uint32_t kBias2 = 0x04000400u; // biased zero, two cells
 __host__ __device__ constexpr int fast_rows(int nb) { return kPadBefore + (nb > 102 ? nb : 102); }  // last row touched: 23 + 72 + 6
@@ -432,14 +433,35 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
     const int plane_elems = rows * kTilePitch;
     const uint8_t *gplane = mag_all + (size_t)slot * slot_stride + (size_t)plane_id * nbins;  // row r at gplane + r*stride
 
-    // raw tile: words covering columns [fo0 - 4, fo0 + 76), zero outside [0, nbins)
+    // raw tile: columns [fo0 - 16, fo0 + 80), zero outside [0, nbins).  All of a thread's copies are in flight at once (cp.async):
+    // with one load -> one store per loop trip this phase was 30 % of the kernel (a chain of L2 round trips per thread).
     constexpr int kWordsPerRow = kRawPitch / 4;
-    for (int v = tid; v < nb * kWordsPerRow; v += kScoreThreads) {
-        const int r = v / kWordsPerRow, wi = v - r * kWordsPerRow;
-        const int c = fo0 - 4 + 4 * wi;
-        uint32_t word = 0;
-        if (c >= 0 && c + 4 <= nbins) word = __ldg(reinterpret_cast<const uint32_t *>(gplane + (size_t)r * g.stride + c));
-        reinterpret_cast<uint32_t *>(raw + (size_t)r * kRawPitch)[wi] = word;
+    if (((((size_t)gplane) | (size_t)g.stride | (size_t)nbins) & 15) == 0) {
+        constexpr int kChunks = kRawPitch / 16, kRowsPerTrip = kScoreThreads / kChunks;   // 6 chunks per row, 42 rows per trip
+        if (tid < kChunks * kRowsPerTrip) {
+            const int r0 = tid / kChunks, j = tid - r0 * kChunks;
+            const int c = fo0 - kRawLead + 16 * j;
+            const bool inside = c >= 0 && c + 16 <= nbins;   // nbins and c are multiples of 16: a chunk is never split
+            for (int r = r0; r < nb; r += kRowsPerTrip) {
+                uint8_t *dst = raw + (size_t)r * kRawPitch + 16 * j;
+                if (inside) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                                 "l"(gplane + (size_t)r * g.stride + c) : "memory");
+                } else {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        for (int v = tid; v < nb * kWordsPerRow; v += kScoreThreads) {
+            const int r = v / kWordsPerRow, wi = v - r * kWordsPerRow;
+            const int c = fo0 - kRawLead + 4 * wi;
+            uint32_t word = 0;
+            if (c >= 0 && c + 4 <= nbins) word = __ldg(reinterpret_cast<const uint32_t *>(gplane + (size_t)r * g.stride + c));
+            reinterpret_cast<uint32_t *>(raw + (size_t)r * kRawPitch)[wi] = word;
+        }
     }
     if (tid < 36) {  // number of terms of a score at time offset to = tid - 12 (ft8_sync_score's num_average) -> 2^32 / terms + 1
         const int to = tid - 12;
@@ -455,14 +477,16 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
     }
     __syncthreads();
     constexpr int kGroups = kTilePitch / 4;  // 18 groups of 4 cells per row
-    for (int v = tid; v < rows * kGroups; v += kScoreThreads) {
-        const int rp = v / kGroups, q = v - rp * kGroups;
+    constexpr int kPrepRows = kScoreThreads / kGroups;   // 14 rows per trip (252 threads busy): no division inside the loop
+    const int rp0 = tid / kGroups, q = tid - rp0 * kGroups;
+    for (int rp = rp0; rp < rows && rp0 < kPrepRows; rp += kPrepRows) {
         const int r = rp - kPadBefore;
         uint2 o0, om, o3, o6;
         if (r < 0 || r >= nb) {
             o0 = om = o3 = o6 = make_uint2(kBias2, kBias2);
         } else {
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(raw + (size_t)r * kRawPitch) + q;  // words: [0] left, [1] the 4 cells, [2] right
+            // words: [0] left, [1] the 4 cells (columns fo0 + 4q ..), [2] right
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(raw + (size_t)r * kRawPitch) + (kRawLead / 4 - 1) + q;
             const uint32_t wl = row[0], wc = row[1], wr = row[2];
             const uint32_t p01 = __byte_perm(wc, 0u, 0x4140), p23 = __byte_perm(wc, 0u, 0x4342);    // (P0,P1) (P2,P3) as 16-bit lanes
             const uint32_t l01 = __byte_perm(p01, wl, 0x1017), l23 = __byte_perm(wc, 0u, 0x4241);   // (P-1,P0) (P1,P2); p01/p23 supply the zero bytes

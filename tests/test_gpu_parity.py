@@ -841,6 +841,36 @@ def test_streams_full_size_whole_path(ctx, oracle, raw_slot):
     assert n[1] == o["n"] and res[1].tobytes() == o["results"].tobytes()
 
 
+@pytest.mark.parametrize("partition", [0, 32])
+def test_pipe_streams_match_unpipelined(pkg, ctx, raw_slot, partition):
+    """ft8b200_pipe_submit_streams (BASELINE config #5 through the pipelined executor): batches of receiver streams of consecutive
+    slots, several in flight, with and without the SM partition -> the records of ft8b200_process_raw_streams, in (stream, slot)
+    order, whatever the batch size."""
+    slots, n_streams = 2, 3
+    one = torch.from_numpy(raw_slot).to(dev())
+    big = one.repeat(n_streams, slots).contiguous()
+    big[1, 72_000_000:] = 0x80                      # a silent second slot on the second receiver
+    big[2, :72_000_000] = big[2, :72_000_000].flip(0)   # another first slot on the third (I/Q swapped and reversed: nothing decodes)
+    torch.cuda.synchronize()
+    ctx.process_raw_streams(big, n_streams, slots)
+    ref_res, ref_n = ctx.fetch_results(n_streams * slots)
+    assert ref_n[0] >= 1 and ref_n[3] == 0
+    pipe = pkg.Pipe(0, 2)
+    if partition:
+        pipe.set_partition(partition)
+    outs, sizes = [], [3, 1, 2, 3, 1]
+    for n in sizes:
+        if pipe.in_flight() == pipe.depth:
+            outs.append(pipe.collect(n_streams * slots))
+        pipe.submit_streams(big[:n], n, slots)
+    while pipe.in_flight():
+        outs.append(pipe.collect(n_streams * slots))
+    assert [len(o[1]) for o in outs] == [n * slots for n in sizes]
+    for (res, n), k in zip(outs, sizes):
+        assert np.array_equal(n, ref_n[: k * slots]) and res.tobytes() == ref_res[: k * slots].tobytes()
+    pipe.close()
+
+
 # ------------------------------------------------------------------------------------------- FT4 (SURVEY section 8f rank 1)
 def ft4_audio(seed, n=6):
     rng = np.random.default_rng(seed)

@@ -129,49 +129,81 @@ def roofline_extra(env, batch, n_slots, hbm_peak, peak_source, sm_mhz):
 
 
 # ------------------------------------------------------------------------------------------------ config #5
-def config5(env, batch, texts):
+def config5(env, batch, texts, depth=3, streams_per_batch=16):
     """256 receiver streams x 8 consecutive slots, sharded BY STREAM over the GPUs (tools/shard.py), decimator state carried
-    through the slot boundaries (ft8b200_process_raw_streams); spot records of every rank gathered with NCCL inside the timed
-    region.  The rank's resident batch (rows = consecutive slots) is read as streams of 8 slots; with fewer than 8 GPUs a rank
-    owns more streams than are resident and passes over them again (same bytes, same work)."""
+    through the slot boundaries, through the pipelined executor (ft8b200_pipe_submit_streams: 16 streams x 8 slots per batch,
+    `depth` batches in flight, autotuned SM partition -- the back end of a batch next to the block sums of the next one); the
+    spot records of every batch are staged on the device and gathered with NCCL inside the timed region.  The rank's resident
+    batch (rows = consecutive slots) is read as streams of 8 slots; with fewer than 8 GPUs a rank owns more streams than are
+    resident and passes over them again (same bytes, same work)."""
     from tools.shard import shard_range
     torch, pkg = env.torch, env.pkg
     n_streams_total, spp = 256, 8
     lo, hi = shard_range(n_streams_total, env.rank, env.world)
     mine = hi - lo
     resident = batch.shape[0] // spp
-    ctx = pkg.Context(env.local)
-    plan = []
-    left = mine
-    while left > 0:
-        n = min(left, resident)
-        plan.append(n)
-        left -= n
+    spb = min(streams_per_batch, resident, mine)
+    pipe = pkg.Pipe(env.local, depth)
+    pipe.set_mode(serial=False)
+    try:
+        tuned = pipe.autotune(batch[: spb * spp], spb * spp, candidates=(24, 32, 40), batches=3 * depth + 3)
+        executor = "ft8b200_pipe_t depth %d, %d streams x %d slots per batch, back end on %d SMs (comb+FIR on the %s set)" % (
+            depth, spb, spp, tuned["back_sms"], "front" if tuned["comb_front"] else "back")
+    except Exception as exc:   # a driver without green contexts
+        pipe.set_mode(serial=True)
+        executor = "ft8b200_pipe_t depth %d, serial (%s)" % (depth, exc)
+    M = pipe.M
+    # the rank's batches: (first resident stream, streams)
+    plan, s0 = [], 0
+    while s0 < mine:
+        n = min(spb, mine - s0)
+        first = s0 % resident
+        if first + n > resident:
+            n = resident - first
+        plan.append((first, n))
+        s0 += n
+    recs = torch.zeros((mine * spp, M, 28), dtype=torch.uint8, device=env.device)
+    cnts = torch.zeros(mine * spp, dtype=torch.int32, device=env.device)
+    copied = torch.cuda.Event()
 
     def run(_steps=1):
-        last = None
-        for n in plan:
-            ctx.process_raw_streams(batch[: n * spp], n, spp)
-            r, c = ctx.results_tensors(n * spp)
-            last = env.gather_records(r, c)
+        done = 0
+
+        def collect():
+            nonlocal done
+            r, c = pipe.collect_device()
+            n = c.shape[0]
+            recs[done:done + n].copy_(r.view(n, M, 28))
+            cnts[done:done + n].copy_(c)
+            copied.record()
+            pipe.depend_on(copied)   # the lane's buffers are rewritten only after they have been copied out
+            done += n
+
+        for first, n in plan:
+            if pipe.in_flight() == pipe.depth:
+                collect()
+            pipe.submit_streams(batch[first * spp:(first + n) * spp], n, spp)
+        while pipe.in_flight():
+            collect()
+        last = env.gather_records(recs, cnts)
         torch.cuda.synchronize()
         return last
 
     run(); run()
     ms, gathered, _ = env.timed(run, 1)
     n_slots_total = n_streams_total * spp
-    res = gathered[0].cpu().numpy().view(pkg.result_dtype).reshape(-1, ctx.M)
+    res = gathered[0].cpu().numpy().view(pkg.result_dtype).reshape(-1, M)
     nres = gathered[1].cpu().numpy()
     rec = {"workload": "BASELINE config #5: 256 receiver streams x 8 consecutive 72 MB slots (147 GB), sharded by stream: %d streams per GPU, "
                        "%d resident (the rest are further passes over them)" % (mine, min(mine, resident)),
            "slots_per_s": n_slots_total / (ms * 1e-3), "msps": n_slots_total * 36.0 / (ms * 1e-3), "ms": ms,
            "hbm_gbs_algorithmic_per_gpu": mine * spp * (72_000_000 + 47_936 * 8) / (ms * 1e-3) / 1e9,
-           "scaling": "strong (256 streams whatever the GPU count)", "gather": "NCCL all_gather of the records, inside the timed region" if env.world > 1 else "single GPU"}
+           "scaling": "strong (256 streams whatever the GPU count)", "executor": executor,
+           "gather": "NCCL all_gather of the records, inside the timed region" if env.world > 1 else "single GPU"}
     if env.rank == 0:
         # CPU reference: stream 0 continued through its first two slots (the filter state crosses the flip), vs the GPU's rows 0 and 1
         Ref, orc, kind = _cpu()
-        n_rows = plan[-1] * spp
-        own = slice(0, 2)   # rank 0's records come first in the gathered order; its last pass starts at stream 0 of the resident batch
+        n_rows = mine * spp   # rank 0's records come first in the gathered order, streams in order: rows 0 and 1 = stream 0, slots 0 and 1
         t0 = time.perf_counter()
         host = batch[:2].cpu().numpy()
         same = True
@@ -197,8 +229,7 @@ def config5(env, batch, texts):
         cpu_s = (time.perf_counter() - t0) / 2
         rec.update({"cpu_slots_per_s_1thread": 1.0 / cpu_s, "cpu_kind": kind, "cpu_sample": "stream 0, slots 0-1 (filter state carried across the flip)",
                     "parity": bool(same), "decoded_slots": int((nres[:n_rows] > 0).sum()), "of_slots": int(n_rows)})
-        del own
-    ctx.close()
+    pipe.close()
     return rec
 
 
