@@ -352,9 +352,11 @@ class Context:
         """Unconditioned samples + their peak max(|I|,|Q|) per slot: decoder()'s 0.5/peak scale is applied on load."""
         self._chk(self.L.ft8b200_process_conditioned(C.c_void_p(self.h), _p(d_i), _p(d_q), _p(peak), d_i.shape[0], _st(stream)))
 
-    def fetch_results(self, n_slots: int, stream: int | None = None):
-        res = np.zeros((n_slots, self.M), result_dtype)
-        nres = np.zeros(n_slots, np.int32)
+    def fetch_results(self, n_slots: int, stream: int | None = None, out=None):
+        """Records of the last batch -> host.  out = (result_dtype[n, M], int32[n]) arrays to fill (e.g. views of pinned memory:
+        the copy then runs at the link's rate instead of through the driver's staging buffer); fresh arrays otherwise."""
+        res, nres = out if out is not None else (np.zeros((n_slots, self.M), result_dtype), np.zeros(n_slots, np.int32))
+        assert res.dtype == result_dtype and res.shape == (n_slots, self.M) and nres.dtype == np.int32 and nres.shape == (n_slots,)
         self._chk(self.L.ft8b200_fetch_results(C.c_void_p(self.h), n_slots, _p(res), _p(nres), _st(stream)))
         return res, nres
 

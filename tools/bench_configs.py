@@ -251,15 +251,20 @@ def config4(env, steps):
     ctx.condition(d_i, d_q, peak)    # decoder()'s conditioning: what ft8_subsystem() is handed
     torch.cuda.synchronize()
 
+    pinned = []
+
     def run(k):
         last = None
         for _ in range(k):
             ctx.process_slots(d_i, d_q)
             last = env.gather_records(*ctx.results_tensors(n))
-            if env.rank == 0:
-                last = (last[0].cpu(), last[1].cpu())   # the job's result, every pass: every slot's records on rank 0's host
+            if env.rank == 0:   # the job's result, every pass: every slot's records on rank 0's host (pinned buffers, copies in stream order)
+                if not pinned:
+                    pinned.extend(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in last)
+                pinned[0].copy_(last[0], non_blocking=True)
+                pinned[1].copy_(last[1], non_blocking=True)
         torch.cuda.synchronize()
-        return last
+        return tuple(pinned) if env.rank == 0 else last
 
     run(2)
     reps = max(3, min(steps, 10))
@@ -332,9 +337,13 @@ def config3_daemon(env):
     peak = torch.maximum(d_i.abs().amax(1), d_q.abs().amax(1))
     ctx.condition(d_i, d_q, peak)
 
+    # the caller's result buffers: pinned host memory, allocated once
+    out = (torch.empty((N3, ctx.M * 28), dtype=torch.uint8).pin_memory().numpy().view(pkg.result_dtype).reshape(N3, ctx.M),
+           torch.empty(N3, dtype=torch.int32).pin_memory().numpy())
+
     def run():
         ctx.process_slots(d_i, d_q)
-        return ctx.fetch_results(N3)
+        return ctx.fetch_results(N3, out=out)
     ms = _ev_ms(torch, run, 3)
     res, nres = run()
     Ref, orc, kind = _cpu()
