@@ -400,9 +400,9 @@ sync_score_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g
 // turns its tile of the plane into four 16-bit planes, with a = P - P[c+1], b = P - P[c-1], u = r > 0 ? P - P[r-1] : 0,
 // d = r + 1 < nb ? P - P[r+1] : 0:
 //     W0 = a + b + d   (k = 0)     Wm = a + b + u + d   (k = 1,2,4,5)     W3 = a + u + d   (k = 3)     W6 = a + b + u   (k = 6)
-// each stored with a bias of +1024 (so two cells are computed per 32-bit integer operation without borrows between the halves)
+// each stored with a bias of +256 per difference (so two cells are computed per 32-bit integer operation without borrows between the halves)
 // and with 12 rows before and >= 10 rows after the waterfall holding the biased zero: the reference's `row < 0 -> continue` and
-// `row >= nb -> break` become zero contributions, and a score is 21 loads at compile-time offsets plus 21 adds, minus 21 * 1024.
+// `row >= nb -> break` become zero contributions, and a score is 21 loads at compile-time offsets plus 21 adds, minus the 75 biases.
 // The number of terms it is divided by depends on the time offset only (exact truncating division by multiply-high).
 // The sums are the same integers as the reference's, so the scores are too.
 // grid = (planes * tiles, slots); a tile is kTileF frequency offsets (all 36 time offsets, all rows).
@@ -411,16 +411,40 @@ constexpr int kTilePitch = kTileF + 8;   // 16-bit elements per derived row (71 
 constexpr int kRawPitch = kTileF + 32;   // raw bytes per row: columns fo0 - 16 .. fo0 + 79, whole 16-byte chunks of the waterfall row
 constexpr int kRawLead = 16;             // columns staged before fo0 (4 are needed; 16 keeps the chunks aligned)
 constexpr int kPadBefore = 12;           // time offsets start at -12
-constexpr uint32_t kBias2 = 0x04000400u; // biased zero, two cells
+constexpr uint32_t kBias4 = 0x04000400u; // biased zero of the four-difference plane (two cells): 4 x 256
+constexpr uint32_t kBias3 = 0x03000300u; // ... of the three-difference planes
+constexpr int kBiasPerScore = 3 * (4 * 1024 + 3 * 768);  // 3 groups x (k = 1,2,4,5 on Wm, k = 0,3,6 on W0/W3/W6)
 __host__ __device__ constexpr int fast_rows(int nb) { return kPadBefore + (nb > 102 ? nb : 102); }  // last row touched: 23 + 72 + 6
+
+// Number of terms a score at time offset to = ti - 12 is divided by (ft8_sync_score's num_average), as 2^32 / terms + 1 for the
+// multiply-high division (0: one term or none, no division).  It depends on the waterfall's height only, so the host fills it
+// in once per launch (computed by 36 threads of every CTA it was a serial prologue the other 220 threads waited for: 22 % of
+// the kernel's stall samples).
+struct TermMagic { uint32_t m[36]; };
+static TermMagic term_magic(int nb) {
+    TermMagic tm;
+    for (int ti = 0; ti < 36; ++ti) {
+        const int to = ti - 12;
+        int terms = 0;
+        for (int grp = 0; grp < 3; ++grp)
+            for (int k = 0; k < 7; ++k) {
+                const int row = to + 36 * grp + k;
+                if (row < 0) continue;
+                if (row >= nb) break;
+                terms += (k == 3 ? 1 : 2) + ((k > 0 && row > 0) ? 1 : 0) + ((k < 6 && row + 1 < nb) ? 1 : 0);
+            }
+        tm.m[ti] = terms > 1 ? (0xffffffffu / (uint32_t)terms + 1u) : 0u;
+    }
+    return tm;
+}
 
 // two 16-bit lanes per word, every lane stays non-negative: a' = P + 256 - N in [1, 511]
 __device__ __forceinline__ uint32_t diff2(uint32_t p2, uint32_t n2) { return p2 + 0x01000100u - n2; }
 
 __global__ void __launch_bounds__(kScoreThreads)
-sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int tiles, int16_t *__restrict__ scores_all, SelArgs sa) {
+sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, Geo g, int tiles, int16_t *__restrict__ scores_all, SelArgs sa,
+                      const TermMagic tm) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t s_magic[36];
     __shared__ int s_over;
     const int tid = threadIdx.x, slot = blockIdx.y;
     if (tid == 0) s_over = 0;
@@ -463,18 +487,6 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
             reinterpret_cast<uint32_t *>(raw + (size_t)r * kRawPitch)[wi] = word;
         }
     }
-    if (tid < 36) {  // number of terms of a score at time offset to = tid - 12 (ft8_sync_score's num_average) -> 2^32 / terms + 1
-        const int to = tid - 12;
-        int terms = 0;
-        for (int grp = 0; grp < 3; ++grp)
-            for (int k = 0; k < 7; ++k) {
-                const int row = to + 36 * grp + k;
-                if (row < 0) continue;
-                if (row >= nb) break;
-                terms += (k == 3 ? 1 : 2) + ((k > 0 && row > 0) ? 1 : 0) + ((k < 6 && row + 1 < nb) ? 1 : 0);
-            }
-        s_magic[tid] = terms > 1 ? (0xffffffffu / (uint32_t)terms + 1u) : 0u;  // 0: divide by 1 (or nothing to divide)
-    }
     __syncthreads();
     constexpr int kGroups = kTilePitch / 4;  // 18 groups of 4 cells per row
     constexpr int kPrepRows = kScoreThreads / kGroups;   // 14 rows per trip (252 threads busy): no division inside the loop
@@ -483,7 +495,8 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
         const int r = rp - kPadBefore;
         uint2 o0, om, o3, o6;
         if (r < 0 || r >= nb) {
-            o0 = om = o3 = o6 = make_uint2(kBias2, kBias2);
+            om = make_uint2(kBias4, kBias4);
+            o0 = o3 = o6 = make_uint2(kBias3, kBias3);
         } else {
             // words: [0] left, [1] the 4 cells (columns fo0 + 4q ..), [2] right
             const uint32_t *row = reinterpret_cast<const uint32_t *>(raw + (size_t)r * kRawPitch) + (kRawLead / 4 - 1) + q;
@@ -502,12 +515,11 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
                 const uint32_t wd = row[kWordsPerRow + 1];
                 d01 = diff2(p01, __byte_perm(wd, 0u, 0x4140)); d23 = diff2(p23, __byte_perm(wd, 0u, 0x4342));
             }
-            const uint32_t k1 = 0x01000100u;
             const uint32_t ab01 = a01 + b01, ab23 = a23 + b23, ud01 = u01 + d01, ud23 = u23 + d23;
-            o0 = make_uint2(ab01 + d01 + k1, ab23 + d23 + k1);
+            o0 = make_uint2(ab01 + d01, ab23 + d23);
             om = make_uint2(ab01 + ud01, ab23 + ud23);
-            o3 = make_uint2(a01 + ud01 + k1, a23 + ud23 + k1);
-            o6 = make_uint2(ab01 + u01 + k1, ab23 + u23 + k1);
+            o3 = make_uint2(a01 + ud01, a23 + ud23);
+            o6 = make_uint2(ab01 + u01, ab23 + u23);
         }
         uint2 *dst = reinterpret_cast<uint2 *>(w0 + (size_t)rp * kTilePitch) + q;
         dst[0] = o0;
@@ -521,25 +533,43 @@ sync_score_ft8_kernel(const uint8_t *__restrict__ mag_all, size_t slot_stride, G
     const int pos0 = plane_id * 36 * g.nfo;
     int16_t *scores = scores_all + (size_t)slot * g.npos + pos0;
     constexpr int kCostas8[7] = {3, 1, 4, 0, 6, 5, 2};
-    for (int ti = tid / kTileF; ti < 36; ti += kScoreThreads / kTileF) {  // warp-uniform time offset to = ti - 12: padded row = ti + 36 grp + k
-        const uint16_t *b0 = w0 + ti * kTilePitch + fl, *bm = b0 + plane_elems, *b3 = bm + plane_elems, *b6 = b3 + plane_elems;
+    // A thread scores its frequency offset at kPerThread time offsets ti0, ti0 + 4, ... (warp-uniform; padded row = ti + 36 grp + k).
+    // Fully unrolled: the 21 x 9 loads are immediates off four base registers.  Survivors are rare, so they are looked for once
+    // per thread after the loop (one ballot per warp) instead of once per score.
+    constexpr int kTiStep = kScoreThreads / kTileF, kPerThread = 36 / kTiStep;
+    static_assert(kTiStep * kPerThread == 36, "time offsets must divide evenly among the threads of a column");
+    const int ti0 = tid / kTileF;
+    const uint16_t *b0 = w0 + ti0 * kTilePitch + fl, *bm = b0 + plane_elems, *b3 = bm + plane_elems, *b6 = b3 + plane_elems;
+    int16_t *out = scores + ti0 * g.nfo + fo;
+    const int out_step = kTiStep * g.nfo;
+    int sc[kPerThread];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+        const int row0 = i * kTiStep * kTilePitch;
         int sum = 0;
 #pragma unroll
         for (int grp = 0; grp < 3; ++grp) {
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
                 const uint16_t *w = k == 0 ? b0 : (k == 3 ? b3 : (k == 6 ? b6 : bm));
-                sum += w[(36 * grp + k) * kTilePitch + kCostas8[k]];
+                sum += w[row0 + (36 * grp + k) * kTilePitch + kCostas8[k]];
             }
         }
-        int score = sum - 21 * 1024;
-        const uint32_t magic = s_magic[ti];
+        int score = sum - kBiasPerScore;
+        const uint32_t magic = tm.m[ti0 + i * kTiStep];
         if (magic) {  // truncating division by the number of terms
-            const uint32_t mag_q = __umulhi((uint32_t)(score < 0 ? -score : score), magic);
+            const uint32_t mag_q = __umulhi((uint32_t)abs(score), magic);
             score = score < 0 ? -(int)mag_q : (int)mag_q;
         }
-        if (valid) scores[ti * g.nfo + fo] = (int16_t)score;
-        emit_survivor(sa, slot, valid && score >= sa.min_score, survivor_word(pos0 + ti * g.nfo + fo, score), &s_over);
+        sc[i] = score;
+        if (valid) out[i * out_step] = (int16_t)score;
+        any |= score >= sa.min_score;
+    }
+    if (__ballot_sync(0xffffffffu, any && valid)) {
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i)
+            emit_survivor(sa, slot, valid && sc[i] >= sa.min_score, survivor_word(pos0 + (ti0 + i * kTiStep) * g.nfo + fo, sc[i]), &s_over);
     }
 }
 
@@ -582,7 +612,7 @@ cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slo
         const int tiles = (g.nfo + kTileF - 1) / kTileF;
         e = cudaFuncSetAttribute(sync_score_ft8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         if (e != cudaSuccess) return e;
-        sync_score_ft8_kernel<<<dim3(planes * tiles, n_slots), kScoreThreads, fast_smem, st>>>(d_mag, slot_stride, g, tiles, d_scores, sa);
+        sync_score_ft8_kernel<<<dim3(planes * tiles, n_slots), kScoreThreads, fast_smem, st>>>(d_mag, slot_stride, g, tiles, d_scores, sa, term_magic(g.nb));
     } else if (staged <= 200 * 1024) {
         if (g.nbins == 256 && !ft4) {
             sync_score_kernel<256, true, false><<<grid, kScoreThreads, staged, st>>>(d_mag, slot_stride, g, splits, to_per_cta, d_scores, sa);

@@ -57,6 +57,14 @@ def test_reference_decode_ft8_on_the_library(tmp_path):
     check_decode_ft8(DECODE, str(tmp_path))
 
 
+@pytest.mark.gpu
+@needs_programs
+def test_reference_decode_ft8_on_the_library_deferred_monitor(tmp_path):
+    """The same binary with FT8B200_MONITOR_DEFERRED=1: monitor_process() only appends its block, ft8_find_sync() transforms all
+    93 blocks in one launch (one copy and one synchronisation per recording instead of 93).  Same stdout."""
+    check_decode_ft8(DECODE, str(tmp_path), dict(os.environ, FT8B200_MONITOR_DEFERRED="1"))
+
+
 @needs_programs
 def test_relinked_programs_flow_with_a_cpu_stand_in(tmp_path):
     """No GPU: the SAME two binaries, with `libft8b200.so` resolved to a CPU stand-in built on the oracle
