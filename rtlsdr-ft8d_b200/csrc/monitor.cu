@@ -70,10 +70,11 @@ __device__ __forceinline__ int quantise(float x, const float2 *__restrict__ thr2
 }
 
 // one butterfly of radix P on z[i0 + q m], q < P, with the stage's compact twiddles tq[(q - 1) m + k]
+// ix[q] = where z[i0 + q m] lives (the logical index itself, or its padded place: StaticPlan::pad)
 template <int P>
-__device__ __forceinline__ void butterfly(float2 *z, const float2 *tq, int i0, int m, int k, float2 c1, float2 c2) {
-    if (P == 4) {  // kf_bfly4, kiss_fft.c:38-84
-        cpx f0 = ld(z, i0), f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m), f3 = ld(z, i0 + 3 * m);
+__device__ __forceinline__ void butterfly(float2 *z, const float2 *tq, const int (&ix)[P], int m, int k, float2 c1, float2 c2) {
+    if constexpr (P == 4) {  // kf_bfly4, kiss_fft.c:38-84
+        cpx f0 = ld(z, ix[0]), f1 = ld(z, ix[1]), f2 = ld(z, ix[2]), f3 = ld(z, ix[3]);
         const cpx a = cmul(f1, tq[k]);
         const cpx bb = cmul(f2, tq[m + k]);
         const cpx c = cmul(f3, tq[2 * m + k]);
@@ -82,20 +83,20 @@ __device__ __forceinline__ void butterfly(float2 *z, const float2 *tq, int i0, i
         const cpx s3 = cadd(a, c), s4 = csub(a, c);
         f2 = csub(f0, s3);
         f0 = cadd(f0, s3);
-        st(z, i0, f0);
-        st(z, i0 + 2 * m, f2);
-        st(z, i0 + m, cpx{__fadd_rn(d5.r, s4.i), __fsub_rn(d5.i, s4.r)});
-        st(z, i0 + 3 * m, cpx{__fsub_rn(d5.r, s4.i), __fadd_rn(d5.i, s4.r)});
-    } else if (P == 2) {  // kf_bfly2, kiss_fft.c:15-36
-        cpx f0 = ld(z, i0), f1 = ld(z, i0 + m);
+        st(z, ix[0], f0);
+        st(z, ix[2], f2);
+        st(z, ix[1], cpx{__fadd_rn(d5.r, s4.i), __fsub_rn(d5.i, s4.r)});
+        st(z, ix[3], cpx{__fsub_rn(d5.r, s4.i), __fadd_rn(d5.i, s4.r)});
+    } else if constexpr (P == 2) {  // kf_bfly2, kiss_fft.c:15-36
+        cpx f0 = ld(z, ix[0]), f1 = ld(z, ix[1]);
         const cpx tt = cmul(f1, tq[k]);
         f1 = csub(f0, tt);
         f0 = cadd(f0, tt);
-        st(z, i0, f0);
-        st(z, i0 + m, f1);
-    } else if (P == 3) {  // kf_bfly3, kiss_fft.c:86-128
+        st(z, ix[0], f0);
+        st(z, ix[1], f1);
+    } else if constexpr (P == 3) {  // kf_bfly3, kiss_fft.c:86-128
         const float2 e3 = c1;
-        cpx f0 = ld(z, i0), f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m);
+        cpx f0 = ld(z, ix[0]), f1 = ld(z, ix[1]), f2 = ld(z, ix[2]);
         const cpx s1 = cmul(f1, tq[k]);
         const cpx s2 = cmul(f2, tq[m + k]);
         const cpx s3 = cadd(s1, s2);
@@ -109,19 +110,19 @@ __device__ __forceinline__ void butterfly(float2 *z, const float2 *tq, int i0, i
         f2.i = __fsub_rn(f1.i, s0.r);
         f1.r = __fsub_rn(f1.r, s0.i);
         f1.i = __fadd_rn(f1.i, s0.r);
-        st(z, i0, f0);
-        st(z, i0 + m, f1);
-        st(z, i0 + 2 * m, f2);
+        st(z, ix[0], f0);
+        st(z, ix[1], f1);
+        st(z, ix[2], f2);
     } else {  // P == 5: kf_bfly5, kiss_fft.c:130-190
         const float2 ya = c1, yb = c2;
-        const cpx s0 = ld(z, i0);
-        cpx f1 = ld(z, i0 + m), f2 = ld(z, i0 + 2 * m), f3 = ld(z, i0 + 3 * m), f4 = ld(z, i0 + 4 * m);
+        const cpx s0 = ld(z, ix[0]);
+        cpx f1 = ld(z, ix[1]), f2 = ld(z, ix[2]), f3 = ld(z, ix[3]), f4 = ld(z, ix[4]);
         const cpx s1 = cmul(f1, tq[k]);
         const cpx s2 = cmul(f2, tq[m + k]);
         const cpx s3 = cmul(f3, tq[2 * m + k]);
         const cpx s4 = cmul(f4, tq[3 * m + k]);
         const cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
-        st(z, i0, cpx{__fadd_rn(s0.r, __fadd_rn(s7.r, s8.r)), __fadd_rn(s0.i, __fadd_rn(s7.i, s8.i))});
+        st(z, ix[0], cpx{__fadd_rn(s0.r, __fadd_rn(s7.r, s8.r)), __fadd_rn(s0.i, __fadd_rn(s7.i, s8.i))});
         cpx s5, s6, s11, s12;
         s5.r = __fadd_rn(__fadd_rn(s0.r, __fmul_rn(s7.r, ya.x)), __fmul_rn(s8.r, yb.x));
         s5.i = __fadd_rn(__fadd_rn(s0.i, __fmul_rn(s7.i, ya.x)), __fmul_rn(s8.i, yb.x));
@@ -135,40 +136,82 @@ __device__ __forceinline__ void butterfly(float2 *z, const float2 *tq, int i0, i
         s12.i = __fsub_rn(__fmul_rn(s10.r, yb.y), __fmul_rn(s9.r, ya.y));
         f2 = cadd(s11, s12);
         f3 = csub(s11, s12);
-        st(z, i0 + m, f1);
-        st(z, i0 + 2 * m, f2);
-        st(z, i0 + 3 * m, f3);
-        st(z, i0 + 4 * m, f4);
+        st(z, ix[1], f1);
+        st(z, ix[2], f2);
+        st(z, ix[3], f3);
+        st(z, ix[4], f4);
     }
+}
+template <int P>
+__device__ __forceinline__ void butterfly_at(float2 *z, const float2 *tq, int i0, int m, int k, float2 c1, float2 c2) {
+    int ix[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) ix[q] = i0 + q * m;
+    butterfly<P>(z, tq, ix, m, k, c1, c2);
 }
 
 // Compile-time stage lists of the two geometries in use (kf_factor's decomposition, execution order = innermost recursion first):
 // FT8 at 12 kHz: 3840-point frames -> 1920 = 5 * 3 * 2 * 4 * 4 * 4;  FT4 at 12 kHz: 1152-point frames -> 576 = 3 * 3 * 4 * 4 * 4.
 // The launcher uses them only when the host-built plan (build_plan) is identical; any other size runs the generic stage loop.
-template <int N> struct StaticPlan { static constexpr int ns = 0; };
+// Shared-memory placement (measured in round 2: 47 M bank conflicts per 128 recordings, twice the ideal wavefront count, on a
+// kernel whose shared-memory pipe was ~70 % busy).  Two compile-time knobs per plan, chosen by exhaustive simulation of the
+// 16 x 8-byte banks (tools/fft_bank_sim.py): `pad` -- one unused float2 after every `pad` elements (element i lives at i + i / pad) --
+// and, per stage, which index runs fastest across a warp's butterflies: k (the twiddle index; consecutive elements) or g (the group;
+// stride radix * m, odd after padding).  3840-point frames: pad 240 + {k, g, g, g, k, k} -> 1702 wavefronts per frame against an
+// ideal 1682 (was 3370, the scattered leaf store alone 960).
+template <int N> struct StaticPlan { static constexpr int ns = 0; static constexpr int pad = 0; };
+static_assert(StaticPlan<0>::ns == 0 && StaticPlan<0>::pad == 0, "the generic kernel has no compile-time plan");
 template <> struct StaticPlan<1920> {
     static constexpr int ns = 6;
+    static constexpr int pad = 240;
     __host__ __device__ static constexpr int radix(int s) { constexpr int r[6] = {5, 3, 2, 4, 4, 4}; return r[s]; }
     __host__ __device__ static constexpr int m(int s) { constexpr int v[6] = {1, 5, 15, 30, 120, 480}; return v[s]; }
+    __host__ __device__ static constexpr bool gfast(int s) { constexpr bool v[6] = {false, true, true, true, false, false}; return v[s]; }
 };
 template <> struct StaticPlan<576> {
     static constexpr int ns = 5;
+    static constexpr int pad = 0;
     __host__ __device__ static constexpr int radix(int s) { constexpr int r[5] = {3, 3, 4, 4, 4}; return r[s]; }
     __host__ __device__ static constexpr int m(int s) { constexpr int v[5] = {1, 3, 9, 36, 144}; return v[s]; }
+    __host__ __device__ static constexpr bool gfast(int s) { constexpr bool v[5] = {false, true, false, false, false}; return v[s]; }
 };
+template <int N> __host__ __device__ constexpr int padded(int i) { return StaticPlan<N>::pad > 0 ? i + i / StaticPlan<N>::pad : i; }
+// elements of z: n plus the pad slots
+// (rounded up to an even count: the arrays behind z keep their 16-byte alignment)
+__host__ __device__ constexpr int z_len(int static_n, int n) { return static_n == 1920 ? (padded<1920>(1920 - 1) + 2) & ~1 : n; }
 template <int N> __host__ __device__ constexpr int static_tw_off(int s) { return s == 0 ? 0 : static_tw_off<N>(s - 1) + (StaticPlan<N>::radix(s - 1) - 1) * StaticPlan<N>::m(s - 1); }
 
 template <int N, int S>
 __device__ __forceinline__ void static_stages(float2 *z, const float2 *tws, const FftPlan &plan, int t) {
     if constexpr (S < StaticPlan<N>::ns) {
-        constexpr int p = StaticPlan<N>::radix(S), m = StaticPlan<N>::m(S), nbf = N / p;
+        constexpr int p = StaticPlan<N>::radix(S), m = StaticPlan<N>::m(S), nbf = N / p, groups = nbf / m, B = StaticPlan<N>::pad;
         const float2 *tq = tws + static_tw_off<N>(S);
 #pragma unroll
         for (int b0 = 0; b0 < nbf; b0 += kMonThreads) {
             const int b = b0 + t;
             if (b0 + kMonThreads <= nbf || b < nbf) {
-                const int g = b / m, k = b - g * m;   // m is a compile-time constant: multiply + shift
-                butterfly<p>(z, tq, g * p * m + k, m, k, plan.c1[S], plan.c2[S]);
+                // m and groups are compile-time constants: multiply + shift
+                const int g = StaticPlan<N>::gfast(S) ? b % groups : b / m, k = StaticPlan<N>::gfast(S) ? b / groups : b - g * m;
+                const int i0 = g * p * m + k;
+                int ix[p];
+                if constexpr (B == 0) {
+#pragma unroll
+                    for (int q = 0; q < p; ++q) ix[q] = i0 + q * m;
+                } else if constexpr (B % (p * m) == 0) {          // the butterfly's p legs share a pad block
+                    const int off = g / (B / (p * m));
+#pragma unroll
+                    for (int q = 0; q < p; ++q) ix[q] = i0 + q * m + off;
+                } else if constexpr ((p * m) % B == 0 && B % m == 0) {   // B / m legs per pad block (k < m <= B)
+                    const int off = g * (p * m / B);
+#pragma unroll
+                    for (int q = 0; q < p; ++q) ix[q] = i0 + q * m + off + q / (B / m);
+                } else {                                           // m a multiple of B: each leg spans m / B blocks
+                    static_assert(m % B == 0 && (p * m) % B == 0, "pad block must nest with the stage geometry");
+                    const int off = g * (p * m / B) + k / B;
+#pragma unroll
+                    for (int q = 0; q < p; ++q) ix[q] = i0 + q * m + off + q * (m / B);
+                }
+                butterfly<p>(z, tq, ix, m, k, plan.c1[S], plan.c2[S]);
             }
         }
         __syncthreads();
@@ -176,7 +219,7 @@ __device__ __forceinline__ void static_stages(float2 *z, const float2 *tws, cons
     }
 }
 
-// dynamic smem: z float2[n] | stage twiddles float2[tw_total] | super twiddles float2[n/2 + 1] | thr2 float2[256] | out u8[2 n]
+// dynamic smem: z float2[z_len] | stage twiddles float2[tw_total] | super twiddles float2[n/2 + 1] | thr2 float2[256] | out u8[2 n]
 // kN = 0: generic stage loop from the run-time plan; kN = 1920 / 576: the stage loop unrolled at compile time (StaticPlan)
 template <int kN>
 __global__ void __launch_bounds__(kMonThreads)
@@ -186,7 +229,7 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
                       uint8_t *__restrict__ mag, size_t mag_slot_stride, unsigned int *__restrict__ xmax_bits) {
     extern __shared__ __align__(16) float2 smem2[];
     const int n = kN > 0 ? kN : plan.n, t = threadIdx.x;
-    float2 *z = smem2, *tws = z + n, *sup = tws + plan.tw_total, *thr2 = sup + (n / 2 + 1);
+    float2 *z = smem2, *tws = z + z_len(kN, n), *sup = tws + plan.tw_total, *thr2 = sup + (n / 2 + 1);
     uint8_t *outb = reinterpret_cast<uint8_t *>(thr2 + 256);
     const int it_begin = (int)((long long)blockIdx.x * total_items / gridDim.x), it_end = (int)((long long)(blockIdx.x + 1) * total_items / gridDim.x);
     if (it_begin >= it_end) return;
@@ -206,7 +249,7 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
             const float a = (p0 >= 0 && p0 < n_samples) ? x[p0] : 0.0f;
             const float b = (p1 >= 0 && p1 < n_samples) ? x[p1] : 0.0f;
             const float2 w = *reinterpret_cast<const float2 *>(wnorm + 2 * src);
-            z[inv_perm[src]] = make_float2(__fmul_rn(w.x, a), __fmul_rn(w.y, b));   // (fft_norm * window[pos]) * last_frame[pos], decode_ft8.c:191
+            z[inv_perm[src]] = make_float2(__fmul_rn(w.x, a), __fmul_rn(w.y, b));   // (fft_norm * window[pos]) * last_frame[pos], decode_ft8.c:191; inv_perm holds the (padded) place
         }
         __syncthreads();
         if constexpr (kN > 0) {
@@ -220,10 +263,10 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
                 for (int b = t; b < nbf; b += kMonThreads) {
                     const int g = magic ? (int)__umulhi((unsigned int)b, magic) : b, k = b - g * m;
                     const int i0 = g * p * m + k;
-                    if (p == 4) butterfly<4>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
-                    else if (p == 2) butterfly<2>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
-                    else if (p == 3) butterfly<3>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
-                    else butterfly<5>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    if (p == 4) butterfly_at<4>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    else if (p == 2) butterfly_at<2>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    else if (p == 3) butterfly_at<3>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    else butterfly_at<5>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
                 }
                 __syncthreads();
             }
@@ -234,12 +277,12 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
             cpx lo, hi;  // bins k and n-k
             bool have_hi = false;
             if (k == 0) {
-                const float2 z0 = z[0];
+                const float2 z0 = z[0];   // element 0 is never displaced by the padding
                 lo.r = __fadd_rn(z0.x, z0.y);
                 lo.i = 0.0f;
             } else {
-                const cpx fpk = ld(z, k);
-                const float2 zn = z[n - k];
+                const cpx fpk = ld(z, padded<kN>(k));
+                const float2 zn = z[padded<kN>(n - k)];
                 const cpx fpnk{zn.x, -zn.y};
                 const cpx f1 = cadd(fpk, fpnk), f2 = csub(fpk, fpnk);
                 const cpx tt = cmul(f2, sup[k - 1]);
@@ -289,6 +332,7 @@ struct MonTables {
     float *d_wnorm = nullptr;
     std::vector<float> window;  // Hann, host copy
     float fft_norm = 0;
+    int static_n = 0;           // 1920 / 576: the plan is the one StaticPlan spells out (compile-time stage list, padded placement); else 0
     size_t smem = 0;            // launch shape of monitor_frames_kernel for these tables, worked out once
     long max_grid = 0;
 };
@@ -364,8 +408,16 @@ MonTables *get_tables(int device, int nfft) {
         t->plan.c2[s2] = tw[(size_t)(2 * fs * m) % (size_t)n];
     }
     t->plan.tw_total = (int)tws.size();
+    // compile-time stage list when the host-built plan is exactly the one StaticPlan spells out
+    auto matches = [&](auto tag) {
+        using SP = decltype(tag);
+        if (SP::ns == 0 || t->plan.nstages != SP::ns) return false;
+        for (int s2 = 0; s2 < SP::ns; ++s2) if (t->plan.radix[s2] != SP::radix(s2) || t->plan.m[s2] != SP::m(s2)) return false;
+        return true;
+    };
+    t->static_n = (n == 1920 && matches(StaticPlan<1920>{})) ? 1920 : (n == 576 && matches(StaticPlan<576>{})) ? 576 : 0;
     std::vector<uint16_t> inv((size_t)n);
-    for (int o = 0; o < n; ++o) inv[perm[(size_t)o]] = (uint16_t)o;
+    for (int o = 0; o < n; ++o) inv[perm[(size_t)o]] = (uint16_t)(t->static_n == 1920 ? padded<1920>(o) : o);   // the element's place in z
     perm.swap(inv);
     for (int k = 0; k < n / 2; ++k) {  // kiss_fftr_alloc, kiss_fftr.c:50-56
         const double phase = -3.14159265358979323846264338327 * ((double)(k + 1) / n + .5);
@@ -409,19 +461,12 @@ cudaError_t launch_frames(const MonTables *t, const float *d_audio, size_t slot_
                           int n_slots, int num_bins, int freq_osr, uint8_t *d_mag, size_t mag_slot_stride, unsigned int *d_xmax, cudaStream_t st) {
     const int n = t->plan.n;
     cudaError_t e;
-    // compile-time stage list when the host-built plan is exactly the one StaticPlan spells out
-    auto matches = [&](auto tag) {
-        using SP = decltype(tag);
-        if (SP::ns == 0 || t->plan.nstages != SP::ns) return false;
-        for (int s2 = 0; s2 < SP::ns; ++s2) if (t->plan.radix[s2] != SP::radix(s2) || t->plan.m[s2] != SP::m(s2)) return false;
-        return true;
-    };
     auto kern = monitor_frames_kernel<0>;
-    if (n == 1920 && matches(StaticPlan<1920>{})) kern = monitor_frames_kernel<1920>;
-    else if (n == 576 && matches(StaticPlan<576>{})) kern = monitor_frames_kernel<576>;
+    if (t->static_n == 1920) kern = monitor_frames_kernel<1920>;
+    else if (t->static_n == 576) kern = monitor_frames_kernel<576>;
     if (t->max_grid == 0) {  // once per (device, nfft): monitor_process() launches this 93 times per recording
         // z | stage twiddles | super twiddles | threshold pairs | one frame's bytes (see monitor_frames_kernel)
-        const size_t need = sizeof(float2) * ((size_t)n + (size_t)t->plan.tw_total + (size_t)(n / 2 + 1) + 256) + (((size_t)2 * n + 15) & ~(size_t)15);
+        const size_t need = sizeof(float2) * ((size_t)z_len(t->static_n, n) + (size_t)t->plan.tw_total + (size_t)(n / 2 + 1) + 256) + (((size_t)2 * n + 15) & ~(size_t)15);
         int sms = 0, per_sm = 0;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)) != cudaSuccess) return e;
