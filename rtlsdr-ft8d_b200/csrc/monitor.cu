@@ -222,7 +222,7 @@ __device__ __forceinline__ void static_stages(float2 *z, const float2 *tws, cons
 // dynamic smem: z float2[z_len] | stage twiddles float2[tw_total] | super twiddles float2[n/2 + 1] | thr2 float2[256] | out u8[2 n]
 // kN = 0: generic stage loop from the run-time plan; kN = 1920 / 576: the stage loop unrolled at compile time (StaticPlan)
 template <int kN>
-__global__ void __launch_bounds__(kMonThreads)
+__global__ void __launch_bounds__(kMonThreads, 4)
 monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n_samples, long first_start, int hop, int nfft, FftPlan plan,
                       const uint16_t *__restrict__ inv_perm, const float2 *__restrict__ tw_stage, const float2 *__restrict__ super_tw,
                       const float *__restrict__ wnorm, const float *__restrict__ thr_g, int num_bins, int freq_osr, int n_frames, int total_items,
@@ -237,19 +237,61 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
     for (int k = t; k < n / 2 + 1; k += kMonThreads) sup[k] = super_tw[k];
     for (int k = t; k < 256; k += kMonThreads) thr2[k] = make_float2(thr_g[k], thr_g[k + 1]);
     const int wanted = num_bins * freq_osr;  // bins 0 .. wanted-1 are stored (wanted <= n)
+    const bool osr2 = freq_osr == 2;         // the usual oversampling: no run-time division in the store index
+    auto cell = [&](int k) { return osr2 ? (k & 1) * num_bins + (k >> 1) : (k % freq_osr) * num_bins + k / freq_osr; };
 
-    for (int item = it_begin; item < it_end; ++item) {
+    // Static plans: a thread's sample pairs of the NEXT frame are fetched into registers as soon as the current frame's have been
+    // windowed into z, so the loads are in flight during the whole transform (waiting for them at the top of every frame was 11 % of
+    // the kernel's stall samples).
+    constexpr int kPer = kN > 0 ? (kN + kMonThreads - 1) / kMonThreads : 1;
+    float2 pre[kPer];
+    auto fetch = [&](int item) {
         const int slot = item / n_frames, frame = item - slot * n_frames;
         const float *x = audio + (size_t)slot * slot_stride;
         const long start = first_start + (long)frame * hop;
+        const bool pairs = ((((size_t)x) >> 2) + (size_t)(start & 1)) % 2 == 0;   // x + start is 8-byte aligned (x is a float pointer)
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int src = t + j * kMonThreads;
+            const long p0 = start + 2 * src, p1 = p0 + 1;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (kPer * kMonThreads == n || src < n) {
+                if (pairs && p0 >= 0 && p1 < n_samples) {
+                    v = *reinterpret_cast<const float2 *>(x + p0);
+                } else {
+                    if (p0 >= 0 && p0 < n_samples) v.x = x[p0];
+                    if (p1 >= 0 && p1 < n_samples) v.y = x[p1];
+                }
+            }
+            pre[j] = v;
+        }
+    };
+    if constexpr (kN > 0) fetch(it_begin);
+
+    for (int item = it_begin; item < it_end; ++item) {
+        const int slot = item / n_frames, frame = item - slot * n_frames;
         __syncthreads();  // tables loaded / the previous frame's bytes have left outb and z
         // windowed, normalised frame, packed (even, odd) -> complex, written to kiss_fft's permuted leaf place
-        for (int src = t; src < n; src += kMonThreads) {
-            const long p0 = start + 2 * src, p1 = p0 + 1;
-            const float a = (p0 >= 0 && p0 < n_samples) ? x[p0] : 0.0f;
-            const float b = (p1 >= 0 && p1 < n_samples) ? x[p1] : 0.0f;
-            const float2 w = *reinterpret_cast<const float2 *>(wnorm + 2 * src);
-            z[inv_perm[src]] = make_float2(__fmul_rn(w.x, a), __fmul_rn(w.y, b));   // (fft_norm * window[pos]) * last_frame[pos], decode_ft8.c:191; inv_perm holds the (padded) place
+        if constexpr (kN > 0) {
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int src = t + j * kMonThreads;
+                if (kPer * kMonThreads == n || src < n) {
+                    const float2 w = *reinterpret_cast<const float2 *>(wnorm + 2 * src);
+                    z[inv_perm[src]] = make_float2(__fmul_rn(w.x, pre[j].x), __fmul_rn(w.y, pre[j].y));   // (fft_norm * window[pos]) * last_frame[pos], decode_ft8.c:191; inv_perm holds the (padded) place
+                }
+            }
+            if (item + 1 < it_end) fetch(item + 1);
+        } else {
+            const float *x = audio + (size_t)slot * slot_stride;
+            const long start = first_start + (long)frame * hop;
+            for (int src = t; src < n; src += kMonThreads) {
+                const long p0 = start + 2 * src, p1 = p0 + 1;
+                const float a = (p0 >= 0 && p0 < n_samples) ? x[p0] : 0.0f;
+                const float b = (p1 >= 0 && p1 < n_samples) ? x[p1] : 0.0f;
+                const float2 w = *reinterpret_cast<const float2 *>(wnorm + 2 * src);
+                z[inv_perm[src]] = make_float2(__fmul_rn(w.x, a), __fmul_rn(w.y, b));
+            }
         }
         __syncthreads();
         if constexpr (kN > 0) {
@@ -297,14 +339,14 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
                 const float m2 = __fadd_rn(__fmul_rn(lo.i, lo.i), __fmul_rn(lo.r, lo.r));
                 const float xv = __fadd_rn(1E-12f, m2);
                 xmax = fmaxf(xmax, xv);
-                outb[(k % freq_osr) * num_bins + k / freq_osr] = (uint8_t)quantise(xv, thr2);
+                outb[cell(k)] = (uint8_t)quantise(xv, thr2);
             }
             const int kh = n - k;
             if (have_hi && kh != k && kh < wanted) {
                 const float m2 = __fadd_rn(__fmul_rn(hi.i, hi.i), __fmul_rn(hi.r, hi.r));
                 const float xv = __fadd_rn(1E-12f, m2);
                 xmax = fmaxf(xmax, xv);
-                outb[(kh % freq_osr) * num_bins + kh / freq_osr] = (uint8_t)quantise(xv, thr2);
+                outb[cell(kh)] = (uint8_t)quantise(xv, thr2);
             }
         }
         if (xmax_bits) {
