@@ -119,7 +119,12 @@ def roofline_extra(env, batch, n_slots, hbm_peak, peak_source, sm_mhz):
     sig, first, _ = _batch_signals(pkg, range(n_mon), 4, 300.0, 2800.0, 0.2, 1.2, 0.05, 0.3)
     aud = ctx.synth_audio(sig, first, 1, 0.05, 13)
     ms = _ev_ms(torch, lambda: ctx.monitor_waterfall(aud), 10)
-    out.append(hbm("monitor_frames_kernel", ms, bench.MON_BYTES_PER_SLOT, n_mon, "3840-point real FFT per frame with kiss_fftr's arithmetic: FP32-issue bound like the daemon waterfall"))
+    mon = hbm("monitor_frames_kernel", ms, bench.MON_BYTES_PER_SLOT, n_mon, "3840-point real FFT per frame with kiss_fftr's arithmetic: issue bound like the daemon waterfall "
+                                                                            "(issue_frac = its warp instructions against every issue slot of the GPU); the HBM fraction is what the north star asked to be reported")
+    per_rec = inst.get("monitor", {}).get("warp_inst_per_slot")
+    if per_rec and ms > 0:
+        mon["issue_frac"] = per_rec * n_mon / (ms * 1e-3) / issue_peak
+    out.append(mon)
     mag, nb = ctx.monitor_waterfall(aud)
     ms = _ev_ms(torch, lambda: ctx.find_sync(mag, num_blocks=nb, num_bins=960), 10)
     out.append(issue("sync_score_ft8_kernel + sync_select_kernel at the 12 kHz geometry (960 bins, 137 232 positions)", ms, n_mon, "sync960"))
@@ -142,7 +147,6 @@ def config5(env, batch, texts, depth=3, streams_per_batch=16):
     lo, hi = shard_range(n_streams_total, env.rank, env.world)
     mine = hi - lo
     resident = batch.shape[0] // spp
-    spb = min(streams_per_batch, resident, mine)
     pipe = pkg.Pipe(env.local, depth)
     pipe.set_mode(serial=False)
     partitioned = True
@@ -151,17 +155,21 @@ def config5(env, batch, texts, depth=3, streams_per_batch=16):
     except Exception as exc:   # a driver without green contexts
         partitioned = False
         pipe.set_mode(serial=True)
-        executor = "ft8b200_pipe_t depth %d, serial (%s)" % (depth, exc)
     M = pipe.M
-    # the rank's batches: (first resident stream, streams)
-    plan, s0 = [], 0
-    while s0 < mine:
-        n = min(spb, mine - s0)
-        first = s0 % resident
-        if first + n > resident:
-            n = resident - first
-        plan.append((first, n))
-        s0 += n
+    state = {"plan": []}
+
+    def make_plan(spb):
+        """the rank's batches: (first resident stream, streams)"""
+        plan, s0 = [], 0
+        while s0 < mine:
+            n = min(spb, mine - s0)
+            first = s0 % resident
+            if first + n > resident:
+                n = resident - first
+            plan.append((first, n))
+            s0 += n
+        state["plan"] = plan
+
     recs = torch.zeros((mine * spp, M, 28), dtype=torch.uint8, device=env.device)
     cnts = torch.zeros(mine * spp, dtype=torch.int32, device=env.device)
     copied = torch.cuda.Event()
@@ -179,7 +187,7 @@ def config5(env, batch, texts, depth=3, streams_per_batch=16):
             pipe.depend_on(copied)   # the lane's buffers are rewritten only after they have been copied out
             done += n
 
-        for first, n in plan:
+        for first, n in state["plan"]:
             if pipe.in_flight() == pipe.depth:
                 collect()
             pipe.submit_streams(batch[first * spp:(first + n) * spp], n, spp)
@@ -189,19 +197,33 @@ def config5(env, batch, texts, depth=3, streams_per_batch=16):
         torch.cuda.synchronize()
         return last
 
-    run(); run()
-    if partitioned:
-        # the split is probed on THIS workload (stream batches carry a heavier comb+FIR pass than independent slots): one untimed pass
-        # of the rank's whole plan per candidate, the fastest is kept; every rank takes the same one (max over ranks per candidate)
-        probe = {}
-        for b in (24, 32, 40):
-            pipe.set_partition(b)
-            probe[b] = min(env.timed(run, 1)[0] for _ in range(2))
-        best = min(probe, key=probe.get)
-        pipe.set_partition(best)
-        executor = "ft8b200_pipe_t depth %d, %d streams x %d slots per batch, back end on %d SMs (probed on this workload, ms per pass: %s)" % (
-            depth, spb, spp, best, ", ".join("%d: %.2f" % (b, probe[b]) for b in sorted(probe)))
-        run()
+    # The executor's shape is probed on THIS workload: streams per batch (a rank with few streams needs small batches to have
+    # anything to overlap) x SM split (stream batches carry a heavier comb+FIR pass than independent slots; 0 = no split, the
+    # kernels of consecutive batches back to back on the whole GPU).  One warm and two timed passes of the rank's whole plan per
+    # point, the fastest is kept; every rank takes the same one (times are max over ranks).
+    sizes = sorted({min(s, resident, mine) for s in (streams_per_batch, streams_per_batch // 4)} - {0}, reverse=True)
+    splits = (0, 24, 32, 40) if partitioned else (0,)
+    probe = {}
+    for spb in sizes:
+        make_plan(spb)
+        for bsm in splits:
+            if bsm:
+                pipe.set_mode(serial=False)
+                pipe.set_partition(bsm)
+            else:
+                pipe.set_mode(serial=True)
+            run()
+            probe[(spb, bsm)] = min(env.timed(run, 1)[0] for _ in range(2))
+    spb, bsm = min(probe, key=probe.get)
+    make_plan(spb)
+    if bsm:
+        pipe.set_mode(serial=False)
+        pipe.set_partition(bsm)
+    else:
+        pipe.set_mode(serial=True)
+    executor = "ft8b200_pipe_t depth %d, %d streams x %d slots per batch, %s (probed on this workload, ms per pass at streams/back SMs: %s)" % (
+        depth, spb, spp, ("back end on %d SMs" % bsm) if bsm else "no SM split", ", ".join("%d/%d: %.2f" % (k[0], k[1], v) for k, v in sorted(probe.items())))
+    run()
     ms, gathered, _ = env.timed(run, 1)
     n_slots_total = n_streams_total * spp
     res = gathered[0].cpu().numpy().view(pkg.result_dtype).reshape(-1, M)

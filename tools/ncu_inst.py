@@ -14,7 +14,7 @@ out = {"slots_per_launch": n, "source": sys.argv[1],
        "decode": {"warp_inst_per_slot": inst("decode_kernel") / n},
        "spots": {"warp_inst_per_slot": inst("spots_kernel") / n},
        "waterfall": {"warp_inst_per_slot": inst("waterfall1024_kernel") / n},
-       "monitor": {"warp_inst_per_slot": inst("monitor_frames_kernel_12k") / n},
+       "monitor": {"warp_inst_per_slot": sum(v.get("warp_insts", 0.0) for k, v in d.items() if k.startswith("monitor_frames_kernel") and k.endswith("_12k")) / n},
        "sync960": {"warp_inst_per_slot": (d.get("sync_score_ft8_kernel_12k", {}).get("warp_insts", 0.0) + d.get("sync_select_kernel_12k", {}).get("warp_insts", 0.0)) / n}}
 json.dump(out, open(sys.argv[3], "w"), indent=1)
 print(json.dumps(out))
