@@ -43,6 +43,16 @@ struct DevBuf {
         bytes = need;
         return 0;
     }
+    // for buffers a kernel may read ahead of what was written into them (the selection fetches a slot's first 32 survivor words
+    // together with the count that says how many of them exist): defined contents from the start
+    int ensure_zeroed(size_t need) {
+        if (need <= bytes) return 0;
+        const int rc = ensure(need);
+        if (rc) return rc;
+        cudaError_t e = cudaMemset(p, 0, bytes);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+        return e == cudaSuccess ? 0 : cuda_fail(e, "cudaMemset");
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -117,7 +127,7 @@ int ensure_slot_buffers(ft8b200_ctx_t *ctx, int n_slots) {
 int ensure_scratch(ft8b200_ctx_t *ctx, int npos, int n_slots) {
     int rc0 = ctx->scores.ensure((size_t)n_slots * npos * sizeof(int16_t));
     if (rc0) return rc0;
-    if ((rc0 = ctx->lists.ensure(find_sync_list_bytes(n_slots)))) return rc0;   // survivor lists, score kernel -> selection
+    if ((rc0 = ctx->lists.ensure_zeroed(find_sync_list_bytes(n_slots)))) return rc0;   // survivor lists, score kernel -> selection
     if ((rc0 = ctx->work.ensure((size_t)n_slots * ctx->cfg.max_candidates * sizeof(uint32_t)))) return rc0;
     if ((rc0 = ctx->work_total.ensure(4 * sizeof(unsigned int)))) return rc0;
     return 0;

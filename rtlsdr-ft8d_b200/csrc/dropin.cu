@@ -172,7 +172,8 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
     static uint32_t *lists = nullptr;   // survivor list of the one slot (score kernel -> selection)
     static int16_t *scores = nullptr;
     static int scratch_npos = 0;
-    if (!lists && cudaMalloc(&lists, find_sync_list_bytes(1)) != cudaSuccess) die("ft8_find_sync (scratch)");
+    if (!lists && (cudaMalloc(&lists, find_sync_list_bytes(1)) != cudaSuccess || cudaMemset(lists, 0, find_sync_list_bytes(1)) != cudaSuccess ||
+                   cudaStreamSynchronize(0) != cudaSuccess)) die("ft8_find_sync (scratch)");   // zeroed: the selection reads a slot's first words ahead of its count
     if (npos > scratch_npos) {
         cudaFree(scores);
         if (cudaMalloc(&scores, (size_t)npos * sizeof(int16_t)) != cudaSuccess) die("ft8_find_sync (scratch)");

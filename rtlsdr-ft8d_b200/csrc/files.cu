@@ -217,6 +217,10 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
                pool.alloc(&d_nres, S * sizeof(int32_t)) == cudaSuccess && pool.alloc(&d_uscore, S * M * sizeof(int32_t)) == cudaSuccess &&
                pool.alloc(&d_ucand, S * M * sizeof(int32_t)) == cudaSuccess && pool.alloc(&d_ufreq, S * M * sizeof(float)) == cudaSuccess;
     if (!okc) return FT8B200_ENOMEM;
+    // read back whole below, written only up to each recording's count: defined bytes behind the counts
+    if (cudaMemsetAsync(d_umsg, 0, S * M * sizeof(message_t), st) != cudaSuccess || cudaMemsetAsync(d_ucand, 0, S * M * sizeof(int32_t), st) != cudaSuccess ||
+        cudaMemsetAsync(d_cand, 0, S * K * sizeof(candidate_t), st) != cudaSuccess)
+        return FT8B200_ECUDA;
     int nb = 0, rc;
     if ((rc = ft8b200_monitor_waterfall(ctx, d_audio, stride, n_samples, n, sample_rate, tosr, fosr, protocol, d_mag, mag_stride, &nb, nullptr))) return rc;
     for (int k = 0; k < n; ++k) h_count[k] = 0;

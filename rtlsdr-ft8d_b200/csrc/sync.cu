@@ -172,7 +172,7 @@ __device__ void select_slot(const int16_t *__restrict__ scores, const Geo &g, co
             // (b) heap full: 32 survivors per step against the root score, which only ever rises
             if (n_list > max_cand) {
                 __syncwarp();
-                int root = ent_score(heap[0]);
+                int root = __shfl_sync(0xffffffffu, lane == 0 ? ent_score(heap[0]) : 0, 0);   // only lane 0 touches the heap
                 for (int base = max_cand; base < n_list; base += 32) {
                     const int e = base + lane;
                     const uint32_t v = e < n_list ? surv[e] : 0u;

@@ -491,6 +491,44 @@ def test_stream_callback_matches_reference_chunking(pkg, ctx, oracle, raw_slot):
     st.close()
 
 
+def test_callback_thread_and_decoder_thread(pkg, ctx, raw_slot):
+    """The daemon's two threads: librtlsdr's USB thread in rtlsdr_callback() (rtlsdr_ft8d.c:214) while the decoder thread works on
+    the slot that was just flipped out (:274, decoder() :221-285).  Slot n is decoded -- repeatedly -- while slot n+1 arrives; the
+    spots of both slots and the samples of slot n+1 are those of the same calls made one after the other."""
+    import threading
+    second = np.roll(raw_slot, 2 * 1000)   # the same signal 1000 samples later: another slot with a message in it
+
+    def feed(st, buf):
+        for o in range(0, buf.size, 65536):
+            st.callback(buf[o:o + 65536])
+
+    serial = pkg.Stream(ctx)
+    feed(serial, raw_slot); serial.flip()
+    want_a = serial.decode()
+    feed(serial, second); serial.flip()
+    want_i, want_q, want_n = serial.fetch()
+    want_b = serial.decode()
+    serial.close()
+    assert want_a[1] >= 1 and want_b[1] >= 1
+
+    st = pkg.Stream(ctx)
+    feed(st, raw_slot); st.flip()
+    usb = threading.Thread(target=feed, args=(st, second))
+    usb.start()
+    rounds = 0
+    while usb.is_alive() or rounds < 3:   # ctypes releases the GIL in every call: the two threads really overlap
+        res, n = st.decode()
+        assert n == want_a[1] and res.tobytes() == want_a[0].tobytes()
+        rounds += 1
+    usb.join()
+    st.flip()
+    gi, gq, n = st.fetch()
+    assert n == want_n and bits_equal(gi, want_i) and bits_equal(gq, want_q)
+    res, n = st.decode()
+    assert n == want_b[1] and res.tobytes() == want_b[0].tobytes()
+    st.close()
+
+
 def test_default_stream_callback(pkg, oracle):
     """ctx == NULL: the process-wide stream, like the reference's function-static state."""
     rng = np.random.default_rng(9)
