@@ -1210,3 +1210,42 @@ def test_crowded_band_gfsk_parity(pkg, ctx500, oracle):
         assert n[s] == o["n"] and res[s].tobytes() == o["results"].tobytes()
         total += int(n[s])
     assert total >= 20
+
+
+def test_bulk_randomised_parity_sweep(pkg, ctx, ctx500, oracle):
+    """Breadth rather than a new case: 64 slots of 1..60 overlapping GFSK signals (-24..+5 dB, random DT / frequency) through
+    waterfall -> sync -> LDPC -> CRC -> unpack -> spot table in ONE batch, every slot's decoder_results[] (content, order, stale gaps)
+    against the oracle's ft8_subsystem on the same samples -- with the daemon's limits (K = 120 / 50 messages) and with config #3's
+    (K = 500 / 200); then 24 recordings of the 12 kHz path (FT8 and FT4) against decode_ft8's main()."""
+    def amp(snr_db):
+        return float(np.sqrt(2.0 * (2500.0 / 3200.0) * 10.0 ** (snr_db / 10.0)))
+    rng = np.random.default_rng(4242)
+    n_slots = 64
+    sigs, firsts = [], [0]
+    for s in range(n_slots):
+        g, _ = _gfsk_signals(pkg, rng, 1 + (s * 59) // (n_slots - 1), 50.0, 1500.0, -0.5, 1.5, amp(-24.0), amp(5.0))
+        sigs.append(g); firsts.append(firsts[-1] + g.size)
+    d_i, d_q = ctx500.synth_slots(np.concatenate(sigs), firsts, 1.0, 23)
+    peak = torch.maximum(d_i.abs().amax(1), d_q.abs().amax(1))
+    h_i, h_q = d_i.cpu().numpy(), d_q.cpu().numpy()
+    decoded = 0
+    for c, K, M in ((ctx, 120, 50), (ctx500, 500, 200)):
+        c.process_conditioned(d_i, d_q, peak)
+        res, n = c.fetch_results(n_slots)
+        for s in range(n_slots):
+            o = oracle.subsystem(*oracle.condition(h_i[s], h_q[s], 48000)[:2], max_cand=K, max_msgs=M)
+            assert n[s] == o["n"] and res[s].tobytes() == o["results"].tobytes(), (K, s)
+            decoded += int(n[s])
+    assert decoded >= 20 * n_slots // 4
+    for proto, n_samp, n_rec in ((1, 180_000, 16), (0, 90_000, 8)):
+        items, first = [], [0]
+        for r in range(n_rec):
+            for _ in range(1 + 4 * r):
+                to, de, ex = synth.random_message(rng)
+                items.append((pkg.pack77_std(to, de, ex), float(rng.uniform(200.0, 2900.0)), float(rng.uniform(0.0, 1.5)), float(rng.uniform(0.02, 0.5))))
+            first.append(len(items))
+        aud = ctx.synth_audio(pkg.make_signals(items, gfsk=True), first, proto, 0.05, 29, n_samples=n_samp)
+        lines = pkg.decode_audio(ctx, aud, 12000, proto)
+        h_a = aud.cpu().numpy()
+        for r in range(n_rec):
+            assert [pkg.format_decoded(x) for x in lines[r]] == oracle.decode_ft8_lines(h_a[r], 12000, protocol=proto), (proto, r)
