@@ -83,6 +83,7 @@ struct ft8b200_cluster {
     std::vector<ncclComm_t> comms;
     std::deque<Step> steps;
     uint64_t gathers = 0;
+    bool broken = false;                    // a step failed part-way (some devices submitted / handed out, others not): no further steps
     std::string err;
 };
 
@@ -97,6 +98,17 @@ int cfail(ft8b200_cluster_t *c, int code, const std::string &msg) {
         cudaError_t e__ = (call);                                                                                     \
         if (e__ != cudaSuccess) return cfail(c, FT8B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
+
+// a failure in the middle of a step leaves the devices' pipes out of step with each other: the cluster refuses further work
+int cbreak(ft8b200_cluster_t *c, int code, const std::string &msg) {
+    c->broken = true;
+    return cfail(c, code, msg);
+}
+int refuse_if_broken(ft8b200_cluster_t *c) {
+    if (!c->broken) return 0;
+    if (c->err.rfind("cluster stopped", 0) != 0) c->err = "cluster stopped after a failed step: " + c->err;
+    return FT8B200_ECUDA;
+}
 
 size_t row_bytes(const ft8b200_cluster_t *c) { return (size_t)c->cfg.max_messages * sizeof(struct decoder_results) + sizeof(int32_t); }
 
@@ -242,16 +254,18 @@ int ft8b200_cluster_shard(ft8b200_cluster_t *c, int n_items, int device_index, i
 int ft8b200_cluster_submit_streams(ft8b200_cluster_t *c, const uint8_t *const *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes,
                                    const int *n_streams_per_device, int slots_per_stream, size_t bytes_per_slot) {
     if (!c || !d_iq || !n_streams_per_device || slots_per_stream < 1) return c ? cfail(c, FT8B200_EINVAL, "ft8b200_cluster_submit: bad argument") : FT8B200_EINVAL;
+    if (int rb = refuse_if_broken(c)) return rb;
+    for (int d = 0; d < c->n; ++d)
+        if (n_streams_per_device[d] > 0 && !d_iq[d]) return cfail(c, FT8B200_EINVAL, "ft8b200_cluster_submit: null input for a device with work");
     Step st;
     for (int d = 0; d < c->n; ++d) {
         const int n = n_streams_per_device[d];
         int rc = 0;
         if (n > 0) {
-            if (!d_iq[d]) return cfail(c, FT8B200_EINVAL, "ft8b200_cluster_submit: null input for a device with work");
             rc = slots_per_stream > 1 ? ft8b200_pipe_submit_streams(c->pipes[(size_t)d], d_iq[d], bytes_per_stream, stream_stride_bytes, n, slots_per_stream, bytes_per_slot)
                                       : ft8b200_pipe_submit(c->pipes[(size_t)d], d_iq[d], bytes_per_stream, stream_stride_bytes, n);
         }
-        if (rc) return cfail(c, rc, std::string("device ") + std::to_string(d) + ": " + ft8b200_pipe_error(c->pipes[(size_t)d]));
+        if (rc) return (d > 0 ? cbreak : cfail)(c, rc, std::string("device ") + std::to_string(d) + ": " + ft8b200_pipe_error(c->pipes[(size_t)d]));
         st.rows.push_back(n > 0 ? n * slots_per_stream : 0);
     }
     c->steps.push_back(st);
@@ -265,13 +279,14 @@ int ft8b200_cluster_submit(ft8b200_cluster_t *c, const uint8_t *const *d_iq, siz
 // n_slots independent slots in (pinned) host memory, sharded in contiguous blocks over the devices
 int ft8b200_cluster_submit_host(ft8b200_cluster_t *c, const uint8_t *h_iq, size_t bytes_per_stream, int n_slots) {
     if (!c || !h_iq || n_slots < 1) return c ? cfail(c, FT8B200_EINVAL, "ft8b200_cluster_submit_host: bad argument") : FT8B200_EINVAL;
+    if (int rb = refuse_if_broken(c)) return rb;
     Step st;
     for (int d = 0; d < c->n; ++d) {
         int lo, hi;
         shard(n_slots, c->n, d, &lo, &hi);
         if (hi > lo) {
             const int rc = ft8b200_pipe_submit_host(c->pipes[(size_t)d], h_iq + (size_t)lo * bytes_per_stream, bytes_per_stream, hi - lo);
-            if (rc) return cfail(c, rc, std::string("device ") + std::to_string(d) + ": " + ft8b200_pipe_error(c->pipes[(size_t)d]));
+            if (rc) return (d > 0 ? cbreak : cfail)(c, rc, std::string("device ") + std::to_string(d) + ": " + ft8b200_pipe_error(c->pipes[(size_t)d]));
         }
         st.rows.push_back(hi - lo);
     }
@@ -283,6 +298,7 @@ int ft8b200_cluster_submit_host(ft8b200_cluster_t *c, const uint8_t *h_iq, size_
 // and unpack it in (device, slot) order.  Returns the number of slots written, or a negative error.
 int ft8b200_cluster_collect(ft8b200_cluster_t *c, struct decoder_results *h_results, int32_t *h_nresults, int capacity_slots) {
     if (!c || !h_results || !h_nresults) return c ? cfail(c, FT8B200_EINVAL, "ft8b200_cluster_collect: null result buffer") : FT8B200_EINVAL;
+    if (int rb = refuse_if_broken(c)) return rb;
     if (c->steps.empty()) return cfail(c, FT8B200_EINVAL, "ft8b200_cluster_collect: nothing in flight");
     const Step st = c->steps.front();
     int total = 0, max_rows = 0;
@@ -292,6 +308,7 @@ int ft8b200_cluster_collect(ft8b200_cluster_t *c, struct decoder_results *h_resu
     int rc = ensure_gather_buffers(c, (size_t)(max_rows > 0 ? max_rows : 1));
     if (rc) return rc;
     const size_t cap = c->cap_rows, per = cap * row_bytes(c);
+    c->broken = true;   // until the step is through: any failure below leaves some pipes a batch ahead of the others
     // stage every device's rows on its gather stream, ordered behind the batch by the host-side wait of collect_device
     for (int d = 0; d < c->n; ++d) {
         CCU(cudaSetDevice(c->dev[(size_t)d]));
@@ -337,6 +354,7 @@ int ft8b200_cluster_collect(ft8b200_cluster_t *c, struct decoder_results *h_resu
         }
     }
     c->steps.pop_front();
+    c->broken = false;
     return out;
 }
 
