@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -84,6 +85,18 @@ const DriverApi &driver_api() {
     }();
     return api;
 }
+
+// Green contexts are created once per (device, requested split) and kept for the life of the process: the driver (580.159) does not
+// give back the ~4 MiB of device memory a green context holds when cuGreenCtxDestroy is called (tools/greenctx_leak_probe.cu: 8 MiB
+// per create/destroy of a front/back pair, with or without streams and launches), so a pipe that is re-partitioned -- the autotune
+// walks six splits -- or created and destroyed repeatedly would grow without bound.  Pipes on the same device with the same split
+// share the pair (they are confined to the same SM sets, which is what the split asks for); only the lanes' streams are per pipe.
+struct CachedPartition {
+    int device = 0, back_req = 0;
+    Partition part;
+};
+std::mutex g_part_mu;
+std::vector<CachedPartition> g_parts;
 
 }  // namespace
 
@@ -258,7 +271,7 @@ int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant) {
     return 0;
 }
 
-// drop the SM partition: lanes go back to their own streams, the green contexts and their streams are destroyed
+// drop the SM partition: lanes go back to their own streams, the partition's streams are destroyed
 static void partition_release(ft8b200_pipe_t *p) {
     const DriverApi &d = driver_api();
     for (Lane &l : p->lanes) {
@@ -271,9 +284,7 @@ static void partition_release(ft8b200_pipe_t *p) {
         if (l.part_back) d.StreamDestroy(l.part_back);
         l.part_front = l.part_back = nullptr;
     }
-    if (p->part.front) d.GreenCtxDestroy(p->part.front);
-    if (p->part.back) d.GreenCtxDestroy(p->part.back);
-    p->part = Partition();
+    p->part = Partition();   // the green contexts stay in g_parts (see CachedPartition)
 }
 
 int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_out, int *back_sms_out) {
@@ -298,21 +309,39 @@ int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_o
             return pfail(p, FT8B200_ECUDA, std::string(#call) + ": CUresult " + std::to_string((int)r__));          \
         }                                                                                                           \
     } while (0)
-    CUdevice dev;
-    PDRV(d.DeviceGet(&dev, p->cfg.device));
-    CUdevResource all, back, front;
-    PDRV(d.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
-    if ((unsigned)back_sms >= all.sm.smCount) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_set_partition: back_sms must leave SMs for the front end");
-    unsigned int groups = 1;
-    PDRV(d.DevSmResourceSplitByCount(&back, &groups, &all, &front, 0, (unsigned)back_sms));  // rounds up to the architecture's granularity
-    if (groups != 1 || front.sm.smCount == 0) { partition_release(p); return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_set_partition: the driver could not split the SMs that way"); }
-    CUdevResourceDesc dfront, dback;
-    PDRV(d.DevResourceGenerateDesc(&dback, &back, 1));
-    PDRV(d.DevResourceGenerateDesc(&dfront, &front, 1));
-    PDRV(d.GreenCtxCreate(&p->part.back, dback, dev, CU_GREEN_CTX_DEFAULT_STREAM));
-    PDRV(d.GreenCtxCreate(&p->part.front, dfront, dev, CU_GREEN_CTX_DEFAULT_STREAM));
-    p->part.front_sms = (int)front.sm.smCount;
-    p->part.back_sms = (int)back.sm.smCount;
+    {
+        std::lock_guard<std::mutex> lk(g_part_mu);
+        const CachedPartition *hit = nullptr;
+        for (const CachedPartition &c : g_parts)
+            if (c.device == p->cfg.device && c.back_req == back_sms) hit = &c;
+        if (!hit) {
+            CUdevice dev;
+            PDRV(d.DeviceGet(&dev, p->cfg.device));
+            CUdevResource all, back, front;
+            PDRV(d.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+            if ((unsigned)back_sms >= all.sm.smCount) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_set_partition: back_sms must leave SMs for the front end");
+            unsigned int groups = 1;
+            PDRV(d.DevSmResourceSplitByCount(&back, &groups, &all, &front, 0, (unsigned)back_sms));  // rounds up to the architecture's granularity
+            if (groups != 1 || front.sm.smCount == 0) return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_set_partition: the driver could not split the SMs that way");
+            CUdevResourceDesc dfront, dback;
+            PDRV(d.DevResourceGenerateDesc(&dback, &back, 1));
+            PDRV(d.DevResourceGenerateDesc(&dfront, &front, 1));
+            CachedPartition c;
+            c.device = p->cfg.device;
+            c.back_req = back_sms;
+            PDRV(d.GreenCtxCreate(&c.part.back, dback, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+            CUresult rf = d.GreenCtxCreate(&c.part.front, dfront, dev, CU_GREEN_CTX_DEFAULT_STREAM);
+            if (rf != CUDA_SUCCESS) {
+                d.GreenCtxDestroy(c.part.back);
+                return pfail(p, FT8B200_ECUDA, "cuGreenCtxCreate (front): CUresult " + std::to_string((int)rf));
+            }
+            c.part.front_sms = (int)front.sm.smCount;
+            c.part.back_sms = (int)back.sm.smCount;
+            g_parts.push_back(c);
+            hit = &g_parts.back();
+        }
+        p->part = hit->part;
+    }
     for (Lane &l : p->lanes) {
         PDRV(d.GreenCtxStreamCreate(&l.part_front, p->part.front, CU_STREAM_NON_BLOCKING, 0));
         PDRV(d.GreenCtxStreamCreate(&l.part_back, p->part.back, CU_STREAM_NON_BLOCKING, 0));

@@ -1249,3 +1249,44 @@ def test_bulk_randomised_parity_sweep(pkg, ctx, ctx500, oracle):
         h_a = aud.cpu().numpy()
         for r in range(n_rec):
             assert [pkg.format_decoded(x) for x in lines[r]] == oracle.decode_ft8_lines(h_a[r], 12000, protocol=proto), (proto, r)
+
+
+def test_create_destroy_cycles_return_their_memory(pkg, raw_slot):
+    """A daemon library is created and torn down many times over a process's life (initFFTW/freeFFTW per run, a pipe per band
+    change): contexts, pipes with and without an SM partition, receiver streams and monitors are created, USED and destroyed
+    repeatedly; the device's free memory afterwards is what it was after the first cycle (no cudaMalloc left behind)."""
+    small = raw_slot[:12016 * 40]
+    aud = np.zeros(1920 * 4, np.float32)
+
+    def cycle(k):
+        c = pkg.Context(0)
+        d_raw = torch.from_numpy(small).to(dev())
+        c.process_raw(d_raw, 1, small.size)
+        c.fetch_results(1)
+        st = pkg.Stream(c)
+        st.callback(small[:65536]); st.flip(); st.fetch()
+        st.close()
+        c.close()
+        p = pkg.Pipe(0, depth=3)
+        if k % 2:
+            try:
+                p.set_partition(32)
+            except pkg.Ft8Error:
+                pass   # a driver without green contexts
+        p.submit(d_raw, 1, small.size); p.collect(1)
+        p.submit_host(small, 1, small.size); p.collect(1)
+        p.close()
+        m = pkg.Monitor()
+        for o in range(0, aud.size, 1920):
+            m.process(aud[o:o + 1920])
+        m.close()
+        del d_raw
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        return torch.cuda.mem_get_info()[0]
+
+    cycle(0); cycle(1)              # first use: module load, per-device tables, the default context of the monitor
+    free0 = cycle(2)
+    for k in range(3, 15):
+        free = cycle(k)
+    assert free0 - free < (8 << 20), f"{(free0 - free) >> 20} MiB of device memory did not come back after 12 create/destroy cycles"
