@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -109,3 +110,92 @@ def test_bad_arguments_are_rejected_before_any_launch(pkg):
     cfg = pkg.Config(0, 1, 0, 50, 10, 20)
     assert not L.ft8b200_create(C.byref(cfg))
     assert b"bad configuration" in L.ft8b200_last_error()
+
+
+_NULL_SWEEP = r'''
+import ctypes as C, re, sys
+hdr = open(sys.argv[1]).read()
+hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+L = C.CDLL(sys.argv[2])
+decls = re.findall(r"\n(int|uint64_t|uint32_t|void \*|const char \*)\s*(ft8b200_\w+)\s*\(([^;{]*?)\)\s*;", hdr)
+n = 0
+for ret, name, args in decls:
+    params = [a.strip() for a in args.replace("\n", " ").split(",")]
+    first = params[0]
+    if not re.match(r"(const )?ft8b200_(ctx|pipe|cluster)_t \*", first):
+        continue
+    fn = getattr(L, name)
+    argv = []
+    for a in params:
+        if "*" in a: argv.append(C.c_void_p(None))
+        elif "size_t" in a or "uint64_t" in a: argv.append(C.c_uint64(0))
+        elif "float" in a: argv.append(C.c_float(0.0))
+        elif "double" in a: argv.append(C.c_double(0.0))
+        else: argv.append(C.c_int(0))
+    fn.restype = {"int": C.c_int, "uint64_t": C.c_uint64, "uint32_t": C.c_uint32, "void *": C.c_void_p, "const char *": C.c_char_p}[ret]
+    print("call", name, flush=True)
+    r = fn(*argv)
+    if ret == "int" and not (name.endswith("_depth") or name.endswith("_in_flight") or name.endswith("_devices") or name.endswith("_nccl_version")):
+        assert r < 0, (name, r)
+    elif ret in ("uint64_t", "uint32_t"):
+        assert r == 0, (name, r)
+    elif ret == "void *":
+        assert not r, (name, r)
+    n += 1
+print("swept", n)
+'''
+
+
+def test_every_entry_rejects_a_null_handle(tmp_path):
+    """Every ft8b200_* entry that takes a context / pipe / cluster handle, called with that handle NULL and every other argument
+    zero: an error code (or 0 / NULL for the counters and getters), never a crash and never a CUDA call -- runs without a GPU.
+    The signatures are read from include/ft8b200.h, so a new entry point is swept as soon as it is declared."""
+    script = tmp_path / "sweep.py"
+    script.write_text(_NULL_SWEEP)
+    so = os.path.join(ROOT, "rtlsdr-ft8d_b200", "libft8b200.so")
+    p = subprocess.run([sys.executable, str(script), os.path.join(ROOT, "include", "ft8b200.h"), so], capture_output=True, text=True, timeout=120)
+    last = [l for l in p.stdout.splitlines() if l.startswith("call")][-1:] or ["(none)"]
+    assert p.returncode == 0, f"crashed or wrong answer at {last[0]}: rc {p.returncode}\n{p.stderr[-600:]}"
+    swept = int(p.stdout.strip().splitlines()[-1].split()[1])
+    assert swept >= 70, swept
+
+
+_ZERO_SWEEP = _NULL_SWEEP.replace("print(\"swept\", n)", "").replace('''    r = fn(*argv)
+    if ret == "int" and not (name.endswith("_depth") or name.endswith("_in_flight") or name.endswith("_devices") or name.endswith("_nccl_version")):
+        assert r < 0, (name, r)
+    elif ret in ("uint64_t", "uint32_t"):
+        assert r == 0, (name, r)
+    elif ret == "void *":
+        assert not r, (name, r)
+    n += 1''', '''    kind = re.match(r"(const )?ft8b200_(ctx|pipe|cluster)_t", first).group(2)
+    if kind == "cluster" or name in ("ft8b200_device_malloc",):
+        continue
+    argv[0] = C.c_void_p(handles[kind])
+    r = fn(*argv)
+    n += 1''').replace("n = 0\n", '''n = 0
+L.ft8b200_create.restype = C.c_void_p
+L.ft8b200_pipe_create.restype = C.c_void_p
+L.ft8b200_last_error.restype = C.c_char_p
+handles = {"ctx": L.ft8b200_create(None), "pipe": L.ft8b200_pipe_create(None, 2)}
+assert handles["ctx"] and handles["pipe"], L.ft8b200_last_error()
+''') + '''
+# the context still works: one silent slot through the whole path
+import numpy as np
+zi = np.zeros(48000, np.float32); res = np.zeros(50 * 28, np.uint8); nres = C.c_int32(-7)
+rc = L.ft8b200_process_slots_host(C.c_void_p(handles["ctx"]), zi.ctypes.data_as(C.c_void_p), zi.ctypes.data_as(C.c_void_p), 1, res.ctypes.data_as(C.c_void_p), C.byref(nres))
+assert rc == 0 and nres.value == 0, (rc, nres.value, L.ft8b200_last_error())
+print("swept", n)
+'''
+
+
+@pytest.mark.gpu
+def test_every_entry_survives_zero_arguments_on_a_live_handle(tmp_path):
+    """The same sweep on a B200 with LIVE context and pipe handles and every other argument zero / NULL: whatever each entry
+    answers, the process does not crash, nothing is launched on garbage, and the context decodes a slot afterwards."""
+    script = tmp_path / "sweep0.py"
+    script.write_text(_ZERO_SWEEP)
+    so = os.path.join(ROOT, "rtlsdr-ft8d_b200", "libft8b200.so")
+    p = subprocess.run([sys.executable, str(script), os.path.join(ROOT, "include", "ft8b200.h"), so], capture_output=True, text=True, timeout=300)
+    last = [l for l in p.stdout.splitlines() if l.startswith("call")][-1:] or ["(none)"]
+    assert p.returncode == 0, f"crashed at {last[0]}: rc {p.returncode}\n{p.stdout[-300:]}\n{p.stderr[-900:]}"
+    assert int(p.stdout.strip().splitlines()[-1].split()[1]) >= 55
