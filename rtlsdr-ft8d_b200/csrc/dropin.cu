@@ -159,6 +159,7 @@ int ft8_find_sync(const waterfall_t *power, int num_candidates, candidate_t heap
         abort();
     }
     if (num_candidates <= 0) return 0;
+    if (power->num_bins < 8) return 0;   // the reference's `freq_offset + 7 < num_bins` loop never runs (decode.c:189)
     monitor_flush_for_mag(power->mag);   // a deferred monitor (ft8b200_monitor_set_deferred) transforms its pending blocks now
     std::lock_guard<std::mutex> lk(g_mu);
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) die("ft8_find_sync (cudaSetDevice)");  // the decoder thread's current device may differ

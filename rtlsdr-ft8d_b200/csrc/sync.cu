@@ -585,7 +585,13 @@ cudaError_t launch_find_sync(const uint8_t *d_mag, size_t slot_stride, int n_slo
     g.stride = time_osr * freq_osr * num_bins;
     g.nfo = num_bins - 7;
     g.npos = time_osr * freq_osr * 36 * g.nfo;
-    if (g.nfo < 1 || g.nfo >= 4096 || freq_osr >= 4096 || g.npos >= (1 << 20)) return cudaErrorInvalidValue;
+    if (g.nfo < 1) {
+        // fewer than 8 bins: the reference's `freq_offset + 7 < num_bins` loop (decode.c:189) never runs -> no candidates, no error
+        cudaError_t e0 = cudaMemsetAsync(d_ncand, 0, (size_t)n_slots * sizeof(int), st);
+        if (e0 == cudaSuccess && d_work_total) e0 = cudaMemsetAsync(d_work_total, 0, 4 * sizeof(unsigned int), st);
+        return e0;
+    }
+    if (g.nfo >= 4096 || freq_osr >= 4096 || g.npos >= (1 << 20)) return cudaErrorInvalidValue;
     g.nfo_magic = g.nfo > 1 ? 0xffffffffu / (uint32_t)g.nfo + 1u : 0u;   // 0: division by 1
     g.fosr_magic = freq_osr > 1 ? 0xffffffffu / (uint32_t)freq_osr + 1u : 0u;
     SelArgs sa;

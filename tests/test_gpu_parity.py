@@ -1290,3 +1290,26 @@ def test_create_destroy_cycles_return_their_memory(pkg, raw_slot):
     for k in range(3, 15):
         free = cycle(k)
     assert free0 - free < (8 << 20), f"{(free0 - free) >> 20} MiB of device memory did not come back after 12 create/destroy cycles"
+
+
+@pytest.mark.parametrize("dims", [dict(num_blocks=1, num_bins=16, time_osr=1, freq_osr=1), dict(num_blocks=3, num_bins=9, time_osr=2, freq_osr=1),
+                                  dict(num_blocks=6, num_bins=8, time_osr=1, freq_osr=2), dict(num_blocks=13, num_bins=40, time_osr=2, freq_osr=2),
+                                  dict(num_blocks=20, num_bins=7, time_osr=2, freq_osr=2), dict(num_blocks=5, num_bins=3, time_osr=1, freq_osr=1)])
+def test_dropin_on_tiny_waterfalls(pkg, oracle, dims):
+    """ft8_find_sync()/ft8_decode() on waterfalls far smaller than a slot -- a monitor that has seen a few blocks, a band of a few
+    bins: every sync block hangs over an edge, most symbols of a candidate are out of range (zero LLRs), and below 8 bins the
+    reference's loop never runs (decode.c:189): the same candidates, statuses and return values as the oracle, no error."""
+    rng = np.random.default_rng(dims["num_blocks"] * 100 + dims["num_bins"])
+    cells = dims["num_blocks"] * dims["time_osr"] * dims["freq_osr"] * dims["num_bins"]
+    for proto in (1, 0):
+        for t in (10, -50):
+            mag = rng.integers(0, 256, cells, dtype=np.uint8)
+            g = pkg.ft8_find_sync(mag, 30, t, protocol=proto, **dims)
+            o = oracle.find_sync(mag, max_cand=30, min_score=t, protocol=proto, **dims)
+            assert g.tobytes() == o.tobytes(), (dims, proto, t)
+            for c in list(g[:4]) + [np.array([(5, -3, 0, 0, 0)], cand_dtype)[0]]:
+                if dims["num_bins"] < 8:
+                    break
+                ok, msg, st = pkg.ft8_decode(mag, c, 20, protocol=proto, **dims)
+                d = oracle.decode(mag, c, max_iters=20, protocol=proto, **dims)
+                assert ok == bool(d["ok"]) and st.tobytes() == d["status"].tobytes(), (dims, proto, t, c)
