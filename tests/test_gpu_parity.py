@@ -1313,3 +1313,31 @@ def test_dropin_on_tiny_waterfalls(pkg, oracle, dims):
                 ok, msg, st = pkg.ft8_decode(mag, c, 20, protocol=proto, **dims)
                 d = oracle.decode(mag, c, max_iters=20, protocol=proto, **dims)
                 assert ok == bool(d["ok"]) and st.tobytes() == d["status"].tobytes(), (dims, proto, t, c)
+
+
+def test_stream_overrun_and_large_calls(pkg, ctx, oracle):
+    """A decoder that falls behind: more than two slots of samples arrive -- in 30 MB calls, far beyond librtlsdr's 64 KB -- before
+    the buffer is flipped.  The reference keeps filtering and drops what does not fit (`if (idx < 48000)`, rtlsdr_ft8d.c:196-200):
+    the buffer holds the first 48 000 outputs, the count stops there, and the filter state the NEXT slot starts from is that of
+    every byte received."""
+    rng = np.random.default_rng(31)
+    st = pkg.Stream(ctx)
+    o_state = oracle.new_decim()
+    oi, oq = [], []
+    for _ in range(5):
+        chunk = rng.integers(0, 256, size=30_000_000, dtype=np.uint8)
+        st.callback(chunk)
+        a, b = oracle.decim_feed(o_state, chunk, 30_000_000 // 1502 + 2)
+        oi.append(a); oq.append(b)
+    oi = np.concatenate(oi); oq = np.concatenate(oq)
+    assert oi.size > 2 * 48000 and st.count() == 48000
+    st.flip()
+    gi, gq, n = st.fetch()
+    assert n == 48000 and bits_equal(gi, oi[:48000]) and bits_equal(gq, oq[:48000])
+    tail = rng.integers(0, 256, size=10_000_000 + 8 * 3, dtype=np.uint8)
+    st.callback(tail)
+    a, b = oracle.decim_feed(o_state, tail, 7000)
+    st.flip()
+    gi, gq, n = st.fetch()
+    assert n == a.size and bits_equal(gi[:n], a) and bits_equal(gq[:n], b) and not gi[n:].any()
+    st.close()
