@@ -1341,3 +1341,36 @@ def test_stream_overrun_and_large_calls(pkg, ctx, oracle):
     gi, gq, n = st.fetch()
     assert n == a.size and bits_equal(gi[:n], a) and bits_equal(gq[:n], b) and not gi[n:].any()
     st.close()
+
+
+@pytest.mark.parametrize("rate,tosr,fosr,proto", [(8000, 2, 2, 1), (6000, 2, 2, 1), (16000, 2, 2, 1), (24000, 1, 2, 1), (12000, 1, 1, 1), (12000, 4, 1, 1),
+                                                  (12000, 2, 4, 1), (8000, 2, 2, 0), (16000, 2, 2, 0), (12000, 3, 2, 0)])
+def test_monitor_other_rates_and_oversampling(ctx, oracle, rate, tosr, fosr, proto):
+    """decode_ft8 takes the WAV file's own sample rate and compile-time oversampling factors (decode_ft8.c:16-17,111-150): frame sizes
+    other than the two the kernel has compile-time stage plans for (3840 / 1152 points) go through its generic mixed-radix stage loop
+    (2560, 1920, 5120, 768, 7680 ... points; radix order 4, 2, 3, 5 like kf_factor): waterfall bytes identical to the oracle's monitor."""
+    rng = np.random.default_rng(rate + 10 * tosr + fosr)
+    n = int(rate * (15.0 if proto == 1 else 7.5))
+    t = np.arange(n, dtype=np.float64) / rate
+    aud = (0.05 * rng.standard_normal(n) + 0.2 * np.sin(2 * np.pi * 0.11 * rate * t) + 0.02 * np.sin(2 * np.pi * 0.031 * rate * t)).astype(np.float32)
+    ref, info, _ = oracle.monitor_waterfall(aud, rate, tosr, fosr, proto)
+    mag, nb = ctx.monitor_waterfall(torch.from_numpy(np.stack([aud, aud[::-1].copy()])).to(dev()), rate, tosr, fosr, proto)
+    assert nb == int(info[4]) > 0
+    got = mag.cpu().numpy()
+    assert np.array_equal(got[0][: ref.size], ref), f"{int((got[0][: ref.size] != ref).sum())} of {ref.size} cells differ"
+    ref2, _, _ = oracle.monitor_waterfall(aud[::-1].copy(), rate, tosr, fosr, proto)
+    assert np.array_equal(got[1][: ref2.size], ref2)
+
+
+@pytest.mark.parametrize("rate", [11025, 22050, 44100, 48000, 96000])
+def test_monitor_exotic_rates_are_exact_or_refused(pkg, ctx, oracle, rate):
+    """Frame sizes with a factor the kernel has no butterfly for (11 025 Hz: 3528 = 2^3 3^2 7^2) or too large for one CTA's shared
+    memory: the batched call either reproduces the oracle's bytes or returns an error -- never a waterfall that is merely plausible."""
+    rng = np.random.default_rng(rate)
+    aud = (0.1 * rng.standard_normal(int(rate * 2.0))).astype(np.float32)
+    try:
+        mag, nb = ctx.monitor_waterfall(torch.from_numpy(aud[None]).to(dev()), rate, 2, 2, 1)
+    except pkg.Ft8Error:
+        return
+    ref, info, _ = oracle.monitor_waterfall(aud, rate, 2, 2, 1)
+    assert nb == int(info[4]) and np.array_equal(mag.cpu().numpy()[0][: ref.size], ref)
