@@ -1374,3 +1374,41 @@ def test_monitor_exotic_rates_are_exact_or_refused(pkg, ctx, oracle, rate):
         return
     ref, info, _ = oracle.monitor_waterfall(aud, rate, 2, 2, 1)
     assert nb == int(info[4]) and np.array_equal(mag.cpu().numpy()[0][: ref.size], ref)
+
+
+def test_two_contexts_from_two_threads(pkg, raw_slot):
+    """Receivers share a process (256 streams in BASELINE config #5): two contexts on one device, each driven from its own host
+    thread at the same time -- raw batches through the whole path, 3200 sps slots, and a pipe next to them.  Every call's records
+    equal those of the same call made alone (nothing process-global is shared unsynchronised: tables, work counters, scratch)."""
+    import threading
+    d_raw = torch.from_numpy(np.stack([raw_slot, np.roll(raw_slot, 8 * 999), np.roll(raw_slot, 8 * 5000)])).to(dev())
+    ctxs = [pkg.Context(0), pkg.Context(0)]
+    pipe = pkg.Pipe(0, depth=2)
+
+    def work(k, out):
+        c = ctxs[k]
+        for rep in range(6):
+            n = 1 + (rep + k) % 3
+            c.process_raw(d_raw[:n], n)
+            res, cnt = c.fetch_results(n)
+            out.append((n, np.array(res).tobytes(), np.array(cnt).tolist()))
+
+    def work_pipe(out):
+        for rep in range(6):
+            n = 1 + rep % 3
+            pipe.submit(d_raw[:n], n)
+            res, cnt = pipe.collect(n)
+            out.append((n, np.array(res).tobytes(), np.array(cnt).tolist()))
+
+    alone = [[], [], []]
+    work(0, alone[0]); work(1, alone[1]); work_pipe(alone[2])
+    assert all(cnt[0] >= 1 for _, _, cnt in alone[0])
+    for _ in range(3):
+        together = [[], [], []]
+        th = [threading.Thread(target=work, args=(0, together[0])), threading.Thread(target=work, args=(1, together[1])),
+              threading.Thread(target=work_pipe, args=(together[2],))]
+        for t in th: t.start()
+        for t in th: t.join()
+        assert together == alone
+    pipe.close()
+    for c in ctxs: c.close()
