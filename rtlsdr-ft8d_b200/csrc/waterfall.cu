@@ -37,6 +37,7 @@ constexpr int kGroupsPerSlot = kFrames / kFramesPerCta;  // 46
 constexpr int kChunk = 1024;                             // input samples per ring chunk (= hop * frames per group)
 constexpr int kCtasPerSm = 3;
 constexpr uint32_t kRingBytes = 3u * kChunk * 4u;        // one rail of the ring
+constexpr int kOutSkew = 16, kOutPitch = 512 + kOutSkew;
 
 struct cpx { float r, i; };
 __device__ __forceinline__ cpx cmul(cpx a, float2 b) {  // C_MUL: each product rounded, then the add
@@ -114,7 +115,8 @@ struct WfSmem {
     float2 tw_b2[4][3][16];            // tw[4 (k+1) (i0 + 16 a)]: stage m=64
     float win[16][64];                 // window[n(j, t)]: pass A's 16 window values of thread t
     float2 thr2[256];                  // {thr[k], thr[k+1]}: the step thresholds around estimate k
-    uint8_t out[kFramesPerCta][512];
+    float2 tw_2[256];                  // tw[2 i], i < 256, compact: read at stride 2 out of tw_c the 16 lanes of a half-warp would share 8 bank pairs
+    uint8_t out[kFramesPerCta][kOutPitch];  // the frame's 512 bytes; the second 256 start 16 bytes later (kOutSkew): the two rows a warp writes fall on different banks
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -127,7 +129,7 @@ __device__ __forceinline__ void frame_barrier(int fr) { asm volatile("bar.sync %
 
 // layout of the table blob built by build_waterfall_tables(): floats.  [kBlobTwC, kBlobTwB1) mirrors WfSmem from tw_c on.
 constexpr int kBlobTwC = 0, kBlobTwB2 = kBlobTwC + 768 * 2, kBlobWin = kBlobTwB2 + 4 * 3 * 16 * 2, kBlobThr2 = kBlobWin + 16 * 64,
-              kBlobTwB1 = kBlobThr2 + 256 * 2, kBlobTwA = kBlobTwB1 + 3 * 16 * 2, kBlobFloats = kBlobTwA + 9 * 2;
+              kBlobTw2 = kBlobThr2 + 256 * 2, kBlobTwB1 = kBlobTw2 + 256 * 2, kBlobTwA = kBlobTwB1 + 3 * 16 * 2, kBlobFloats = kBlobTwA + 9 * 2;
 
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 waterfall1024_kernel(const float *__restrict__ d_i, const float *__restrict__ d_q, const float *__restrict__ peak,
@@ -164,9 +166,9 @@ waterfall1024_kernel(const float *__restrict__ d_i, const float *__restrict__ d_
     const uint32_t Rwin = smem_u32(&sm.win[0][t]);                       // + 256 j
     const uint32_t Rtb2 = smem_u32(&sm.tw_b2[0][0][i0]);                  // + 128 (3 a + k)
     const uint32_t Rtc1 = smem_u32(sm.tw_c) + 8u * (uint32_t)t;          // tw[i],  i = t + 64 u: + 512 u
-    const uint32_t Rtc2 = smem_u32(sm.tw_c) + 16u * (uint32_t)t;         // tw[2i]:               + 1024 u
+    const uint32_t Rtc2 = smem_u32(sm.tw_2) + 8u * (uint32_t)t;          // tw[2i] = tw_2[i]:     + 512 u
     const uint32_t Rtc3 = smem_u32(sm.tw_c) + 24u * (uint32_t)t;         // tw[3i]:               + 1536 u
-    const uint32_t Rout = smem_u32(sm.out[fr]) + 256u * (uint32_t)(t & 1) + (uint32_t)(t >> 1);  // + 32 u (+ 128)
+    const uint32_t Rout = smem_u32(sm.out[fr]) + (256u + kOutSkew) * (uint32_t)(t & 1) + (uint32_t)(t >> 1);  // + 32 u (+ 128)
     const uint32_t thr_b = smem_u32(sm.thr2);
     const uint32_t ring_b = smem_u32(sm.ring_i) + 4u * (uint32_t)(256 * fr + r3);  // sample 256 fr + r3 of ring slot 0, I rail
 
@@ -262,7 +264,7 @@ waterfall1024_kernel(const float *__restrict__ d_i, const float *__restrict__ d_
                 const float2 v3 = lds64((RC ^ (8u * (uint32_t)(u + 12))) + 512u * (uint32_t)u + 6144u);
                 cpx f0{v0.x, v0.y}, f1{v1.x, v1.y}, f2{v2.x, v2.y}, f3{v3.x, v3.y};
                 const cpx a = cmul(f1, lds64(Rtc1 + 512u * (uint32_t)u));
-                const cpx b = cmul(f2, lds64(Rtc2 + 1024u * (uint32_t)u));
+                const cpx b = cmul(f2, lds64(Rtc2 + 512u * (uint32_t)u));
                 const cpx c = cmul(f3, lds64(Rtc3 + 1536u * (uint32_t)u));
                 const cpx d5 = csub(f0, b);
                 f0 = cadd(f0, b);
@@ -283,7 +285,7 @@ waterfall1024_kernel(const float *__restrict__ d_i, const float *__restrict__ d_
         frame_barrier(fr);
         if (t < 32) {  // the frame's 512 bytes, 16 per lane
             uint4 *dst = reinterpret_cast<uint4 *>(mag + (size_t)slot * kWfBytes + (size_t)(g * kFramesPerCta + fr) * 512);
-            dst[t] = reinterpret_cast<const uint4 *>(sm.out[fr])[t];
+            dst[t] = reinterpret_cast<const uint4 *>(sm.out[fr])[t < 16 ? t : t + kOutSkew / 16];
         }
     }
 }
@@ -338,6 +340,8 @@ void build_waterfall_tables(const float *window, const float2 *tw, const float *
             blob[kBlobWin + j * 64 + t] = window[c * 64 + r3];
         }
     for (int k = 0; k < 256; ++k) { blob[kBlobThr2 + 2 * k] = thr257[k]; blob[kBlobThr2 + 2 * k + 1] = thr257[k + 1]; }
+    float2 *t2 = reinterpret_cast<float2 *>(blob + kBlobTw2);
+    for (int i = 0; i < 256; ++i) t2[i] = tw[2 * i];
     float2 *b1 = reinterpret_cast<float2 *>(blob + kBlobTwB1);
     for (int k = 0; k < 3; ++k)
         for (int i0 = 0; i0 < 16; ++i0) b1[k * 16 + i0] = tw[16 * (k + 1) * i0];
@@ -354,7 +358,8 @@ cudaError_t launch_waterfall(const DeviceTables &tb, const float *d_i, const flo
                              int sm_count, cudaStream_t st, int *launches) {
     static_assert(kFrames % kFramesPerCta == 0, "184 frames = 46 groups of 4");
     static_assert(offsetof(WfSmem, tw_b2) - offsetof(WfSmem, tw_c) == kBlobTwB2 * 4 && offsetof(WfSmem, win) - offsetof(WfSmem, tw_c) == kBlobWin * 4 &&
-                      offsetof(WfSmem, thr2) - offsetof(WfSmem, tw_c) == kBlobThr2 * 4 && offsetof(WfSmem, out) - offsetof(WfSmem, tw_c) == kBlobTwB1 * 4,
+                      offsetof(WfSmem, thr2) - offsetof(WfSmem, tw_c) == kBlobThr2 * 4 && offsetof(WfSmem, tw_2) - offsetof(WfSmem, tw_c) == kBlobTw2 * 4 &&
+                      offsetof(WfSmem, out) - offsetof(WfSmem, tw_c) == kBlobTwB1 * 4 && offsetof(WfSmem, out) % 16 == 0 && kOutPitch % 16 == 0,
                   "the blob's shared-memory part mirrors WfSmem from tw_c on");
     static_assert(offsetof(WfSmem, ex) == 0 && offsetof(WfSmem, tw_c) % 16 == 0 && offsetof(WfSmem, ring_q) - offsetof(WfSmem, ring_i) == kRingBytes, "WfSmem layout");
     static_assert(kBlobTwB1 % 4 == 0, "blob is copied in 16-byte pieces");
