@@ -21,7 +21,9 @@ int fail(int code, const std::string &msg) {
     return code;
 }
 int cuda_fail(cudaError_t e, const char *what) {
-    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    const cudaError_t held = cudaGetLastError();   // read = clear (see cuda_error in common.cuh)
+    if (e == cudaSuccess) e = held;
+    g_err = std::string(what) + ": " + (e == cudaSuccess ? "failed" : cudaGetErrorString(e));
     return FT8B200_ECUDA;
 }
 #define CU(call)                                              \
@@ -312,6 +314,7 @@ int ft8b200_waterfall(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, co
 // find_sync / decode with an explicit protocol (the C entry points use the context's, ft8b200_set_protocol): what the whole-
 // recording calls of files.cu use, so that they neither change nor depend on the protocol selected for the stage-wise API
 namespace ft8b200 {
+int cuda_error(cudaError_t e, const char *where) { return cuda_fail(e, where); }
 int ctx_device(ft8b200_ctx_t *ctx) { return ctx ? ctx->cfg.device : -1; }
 int ctx_sm_count(ft8b200_ctx_t *ctx) { return ctx ? ctx->sm_count : 0; }
 
@@ -620,7 +623,7 @@ int ft8b200_selfcheck_pade(ft8b200_ctx_t *ctx, uint64_t *counts5) {
     unsigned long long c[5] = {0, 0, 0, 0, 0};
     if (int rc = ctx_enter(ctx)) return rc;
     cudaError_t e = run_pade_check(c, ctx->sm_count, ctx->stream);
-    if (e != cudaSuccess) return fail(FT8B200_ECUDA, cudaGetErrorString(e));
+    if (e != cudaSuccess) return cuda_fail(e, __func__);
     for (int k = 0; k < 5; ++k) counts5[k] = c[k];
     return 0;
 }
@@ -630,7 +633,7 @@ int ft8b200_selfcheck_quantiser(ft8b200_ctx_t *ctx, uint64_t *counts3) {
     if (int rc = ctx_enter(ctx)) return rc;
     unsigned long long c[3] = {0, 0, 0};
     cudaError_t e = run_quantiser_check(ctx->tb.db_thresholds, c, ctx->sm_count, ctx->stream);
-    if (e != cudaSuccess) return fail(FT8B200_ECUDA, cudaGetErrorString(e));
+    if (e != cudaSuccess) return cuda_fail(e, __func__);
     for (int k = 0; k < 3; ++k) counts3[k] = c[k];
     return 0;
 }

@@ -96,7 +96,7 @@ int cfail(ft8b200_cluster_t *c, int code, const std::string &msg) {
 #define CCU(call)                                                                                                     \
     do {                                                                                                              \
         cudaError_t e__ = (call);                                                                                     \
-        if (e__ != cudaSuccess) return cfail(c, FT8B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+        if (e__ != cudaSuccess) { (void)cudaGetLastError(); return cfail(c, FT8B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } \
     } while (0)
 
 // a failure in the middle of a step leaves the devices' pipes out of step with each other: the cluster refuses further work

@@ -71,6 +71,12 @@ cudaError_t run_pade_check(unsigned long long *h_counts5, int sm_count, cudaStre
 
 // api.cu: the context's device ordinal; find_sync / decode with an explicit protocol (independent of ft8b200_set_protocol)
 int ctx_device(ft8b200_ctx_t *ctx);
+// A failed CUDA runtime call also stays behind as the runtime's "last error" until somebody reads it -- the host application's next
+// check (torch's, the daemon's own) would then report OUR failure as its own.  Every error path of the library goes through here:
+// the reason goes to ft8b200_last_error(), the runtime's error state is cleared (a sticky error survives that, as it should),
+// and FT8B200_ECUDA is returned.  e == cudaSuccess: whatever the runtime holds as its last error is taken instead.
+int cuda_error(cudaError_t e, const char *where);
+#define FT8B200_CUDA_FAIL() ::ft8b200::cuda_error(cudaSuccess, __func__)
 int ctx_sm_count(ft8b200_ctx_t *ctx);
 int find_sync_proto(ft8b200_ctx_t *ctx, int protocol, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins,
                     int time_osr, int freq_osr, candidate_t *d_cand, int *d_ncand, void *stream);

@@ -152,7 +152,7 @@ int ft8b200_load_wav(float *signal, int *num_samples, int *sample_rate, const ch
 int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n, struct decoder_results *h_results, int32_t *h_nresults,
                             int32_t *h_samples) {
     if (!ctx || !paths || n < 1 || !h_results || !h_nresults) return FT8B200_EINVAL;
-    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;  // the caller's current device may be another one
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();  // the caller's current device may be another one
     std::vector<float> hi((size_t)n * kSlot), hq((size_t)n * kSlot), peak((size_t)n, 0.0f);
     for (int k = 0; k < n; ++k) {
         int rec = 0;
@@ -170,7 +170,7 @@ int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n,
     if (cudaMemcpyAsync(d_i, hi.data(), bytes, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(d_q, hq.data(), bytes, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(d_peak, peak.data(), sizeof(float) * n, cudaMemcpyHostToDevice, st) != cudaSuccess)
-        return FT8B200_ECUDA;
+        return FT8B200_CUDA_FAIL();
     int rc = ft8b200_process_conditioned(ctx, d_i, d_q, d_peak, n, nullptr);
     if (rc) return rc;
     rc = ft8b200_fetch_results(ctx, n, h_results, h_nresults, nullptr);
@@ -187,7 +187,7 @@ int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n,
 int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride, int n_samples, int n, int sample_rate, int protocol,
                          ft8b200_decoded_t *h_out, int32_t *h_count, int max_out_per_recording) {
     if (!ctx || !d_audio || n < 1 || !h_out || !h_count || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return FT8B200_EINVAL;
-    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     ft8b200_config_t cfg;
     if (ft8b200_get_config(ctx, &cfg)) return FT8B200_EINVAL;
     const int K = cfg.max_candidates, M = cfg.max_messages;
@@ -220,7 +220,7 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
     // read back whole below, written only up to each recording's count: defined bytes behind the counts
     if (cudaMemsetAsync(d_umsg, 0, S * M * sizeof(message_t), st) != cudaSuccess || cudaMemsetAsync(d_ucand, 0, S * M * sizeof(int32_t), st) != cudaSuccess ||
         cudaMemsetAsync(d_cand, 0, S * K * sizeof(candidate_t), st) != cudaSuccess)
-        return FT8B200_ECUDA;
+        return FT8B200_CUDA_FAIL();
     int nb = 0, rc;
     if ((rc = ft8b200_monitor_waterfall(ctx, d_audio, stride, n_samples, n, sample_rate, tosr, fosr, protocol, d_mag, mag_stride, &nb, nullptr))) return rc;
     for (int k = 0; k < n; ++k) h_count[k] = 0;
@@ -238,7 +238,7 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
           cudaMemcpyAsync(nres.data(), d_nres, S * sizeof(int32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
           cudaMemcpyAsync(cand.data(), d_cand, S * K * sizeof(candidate_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
           cudaStreamSynchronize(st) == cudaSuccess;
-    if (!okc) return FT8B200_ECUDA;
+    if (!okc) return FT8B200_CUDA_FAIL();
     for (int s = 0; s < n; ++s) {
         h_count[s] = nres[(size_t)s];
         for (int k = 0; k < nres[(size_t)s] && k < M; ++k) {
@@ -258,7 +258,7 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
 int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n, int protocol, ft8b200_decoded_t *h_out, int32_t *h_count,
                              int max_out_per_recording, int32_t *h_status) {
     if (!ctx || !paths || n < 1 || !h_out || !h_count) return FT8B200_EINVAL;
-    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     const int cap = 15 * 12000;  // decode_ft8.c:271-273: float signal[15 * sample_rate]
     std::vector<int16_t> raw((size_t)n * cap, 0);
     std::vector<int> ns((size_t)n, 0), status((size_t)n, 0);
@@ -280,10 +280,10 @@ int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n
     float *d_audio = nullptr;
     if (pool.alloc(&d_raw, (size_t)n * cap * sizeof(int16_t)) != cudaSuccess || pool.alloc(&d_audio, (size_t)n * cap * sizeof(float)) != cudaSuccess)
         return FT8B200_ENOMEM;
-    if (cudaMemcpyAsync(d_raw, raw.data(), (size_t)n * cap * sizeof(int16_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return FT8B200_ECUDA;
+    if (cudaMemcpyAsync(d_raw, raw.data(), (size_t)n * cap * sizeof(int16_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return FT8B200_CUDA_FAIL();
     const size_t total = (size_t)n * cap;
     s16_to_float_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_raw, d_audio, total);
-    if (cudaGetLastError() != cudaSuccess) return FT8B200_ECUDA;
+    if (cudaGetLastError() != cudaSuccess) return FT8B200_CUDA_FAIL();
     // recordings of different lengths: decode groups of equal length together (usually all are 15 s)
     std::vector<char> done((size_t)n, 0);
     for (int k = 0; k < n; ++k) {

@@ -590,7 +590,7 @@ int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t s
     const MonGeom g = geometry(sample_rate, time_osr, freq_osr, protocol);
     if (g.block_size < 2 || g.subblock_size * time_osr != g.block_size) return FT8B200_EINVAL;
     const int device = ctx_device(ctx);
-    if (cudaSetDevice(device) != cudaSuccess) return FT8B200_ECUDA;  // tables and launches belong to the context's device, not the caller's current one
+    if (cudaSetDevice(device) != cudaSuccess) return FT8B200_CUDA_FAIL();  // tables and launches belong to the context's device, not the caller's current one
     const MonTables *t = get_tables(device, g.nfft);
     if (!t || !thresholds(device)) return FT8B200_EINVAL;
     int nb = n_samples / g.block_size;
@@ -603,7 +603,7 @@ int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t s
     // frame f ends at sample (f+1)*subblock; the reference's last_frame starts out as (zeroed) history
     cudaError_t e = launch_frames(t, d_audio, slot_stride_samples, n_samples, (long)g.subblock_size - g.nfft, g.subblock_size, nb * time_osr, n_slots,
                                   g.num_bins, freq_osr, d_mag, mag_slot_stride, nullptr, st);
-    return e == cudaSuccess ? 0 : FT8B200_ECUDA;
+    return e == cudaSuccess ? 0 : ::ft8b200::cuda_error(e, __func__);
 }
 
 void monitor_init(monitor_t *me, const monitor_config_t *cfg) {

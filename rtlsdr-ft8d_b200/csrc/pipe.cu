@@ -127,7 +127,7 @@ int pfail(ft8b200_pipe_t *p, int code, const std::string &msg) {
 #define PCU(call)                                                                                   \
     do {                                                                                            \
         cudaError_t e__ = (call);                                                                   \
-        if (e__ != cudaSuccess) return pfail(p, FT8B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+        if (e__ != cudaSuccess) { (void)cudaGetLastError(); return pfail(p, FT8B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } \
     } while (0)
 
 int lane_results(ft8b200_pipe_t *p, Lane &l, int n_slots) {

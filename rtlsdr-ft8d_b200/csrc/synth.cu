@@ -358,7 +358,7 @@ int upload_signals(const ft8b200_signal_t *h_signals, const int *h_first, int n_
     }
     // the pageable host vector must outlive the async copies
     ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
-    if (!ok) { cudaFree(*d_sigs); cudaFree(*d_first); return FT8B200_ECUDA; }
+    if (!ok) { cudaFree(*d_sigs); cudaFree(*d_first); return FT8B200_CUDA_FAIL(); }
     return 0;
 }
 
@@ -532,7 +532,7 @@ int ft8b200_encode_tones(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, i
     memset(sig.data(), 0, sig.size() * sizeof(ft8b200_signal_t));
     for (int k = 0; k < n; ++k) { memcpy(sig[(size_t)k].payload, h_payloads + 10 * (size_t)k, 10); first[(size_t)k] = k; }
     first[(size_t)n] = n;
-    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;  // tables (per device) and buffers belong to the context's device
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();  // tables (per device) and buffers belong to the context's device
     cudaStream_t st = (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;
@@ -541,7 +541,7 @@ int ft8b200_encode_tones(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, i
     std::vector<SigDev> back((size_t)n);
     const bool ok = cudaMemcpy(back.data(), d_sigs, sizeof(SigDev) * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess;
     cudaFree(d_sigs); cudaFree(d_first);
-    if (!ok) return FT8B200_ECUDA;
+    if (!ok) return FT8B200_CUDA_FAIL();
     for (int k = 0; k < n; ++k) memcpy(h_tones + (size_t)k * kMaxSym, back[(size_t)k].tones, kMaxSym);
     return 0;
 }
@@ -554,7 +554,7 @@ int ft8b200_synth_raw(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, con
     if (!ctx || !d_iq || !check_first(h_first, n_slots) || (bytes_per_slot & 1) || slot_stride_bytes < bytes_per_slot || (slot_stride_bytes & 15) ||
         (((size_t)d_iq) & 15))
         return FT8B200_EINVAL;
-    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;
@@ -567,14 +567,14 @@ int ft8b200_synth_raw(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, con
     synth_raw_kernel<<<grid, 256, 0, st>>>(d_sigs, d_first, gf, noise_q8, seed, first_slot_index, d_iq, slot_stride_bytes, n_samples);
     const bool ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
     cudaFree(d_sigs); cudaFree(d_first);
-    return ok ? 0 : FT8B200_ECUDA;
+    return ok ? 0 : FT8B200_CUDA_FAIL();
 }
 
 // kind 1: complex baseband at 3200 sps (d_q != NULL, 48000 samples per slot typical); kind 2: real audio at 12 kHz
 static int synth_float(ft8b200_ctx_t *ctx, int kind, int protocol, const ft8b200_signal_t *h_signals, const int *h_first, int n_slots,
                        float noise_sigma, uint64_t seed, int first_slot_index, float *d_i, float *d_q, size_t slot_stride, int n_samples, void *stream) {
     if (!ctx || !d_i || (kind == 1 && !d_q) || !check_first(h_first, n_slots) || n_samples < 1 || slot_stride < (size_t)n_samples) return FT8B200_EINVAL;
-    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_ECUDA;
+    if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
     int *d_first = nullptr;
@@ -588,7 +588,7 @@ static int synth_float(ft8b200_ctx_t *ctx, int kind, int protocol, const ft8b200
     else synth_float_kernel<1920, false><<<grid, 256, 0, st>>>(d_sigs, d_first, gf, scale, seed, first_slot_index, d_i, nullptr, slot_stride, n_samples);
     const bool ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
     cudaFree(d_sigs); cudaFree(d_first);
-    return ok ? 0 : FT8B200_ECUDA;
+    return ok ? 0 : FT8B200_CUDA_FAIL();
 }
 
 int ft8b200_synth_slots(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, const int *h_first, int n_slots, float noise_sigma, uint64_t seed,
