@@ -113,7 +113,7 @@ float orc_condition(float *i_s, float *q_s, size_t n_valid, size_t n_total) {
 
 /* ======================================================================================
  * FFT: kiss_fft's float arithmetic restated (decimation in time, radix 4 first, then
- * 2, 3, 5), same twiddle table, same operation order inside every butterfly.
+ * 2, 3, 5, then the generic butterfly), same twiddle table, same operation order inside every butterfly.
  * ref: ft8_lib/fft/kiss_fft.c:15-382, _kiss_fft_guts.h:81-83 (C_MUL), kiss_fftr.c:22-115
  * ====================================================================================== */
 typedef struct { float r, i; } cpx;
@@ -228,9 +228,27 @@ static void combine(const fft_plan_t *p, cpx *F, int stride, int radix, int m) {
             *f2 = cadd(s11, s12);
             *f3 = csub(s11, s12);
         }
-    } else {
-        fprintf(stderr, "ft8_oracle: unsupported FFT radix %d\n", radix);
-        abort();
+    } else { /* ref: kf_bfly_generic, kiss_fft.c:192-229 -- any other radix (7, 11, 13 ... or what is left of n when it is prime) */
+        const int Norig = p->n;
+        cpx *scratch = (cpx *)malloc(sizeof(cpx) * (size_t)radix);
+        for (int u = 0; u < m; ++u) {
+            int k = u;
+            for (int q1 = 0; q1 < radix; ++q1) { scratch[q1] = F[k]; k += m; }
+            k = u;
+            for (int q1 = 0; q1 < radix; ++q1) {
+                int twidx = 0;
+                F[k] = scratch[0];
+                for (int q = 1; q < radix; ++q) {
+                    twidx += stride * k;
+                    if (twidx >= Norig) twidx -= Norig;
+                    const cpx t = cmul(scratch[q], tw[twidx]);
+                    F[k].r += t.r; /* C_ADDTO */
+                    F[k].i += t.i;
+                }
+                k += m;
+            }
+        }
+        free(scratch);
     }
 }
 
