@@ -142,6 +142,30 @@ __device__ __forceinline__ void butterfly(float2 *z, const float2 *tq, const int
         st(z, ix[4], f4);
     }
 }
+// kf_bfly_generic, kiss_fft.c:192-229: any other radix p (7, 11, 13 ...: frame sizes of 11.025 / 22.05 / 44.1 kHz audio).  zg = the
+// group's first element, u < m; tw = the FULL twiddle table tw[0 .. norig) in global memory (the compact per-stage tables only hold
+// tw[q k fstride] for k < m).  The p inputs are read before anything is written, as the reference's scratch[] does.
+constexpr int kMaxRadix = 32;
+__device__ __noinline__ void butterfly_generic(float2 *zg, const float2 *__restrict__ tw, int u, int m, int p, int fstride, int norig) {
+    cpx scratch[kMaxRadix];
+    int k = u;
+    for (int q1 = 0; q1 < p; ++q1) { scratch[q1] = ld(zg, k); k += m; }
+    k = u;
+    for (int q1 = 0; q1 < p; ++q1) {
+        int twidx = 0;
+        cpx acc = scratch[0];
+        for (int q = 1; q < p; ++q) {
+            twidx += fstride * k;
+            if (twidx >= norig) twidx -= norig;
+            const cpx tt = cmul(scratch[q], __ldg(tw + twidx));
+            acc.r = __fadd_rn(acc.r, tt.r);   // C_ADDTO
+            acc.i = __fadd_rn(acc.i, tt.i);
+        }
+        st(zg, k, acc);
+        k += m;
+    }
+}
+
 template <int P>
 __device__ __forceinline__ void butterfly_at(float2 *z, const float2 *tq, int i0, int m, int k, float2 c1, float2 c2) {
     int ix[P];
@@ -308,7 +332,8 @@ monitor_frames_kernel(const float *__restrict__ audio, size_t slot_stride, int n
                     if (p == 4) butterfly_at<4>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
                     else if (p == 2) butterfly_at<2>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
                     else if (p == 3) butterfly_at<3>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
-                    else butterfly_at<5>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    else if (p == 5) butterfly_at<5>(z, tq, i0, m, k, plan.c1[s], plan.c2[s]);
+                    else butterfly_generic(z + g * p * m, tw_stage + plan.tw_total, k, m, p, plan.fstride[s], n);   // the full table follows the compact ones
                 }
                 __syncthreads();
             }
@@ -390,7 +415,7 @@ bool build_plan(int n, FftPlan &plan, std::vector<uint16_t> &perm) {
             if (q > lim) q = left;
         }
         left /= q;
-        if (nf >= kMaxStages || (q != 2 && q != 3 && q != 4 && q != 5)) return false;
+        if (nf >= kMaxStages || q > kMaxRadix) return false;   // 2, 3, 4, 5 have their own butterflies, anything else up to kMaxRadix the generic one
         radix[nf] = q;
         rem[nf] = left;
         ++nf;
@@ -443,13 +468,17 @@ MonTables *get_tables(int device, int nfft) {
     for (int s2 = 0; s2 < t->plan.nstages; ++s2) {
         const int p = t->plan.radix[s2], m = t->plan.m[s2], fs = t->plan.fstride[s2];
         t->plan.tw_off[s2] = (int)tws.size();
-        for (int q = 1; q < p; ++q)
-            for (int k = 0; k < m; ++k) tws.push_back(tw[(size_t)(q * k * fs)]);
+        if (p <= 5)   // the generic butterfly reads the full table instead
+            for (int q = 1; q < p; ++q)
+                for (int k = 0; k < m; ++k) tws.push_back(tw[(size_t)(q * k * fs)]);
         t->plan.magic[s2] = m > 1 ? (unsigned int)((0x100000000ull + (unsigned long long)m - 1) / (unsigned long long)m) : 0u;
         t->plan.c1[s2] = tw[(size_t)(fs * m) % (size_t)n];
         t->plan.c2[s2] = tw[(size_t)(2 * fs * m) % (size_t)n];
     }
     t->plan.tw_total = (int)tws.size();
+    bool any_generic = false;
+    for (int s2 = 0; s2 < t->plan.nstages; ++s2) any_generic |= t->plan.radix[s2] > 5;
+    if (any_generic) tws.insert(tws.end(), tw.begin(), tw.end());   // behind the compact tables: what butterfly_generic indexes (global memory only)
     // compile-time stage list when the host-built plan is exactly the one StaticPlan spells out
     auto matches = [&](auto tag) {
         using SP = decltype(tag);
@@ -613,7 +642,7 @@ void monitor_init(monitor_t *me, const monitor_config_t *cfg) {
     if (cudaSetDevice(device) != cudaSuccess) die("monitor_init: cudaSetDevice");
     const MonTables *t = get_tables(device, g.nfft);
     if (!t || !thresholds(device)) {
-        fprintf(stderr, "libft8b200: monitor_init: unsupported FFT size %d (radices 2,3,4,5 only)\n", g.nfft);
+        fprintf(stderr, "libft8b200: monitor_init: unsupported FFT size %d (a prime factor above %d, or more than 65535 points)\n", g.nfft, 32);
         abort();
     }
     me->symbol_period = g.symbol_period;

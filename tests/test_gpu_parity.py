@@ -1364,13 +1364,16 @@ def test_monitor_other_rates_and_oversampling(ctx, oracle, rate, tosr, fosr, pro
 
 @pytest.mark.parametrize("rate", [11025, 22050, 44100, 48000, 96000])
 def test_monitor_exotic_rates_are_exact_or_refused(pkg, ctx, oracle, rate):
-    """Frame sizes with a factor the kernel has no butterfly for (11 025 Hz: 3528 = 2^3 3^2 7^2) or too large for one CTA's shared
-    memory: the batched call either reproduces the oracle's bytes or returns an error -- never a waterfall that is merely plausible."""
+    """Audio rates whose frames have prime factors beyond 5 (11 025 Hz: 3528 = 2^3 3^2 7^2; 22 050, 44 100 likewise) go through
+    kiss_fft's GENERIC butterfly (kf_bfly_generic, kiss_fft.c:192-229), restated in the kernel's generic stage loop: identical bytes.
+    A frame too large for one CTA's shared memory (96 kHz: 30 720 points) is refused with a reason -- the batched call either
+    reproduces the oracle's bytes or returns an error, never a waterfall that is merely plausible."""
     rng = np.random.default_rng(rate)
     aud = (0.1 * rng.standard_normal(int(rate * 2.0))).astype(np.float32)
     try:
         mag, nb = ctx.monitor_waterfall(torch.from_numpy(aud[None]).to(dev()), rate, 2, 2, 1)
     except pkg.Ft8Error as e:
+        assert rate > 48000, f"{rate} Hz must be supported: {e}"
         # refused: with a reason, and without leaving its CUDA error behind as the runtime's "last error" for the application's own
         # next call to trip over (torch checks it after every launch)
         assert "monitor" in str(e) or "ft8b200" in str(e)
@@ -1417,3 +1420,20 @@ def test_two_contexts_from_two_threads(pkg, raw_slot):
         assert together == alone
     pipe.close()
     for c in ctxs: c.close()
+
+
+def test_monitor_dropin_at_11025_hz(pkg, oracle):
+    """monitor_init/monitor_process with a WAV file's own rate of 11 025 Hz (block 1764, 3528-point frames, radix-7 stages) and
+    ft8_find_sync on the result: the drop-in's waterfall bytes and candidates are the oracle's."""
+    rng = np.random.default_rng(11025)
+    aud = (0.1 * rng.standard_normal(11025 * 15)).astype(np.float32)
+    mon = pkg.Monitor(11025, 2, 2, 1)
+    assert (mon.me.block_size, mon.me.nfft, mon.me.wf.num_bins) == (1764, 3528, 882)
+    for o in range(0, aud.size - 1764 + 1, 1764):
+        mon.process(aud[o:o + 1764])
+    ref, info, _ = oracle.monitor_waterfall(aud, 11025, 2, 2, 1)
+    got = mon.mag()
+    assert mon.me.wf.num_blocks == int(info[4]) and np.array_equal(got[: ref.size], ref)
+    dims = dict(num_blocks=int(info[4]), num_bins=882, time_osr=2, freq_osr=2)
+    assert mon.find_sync(40, 5).tobytes() == oracle.find_sync(ref, max_cand=40, min_score=5, **dims).tobytes()
+    mon.close()

@@ -242,7 +242,7 @@ def test_encoder_and_crc_vs_reference(oracle):
 def test_fft_vs_kiss(oracle):
     mon = ReferenceMonitor()
     rng = np.random.default_rng(9)
-    for n in (3840, 1152, 128, 960, 60):
+    for n in (3840, 1152, 128, 960, 60, 3528, 14112, 154, 442, 202, 98):   # the last six: kf_bfly_generic (radix 7, 11, 13, 17, 101)
         x = rng.standard_normal(n).astype(np.float32)
         assert np.array_equal(oracle.fft_r2c(x).view(np.uint32), mon.fftr(x).view(np.uint32)), n
 
