@@ -261,13 +261,13 @@ int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     const int cap = 15 * 12000;  // decode_ft8.c:271-273: float signal[15 * sample_rate]
     std::vector<int16_t> raw((size_t)n * cap, 0);
-    std::vector<int> ns((size_t)n, 0), status((size_t)n, 0);
-    int rate = 12000, max_n = 0;
+    std::vector<int> ns((size_t)n, 0), status((size_t)n, 0), rates((size_t)n, 12000);
+    int max_n = 0;
     for (int k = 0; k < n; ++k) {
         int num = cap, sr = 12000;
         status[(size_t)k] = ft8b200_load_wav_s16(&raw[(size_t)k * cap], nullptr, &num, &sr, paths[k]);
         if (status[(size_t)k] < 0) num = 0;
-        else rate = sr;  // all recordings of a batch are expected to share one sample rate
+        else rates[(size_t)k] = sr;  // decode_ft8 takes every file at its own rate (decode_ft8.c:277-285)
         ns[(size_t)k] = num;
         if (num > max_n) max_n = num;
         if (h_status) h_status[k] = status[(size_t)k];
@@ -284,13 +284,13 @@ int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n
     const size_t total = (size_t)n * cap;
     s16_to_float_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_raw, d_audio, total);
     if (cudaGetLastError() != cudaSuccess) return FT8B200_CUDA_FAIL();
-    // recordings of different lengths: decode groups of equal length together (usually all are 15 s)
+    // recordings of different lengths or rates: neighbours of equal length and rate are decoded together (usually all are 15 s at 12 kHz)
     std::vector<char> done((size_t)n, 0);
     for (int k = 0; k < n; ++k) {
         if (done[(size_t)k] || ns[(size_t)k] == 0) continue;
         int run = 1;
-        while (k + run < n && ns[(size_t)(k + run)] == ns[(size_t)k]) ++run;
-        int rc = ft8b200_decode_audio(ctx, d_audio + (size_t)k * cap, (size_t)cap, ns[(size_t)k], run, rate, protocol,
+        while (k + run < n && ns[(size_t)(k + run)] == ns[(size_t)k] && rates[(size_t)(k + run)] == rates[(size_t)k]) ++run;
+        int rc = ft8b200_decode_audio(ctx, d_audio + (size_t)k * cap, (size_t)cap, ns[(size_t)k], run, rates[(size_t)k], protocol,
                                       h_out + (size_t)k * max_out_per_recording, h_count + k, max_out_per_recording);
         if (rc) return rc;
         for (int j = 0; j < run; ++j) done[(size_t)(k + j)] = 1;

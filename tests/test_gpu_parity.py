@@ -991,10 +991,10 @@ def test_ft4_dropin(pkg, oracle):
 
 
 # ------------------------------------------------------------------------------------------- recordings on disk
-def _write_wav(path, pcm):
+def _write_wav(path, pcm, rate=12000):
     import wave
     with wave.open(str(path), "wb") as w:
-        w.setnchannels(1); w.setsampwidth(2); w.setframerate(12000)
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(rate)
         w.writeframes(np.ascontiguousarray(pcm, np.int16).tobytes())
 
 
@@ -1045,6 +1045,17 @@ def test_wav_batch_ft4_and_short_files(pkg, ctx, oracle, tmp_path):
         want = oracle.decode_ft8_lines(pcm8[:L].astype(np.float32) / np.float32(32768.0), 12000)
         assert [pkg.format_decoded(r) for r in outs[k]] == want
     assert len(outs[0]) >= 2 and len(outs[3]) == 0
+    # files of different sample rates in one call: each is taken at its own rate, like decode_ft8 does (decode_ft8.c:277-285);
+    # the 16 kHz file is the same audio played a third faster (so a signal 1/3 higher and shorter: whatever decode_ft8 makes of it)
+    rates = [12000, 16000, 16000, 12000, 11025]
+    paths = []
+    for k, r in enumerate(rates):
+        paths.append(tmp_path / f"mixed_{k}.wav"); _write_wav(paths[-1], pcm8[:150_000 + 1000 * k], r)
+    outs, status = pkg.decode_wav_files(ctx, [str(p) for p in paths])
+    for k, r in enumerate(rates):
+        want = oracle.decode_ft8_lines(pcm8[:150_000 + 1000 * k].astype(np.float32) / np.float32(32768.0), r)
+        assert [pkg.format_decoded(x) for x in outs[k]] == want, (k, r)
+    assert len(outs[0]) >= 2
 
 
 def test_iq_and_c2_files(pkg, ctx, oracle, slots, tmp_path):
