@@ -315,6 +315,8 @@ int ft8b200_waterfall(ft8b200_ctx_t *ctx, const float *d_i, const float *d_q, co
 // recording calls of files.cu use, so that they neither change nor depend on the protocol selected for the stage-wise API
 namespace ft8b200 {
 int cuda_error(cudaError_t e, const char *where) { return cuda_fail(e, where); }
+int api_error(int code, const char *why) { return fail(code, why); }
+int bad_argument(const char *func) { return fail(FT8B200_EINVAL, std::string(func) + ": bad argument"); }
 int ctx_device(ft8b200_ctx_t *ctx) { return ctx ? ctx->cfg.device : -1; }
 int ctx_sm_count(ft8b200_ctx_t *ctx) { return ctx ? ctx->sm_count : 0; }
 

@@ -242,7 +242,7 @@ uint64_t ft8b200_cluster_kernel_launches(ft8b200_cluster_t *c) {
 }
 
 int ft8b200_cluster_shard(ft8b200_cluster_t *c, int n_items, int device_index, int *first, int *count) {
-    if (!c || device_index < 0 || device_index >= c->n || n_items < 0) return FT8B200_EINVAL;
+    if (!c || device_index < 0 || device_index >= c->n || n_items < 0) return FT8B200_BAD_ARG();
     int lo, hi;
     shard(n_items, c->n, device_index, &lo, &hi);
     if (first) *first = lo;

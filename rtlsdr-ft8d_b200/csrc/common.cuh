@@ -76,6 +76,9 @@ int ctx_device(ft8b200_ctx_t *ctx);
 // the reason goes to ft8b200_last_error(), the runtime's error state is cleared (a sticky error survives that, as it should),
 // and FT8B200_ECUDA is returned.  e == cudaSuccess: whatever the runtime holds as its last error is taken instead.
 int cuda_error(cudaError_t e, const char *where);
+int api_error(int code, const char *why);   // `code` back, `why` into ft8b200_last_error()
+int bad_argument(const char *func);        // FT8B200_EINVAL, "<func>: bad argument" into ft8b200_last_error()
+#define FT8B200_BAD_ARG() ::ft8b200::bad_argument(__func__)
 #define FT8B200_CUDA_FAIL() ::ft8b200::cuda_error(cudaSuccess, __func__)
 int ctx_sm_count(ft8b200_ctx_t *ctx);
 int find_sync_proto(ft8b200_ctx_t *ctx, int protocol, const uint8_t *d_mag, size_t slot_stride_bytes, int n_slots, int num_blocks, int num_bins,

@@ -151,7 +151,7 @@ int ft8b200_load_wav(float *signal, int *num_samples, int *sample_rate, const ch
 // Unreadable files and unknown extensions give 0 samples and 0 results (the reference prints a message and returns).
 int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n, struct decoder_results *h_results, int32_t *h_nresults,
                             int32_t *h_samples) {
-    if (!ctx || !paths || n < 1 || !h_results || !h_nresults) return FT8B200_EINVAL;
+    if (!ctx || !paths || n < 1 || !h_results || !h_nresults) return FT8B200_BAD_ARG();
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();  // the caller's current device may be another one
     std::vector<float> hi((size_t)n * kSlot), hq((size_t)n * kSlot), peak((size_t)n, 0.0f);
     for (int k = 0; k < n; ++k) {
@@ -186,12 +186,12 @@ int ft8b200_decode_iq_files(ft8b200_ctx_t *ctx, const char *const *paths, int n,
 // The context must have been created with max_candidates 120 / max_messages 50 to reproduce decode_ft8 exactly.
 int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride, int n_samples, int n, int sample_rate, int protocol,
                          ft8b200_decoded_t *h_out, int32_t *h_count, int max_out_per_recording) {
-    if (!ctx || !d_audio || n < 1 || !h_out || !h_count || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return FT8B200_EINVAL;
+    if (!ctx || !d_audio || n < 1 || !h_out || !h_count || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return FT8B200_BAD_ARG();
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     ft8b200_config_t cfg;
-    if (ft8b200_get_config(ctx, &cfg)) return FT8B200_EINVAL;
+    if (ft8b200_get_config(ctx, &cfg)) return FT8B200_BAD_ARG();
     const int K = cfg.max_candidates, M = cfg.max_messages;
-    if (max_out_per_recording < M) return FT8B200_EINVAL;
+    if (max_out_per_recording < M) return FT8B200_BAD_ARG();
     const int tosr = 2, fosr = 2;  // kTime_osr, kFreq_osr (decode_ft8.c:27-28)
     const float symbol_period = (protocol == PROTO_FT4) ? 0.048f : 0.160f;
     const float slot_time = (protocol == PROTO_FT4) ? 7.5f : 15.0f;
@@ -257,7 +257,7 @@ int ft8b200_decode_audio(ft8b200_ctx_t *ctx, const float *d_audio, size_t stride
 
 int ft8b200_decode_wav_files(ft8b200_ctx_t *ctx, const char *const *paths, int n, int protocol, ft8b200_decoded_t *h_out, int32_t *h_count,
                              int max_out_per_recording, int32_t *h_status) {
-    if (!ctx || !paths || n < 1 || !h_out || !h_count) return FT8B200_EINVAL;
+    if (!ctx || !paths || n < 1 || !h_out || !h_count) return FT8B200_BAD_ARG();
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     const int cap = 15 * 12000;  // decode_ft8.c:271-273: float signal[15 * sample_rate]
     std::vector<int16_t> raw((size_t)n * cap, 0);

@@ -538,8 +538,10 @@ cudaError_t launch_frames(const MonTables *t, const float *d_audio, size_t slot_
     if (t->max_grid == 0) {  // once per (device, nfft): monitor_process() launches this 93 times per recording
         // z | stage twiddles | super twiddles | threshold pairs | one frame's bytes (see monitor_frames_kernel)
         const size_t need = sizeof(float2) * ((size_t)z_len(t->static_n, n) + (size_t)t->plan.tw_total + (size_t)(n / 2 + 1) + 256) + (((size_t)2 * n + 15) & ~(size_t)15);
-        int sms = 0, per_sm = 0;
+        int sms = 0, per_sm = 0, optin = 0;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, t->device)) != cudaSuccess) return e;
+        if (need > (size_t)optin) return cudaErrorInvalidConfiguration;   // the frame does not fit one CTA's shared memory: refused, no CUDA call fails
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMonThreads, need)) != cudaSuccess) return e;
         MonTables *mt = const_cast<MonTables *>(t);
@@ -615,23 +617,33 @@ extern "C" {
 
 int ft8b200_monitor_waterfall(ft8b200_ctx_t *ctx, const float *d_audio, size_t slot_stride_samples, int n_samples, int n_slots, int sample_rate,
                               int time_osr, int freq_osr, int protocol, uint8_t *d_mag, size_t mag_slot_stride, int *num_blocks_out, void *stream) {
-    if (!ctx || !d_audio || !d_mag || n_slots < 1 || n_samples < 0 || time_osr < 1 || freq_osr < 1) return FT8B200_EINVAL;
+    if (!ctx || !d_audio || !d_mag || n_slots < 1 || n_samples < 0 || time_osr < 1 || freq_osr < 1) return api_error(FT8B200_EINVAL, "ft8b200_monitor_waterfall: bad argument");
     const MonGeom g = geometry(sample_rate, time_osr, freq_osr, protocol);
-    if (g.block_size < 2 || g.subblock_size * time_osr != g.block_size) return FT8B200_EINVAL;
+    if (g.block_size < 2 || g.subblock_size * time_osr != g.block_size)
+        return api_error(FT8B200_EINVAL, "ft8b200_monitor_waterfall: the block of one symbol period does not divide by time_osr at this sample rate");
     const int device = ctx_device(ctx);
     if (cudaSetDevice(device) != cudaSuccess) return FT8B200_CUDA_FAIL();  // tables and launches belong to the context's device, not the caller's current one
     const MonTables *t = get_tables(device, g.nfft);
-    if (!t || !thresholds(device)) return FT8B200_EINVAL;
+    if (!t || !thresholds(device)) {
+        char why[160];
+        snprintf(why, sizeof(why), "ft8b200_monitor_waterfall: unsupported frame size %d (odd, a prime factor above %d, or more than 131070 points)", g.nfft, kMaxRadix);
+        return api_error(FT8B200_EINVAL, why);
+    }
     int nb = n_samples / g.block_size;
     if (nb > g.max_blocks) nb = g.max_blocks;
     if (num_blocks_out) *num_blocks_out = nb;
     if (nb == 0) return 0;
     const size_t stride = (size_t)time_osr * freq_osr * g.num_bins;
-    if (mag_slot_stride < (size_t)nb * stride) return FT8B200_EINVAL;
+    if (mag_slot_stride < (size_t)nb * stride) return api_error(FT8B200_EINVAL, "ft8b200_monitor_waterfall: mag_slot_stride is smaller than one recording's waterfall");
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     // frame f ends at sample (f+1)*subblock; the reference's last_frame starts out as (zeroed) history
     cudaError_t e = launch_frames(t, d_audio, slot_stride_samples, n_samples, (long)g.subblock_size - g.nfft, g.subblock_size, nb * time_osr, n_slots,
                                   g.num_bins, freq_osr, d_mag, mag_slot_stride, nullptr, st);
+    if (e == cudaErrorInvalidConfiguration) {
+        char why[160];
+        snprintf(why, sizeof(why), "ft8b200_monitor_waterfall: a frame of %d points (sample rate %d) does not fit one CTA's shared memory", g.nfft, sample_rate);
+        return ::ft8b200::cuda_error(e, why);
+    }
     return e == cudaSuccess ? 0 : ::ft8b200::cuda_error(e, __func__);
 }
 
@@ -737,7 +749,7 @@ void monitor_process(monitor_t *me, const float *frame) {
 // not yet reflect the appended blocks (wf.num_blocks does).  ft8_find_sync() and ft8_decode() flush by themselves.
 int ft8b200_monitor_flush(monitor_t *me) {
     MonitorDev *d = me ? (MonitorDev *)me->fft_work : nullptr;
-    if (!d) return FT8B200_EINVAL;
+    if (!d) return FT8B200_BAD_ARG();
     if (d->pending == 0) return 0;
     if (cudaSetDevice(d->tables->device) != cudaSuccess) die("ft8b200_monitor_flush: cudaSetDevice");
     const int blocks = d->pending;
@@ -748,7 +760,7 @@ int ft8b200_monitor_flush(monitor_t *me) {
 
 int ft8b200_monitor_set_deferred(monitor_t *me, int on) {
     MonitorDev *d = me ? (MonitorDev *)me->fft_work : nullptr;
-    if (!d) return FT8B200_EINVAL;
+    if (!d) return FT8B200_BAD_ARG();
     if (!on) ft8b200_monitor_flush(me);
     std::lock_guard<std::mutex> lk(g_deferred_mu);
     for (size_t k = 0; k < g_deferred.size(); ++k)

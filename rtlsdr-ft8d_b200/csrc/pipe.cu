@@ -145,7 +145,7 @@ int lane_results(ft8b200_pipe_t *p, Lane &l, int n_slots) {
 // continuous receivers cut into `segs` consecutive slots of seg_bytes each (ft8b200_process_raw_streams): n_slots * segs result rows
 int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t bytes_per_stream, size_t stride, int n_slots, int segs = 1,
            size_t seg_bytes = 0) {
-    if (!p) return FT8B200_EINVAL;
+    if (!p) return FT8B200_BAD_ARG();
     if ((!h_iq && !d_iq) || n_slots < 1 || (bytes_per_stream & 7) || segs < 1) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_submit: bad argument");
     const int n_rows = n_slots * segs;
     if (p->count == (int)p->lanes.size()) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_submit: every lane is in flight, collect first");
@@ -196,7 +196,7 @@ int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t b
 // host samples are copied H2D on the lane's stream, then waterfall -> sync -> decode -> spots, records back through the
 // lane's pinned buffers.  d_peak != NULL: the samples are unconditioned, decoder()'s 0.5/peak scale is applied on load.
 int submit_slots(ft8b200_pipe_t *p, const float *h_i, const float *h_q, const float *d_i, const float *d_q, const float *d_peak, int n_slots) {
-    if (!p) return FT8B200_EINVAL;
+    if (!p) return FT8B200_BAD_ARG();
     if (!((h_i && h_q) || (d_i && d_q)) || n_slots < 1) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_submit_slots: bad argument");
     if (p->count == (int)p->lanes.size()) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_submit_slots: every lane is in flight, collect first");
     PCU(cudaSetDevice(p->cfg.device));
@@ -259,7 +259,7 @@ ft8b200_pipe_t *ft8b200_pipe_create(const ft8b200_config_t *cfg_in, int depth) {
 static void partition_release(ft8b200_pipe_t *p);
 
 int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant) {
-    if (!p || (mode != FT8B200_PIPE_OVERLAP && mode != FT8B200_PIPE_SERIAL)) return FT8B200_EINVAL;
+    if (!p || (mode != FT8B200_PIPE_OVERLAP && mode != FT8B200_PIPE_SERIAL)) return FT8B200_BAD_ARG();
     if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_set_mode: batches in flight");
     if (p->part.front || p->part.back) partition_release(p);  // both modes time-share the whole GPU
     p->mode = mode;
@@ -288,7 +288,7 @@ static void partition_release(ft8b200_pipe_t *p) {
 }
 
 int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_out, int *back_sms_out) {
-    if (!p || back_sms < 0) return FT8B200_EINVAL;
+    if (!p || back_sms < 0) return FT8B200_BAD_ARG();
     if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_set_partition: batches in flight");
     PCU(cudaSetDevice(p->cfg.device));
     const DriverApi &d = driver_api();
@@ -359,7 +359,7 @@ int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_o
 
 int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots,
                           const int *candidates, int n_candidates, int batches, int *best_back_sms, int *best_comb_front, float *ms_out) {
-    if (!p || !d_iq || !candidates || n_candidates < 1 || n_slots < 1) return FT8B200_EINVAL;
+    if (!p || !d_iq || !candidates || n_candidates < 1 || n_slots < 1) return FT8B200_BAD_ARG();
     if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_autotune: batches in flight");
     if (batches < (int)p->lanes.size() + 2) batches = (int)p->lanes.size() + 2;
     PCU(cudaSetDevice(p->cfg.device));
@@ -463,7 +463,7 @@ int ft8b200_pipe_submit_slots_host(ft8b200_pipe_t *p, const float *h_i, const fl
 
 static int pop(ft8b200_pipe_t *p, struct decoder_results *h_results, int32_t *h_nresults, int capacity_slots, struct decoder_results **d_results,
                int32_t **d_nresults) {
-    if (!p) return FT8B200_EINVAL;
+    if (!p) return FT8B200_BAD_ARG();
     if (p->count == 0) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_collect: nothing in flight");
     Lane &l = p->lanes[p->head];
     if (h_results && (capacity_slots < l.n_slots || !h_nresults)) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_collect: result buffers too small");
@@ -502,13 +502,13 @@ int ft8b200_pipe_collect_device(ft8b200_pipe_t *p, struct decoder_results **d_re
 }
 
 int ft8b200_pipe_depend_on(ft8b200_pipe_t *p, void *cuda_event) {
-    if (!p) return FT8B200_EINVAL;
+    if (!p) return FT8B200_BAD_ARG();
     p->dependency = reinterpret_cast<cudaEvent_t>(cuda_event);
     return 0;
 }
 
 int ft8b200_pipe_set_profiling(ft8b200_pipe_t *p, int on) {
-    if (!p) return FT8B200_EINVAL;
+    if (!p) return FT8B200_BAD_ARG();
     p->profiling = on != 0;
     for (Lane &l : p->lanes) ft8b200_set_profiling(l.ctx, on);
     for (double &v : p->stage_ms) v = 0.0;
@@ -526,7 +526,7 @@ int ft8b200_pipe_set_profiling(ft8b200_pipe_t *p, int on) {
 // Device timeline of the batches collected since profiling was switched on: 12 floats per batch (begin, end of block sums,
 // comb+FIR, waterfall, sync, decode, spots in ms since that moment).  Returns the number of batches written (<= max_batches).
 int ft8b200_pipe_timeline(ft8b200_pipe_t *p, float *out, int max_batches) {
-    if (!p || !out || max_batches < 0) return FT8B200_EINVAL;
+    if (!p || !out || max_batches < 0) return FT8B200_BAD_ARG();
     int n = (int)(p->timeline.size() / 12);
     if (n > max_batches) n = max_batches;
     memcpy(out, p->timeline.data(), (size_t)n * 12 * sizeof(float));
@@ -535,7 +535,7 @@ int ft8b200_pipe_timeline(ft8b200_pipe_t *p, float *out, int max_batches) {
 
 // sums over the batches collected since profiling was switched on: ms[0..5] as ft8b200_stage_times, *batches = how many
 int ft8b200_pipe_stage_times(ft8b200_pipe_t *p, double *ms, int n, uint64_t *batches) {
-    if (!p || !ms || n < 6) return FT8B200_EINVAL;
+    if (!p || !ms || n < 6) return FT8B200_BAD_ARG();
     for (int k = 0; k < 6; ++k) ms[k] = p->stage_ms[k];
     if (batches) *batches = p->batches;
     return 0;

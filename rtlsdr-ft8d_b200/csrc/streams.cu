@@ -227,7 +227,7 @@ int ft8b200_stream_flip(ft8b200_stream_t *s) {
 }
 
 int ft8b200_stream_fetch(ft8b200_stream_t *s, float *h_i, float *h_q, uint32_t *n_valid) {
-    if (!h_i || !h_q) return FT8B200_EINVAL;
+    if (!h_i || !h_q) return FT8B200_BAD_ARG();
     if (!s) s = default_stream();
     std::lock_guard<std::mutex> lk(s->mu);
     CK(cudaSetDevice(s->device));
@@ -240,7 +240,7 @@ int ft8b200_stream_fetch(ft8b200_stream_t *s, float *h_i, float *h_q, uint32_t *
 }
 
 int ft8b200_stream_decode(ft8b200_stream_t *s, struct decoder_results *h_results, int32_t *h_nresults) {
-    if (!h_results || !h_nresults) return FT8B200_EINVAL;
+    if (!h_results || !h_nresults) return FT8B200_BAD_ARG();
     if (!s) s = default_stream();
     int prev;
     {

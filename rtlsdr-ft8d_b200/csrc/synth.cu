@@ -320,7 +320,7 @@ GfskDev gfsk_tables(int kind, int protocol) {
 // host descriptors -> device descriptors (frequency words in double, once per signal), then the prepare kernel
 int upload_signals(const ft8b200_signal_t *h_signals, const int *h_first, int n_slots, int kind, int protocol, SigDev **d_sigs, int **d_first,
                    GfskDev *gf_out, cudaStream_t st) {
-    if (!h_signals && h_first[n_slots] > 0) return FT8B200_EINVAL;
+    if (!h_signals && h_first[n_slots] > 0) return FT8B200_BAD_ARG();
     const int n = h_first[n_slots];
     const Layout L = layout_of(kind, protocol);
     bool any_gfsk = false;
@@ -526,7 +526,7 @@ int ft8b200_pack77(const char *msg, uint8_t *payload10) {
 
 // channel symbols of n payloads (10 bytes each) on the device: d_tones = n x 105 bytes (FT8 fills the first 79)
 int ft8b200_encode_tones(ft8b200_ctx_t *ctx, const uint8_t *h_payloads, int n, int protocol, uint8_t *h_tones) {
-    if (!ctx || !h_payloads || !h_tones || n < 1 || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return FT8B200_EINVAL;
+    if (!ctx || !h_payloads || !h_tones || n < 1 || (protocol != PROTO_FT4 && protocol != PROTO_FT8)) return FT8B200_BAD_ARG();
     std::vector<ft8b200_signal_t> sig((size_t)n);
     std::vector<int> first((size_t)n + 1);
     memset(sig.data(), 0, sig.size() * sizeof(ft8b200_signal_t));
@@ -553,7 +553,7 @@ int ft8b200_synth_raw(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, con
                       int first_slot_index, uint8_t *d_iq, size_t slot_stride_bytes, size_t bytes_per_slot, void *stream) {
     if (!ctx || !d_iq || !check_first(h_first, n_slots) || (bytes_per_slot & 1) || slot_stride_bytes < bytes_per_slot || (slot_stride_bytes & 15) ||
         (((size_t)d_iq) & 15))
-        return FT8B200_EINVAL;
+        return FT8B200_BAD_ARG();
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
@@ -573,7 +573,7 @@ int ft8b200_synth_raw(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, con
 // kind 1: complex baseband at 3200 sps (d_q != NULL, 48000 samples per slot typical); kind 2: real audio at 12 kHz
 static int synth_float(ft8b200_ctx_t *ctx, int kind, int protocol, const ft8b200_signal_t *h_signals, const int *h_first, int n_slots,
                        float noise_sigma, uint64_t seed, int first_slot_index, float *d_i, float *d_q, size_t slot_stride, int n_samples, void *stream) {
-    if (!ctx || !d_i || (kind == 1 && !d_q) || !check_first(h_first, n_slots) || n_samples < 1 || slot_stride < (size_t)n_samples) return FT8B200_EINVAL;
+    if (!ctx || !d_i || (kind == 1 && !d_q) || !check_first(h_first, n_slots) || n_samples < 1 || slot_stride < (size_t)n_samples) return FT8B200_BAD_ARG();
     if (cudaSetDevice(ctx_device(ctx)) != cudaSuccess) return FT8B200_CUDA_FAIL();
     cudaStream_t st = stream ? (cudaStream_t)stream : (cudaStream_t)ft8b200_cuda_stream(ctx);
     SigDev *d_sigs = nullptr;
@@ -598,7 +598,7 @@ int ft8b200_synth_slots(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, c
 
 int ft8b200_synth_audio(ft8b200_ctx_t *ctx, const ft8b200_signal_t *h_signals, const int *h_first, int n_slots, int protocol, float noise_sigma,
                         uint64_t seed, int first_slot_index, float *d_audio, size_t slot_stride_samples, int n_samples, void *stream) {
-    if (protocol != PROTO_FT4 && protocol != PROTO_FT8) return FT8B200_EINVAL;
+    if (protocol != PROTO_FT4 && protocol != PROTO_FT8) return FT8B200_BAD_ARG();
     return synth_float(ctx, 2, protocol, h_signals, h_first, n_slots, noise_sigma, seed, first_slot_index, d_audio, nullptr, slot_stride_samples, n_samples, stream);
 }
 
