@@ -424,10 +424,11 @@ def main():
         return cluster_arm(args, config)
 
     env = Env(args)
+    run_info = {}   # how THIS arm ran the workload (executor, SM split, CPU binding): `config` itself only names the workload and is the same in every arm
     torch, dist, pkg = env.torch, env.dist, env.pkg
     device, local = env.device, env.local
     if env.numa:
-        config["numa"] = env.numa
+        run_info["numa"] = env.numa
 
     B = args.slots
     if args.chunks < 1 or B % args.chunks:
@@ -444,18 +445,18 @@ def main():
         # green contexts: disjoint SM sets for the HBM-bound decimator and the issue-bound back end (ft8b200_pipe_set_partition)
         try:
             if args.back_sms < 0:
-                tuned = pipe.autotune(batch[:Bc], Bc, candidates=(24, 32, 40), batches=3 * args.depth + 3)
-                config["sm_partition"] = {"chosen_by": "ft8b200_pipe_autotune (ms per %d-slot batch at each point)" % Bc, **tuned}
+                tuned = pipe.autotune(batch[:Bc], Bc, candidates=(24, 32, 40), batches=48)
+                run_info["sm_partition"] = {"chosen_by": "ft8b200_pipe_autotune (ms per %d-slot batch at each point)" % Bc, **tuned}
                 mode_txt = "SM partition: back end of batch n on %d SMs (comb+FIR on the %s set), decimator of batch n+1 on the others" % (
                     tuned["back_sms"], "front" if tuned["comb_front"] else "back")
             else:
-                config["sm_partition"] = dict(zip(("front_sms", "back_sms"), pipe.set_partition(args.back_sms)))
+                run_info["sm_partition"] = dict(zip(("front_sms", "back_sms"), pipe.set_partition(args.back_sms)))
                 mode_txt = "SM partition: back end of batch n on >= %d SMs, decimator of batch n+1 on the others" % args.back_sms
         except Exception as exc:  # a driver without green contexts: same kernels, consecutive batches back to back on the whole GPU
-            config["sm_partition"] = "unavailable (%s): running serial" % exc
+            run_info["sm_partition"] = "unavailable (%s): running serial" % exc
             pipe.set_mode(serial=True, decimator_variant=args.k1_variant)
             args.back_sms = 0
-    config["executor"] = "ft8b200_pipe_t depth %d, %d batches of %d slots per step, %s" % (args.depth, args.chunks, Bc, mode_txt)
+    run_info["executor"] = "ft8b200_pipe_t depth %d, %d batches of %d slots per step, %s" % (args.depth, args.chunks, Bc, mode_txt)
     M = pipe.M
 
     gather = StepGather(env, pipe, args.chunks, Bc) if world > 1 and not os.environ.get("BENCH_NOGATHER") else None
@@ -557,7 +558,7 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": "slots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-           "data": "synthetic (generated on the device by ft8b200_synth_raw)", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+           "data": "synthetic (generated on the device by ft8b200_synth_raw)", "config": config, "run": run_info, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
            "decoded_ok_slots_in_first_batch": n_good_local, "verify": verify}
 
     pipe.close()
@@ -624,7 +625,7 @@ def cluster_arm(args, config):
         p = cl.pipe(d)
         p.set_mode(serial=True)
         try:
-            part.append(p.autotune(bufs[d][:Bc], Bc, candidates=(24, 32, 40), batches=3 * args.depth + 3) if args.back_sms < 0 else
+            part.append(p.autotune(bufs[d][:Bc], Bc, candidates=(24, 32, 40), batches=48) if args.back_sms < 0 else
                         (dict(zip(("front_sms", "back_sms"), p.set_partition(args.back_sms))) if args.back_sms > 0 else "serial"))
         except Exception as exc:
             part.append("unavailable (%s)" % exc)
@@ -659,12 +660,12 @@ def cluster_arm(args, config):
     sync_all()
     secs = time.perf_counter() - t0
     cfg = dict(config)
-    cfg["parallelism"] = "ONE process, ft8b200_cluster_t: %d devices, slots sharded by device, records gathered by the library (grouped ncclAllGather, NCCL %d)" % (n, cl.nccl_version())
-    cfg["executor"] = "one ft8b200_pipe_t of depth %d per device, %d batches of %d slots per device per step" % (args.depth, args.chunks, Bc)
-    cfg["sm_partition"] = part
+    run_info = {"parallelism": "ONE process, ft8b200_cluster_t: %d devices, slots sharded by device, records gathered by the library (grouped ncclAllGather, NCCL %d)" % (n, cl.nccl_version()),
+                "executor": "one ft8b200_pipe_t of depth %d per device, %d batches of %d slots per device per step" % (args.depth, args.chunks, Bc),
+                "sm_partition": part}
     out = {"impl": "cluster", "metric": METRIC, "value": n * B * args.steps / secs, "unit": "slots/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-           "data": "synthetic (generated on each device by ft8b200_synth_raw)", "config": cfg, "gpu_launches": int(cl.launches() - launches0),
+           "data": "synthetic (generated on each device by ft8b200_synth_raw)", "config": cfg, "run": run_info, "gpu_launches": int(cl.launches() - launches0),
            "nccl_gathers": int(cl.gathers() - gathers0), "verify": {"slots_decoded_to_their_own_message": int(n_good), "of": n * B},
            "timed": "host clock between synchronisations of all devices"}
     cl.close()
@@ -698,12 +699,11 @@ def reference_arm(args, rank, world, config):
         t += secs
     value = n * args.steps / t
     kind = cpu_kind()
-    cfg = dict(config)
-    cfg["executor"] = "n/a (CPU arm)"
-    cfg["reference_sample"] = "%d slots per step over %d worker processes" % (n, cores)
+    cfg = dict(config)   # the workload, word for word what the CUDA arm prints
+    run_info = {"executor": "n/a (CPU arm)", "reference_sample": "%d slots per step over %d worker processes" % (n, cores)}
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "slots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-           "data": "synthetic (same slots as the CUDA arm, made on the host by the synthesiser's bit-identical CPU twin)", "config": cfg,
+           "data": "synthetic (same slots as the CUDA arm, made on the host by the synthesiser's bit-identical CPU twin)", "config": cfg, "run": run_info,
            "cpu_baseline": {"value": value, "unit": "slots/s", "cores": cores, "kind": kind,
                             "sample": "%d slots per step, one forked process per slot on %d cores (the reference itself is single-threaded)" % (n, cores)},
            "e2e": {"value": value, "unit": "slots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

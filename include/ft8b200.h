@@ -363,10 +363,13 @@ int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant);
  * back_sms == 0 removes the partition.  Results are identical in every mode.  Needs depth >= 2 and no batch in flight. */
 int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms, int *back_sms_out);
 /* Chooses the partition by measurement: for every back_sms in `candidates` (0 = no partition, serial kernels) and both placements
- * of the comb+FIR pass, `batches` batches of the caller's device-resident input (as for ft8b200_pipe_submit) are pushed through the
- * executor and timed; the fastest setting is left in place and reported (best_back_sms, best_comb_front, ms per batch of each
- * point in ms_out[2 * n_candidates], comb_front = 0 first; any of the three may be NULL).  The split that balances the HBM-bound
- * front end against the issue-bound back end depends on the batch's candidate load and on the box; nothing in the results does. */
+ * of the comb+FIR pass, batches of the caller's device-resident input (as for ft8b200_pipe_submit) are pushed through the executor
+ * and the STEADY-STATE interval between completed batches is timed: `batches` / 2 batches run first, untimed (a back partition that
+ * is too small only throttles the front end once the lanes' slack is used up), then `batches` are timed from completion to
+ * completion.  Of the settings within 0.3 % of the fastest the one with the largest back partition is left in place and reported
+ * (best_back_sms, best_comb_front, ms per batch of each point in ms_out[2 * n_candidates], comb_front = 0 first; any of the three
+ * may be NULL).  The split that balances the HBM-bound front end against the issue-bound back end depends on the batch's candidate
+ * load and on the box; nothing in the results does. */
 int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots,
                           const int *candidates, int n_candidates, int batches, int *best_back_sms, int *best_comb_front, float *ms_out);
 void ft8b200_pipe_destroy(ft8b200_pipe_t *p);

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -365,11 +366,9 @@ int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_p
     PCU(cudaSetDevice(p->cfg.device));
     std::vector<struct decoder_results> res((size_t)n_slots * p->cfg.max_messages);
     std::vector<int32_t> cnt((size_t)n_slots);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    PCU(cudaEventCreate(&e0));
-    PCU(cudaEventCreate(&e1));
     float best = -1.0f;
     int best_sms = 0, best_comb = 0, rc = 0;
+    std::vector<float> all_ms((size_t)2 * (size_t)n_candidates, -1.0f);
     auto apply = [&](int sms, int comb) -> int {
         int r = ft8b200_pipe_set_partition(p, sms, nullptr, nullptr);
         if (r) return r;
@@ -384,8 +383,16 @@ int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_p
             if (apply(candidates[c], comb) != 0) { if (ms_out) ms_out[2 * c + comb] = -1.0f; continue; }   // e.g. a split the driver refuses
             for (int pass = 0; pass < 2 && !rc; ++pass) {  // pass 0 warms the lanes' workspaces up
                 int submitted = 0, collected = 0;
-                const int n = pass == 0 ? (int)p->lanes.size() : batches;
-                if (pass == 1) PCU(cudaEventRecord(e0, p->lanes[0].st));
+                // What is timed is the STEADY-STATE interval between completed batches.  The start of a run is not representative either
+                // way: its first `depth` batches still find free lanes and an idle back end, which flatters a back partition that is too
+                // small (its backlog only shows once the lanes have run out), and the backlog of those first batches then drains in a
+                // burst; the end of a run adds the last batch's back end, which a short probe spreads over few batches.  So the clock
+                // starts when as many batches as the probe times have been collected before it (a back end that is 10 % too slow needs
+                // ~15 batches to use up the lanes' slack) (collect returns on a batch's completion event) and
+                // stops at the last completion; nothing after it is waited for.
+                const int lead = batches / 2 > (int)p->lanes.size() ? batches / 2 : (int)p->lanes.size();
+                const int n = pass == 0 ? (int)p->lanes.size() : batches + lead;
+                std::chrono::steady_clock::time_point t0, t1;
                 while (collected < n && !rc) {
                     while (submitted < n && p->count < (int)p->lanes.size() && !rc) {
                         rc = submit(p, nullptr, d_iq, bytes_per_stream, stream_stride_bytes, n_slots);
@@ -395,23 +402,31 @@ int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_p
                     const int got = ft8b200_pipe_collect(p, res.data(), cnt.data(), n_slots);
                     if (got < 0) rc = got;
                     ++collected;
+                    if (collected == lead) t0 = std::chrono::steady_clock::now();
                 }
                 if (pass == 1 && !rc) {
-                    // every batch has been collected (host-synchronised), so an event recorded now closes the interval
-                    PCU(cudaEventRecord(e1, p->lanes[0].st));
-                    PCU(cudaEventSynchronize(e1));
-                    PCU(cudaEventElapsedTime(&ms, e0, e1));
-                    ms /= (float)batches;
+                    t1 = std::chrono::steady_clock::now();
+                    ms = std::chrono::duration<float, std::milli>(t1 - t0).count() / (float)batches;
                 }
             }
             if (ms_out) ms_out[2 * c + comb] = ms;
-            if (!rc && ms > 0.0f && (best < 0.0f || ms < best)) { best = ms; best_sms = candidates[c]; best_comb = comb; }
+            all_ms[(size_t)(2 * c + comb)] = rc ? -1.0f : ms;
+            if (!rc && ms > 0.0f && (best < 0.0f || ms < best)) best = ms;
         }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (rc) return rc;
     if (best < 0.0f) return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_autotune: no candidate could be measured");
+    // Points within 0.3 % of the fastest are the same within the probe's noise; among them the LARGEST back-end partition is kept (a
+    // back end that only just hides under the next batch's block sums is the one a busier slot mix tips over).  The probe itself has
+    // to be long: timed over 12 batches from the start of a run, 24 SMs looked 0.1 % faster than 32 and then ran a 20-step bench at
+    // 81.1 k slots/s instead of 85.5 k -- the too-small partition's backlog only throttles the front end once the lanes' slack is gone.
+    float kept = -1.0f;
+    for (int c = 0; c < n_candidates; ++c)
+        for (int comb = 0; comb < 2; ++comb) {
+            const float ms = all_ms[(size_t)(2 * c + comb)];
+            if (ms <= 0.0f || ms > best * 1.003f) continue;
+            if (kept < 0.0f || candidates[c] > best_sms || (candidates[c] == best_sms && ms < kept)) { kept = ms; best_sms = candidates[c]; best_comb = comb; }
+        }
     if ((rc = apply(best_sms, best_comb))) return rc;
     if (best_back_sms) *best_back_sms = best_sms;
     if (best_comb_front) *best_comb_front = best_comb;

@@ -12,7 +12,7 @@ import json, sys
 d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
 s = d["roofline"]["stage_ms_per_launch"]
 print("%-22s %8.0f slots/s  %.3f ms/step  k1 %.3f  back %.3f  part %s" % (sys.argv[1], d["value"], d["ms_per_step"], s["block_sums"],
-      sum(v for k, v in s.items() if k != "block_sums"), d["config"].get("sm_partition")))
+      sum(v for k, v in s.items() if k != "block_sums"), d.get("run", d["config"]).get("sm_partition")))
 P
 }
 for B in 24 32 40; do run back$B --back-sms $B; done
