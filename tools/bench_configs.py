@@ -174,7 +174,12 @@ def config5(env, batch, texts, depth=3, streams_per_batch=16):
     cnts = torch.zeros(mine * spp, dtype=torch.int32, device=env.device)
     copied = torch.cuda.Event()
 
-    def run(_steps=1):
+    def run(passes=1):
+        for _ in range(max(int(passes), 1)):
+            last = one_pass()
+        return last
+
+    def one_pass():
         done = 0
 
         def collect():
@@ -199,7 +204,7 @@ def config5(env, batch, texts, depth=3, streams_per_batch=16):
 
     # The executor's shape is probed on THIS workload: streams per batch (a rank with few streams needs small batches to have
     # anything to overlap) x SM split (stream batches carry a heavier comb+FIR pass than independent slots; 0 = no split, the
-    # kernels of consecutive batches back to back on the whole GPU).  One warm and two timed passes of the rank's whole plan per
+    # kernels of consecutive batches back to back on the whole GPU).  One warm and three timed passes (median kept) of the rank's whole plan per
     # point, the fastest is kept; every rank takes the same one (times are max over ranks).
     sizes = sorted({min(s, resident, mine) for s in (streams_per_batch, streams_per_batch // 4)} - {0}, reverse=True)
     splits = (0, 24, 32, 40) if partitioned else (0,)
@@ -213,7 +218,7 @@ def config5(env, batch, texts, depth=3, streams_per_batch=16):
             else:
                 pipe.set_mode(serial=True)
             run()
-            probe[(spb, bsm)] = min(env.timed(run, 1)[0] for _ in range(2))
+            probe[(spb, bsm)] = sorted(env.timed(run, 1)[0] for _ in range(3))[1]   # the median of three passes: the minimum of two picked lucky passes
     spb, bsm = min(probe, key=probe.get)
     make_plan(spb)
     if bsm:
@@ -224,7 +229,9 @@ def config5(env, batch, texts, depth=3, streams_per_batch=16):
     executor = "ft8b200_pipe_t depth %d, %d streams x %d slots per batch, %s (probed on this workload, ms per pass at streams/back SMs: %s)" % (
         depth, spb, spp, ("back end on %d SMs" % bsm) if bsm else "no SM split", ", ".join("%d/%d: %.2f" % (k[0], k[1], v) for k, v in sorted(probe.items())))
     run()
-    ms, gathered, _ = env.timed(run, 1)
+    kpass = 3   # the job three times over in one timed region (a single 25 ms pass carries +-5 % of launch jitter)
+    ms, gathered, _ = env.timed(run, kpass)
+    ms /= kpass
     n_slots_total = n_streams_total * spp
     res = gathered[0].cpu().numpy().view(pkg.result_dtype).reshape(-1, M)
     nres = gathered[1].cpu().numpy()
