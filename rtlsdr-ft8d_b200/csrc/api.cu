@@ -498,7 +498,9 @@ static int process_raw_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t byte
         const int r0 = s0 * segs, nr = n * segs;
         BlockSums *sg = ctx->sums.as<BlockSums>() + (size_t)s0 * sstride + kHistBlocks;
         mark(ctx, 0, g, false, st);
-        CU(launch_cic_block_sums(d_iq + (size_t)s0 * stream_stride_bytes, stream_stride_bytes, n, blocks, sg, sstride, ctx->k1_variant, ctx->sm_count, st, &ctx->launches));
+        CU(launch_cic_block_sums(d_iq + (size_t)s0 * stream_stride_bytes, stream_stride_bytes, n, blocks, sg, sstride,
+                                 (ctx->k1_variant == 0 && ctx->sm_back > 0) ? kK1StreamingDense : ctx->k1_variant,   // on a front partition: see cic_block_sums_kernel
+                                 ctx->sm_count, st, &ctx->launches));
         mark(ctx, 0, g, true, st);
         if (side && s0 + per >= n_slots) {
             // the next batch's block sums (another lane) may start now: comb+FIR below is 2 % of the front end's bytes and

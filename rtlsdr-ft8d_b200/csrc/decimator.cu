@@ -214,7 +214,12 @@ __device__ __forceinline__ void super_block_sums(const uint4 *base, int lane, ui
 constexpr int kWarpsPerCta = 8;
 
 // Kernel 1: block sums of full, 16-byte aligned super-blocks.  One warp per super-block.
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+// kMinCtas = 4: 58 registers, 4 CTAs per SM -- the fastest form on the whole GPU (1.372 ms per 128 slots).  kMinCtas = 5: 48 registers
+// (five spilled words), 5 CTAs per SM = a quarter more loads in flight per SM: 1.1 % slower on 148 SMs, but on the 116 SMs the
+// SM-partitioned executor leaves it -- fewer SMs have to carry the same bytes in flight -- 0.8 % faster (1.463 -> 1.450 ms), and the
+// same at the clocks the power cap allows in a long run (launch_cic_block_sums takes the choice from its caller).
+template <int kMinCtas>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtas)
 cic_block_sums_kernel(const uint8_t *__restrict__ iq, size_t stream_stride_bytes, int supers_per_stream, size_t sums_stride,
                       BlockSums *__restrict__ sums) {
     __shared__ uint4 s_sums[kWarpsPerCta][8];
@@ -575,7 +580,7 @@ static cudaError_t launch_tma(const uint8_t *d_iq, size_t stream_stride_bytes, i
 cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_bytes, int n_streams, int blocks_per_stream, BlockSums *d_sums,
                                   size_t sums_stride, int variant, int sm_count, cudaStream_t st, int *launches) {
     const int supers = blocks_per_stream / 8;
-    if (supers > 0 && variant >= 1 && (long)supers * n_streams < (1l << 31)) {
+    if (supers > 0 && variant >= 1 && (long)supers * n_streams < (1l << 31)) {   // (kK1StreamingDense is negative: the streaming branch below)
         static std::atomic<unsigned int> next_pair{0};  // contexts and lanes on any host thread draw from one pool
         int dev = 0;
         cudaGetDevice(&dev);
@@ -595,7 +600,8 @@ cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_byte
         ++*launches;
     } else if (supers > 0) {
         dim3 grid((supers + kWarpsPerCta - 1) / kWarpsPerCta, n_streams);
-        cic_block_sums_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, sums_stride, d_sums);
+        if (variant == kK1StreamingDense) cic_block_sums_kernel<5><<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, sums_stride, d_sums);
+        else cic_block_sums_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, sums_stride, d_sums);
         ++*launches;
     }
     const int rest = blocks_per_stream - supers * 8;
