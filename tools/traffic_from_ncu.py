@@ -3,7 +3,8 @@
 -> the JSON bench.py's roofline.traffic reads.  usage: tools/traffic_from_ncu.py profiles/ncu_summary_r2.json 128 profiles/traffic_r2.json"""
 import json, sys
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-d = json.load(open(sys.argv[1]))["cic_block_sums_kernel"]
+summary = json.load(open(sys.argv[1]))
+d = summary[next(k for k in sorted(summary) if k.startswith("cic_block_sums_kernel"))]   # "cic_block_sums_kernel<4>": the whole-GPU shape
 n = int(sys.argv[2])
 tot = d["dram_read"] * UNIT[d["dram_read_unit"]] + d["dram_write"] * UNIT[d["dram_write_unit"]]
 alg = 72_000_000 + 47_936 * 8   # SURVEY 8d: raw IQ in, two float rails out, per slot
