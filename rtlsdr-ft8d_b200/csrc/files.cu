@@ -133,9 +133,18 @@ int ft8b200_load_wav_s16(int16_t *raw_s16, float *signal, int *num_samples, int 
     std::vector<int16_t> tmp;
     int16_t *dst = raw_s16;
     if (!dst) { tmp.resize((size_t)n); dst = tmp.data(); }
-    const size_t got = fread(dst, align, (size_t)n, f);
+    if (align == 2) {
+        const size_t got = fread(dst, 2, (size_t)n, f);
+        for (size_t k = got; k < (size_t)n; ++k) dst[k] = 0;
+    } else {
+        // a header whose blockAlign is not 2 although it says mono 16-bit: the reference reads n * blockAlign bytes into a buffer of that
+        // size and then takes its first n int16 (wave.c:104-121); the same here, through a buffer of our own (the caller's holds n samples)
+        std::vector<uint8_t> bytes((size_t)n * (align > 2 ? align : 2), 0);
+        const size_t got = fread(bytes.data(), align, (size_t)n, f);
+        (void)got;   // what a short file did not deliver stays zero
+        memcpy(dst, bytes.data(), (size_t)n * sizeof(int16_t));
+    }
     fclose(f);
-    for (size_t k = got; k < (size_t)n; ++k) dst[k] = 0;
     if (signal)
         for (int k = 0; k < n; ++k) signal[k] = dst[k] / 32768.0f;
     *num_samples = n;
