@@ -227,3 +227,10 @@ def test_wav_with_wrong_block_align_reads_like_the_reference(pkg, tmp_path):
     assert ns.value == n and sr.value == 12000
     assert np.array_equal(raw[:n], data[:n]) and (raw[n:] == 0x5A5A).all(), "exactly n samples, the first n int16 of the data"
     assert np.array_equal(sig[:n], data[:n].astype(np.float32) / np.float32(32768.0)) and (sig[n:] == 7.0).all()
+
+
+def test_host_entries_survive_fuzzed_arguments():
+    """pack77 on arbitrary byte strings and the three report builders on records without terminators, at every output capacity
+    from 0 up (tools/fuzz_host_entries.py; clean under ASan/UBSan too, profiles/sanitizer_r2.md): no crash, no heap damage."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_host_entries.py"), "1"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "fuzzed 4000" in p.stdout, (p.returncode, p.stderr[-500:])
