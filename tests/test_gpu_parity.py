@@ -1448,3 +1448,31 @@ def test_monitor_dropin_at_11025_hz(pkg, oracle):
     dims = dict(num_blocks=int(info[4]), num_bins=882, time_osr=2, freq_osr=2)
     assert mon.find_sync(40, 5).tobytes() == oracle.find_sync(ref, max_cand=40, min_score=5, **dims).tobytes()
     mon.close()
+
+
+def test_decode_with_candidates_from_nowhere(pkg, ctx, oracle, slots, bp_variant):
+    """Candidates that did not come from ft8_find_sync -- frequency offsets beyond the band or negative, sub-offsets beyond the
+    oversampling factors, time offsets far outside the slot: the reference would read outside the waterfall (it range-checks the
+    block only, decode.c:275-279).  The library reads nothing outside the slot (this test is part of the memcheck pass): such
+    candidates fail like dead ones, the valid candidates next to them in the same launch decode as always, and the drop-in call
+    answers false instead of taking the process down."""
+    real = oracle.waterfall(*slots[0])
+    good = oracle.find_sync(real)[:3]
+    wild = [(20, 0, 30000, 0, 0), (20, 0, -5, 0, 0), (20, 3, 249, 0, 0), (20, 3, 100, 7, 0), (20, 3, 100, 1, 200), (20, 30000, 10, 0, 0),
+            (20, -30000, 10, 1, 1), (20, 32767, 32767, 255, 255), (20, -32768, -32768, 255, 255)]
+    cands = np.zeros((1, ctx.K), cand_dtype)
+    for q, c in enumerate(list(good) + wild):
+        cands[0, q] = tuple(c)
+    n = len(good) + len(wild)
+    d_mag = torch.from_numpy(real[None]).to(dev())
+    d_cand = torch.from_numpy(cands.view(np.uint8).reshape(1, ctx.K, 8)).to(dev())
+    ok, stage, status, msg, plain, llr = ctx.decode(d_mag, d_cand, torch.tensor([n], dtype=torch.int32, device=dev()), want_plain=True, want_llr=True)
+    torch.cuda.synchronize()
+    for q, c in enumerate(good):
+        d = oracle.decode(real, c)
+        assert int(ok[0, q]) == d["ok"] and bits_equal(np.nan_to_num(llr[0, q].cpu().numpy()), np.nan_to_num(d["llr"]))
+    assert not ok[0, len(good):n].any(), "a candidate outside the waterfall cannot decode"
+    for c in wild[:5]:
+        okd, _, _ = pkg.ft8_decode(real, np.array([c], cand_dtype)[0], 20)
+        assert okd is False
+    assert int((torch.zeros(4, device=dev()) + 1).sum().item()) == 4
