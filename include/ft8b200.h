@@ -360,8 +360,17 @@ int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant);
  * comb+FIR) of batch n+1 runs on one disjoint set of SMs while the issue/latency-bound back end (waterfall, sync, LDPC,
  * spots) of batch n runs on the other `back_sms` SMs (rounded up by the driver to its granularity, 8 SMs on sm_100; the
  * sizes actually provisioned come back through front_sms/back_sms, either may be NULL).  Implies FT8B200_PIPE_OVERLAP.
- * back_sms == 0 removes the partition.  Results are identical in every mode.  Needs depth >= 2 and no batch in flight. */
+ * back_sms == 0 removes the partition.  Results are identical in every mode.  Needs depth >= 2 and no batch in flight.
+ * SM layout: back_sms + 1000 * layout.  layout 0 = the driver's split by count (the first back_sms SMs of its enumeration, the rest
+ * in front).  layout 1..6 = the SMs are split into the driver's groups of 8 and the back partition is composed of groups spread
+ * over the enumeration (1: evenly from the first group, 2: evenly, centred, 3: the last groups, 4: every second group, 5: spread
+ * neighbouring pairs, 6: the first groups), the front end gets every other group plus the remainder.  An HBM-bound front end
+ * that loses whole GPCs loses their ports into the L2 fabric as well as their SMs; which layout is best depends on the GPU's
+ * floor-sweeping, so ft8b200_pipe_autotune accepts encoded candidates and measures them. */
 int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms, int *back_sms_out);
+/* Diagnostic: the hardware SM ids (%smid) the front (which = 0) or back (which = 1) partition runs on, as a 256-bit mask
+ * (mask8[id / 32] bit id % 32); without a partition, the SMs of the whole GPU. */
+int ft8b200_pipe_partition_smids(ft8b200_pipe_t *p, int which, uint32_t *mask8);
 /* Chooses the partition by measurement: for every back_sms in `candidates` (0 = no partition, serial kernels) and both placements
  * of the comb+FIR pass, batches of the caller's device-resident input (as for ft8b200_pipe_submit) are pushed through the executor
  * and the STEADY-STATE interval between completed batches is timed: `batches` / 2 batches run first, untimed (a back partition that

@@ -504,6 +504,12 @@ class Pipe:
         self._chk(self.L.ft8b200_pipe_set_partition(C.c_void_p(self.h), int(back_sms), C.byref(f), C.byref(b)))
         return f.value, b.value
 
+    def partition_smids(self, which: int):
+        """Hardware SM ids (%smid) the front (0) / back (1) partition runs on (diagnostic)."""
+        m = (C.c_uint32 * 8)()
+        self._chk(self.L.ft8b200_pipe_partition_smids(C.c_void_p(self.h), int(which), m))
+        return [32 * w + b for w in range(8) for b in range(32) if (m[w] >> b) & 1]
+
     def autotune(self, iq, n_slots: int, candidates=(24, 32, 40), batches: int = 12, bytes_per_stream: int = RAW_SLOT_BYTES, stride: int | None = None):
         """ft8b200_pipe_autotune: measure every (back_sms, comb+FIR placement) point on `iq`, keep the fastest.
         -> dict(back_sms, comb_front, points={(back_sms, comb_front): ms_per_batch})."""

@@ -235,6 +235,14 @@ int submit_slots(ft8b200_pipe_t *p, const float *h_i, const float *h_q, const fl
     return 0;
 }
 
+__global__ void smid_probe_kernel(unsigned int *mask) {
+    unsigned int id;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(id));
+    const long long t0 = clock64();
+    while (clock64() - t0 < 30000) { }   // hold the SM long enough for the grid to spread over every SM of the partition
+    if (threadIdx.x == 0 && id < 256) atomicOr(mask + (id >> 5), 1u << (id & 31));
+}
+
 }  // namespace
 
 extern "C" {
@@ -288,6 +296,33 @@ static void partition_release(ft8b200_pipe_t *p) {
     p->part = Partition();   // the green contexts stay in g_parts (see CachedPartition)
 }
 
+// Which SMs the back partition gets.  cuDevSmResourceSplitByCount hands the SMs out in groups of the architecture's granularity
+// (8 on sm_100); asked for ONE group of back_sms it returns the first back_sms SMs of the driver's enumeration and the rest as the
+// remainder -- on a two-die GPU with eight GPCs that takes whole GPCs away from the front end, and an HBM-bound kernel then loses
+// those GPCs' paths into the L2 fabric, not just their SMs.  layout > 0 (encoded by the caller as back_sms + 1000 * layout) asks
+// the driver for groups of 8 instead and composes the back partition from groups spread over the enumeration, the front end from
+// all the others plus the remainder (cuDevResourceGenerateDesc accepts several SM resources of one split).  Which layout is best is
+// a property of the box (floor-swept SMs differ from GPU to GPU): ft8b200_pipe_autotune measures them.
+static int pick_groups(int layout, int n_groups, int n_back, int *idx) {
+    if (n_back < 1 || n_back >= n_groups) return -1;
+    for (int i = 0; i < n_back; ++i) {
+        int g;
+        switch (layout) {
+            case 1: g = (i * n_groups) / n_back; break;                       // evenly spread from the first group
+            case 2: g = ((2 * i + 1) * n_groups) / (2 * n_back); break;       // evenly spread, centred
+            case 3: g = n_groups - n_back + i; break;                         // the last groups
+            case 4: g = 2 * i; break;                                         // every second group from the first
+            case 5: g = (i & 1) + (i / 2) * (2 * n_groups / n_back); break;   // neighbouring pairs, spread
+            case 6: g = i; break;                                             // the first groups (what layout 0 does, as a control)
+            default: return -1;
+        }
+        if (g < 0 || g >= n_groups) return -1;
+        for (int k = 0; k < i; ++k) if (idx[k] == g) return -1;
+        idx[i] = g;
+    }
+    return 0;
+}
+
 int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_out, int *back_sms_out) {
     if (!p || back_sms < 0) return FT8B200_BAD_ARG();
     if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_set_partition: batches in flight");
@@ -295,6 +330,10 @@ int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_o
     const DriverApi &d = driver_api();
     if (p->part.front || p->part.back) partition_release(p);
     p->prev_front = nullptr;
+    const int back_req = back_sms;           // cache key: size and layout
+    const int layout = back_sms / 1000;
+    back_sms %= 1000;
+    if (layout > 6 || (layout > 0 && back_sms == 0)) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_set_partition: no such SM layout");
     if (back_sms == 0) {
         if (front_sms_out) *front_sms_out = 0;
         if (back_sms_out) *back_sms_out = 0;
@@ -314,30 +353,57 @@ int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_o
         std::lock_guard<std::mutex> lk(g_part_mu);
         const CachedPartition *hit = nullptr;
         for (const CachedPartition &c : g_parts)
-            if (c.device == p->cfg.device && c.back_req == back_sms) hit = &c;
+            if (c.device == p->cfg.device && c.back_req == back_req) hit = &c;
         if (!hit) {
             CUdevice dev;
             PDRV(d.DeviceGet(&dev, p->cfg.device));
-            CUdevResource all, back, front;
+            CUdevResource all;
             PDRV(d.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
             if ((unsigned)back_sms >= all.sm.smCount) return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_set_partition: back_sms must leave SMs for the front end");
-            unsigned int groups = 1;
-            PDRV(d.DevSmResourceSplitByCount(&back, &groups, &all, &front, 0, (unsigned)back_sms));  // rounds up to the architecture's granularity
-            if (groups != 1 || front.sm.smCount == 0) return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_set_partition: the driver could not split the SMs that way");
             CUdevResourceDesc dfront, dback;
-            PDRV(d.DevResourceGenerateDesc(&dback, &back, 1));
-            PDRV(d.DevResourceGenerateDesc(&dfront, &front, 1));
+            unsigned int n_front_sms = 0, n_back_sms = 0;
+            if (layout == 0) {
+                CUdevResource back, front;
+                unsigned int groups = 1;
+                PDRV(d.DevSmResourceSplitByCount(&back, &groups, &all, &front, 0, (unsigned)back_sms));  // rounds up to the architecture's granularity
+                if (groups != 1 || front.sm.smCount == 0) return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_set_partition: the driver could not split the SMs that way");
+                PDRV(d.DevResourceGenerateDesc(&dback, &back, 1));
+                PDRV(d.DevResourceGenerateDesc(&dfront, &front, 1));
+                n_front_sms = front.sm.smCount;
+                n_back_sms = back.sm.smCount;
+            } else {
+                constexpr unsigned kGran = 8, kMaxGroups = 64;
+                CUdevResource grp[kMaxGroups], rem, sel_back[kMaxGroups], sel_front[kMaxGroups + 1];
+                unsigned int groups = all.sm.smCount / kGran;
+                if (groups > kMaxGroups) groups = kMaxGroups;
+                memset(&rem, 0, sizeof(rem));
+                PDRV(d.DevSmResourceSplitByCount(grp, &groups, &all, &rem, 0, kGran));
+                const int n_back = (back_sms + (int)kGran - 1) / (int)kGran;
+                int idx[kMaxGroups];
+                if (groups < 2 || pick_groups(layout, (int)groups, n_back, idx))
+                    return pfail(p, FT8B200_EINVAL, "ft8b200_pipe_set_partition: no such layout for this split");
+                unsigned nb = 0, nf = 0;
+                for (unsigned g = 0; g < groups; ++g) {
+                    bool is_back = false;
+                    for (int k = 0; k < n_back; ++k) is_back |= idx[k] == (int)g;
+                    if (is_back) { sel_back[nb++] = grp[g]; n_back_sms += grp[g].sm.smCount; }
+                    else { sel_front[nf++] = grp[g]; n_front_sms += grp[g].sm.smCount; }
+                }
+                if (rem.type == CU_DEV_RESOURCE_TYPE_SM && rem.sm.smCount > 0) { sel_front[nf++] = rem; n_front_sms += rem.sm.smCount; }
+                PDRV(d.DevResourceGenerateDesc(&dback, sel_back, nb));
+                PDRV(d.DevResourceGenerateDesc(&dfront, sel_front, nf));
+            }
             CachedPartition c;
             c.device = p->cfg.device;
-            c.back_req = back_sms;
+            c.back_req = back_req;
             PDRV(d.GreenCtxCreate(&c.part.back, dback, dev, CU_GREEN_CTX_DEFAULT_STREAM));
             CUresult rf = d.GreenCtxCreate(&c.part.front, dfront, dev, CU_GREEN_CTX_DEFAULT_STREAM);
             if (rf != CUDA_SUCCESS) {
                 d.GreenCtxDestroy(c.part.back);
                 return pfail(p, FT8B200_ECUDA, "cuGreenCtxCreate (front): CUresult " + std::to_string((int)rf));
             }
-            c.part.front_sms = (int)front.sm.smCount;
-            c.part.back_sms = (int)back.sm.smCount;
+            c.part.front_sms = (int)n_front_sms;
+            c.part.back_sms = (int)n_back_sms;
             g_parts.push_back(c);
             hit = &g_parts.back();
         }
@@ -425,11 +491,31 @@ int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_p
         for (int comb = 0; comb < 2; ++comb) {
             const float ms = all_ms[(size_t)(2 * c + comb)];
             if (ms <= 0.0f || ms > best * 1.003f) continue;
-            if (kept < 0.0f || candidates[c] > best_sms || (candidates[c] == best_sms && ms < kept)) { kept = ms; best_sms = candidates[c]; best_comb = comb; }
+            // (size = candidate % 1000; the thousands carry the SM layout, see ft8b200_pipe_set_partition)
+            if (kept < 0.0f || candidates[c] % 1000 > best_sms % 1000 || (candidates[c] % 1000 == best_sms % 1000 && ms < kept)) { kept = ms; best_sms = candidates[c]; best_comb = comb; }
         }
     if ((rc = apply(best_sms, best_comb))) return rc;
     if (best_back_sms) *best_back_sms = best_sms;
     if (best_comb_front) *best_comb_front = best_comb;
+    return 0;
+}
+
+// Diagnostic: which SMs (hardware %smid) the front (which = 0) or back (which = 1) partition runs on, as a 256-bit mask.
+int ft8b200_pipe_partition_smids(ft8b200_pipe_t *p, int which, uint32_t *mask8) {
+    if (!p || !mask8 || which < 0 || which > 1) return FT8B200_BAD_ARG();
+    if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_partition_smids: batches in flight");
+    PCU(cudaSetDevice(p->cfg.device));
+    Lane &l = p->lanes[0];
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(which ? l.part_back : l.part_front);
+    if (!st) st = l.st;  // no partition: the whole GPU
+    unsigned int *d_mask = nullptr;
+    PCU(cudaMalloc(&d_mask, 8 * sizeof(unsigned int)));
+    cudaMemsetAsync(d_mask, 0, 8 * sizeof(unsigned int), st);
+    smid_probe_kernel<<<2048, 1024, 0, st>>>(d_mask);
+    cudaError_t e = cudaMemcpyAsync(mask8, d_mask, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_mask);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return pfail(p, FT8B200_ECUDA, std::string("ft8b200_pipe_partition_smids: ") + cudaGetErrorString(e)); }
     return 0;
 }
 

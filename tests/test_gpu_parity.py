@@ -783,6 +783,41 @@ def test_pipe_sm_partition(pkg, ctx, oracle, raw_slot, depth, back_sms):
     one.close()
 
 
+def test_pipe_sm_partition_layouts(pkg, ctx, raw_slot):
+    """ft8b200_pipe_set_partition(back_sms + 1000 * layout): the back partition composed of the driver's 8-SM groups in every
+    layout is disjoint from the front partition, both cover the GPU, and the records are those of the unpipelined call."""
+    B = 4
+    big = _mixed_batch(raw_slot, B)
+    torch.cuda.synchronize()
+    ctx.process_raw(big, B)
+    ref_res, ref_n = ctx.fetch_results(B)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    pipe = pkg.Pipe(0, 3)
+    whole = set(pipe.partition_smids(0))
+    assert len(whole) == n_sm
+    seen = set()
+    for layout in range(0, 7):
+        f, b = pipe.set_partition(32 + 1000 * layout)
+        assert b == 32 and f == n_sm - 32
+        back, front = set(pipe.partition_smids(1)), set(pipe.partition_smids(0))
+        assert len(back) == 32 and len(front) == f and not (back & front) and (back | front) == whole
+        seen.add(tuple(sorted(back)))
+        for _ in range(4):
+            if pipe.in_flight() == pipe.depth:
+                res, n = pipe.collect(B)
+                assert np.array_equal(n, ref_n) and res.tobytes() == ref_res.tobytes()
+            pipe.submit(big, B)
+        while pipe.in_flight():
+            res, n = pipe.collect(B)
+            assert np.array_equal(n, ref_n) and res.tobytes() == ref_res.tobytes()
+    assert len(seen) >= 3   # the layouts really are different SM sets
+    with pytest.raises(pkg.Ft8Error):
+        pipe.set_partition(7032)
+    with pytest.raises(pkg.Ft8Error):
+        pipe.set_partition(2000)
+    pipe.close()
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_bulk_copy_decimator_variants(pkg, oracle, variant):
     """The persistent cp.async.bulk + mbarrier cic_block_sums kernel (every ring shape) is bit-identical to the oracle,
