@@ -445,6 +445,7 @@ def main():
         # green contexts: disjoint SM sets for the HBM-bound decimator and the issue-bound back end (ft8b200_pipe_set_partition)
         try:
             if args.back_sms < 0:
+                pipe.set_profiling(True)   # the timed region records stage events: the probe must carry the same (small) per-stage cost
                 tuned = pipe.autotune(batch[:Bc], Bc, candidates=(24, 32, 40), batches=48)
                 run_info["sm_partition"] = {"chosen_by": "ft8b200_pipe_autotune (ms per %d-slot batch at each point)" % Bc, **tuned}
                 mode_txt = "SM partition: back end of batch n on %d SMs (comb+FIR on the %s set), decimator of batch n+1 on the others" % (

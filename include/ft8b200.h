@@ -323,6 +323,14 @@ void *ft8b200_front_event(ft8b200_ctx_t *ctx);
 /* One-shot: the cic_block_sums kernel of the NEXT ft8b200_process_raw* call on this context starts only after `cuda_event` (a
  * cudaEvent_t) has completed; the call's buffer initialisation ahead of it does not wait.  What ft8b200_pipe_t chains its lanes with. */
 int ft8b200_set_front_wait(ft8b200_ctx_t *ctx, void *cuda_event);
+/* The same for the back end: ft8b200_back_event() = the cudaEvent_t recorded on the back-end stream behind the spot table of the last
+ * ft8b200_process_raw* call (NULL unless ft8b200_set_side_backend is on); ft8b200_set_back_wait: one-shot, the back end (comb+FIR when
+ * it runs on the back set, waterfall ... spots) of the NEXT call starts only after `cuda_event`.  ft8b200_pipe_t chains the lanes'
+ * back ends with it on an SM partition: two batches' back ends sharing a back partition that one of them fills slow each other
+ * down, and a partition that is only just large enough then falls behind for good (measured: 24 back-end SMs, 1.417 ms per batch
+ * while the backlog was under one batch, 1.547 once it was not). */
+void *ft8b200_back_event(ft8b200_ctx_t *ctx);
+int ft8b200_set_back_wait(ft8b200_ctx_t *ctx, void *cuda_event);
 /* device pointers to the last batch's outputs: results (n_slots x max_messages), counts (n_slots) */
 int ft8b200_results_device(ft8b200_ctx_t *ctx, struct decoder_results **d_results, int32_t **d_nresults);
 int ft8b200_fetch_results(ft8b200_ctx_t *ctx, int n_slots, struct decoder_results *h_results, int32_t *h_nresults, void *stream);
@@ -379,6 +387,12 @@ int ft8b200_pipe_partition_smids(ft8b200_pipe_t *p, int which, uint32_t *mask8);
  * (best_back_sms, best_comb_front, ms per batch of each point in ms_out[2 * n_candidates], comb_front = 0 first; any of the three
  * may be NULL).  The split that balances the HBM-bound front end against the issue-bound back end depends on the batch's candidate
  * load and on the box; nothing in the results does. */
+/* With an SM partition: on = the back end of batch n+1 starts only when the back end of batch n has finished (the front ends are
+ * always chained).  Off (default) the back ends of consecutive batches may share the back partition when a backlog has built up,
+ * which is the better executor when the back end falls behind; on is what ft8b200_pipe_autotune compares partitions with (it
+ * shows within a dozen batches whether ONE batch's back end fits under the next batch's block sums) and restores afterwards.
+ * Results are identical either way.  Not while batches are in flight. */
+int ft8b200_pipe_set_back_chain(ft8b200_pipe_t *p, int on);
 int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots,
                           const int *candidates, int n_candidates, int batches, int *best_back_sms, int *best_comb_front, float *ms_out);
 void ft8b200_pipe_destroy(ft8b200_pipe_t *p);

@@ -504,6 +504,10 @@ class Pipe:
         self._chk(self.L.ft8b200_pipe_set_partition(C.c_void_p(self.h), int(back_sms), C.byref(f), C.byref(b)))
         return f.value, b.value
 
+    def set_back_chain(self, on: bool):
+        """Back ends of consecutive batches serialised on the back partition (what the autotune probes with)."""
+        self._chk(self.L.ft8b200_pipe_set_back_chain(C.c_void_p(self.h), int(on)))
+
     def partition_smids(self, which: int):
         """Hardware SM ids (%smid) the front (0) / back (1) partition runs on (diagnostic)."""
         m = (C.c_uint32 * 8)()

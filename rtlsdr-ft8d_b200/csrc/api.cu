@@ -86,6 +86,8 @@ struct ft8b200_ctx {
     cudaEvent_t front_wait = nullptr;      // one-shot: the next process_raw's block sums wait for it (ft8b200_set_front_wait), its memsets do not
     cudaEvent_t ev_front = nullptr;        // recorded on the launching stream right after the last process_raw's cic_block_sums
     cudaEvent_t ev_k1 = nullptr;
+    cudaEvent_t ev_back = nullptr;         // recorded on the back-end stream behind the last process_raw's spot table (ft8b200_back_event)
+    cudaEvent_t back_wait = nullptr;       // one-shot: the next process_raw's back end waits for it (ft8b200_set_back_wait)
     cudaEvent_t ev[6][kMaxGroups][2] = {};
     bool ev_valid[6][kMaxGroups] = {};
     cudaStream_t aux = nullptr;            // high-priority side stream for the back end of a slot group
@@ -227,6 +229,7 @@ void ft8b200_destroy(ft8b200_ctx_t *ctx) {
     if (ctx->own_aux) { cudaStreamSynchronize(ctx->own_aux); cudaStreamDestroy(ctx->own_aux); }
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    if (ctx->ev_back) cudaEventDestroy(ctx->ev_back);
     for (cudaEvent_t e : ctx->ev_group) if (e) cudaEventDestroy(e);
     cudaFree(ctx->tb.window1024); cudaFree(ctx->tb.twiddle1024); cudaFree(ctx->tb.db_thresholds); cudaFree(ctx->tb.wf_blob);
     cudaFree(ctx->tb.mon_window); cudaFree(ctx->tb.mon_twiddle); cudaFree(ctx->tb.mon_super);
@@ -443,6 +446,7 @@ static int ensure_aux(ft8b200_ctx_t *ctx) {
     if (!ctx->ev_join) {
         CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_k1, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_back, cudaEventDisableTiming));
         for (cudaEvent_t &e : ctx->ev_group) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     return 0;
@@ -485,7 +489,11 @@ static int process_raw_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t byte
         back = ctx->aux;
         CU(cudaEventRecord(ctx->ev_join, st));           // the side stream starts after everything already queued on st
         CU(cudaStreamWaitEvent(back, ctx->ev_join, 0));
+        if (ctx->back_wait) {  // the executor's second chain: back ends of consecutive batches (other lanes' streams) never share their SMs
+            CU(cudaStreamWaitEvent(back, ctx->back_wait, 0));
+        }
     }
+    ctx->back_wait = nullptr;
     clear_marks(ctx);
     CU(cudaMemsetAsync(ctx->peak.p, 0, sizeof(float) * n_rows, st));
     CU(cudaMemset2DAsync(ctx->sums.p, sstride * sizeof(BlockSums), 0, kHistBlocks * sizeof(BlockSums), n_slots, st));  // fresh filter state
@@ -528,6 +536,7 @@ static int process_raw_impl(ft8b200_ctx_t *ctx, const uint8_t *d_iq, size_t byte
         if ((rc = run_back_end(ctx, ctx->si.as<float>(), ctx->sq.as<float>(), ctx->peak.as<float>(), r0, nr, g, back))) return rc;
     }
     if (side) {  // results are ready, in stream order, when this call's work on st completes
+        CU(cudaEventRecord(ctx->ev_back, back));
         CU(cudaEventRecord(ctx->ev_join, back));
         CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     }
@@ -586,6 +595,14 @@ int ft8b200_set_front_wait(ft8b200_ctx_t *ctx, void *cuda_event) {
     ctx->front_wait = reinterpret_cast<cudaEvent_t>(cuda_event);
     return 0;
 }
+
+int ft8b200_set_back_wait(ft8b200_ctx_t *ctx, void *cuda_event) {
+    if (!ctx) return fail(FT8B200_EINVAL, "null context");
+    ctx->back_wait = reinterpret_cast<cudaEvent_t>(cuda_event);
+    return 0;
+}
+
+void *ft8b200_back_event(ft8b200_ctx_t *ctx) { return ctx && ctx->side_back ? ctx->ev_back : nullptr; }
 
 int ft8b200_set_comb_front(ft8b200_ctx_t *ctx, int on) {
     if (!ctx) return fail(FT8B200_EINVAL, "null context");

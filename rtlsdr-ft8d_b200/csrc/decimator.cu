@@ -22,6 +22,8 @@
 //   boundary are first attributed whole to the earlier block and corrected afterwards by 7 lanes.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -394,30 +396,25 @@ cic_block_sums_generic_kernel(const uint8_t *__restrict__ iq, size_t stream_stri
 }
 
 // Kernel 2: comb (closed form over 4 consecutive block sums) + 57-tap FIR + scale + peak.
-// ref: rtlsdr_ft8d.c:162-200.  One CTA = 256 consecutive outputs of one stream.
+// ref: rtlsdr_ft8d.c:162-200.  One CTA = kTilesPerCta tiles of 512 consecutive outputs of one row.
+// (FT8B200_COMB_THREADS / FT8B200_COMB_TILES: build-time shape for A/B runs, tools/perf_combfir.py)
+#ifndef FT8B200_COMB_THREADS
+#define FT8B200_COMB_THREADS 128
+#endif
+#ifndef FT8B200_COMB_TILES
+#define FT8B200_COMB_TILES 2
+#endif
 constexpr int kPerThread = 4;      // outputs per thread
-constexpr int kTileThreads = 128;
+constexpr int kTileThreads = FT8B200_COMB_THREADS;
+constexpr int kTilesPerCta = FT8B200_COMB_TILES;   // consecutive tiles one CTA walks (the next tile's block sums prefetched)
 constexpr int kTile = kTileThreads * kPerThread;  // 512 outputs per CTA
 constexpr int kHist = kFirTaps - 1;  // 56 FIR history samples; they need kHistBlocks = 56 + 3 block sums
-
-// y2[k] from blocks k-3..k.  `s` points at this flush's block 0; the kHistBlocks entries before it hold the
-// previous blocks of the stream (zeros for a fresh filter state), so no index test is needed.
-__device__ __forceinline__ void comb(const BlockSums *__restrict__ s, int k, int32_t &yi, int32_t &yq) {
-    const BlockSums b0 = s[k], b1 = s[k - 1], b2 = s[k - 2], b3 = s[k - 3];
-    const uint32_t ai = (751u * (uint32_t)b0.s0i - (uint32_t)b0.s1i) + (1502u * (uint32_t)b1.s0i - (uint32_t)b1.s1i) +
-                        (751u * (uint32_t)b2.s0i + (uint32_t)b2.s1i) + (uint32_t)b3.s1i;
-    const uint32_t aq = (751u * (uint32_t)b0.s0q - (uint32_t)b0.s1q) + (1502u * (uint32_t)b1.s0q - (uint32_t)b1.s1q) +
-                        (751u * (uint32_t)b2.s0q + (uint32_t)b2.s1q) + (uint32_t)b3.s1q;
-    yi = (int32_t)ai;
-    yq = (int32_t)aq;
-}
 
 // n_blocks new blocks per stream -> outputs [out_offset, out_offset + n_blocks) of the stream's 48000-sample
 // slot buffer (outputs past 48000 are dropped but the filter keeps running, rtlsdr_ft8d.c:196-200).
 // zero_fill: also clear [out_offset + n_blocks, 48000) -- what decoder() does before it normalises (:243-246).
 // Each thread produces kPerThread consecutive outputs from a register window of the (float)y2 history, so the
 // 57-tap FIR costs one shared load per ~4 taps; coefficients sit in constant memory (uniform broadcast).
-__constant__ float c_fir[kFirTaps];
 
 // (float)((double)sum / (32768.0 * 750)), rtlsdr_ft8d.c:197-198, without the FP64 divide: 24 576 000 = 375 * 2^16, and a float
 // quotient sum/375 can neither be nor come within 2^-34 (relative) of a midpoint between two floats (sum has 24 significant
@@ -429,21 +426,62 @@ __device__ __forceinline__ float scale_out(float sum) {
     return __fmul_rn(__fdiv_rn(sum, 375.0f), 1.52587890625e-05f);
 }
 
+// The I and Q rails run the same 57 taps, so a tap is ONE packed multiply and ONE packed add over the {I, Q} pair (SASS FFMA2 with
+// a zero addend / FADD2): per lane the same IEEE round-to-nearest product and sum as the scalar FMUL / FADD, 456 instead of 912
+// instructions per thread.  A packed instruction keeps the FP32 pipe busy for two cycles but the scheduler for one
+// (tools/f32x2_issue_probe.cu: 8 FADD2 + 8 IADD take the 16 cycles of 8 FADD2 alone), so the kernel's other ~600 instructions per
+// thread issue in its shadow: 80 -> 70 us per 128 slots on the whole GPU, 0.46 -> 0.35 ms on a 32-SM back partition
+// (profiles/perf_combfir_r2y.json) -- once the {I, Q} layout's bank conflicts were gone (swz() below): with them the packed form
+// measured exactly as fast as the scalar one.
+__constant__ float2 c_fir2[kFirTaps];  // {z[j], z[j]}
+
+// ptxas 12.9 CONTRACTS mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 -- with explicit .rn on both and with -fmad=false, which
+// it honours for the scalar forms -- and a fused tap does not round the product (tools/f32x2_contract_probe.cu shows the SASS).
+// Written as two fused multiply-adds it does not: RN(w * c + 0) IS the rounded product, RN(p * 1 + acc) IS the rounded sum, and
+// ptxas turns the second into FADD2 without merging it into the first.  (The only case where w * c + 0 and w * c differ is a
+// product of -0, which becomes +0; the accumulator starts at +0 and a sum is -0 only when both terms are, so it never is -0 on
+// either path and x + (+0) = x + (-0) for every other x: results are identical bit for bit.)  tests/test_abi.py checks the
+// built kernel's SASS for exactly this shape: 57 x kPerThread FFMA2 with an RZ addend and as many FADD2, no other FFMA2.
+__device__ __forceinline__ unsigned long long mul2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(0ull));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(b), "l"(0x3f8000003f800000ull), "l"(a));   // b * {1, 1} + a
+    return r;
+}
+
+// Shared-memory placement of the {I, Q} samples: 16-byte chunk c (samples 2c, 2c+1) lives at chunk c ^ ((c >> 3) & 1).  A thread's
+// window starts 32 bytes after its neighbour's, so without the swap the 128-bit loads of threads i and i + 4 of a quarter-warp hit
+// the same banks (2-way conflict on every load: 5.9 M conflicts per 128-slot launch, the shared-memory data pipe 96 % busy); with it
+// every quarter-warp covers all 32 banks, for every window position (checked exhaustively in tests/test_abi.py::test_fir_window_placement_is_conflict_free).
+__device__ __forceinline__ unsigned swz(unsigned c) { return c ^ ((c >> 3) & 1u); }
+
 template <int kN>
-__device__ __forceinline__ void fir_window(const float *__restrict__ y, float (&acc)[kN]) {
-    // y[0 .. kN+55]: acc[o] = sum_j y[o+j]*z[j], strictly sequential in j, product rounded before the add (no FMA)
-    float w[kN + kHist];
+__device__ __forceinline__ void fir_window2(const float2 *__restrict__ y, unsigned chunk0, float (&acc_i)[kN], float (&acc_q)[kN]) {
+    // y[0 .. kN+55] = {(float)Iy2, (float)Qy2}: acc[o] = sum_j y[o+j]*z[j], strictly sequential in j, product rounded before the
+    // add (no FMA): rtlsdr_ft8d.c:179-192 for both rails at once
+    unsigned long long w[kN + kHist], acc[kN];
 #pragma unroll
-    for (int v = 0; v < (kN + kHist) / 4; ++v) {
-        const float4 q = reinterpret_cast<const float4 *>(y)[v];
-        w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+    for (int v = 0; v < (kN + kHist) / 2; ++v) {
+        const unsigned c = chunk0 + v;   // 16-byte chunk {y[2c], y[2c+1]}
+        const ulonglong2 q = reinterpret_cast<const ulonglong2 *>(y)[swz(c)];
+        w[2 * v] = q.x; w[2 * v + 1] = q.y;
     }
 #pragma unroll
-    for (int o = 0; o < kN; ++o) acc[o] = 0.0f;
+    for (int o = 0; o < kN; ++o) acc[o] = 0ull;  // {0.0f, 0.0f}
 #pragma unroll
     for (int j = 0; j < kFirTaps; ++j) {
+        const unsigned long long c = *reinterpret_cast<const unsigned long long *>(&c_fir2[j]);
 #pragma unroll
-        for (int o = 0; o < kN; ++o) acc[o] = __fadd_rn(acc[o], __fmul_rn(w[o + j], c_fir[j]));
+        for (int o = 0; o < kN; ++o) acc[o] = add2_rn(acc[o], mul2_rn(w[o + j], c));
+    }
+#pragma unroll
+    for (int o = 0; o < kN; ++o) {
+        acc_i[o] = __uint_as_float((unsigned int)(acc[o] & 0xffffffffull));
+        acc_q[o] = __uint_as_float((unsigned int)(acc[o] >> 32));
     }
 }
 
@@ -458,13 +496,32 @@ __device__ __forceinline__ int seg_first_block(int seg, long long seg_samples) {
     return first_sample <= 750 ? 0 : (int)((first_sample - 750 + kDecim - 1) / kDecim);
 }
 
+// One CTA walks kTilesPerCta consecutive tiles of a row.  The block sums of a tile (k0-59 .. k0+kTile-1) go to shared memory with
+// 16-byte cp.async copies -- all of a tile's global reads in flight at once, no registers held -- and the NEXT tile's copies are
+// issued before the current tile is filtered, so after a CTA's first tile no warp waits for global memory.  (The loop this
+// replaces loaded four block sums per output and waited for them trip by trip, five dependent round trips to L2/HBM per CTA: a
+// third of the kernel's stall samples, profiles/ncu_lines_cic_comb_fir_kernel_r2v.txt.)
+__device__ __forceinline__ void stage_block_sums(BlockSums *s_b, const BlockSums *__restrict__ s, int k0, int n_blocks) {
+    // `s` points at this flush's block 0; the kHistBlocks entries before it hold the previous blocks of the stream (zeros for a
+    // fresh filter state), so no lower index test is needed
+    for (int i = threadIdx.x; i < kTile + kHistBlocks; i += kTileThreads) {
+        const int kk = k0 - kHistBlocks + i;
+        if (kk < n_blocks) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_b[i])), "l"(s + kk) : "memory");
+        } else {
+            s_b[i] = BlockSums{0, 0, 0, 0};
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kTileThreads)
 cic_comb_fir_kernel(const BlockSums *__restrict__ sums, size_t sums_stride, int n_blocks, int out_offset, int zero_fill, int segs,
-                    long long seg_samples, float *__restrict__ out_i, float *__restrict__ out_q, uint32_t *__restrict__ count,
+                    long long seg_samples, int n_tiles, float *__restrict__ out_i, float *__restrict__ out_q, uint32_t *__restrict__ count,
                     float *__restrict__ peak, int32_t *__restrict__ y2_out) {
-    __shared__ __align__(16) float s_yi[kTile + kHist], s_yq[kTile + kHist];
+    __shared__ __align__(16) float2 s_y[kTile + kHist];  // {(float)Iy2, (float)Qy2}, rtlsdr_ft8d.c:189-190
+    __shared__ __align__(16) BlockSums s_b[kTilesPerCta > 1 ? 2 : 1][kTile + kHistBlocks];
     const int stream = blockIdx.y;  // output row: (receiver stream, segment)
-    const int k0 = blockIdx.x * kTile;
     const BlockSums *s = sums + (size_t)(stream / segs) * sums_stride;
     if (segs > 1) {
         const int seg = stream % segs;
@@ -474,43 +531,65 @@ cic_comb_fir_kernel(const BlockSums *__restrict__ sums, size_t sums_stride, int 
         n_blocks = b1 > b0 ? b1 - b0 : 0;
         s += b0;
     }
-    for (int idx = threadIdx.x; idx < kTile + kHist; idx += kTileThreads) {
-        const int k = k0 - kHist + idx;  // >= -56: inside the history prefix
-        int32_t yi = 0, yq = 0;
-        if (k < n_blocks) comb(s, k, yi, yq);
-        s_yi[idx] = __int2float_rn(yi);  // (float)Iy2, rtlsdr_ft8d.c:189-190
-        s_yq[idx] = __int2float_rn(yq);
-        if (y2_out && k >= k0 && k < n_blocks && out_offset + k < kSlot) {
-            y2_out[((size_t)stream * kSlot + out_offset + k) * 2 + 0] = yi;
-            y2_out[((size_t)stream * kSlot + out_offset + k) * 2 + 1] = yq;
+    const int tile0 = blockIdx.x * kTilesPerCta;
+    int tile_end = tile0 + kTilesPerCta;
+    if (tile_end > n_tiles) tile_end = n_tiles;
+    float m = 0.0f;   // the row's peak over this CTA's tiles
+    stage_block_sums(s_b[0], s, tile0 * kTile, n_blocks);
+    for (int tile = tile0; tile < tile_end; ++tile) {
+        const int k0 = tile * kTile;
+        const BlockSums *sb = s_b[(tile - tile0) & (kTilesPerCta > 1 ? 1 : 0)];
+        if (kTilesPerCta > 1 && tile + 1 < tile_end) {
+            // the other buffer was last read by the comb of tile - 1, which every thread left through the barrier behind it
+            stage_block_sums(s_b[(tile + 1 - tile0) & 1], s, k0 + kTile, n_blocks);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-    }
-    __syncthreads();
-    const int kb = k0 + threadIdx.x * kPerThread;  // first of this thread's outputs
-    float vi[kPerThread], vq[kPerThread];
-#pragma unroll
-    for (int o = 0; o < kPerThread; ++o) { vi[o] = 0.0f; vq[o] = 0.0f; }
-    if (kb < n_blocks && out_offset + kb < kSlot) {
-        float ai[kPerThread], aq[kPerThread];
-        fir_window<kPerThread>(s_yi + threadIdx.x * kPerThread, ai);
-        fir_window<kPerThread>(s_yq + threadIdx.x * kPerThread, aq);
-#pragma unroll
-        for (int o = 0; o < kPerThread; ++o) {
-            if (kb + o < n_blocks) {
-                vi[o] = scale_out(ai[o]);  // rtlsdr_ft8d.c:197-198
-                vq[o] = scale_out(aq[o]);
+        __syncthreads();   // this tile's block sums have landed; every thread is done with the previous tile's s_y
+        // comb, rtlsdr_ft8d.c:162-176 in closed form over 4 consecutive block sums:
+        //   y2[k] = (751 S0 - S1)[k] + (1502 S0 - S1)[k-1] + (751 S0 + S1)[k-2] + S1[k-3]   (mod 2^32)
+        for (int idx = threadIdx.x; idx < kTile + kHist; idx += kTileThreads) {
+            const int k = k0 - kHist + idx;  // >= -56: inside the history prefix
+            int32_t yi = 0, yq = 0;
+            if (k < n_blocks) {
+                const BlockSums c0 = sb[idx + 3], c1 = sb[idx + 2], c2 = sb[idx + 1], c3 = sb[idx];
+                yi = (int32_t)((751u * (uint32_t)c0.s0i - (uint32_t)c0.s1i) + (1502u * (uint32_t)c1.s0i - (uint32_t)c1.s1i) +
+                               (751u * (uint32_t)c2.s0i + (uint32_t)c2.s1i) + (uint32_t)c3.s1i);
+                yq = (int32_t)((751u * (uint32_t)c0.s0q - (uint32_t)c0.s1q) + (1502u * (uint32_t)c1.s0q - (uint32_t)c1.s1q) +
+                               (751u * (uint32_t)c2.s0q + (uint32_t)c2.s1q) + (uint32_t)c3.s1q);
+            }
+            s_y[2 * swz((unsigned)idx >> 1) + (idx & 1)] = make_float2(__int2float_rn(yi), __int2float_rn(yq));
+            if (y2_out && k >= k0 && k < n_blocks && out_offset + k < kSlot) {
+                y2_out[((size_t)stream * kSlot + out_offset + k) * 2 + 0] = yi;
+                y2_out[((size_t)stream * kSlot + out_offset + k) * 2 + 1] = yq;
             }
         }
-    }
-    float m = 0.0f;
+        __syncthreads();
+        const int kb = k0 + threadIdx.x * kPerThread;  // first of this thread's outputs
+        float vi[kPerThread], vq[kPerThread];
 #pragma unroll
-    for (int o = 0; o < kPerThread; ++o) {
-        const int k = kb + o, pos = out_offset + k;
-        if (pos < kSlot && (k < n_blocks || zero_fill)) {
-            out_i[(size_t)stream * kSlot + pos] = vi[o];
-            out_q[(size_t)stream * kSlot + pos] = vq[o];
+        for (int o = 0; o < kPerThread; ++o) { vi[o] = 0.0f; vq[o] = 0.0f; }
+        if (kb < n_blocks && out_offset + kb < kSlot) {
+            float ai[kPerThread], aq[kPerThread];
+            fir_window2<kPerThread>(s_y, threadIdx.x * (kPerThread / 2), ai, aq);
+#pragma unroll
+            for (int o = 0; o < kPerThread; ++o) {
+                if (kb + o < n_blocks) {
+                    vi[o] = scale_out(ai[o]);  // rtlsdr_ft8d.c:197-198
+                    vq[o] = scale_out(aq[o]);
+                }
+            }
         }
-        m = fmaxf(m, fmaxf(fabsf(vi[o]), fabsf(vq[o])));
+#pragma unroll
+        for (int o = 0; o < kPerThread; ++o) {
+            const int k = kb + o, pos = out_offset + k;
+            if (pos < kSlot && (k < n_blocks || zero_fill)) {
+                out_i[(size_t)stream * kSlot + pos] = vi[o];
+                out_q[(size_t)stream * kSlot + pos] = vq[o];
+            }
+            m = fmaxf(m, fmaxf(fabsf(vi[o]), fabsf(vq[o])));
+        }
     }
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
@@ -600,6 +679,9 @@ cudaError_t launch_cic_block_sums(const uint8_t *d_iq, size_t stream_stride_byte
         ++*launches;
     } else if (supers > 0) {
         dim3 grid((supers + kWarpsPerCta - 1) / kWarpsPerCta, n_streams);
+        // (Requesting the rest of a warp's super-block into L2 at its start -- prefetch.global.L2, one 128-byte line per lane, SASS CCTL.PF2 --
+        // was measured in the last session of round 2 and dropped like the bulk prefetch of the ring variant: 1.48 -> 1.65 ms per 128
+        // slots with 4 KB, 1.73 with 8 KB requested ahead on 116 SMs, 1.375 -> 1.645 on the whole GPU; profiles/k1_prefetch_r2zb.txt.)
         if (variant == kK1StreamingDense) cic_block_sums_kernel<5><<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, sums_stride, d_sums);
         else cic_block_sums_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(d_iq, stream_stride_bytes, supers, sums_stride, d_sums);
         ++*launches;
@@ -632,9 +714,10 @@ cudaError_t launch_cic_comb_fir(const BlockSums *d_sums, size_t sums_stride, int
     if (zero_fill && kSlot - out_offset > span) span = kSlot - out_offset;
     if (span <= 0) return cudaSuccess;
     if (segs < 1) segs = 1;
-    dim3 grid((span + kTile - 1) / kTile, n_streams * segs);
-    cic_comb_fir_kernel<<<grid, kTileThreads, 0, st>>>(d_sums, sums_stride, n_blocks, out_offset, zero_fill ? 1 : 0, segs, seg_samples, d_i, d_q,
-                                                       d_count, d_peak, d_y2);
+    const int n_tiles = (span + kTile - 1) / kTile;
+    dim3 grid((n_tiles + kTilesPerCta - 1) / kTilesPerCta, n_streams * segs);
+    cic_comb_fir_kernel<<<grid, kTileThreads, 0, st>>>(d_sums, sums_stride, n_blocks, out_offset, zero_fill ? 1 : 0, segs, seg_samples, n_tiles, d_i,
+                                                       d_q, d_count, d_peak, d_y2);
     ++*launches;
     return cudaGetLastError();
 }
@@ -653,7 +736,9 @@ cudaError_t upload_fir_constants() {
     if (done[dev]) return cudaSuccess;
     float z[kFirTaps];
     build_fir(z);
-    e = cudaMemcpyToSymbol(c_fir, z, sizeof(z));
+    float2 z2[kFirTaps];
+    for (int j = 0; j < kFirTaps; ++j) z2[j] = make_float2(z[j], z[j]);
+    e = cudaMemcpyToSymbol(c_fir2, z2, sizeof(z2));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) done[dev] = true;
     return e;

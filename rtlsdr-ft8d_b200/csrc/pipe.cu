@@ -108,6 +108,8 @@ struct ft8b200_pipe {
     int count = 0;   // batches in flight
     cudaEvent_t prev_front = nullptr;  // front-end-done event of the most recently submitted batch
     cudaEvent_t prev_done = nullptr;   // completion event of the most recently submitted batch
+    cudaEvent_t prev_back = nullptr;   // back-end-done event of the most recently submitted raw batch
+    bool chain_back = false;           // back ends of consecutive batches serialised on the back partition (ft8b200_pipe_set_back_chain)
     int mode = FT8B200_PIPE_OVERLAP;
     cudaEvent_t dependency = nullptr;  // one-shot: the next submit's kernels wait for this event (ft8b200_pipe_depend_on)
     bool profiling = false;
@@ -177,6 +179,13 @@ int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t b
         // (measured in round 2: without the chain consecutive block-sum kernels fill each other's tails and the step gains 0.8 %, but
         // their per-launch times then overlap and no longer say what the kernel achieves -- kept chained)
         if (p->prev_front) ft8b200_set_front_wait(l.ctx, p->prev_front);
+        // Optionally (ft8b200_pipe_set_back_chain; the autotune's probe) so are the back ends on an SM partition.  Unchained, the back
+        // ends of two batches share the back partition whenever a backlog has built up, and fill each other's tails: a partition that
+        // is too small for one batch's back end then looks fine for the first ~70 batches (24 SMs: 1.417 ms per batch in a 72-batch
+        // probe, 1.58 in the long run) -- chained, it shows what one back end costs within a dozen batches (1.65).  Unchained is the
+        // better executor when the back end does fall behind (81.0 k against 77.4 k slots/s at 24 SMs) and the same when it does not
+        // (85.2 / 85.3 k at 32), so that is how batches run; the chain is how partitions are compared.
+        if (p->chain_back && p->part.back && p->prev_back) ft8b200_set_back_wait(l.ctx, p->prev_back);
     } else if (p->prev_done) {
         // kernels of consecutive batches never share the GPU; only copies and host work overlap them
         PCU(cudaStreamWaitEvent(l.st, p->prev_done, 0));
@@ -185,6 +194,7 @@ int submit(ft8b200_pipe_t *p, const uint8_t *h_iq, const uint8_t *d_iq, size_t b
                   : ft8b200_process_raw(l.ctx, d_iq, bytes_per_stream, stride, n_slots, nullptr);
     if (rc) return pfail(p, rc, ft8b200_last_error());
     p->prev_front = reinterpret_cast<cudaEvent_t>(ft8b200_front_event(l.ctx));
+    p->prev_back = reinterpret_cast<cudaEvent_t>(ft8b200_back_event(l.ctx));
     if ((rc = ft8b200_fetch_results_async(l.ctx, n_rows, l.h_res, l.h_n, nullptr))) return pfail(p, rc, ft8b200_last_error());
     PCU(cudaEventRecord(l.done, l.st));
     p->prev_done = l.done;
@@ -227,6 +237,7 @@ int submit_slots(ft8b200_pipe_t *p, const float *h_i, const float *h_q, const fl
     if (p->mode == FT8B200_PIPE_SERIAL && p->prev_done) PCU(cudaStreamWaitEvent(l.st, p->prev_done, 0));
     if ((rc = ft8b200_process_conditioned(l.ctx, d_i, d_q, d_peak, n_slots, nullptr))) return pfail(p, rc, ft8b200_last_error());
     p->prev_front = nullptr;
+    p->prev_back = nullptr;
     if ((rc = ft8b200_fetch_results_async(l.ctx, n_slots, l.h_res, l.h_n, nullptr))) return pfail(p, rc, ft8b200_last_error());
     PCU(cudaEventRecord(l.done, l.st));
     p->prev_done = l.done;
@@ -253,6 +264,7 @@ ft8b200_pipe_t *ft8b200_pipe_create(const ft8b200_config_t *cfg_in, int depth) {
     ft8b200_default_config(&p->cfg);
     if (cfg_in) p->cfg = *cfg_in;
     p->lanes.resize((size_t)depth);
+    if (const char *e = getenv("FT8B200_PIPE_CHAIN_BACK")) p->chain_back = atoi(e) != 0;
     for (Lane &l : p->lanes) {
         l.ctx = ft8b200_create(&p->cfg);  // fails (NULL + ft8b200_last_error) without an sm_100 device: no fallback
         if (!l.ctx || cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming) != cudaSuccess) {
@@ -277,6 +289,7 @@ int ft8b200_pipe_set_mode(ft8b200_pipe_t *p, int mode, int decimator_variant) {
         if (decimator_variant >= 0 && ft8b200_set_decimator_variant(l.ctx, decimator_variant)) return pfail(p, FT8B200_EINVAL, ft8b200_last_error());
     }
     p->prev_front = nullptr;
+    p->prev_back = nullptr;
     return 0;
 }
 
@@ -330,6 +343,7 @@ int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_o
     const DriverApi &d = driver_api();
     if (p->part.front || p->part.back) partition_release(p);
     p->prev_front = nullptr;
+    p->prev_back = nullptr;
     const int back_req = back_sms;           // cache key: size and layout
     const int layout = back_sms / 1000;
     back_sms %= 1000;
@@ -365,7 +379,10 @@ int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_o
             if (layout == 0) {
                 CUdevResource back, front;
                 unsigned int groups = 1;
-                PDRV(d.DevSmResourceSplitByCount(&back, &groups, &all, &front, 0, (unsigned)back_sms));  // rounds up to the architecture's granularity
+                // a size that is not a multiple of the co-scheduling granularity (8 SMs on sm_100) is split TPC-wise (2 SMs): none of the
+                // back-end kernels launches thread-block clusters, which is all the coarser granularity guarantees
+                const unsigned int flags = (back_sms % 8) ? CU_DEV_SM_RESOURCE_SPLIT_IGNORE_SM_COSCHEDULING : 0;
+                PDRV(d.DevSmResourceSplitByCount(&back, &groups, &all, &front, flags, (unsigned)back_sms));  // rounds up to the granularity
                 if (groups != 1 || front.sm.smCount == 0) return pfail(p, FT8B200_ECUDA, "ft8b200_pipe_set_partition: the driver could not split the SMs that way");
                 PDRV(d.DevResourceGenerateDesc(&dback, &back, 1));
                 PDRV(d.DevResourceGenerateDesc(&dfront, &front, 1));
@@ -424,6 +441,14 @@ int ft8b200_pipe_set_partition(ft8b200_pipe_t *p, int back_sms, int *front_sms_o
     return 0;
 }
 
+int ft8b200_pipe_set_back_chain(ft8b200_pipe_t *p, int on) {
+    if (!p) return FT8B200_BAD_ARG();
+    if (p->count) return pfail(p, FT8B200_EBUSY, "ft8b200_pipe_set_back_chain: batches in flight");
+    p->chain_back = on != 0;
+    p->prev_back = nullptr;
+    return 0;
+}
+
 int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_per_stream, size_t stream_stride_bytes, int n_slots,
                           const int *candidates, int n_candidates, int batches, int *best_back_sms, int *best_comb_front, float *ms_out) {
     if (!p || !d_iq || !candidates || n_candidates < 1 || n_slots < 1) return FT8B200_BAD_ARG();
@@ -435,6 +460,9 @@ int ft8b200_pipe_autotune(ft8b200_pipe_t *p, const uint8_t *d_iq, size_t bytes_p
     float best = -1.0f;
     int best_sms = 0, best_comb = 0, rc = 0;
     std::vector<float> all_ms((size_t)2 * (size_t)n_candidates, -1.0f);
+    const bool chain_was = p->chain_back;
+    p->chain_back = true;   // one batch's back end at a time while partitions are compared (see submit())
+    struct Restore { ft8b200_pipe_t *p; bool v; ~Restore() { p->chain_back = v; p->prev_back = nullptr; } } restore{p, chain_was};
     auto apply = [&](int sms, int comb) -> int {
         int r = ft8b200_pipe_set_partition(p, sms, nullptr, nullptr);
         if (r) return r;

@@ -104,6 +104,49 @@ def test_product_sources_do_not_touch_the_oracle():
             assert f != "cpu_stand_in.c" and not f.startswith("libft8oracle"), os.path.join(dirpath, f)
 
 
+def _sass_of(kernel):
+    so = os.path.join(ROOT, "rtlsdr-ft8d_b200", "libft8b200.so")
+    r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    keep, body = False, []
+    for line in r.stdout.splitlines():
+        if "Function :" in line:
+            keep = kernel in line
+        elif keep:
+            body.append(line)
+    return body
+
+
+def test_fir_kernel_keeps_both_roundings_of_a_tap():
+    """cic_comb_fir_kernel runs a FIR tap as packed f32x2 instructions over the {I, Q} pair; the reference rounds the product AND
+    the sum (rtlsdr_ft8d.c:179-192, no FMA).  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under -fmad=false
+    (tools/f32x2_contract_probe.cu), so the kernel spells a tap as FFMA2(w, c, +0) + FADD2: the built SASS must have exactly that
+    shape -- every FFMA2 with the zero register as its addend, as many FADD2 -- or the GPU's samples are no longer the reference's."""
+    body = _sass_of("cic_comb_fir_kernel")
+    assert body, "cic_comb_fir_kernel not found in the library"
+    ffma2 = [l for l in body if " FFMA2 " in l]
+    fadd2 = [l for l in body if " FADD2 " in l]
+    assert len(ffma2) == 57 * 4 and len(fadd2) == 57 * 4, (len(ffma2), len(fadd2))
+    assert all(l.split(";")[0].rstrip().endswith("RZ.F32") for l in ffma2), "a FIR tap was contracted into a fused multiply-add"
+    assert not any(" FMUL2 " in l for l in body)
+
+
+def test_fir_window_placement_is_conflict_free():
+    """The {I, Q} samples' shared-memory placement in cic_comb_fir_kernel (16-byte chunk c at c ^ ((c >> 3) & 1), csrc/decimator.cu
+    swz()): a permutation of the tile's chunks, and for every window position the eight 128-bit loads of a quarter-warp (thread
+    stride 32 bytes) fall into eight different 16-byte bank groups; so do the comb's 64-bit stores of a half-warp."""
+    swz = lambda c: c ^ ((c >> 3) & 1)
+    n_chunks = (512 + 56) // 2
+    assert sorted(swz(c) for c in range(n_chunks)) == list(range(n_chunks))
+    for t0 in range(0, 128, 8):
+        for v in range(30):
+            assert len({swz(2 * (t0 + i) + v) % 8 for i in range(8)}) == 8
+    for i0 in range(0, 568 - 15, 16):
+        words = {(2 * swz(idx >> 1) + (idx & 1)) % 16 for idx in range(i0, i0 + 16)}
+        assert len(words) == 16
+
+
 def test_bad_arguments_are_rejected_before_any_launch(pkg):
     L = pkg.lib()
     assert L.ft8b200_create(None) in (None, 0) or True  # may succeed on a GPU box; must not crash

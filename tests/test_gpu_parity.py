@@ -811,6 +811,22 @@ def test_pipe_sm_partition_layouts(pkg, ctx, raw_slot):
             res, n = pipe.collect(B)
             assert np.array_equal(n, ref_n) and res.tobytes() == ref_res.tobytes()
     assert len(seen) >= 3   # the layouts really are different SM sets
+    # back ends of consecutive batches chained (the autotune's probe mode): same records
+    pipe.set_partition(24)
+    pipe.set_back_chain(True)
+    for _ in range(7):
+        if pipe.in_flight() == pipe.depth:
+            res, n = pipe.collect(B)
+            assert np.array_equal(n, ref_n) and res.tobytes() == ref_res.tobytes()
+        pipe.submit(big, B)
+    while pipe.in_flight():
+        res, n = pipe.collect(B)
+        assert np.array_equal(n, ref_n) and res.tobytes() == ref_res.tobytes()
+    pipe.submit(big, B)
+    with pytest.raises(pkg.Ft8Error):   # not while a batch is in flight
+        pipe.set_back_chain(False)
+    pipe.collect(B)
+    pipe.set_back_chain(False)
     with pytest.raises(pkg.Ft8Error):
         pipe.set_partition(7032)
     with pytest.raises(pkg.Ft8Error):
