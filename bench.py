@@ -397,6 +397,7 @@ def main():
     ap.add_argument("--cpu-slots", type=int, default=96, help="bounded CPU-baseline sample (slots)")
     ap.add_argument("--cluster", action="store_true", help="single-process arm: all --gpus devices driven from THIS process through ft8b200_cluster_t "
                                                           "(records gathered by the library's own NCCL all-gather); not launched under torchrun")
+    ap.add_argument("--chain-back", action="store_true", help="A/B: with an SM partition, back ends of consecutive batches run one at a time (ft8b200_pipe_set_back_chain)")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (configs, e2e_slots, roofline_extra)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -457,6 +458,9 @@ def main():
             run_info["sm_partition"] = "unavailable (%s): running serial" % exc
             pipe.set_mode(serial=True, decimator_variant=args.k1_variant)
             args.back_sms = 0
+    if args.chain_back and args.back_sms != 0:
+        pipe.set_back_chain(True)
+        mode_txt += ", back ends chained"
     run_info["executor"] = "ft8b200_pipe_t depth %d, %d batches of %d slots per step, %s" % (args.depth, args.chunks, Bc, mode_txt)
     M = pipe.M
 

@@ -264,7 +264,6 @@ ft8b200_pipe_t *ft8b200_pipe_create(const ft8b200_config_t *cfg_in, int depth) {
     ft8b200_default_config(&p->cfg);
     if (cfg_in) p->cfg = *cfg_in;
     p->lanes.resize((size_t)depth);
-    if (const char *e = getenv("FT8B200_PIPE_CHAIN_BACK")) p->chain_back = atoi(e) != 0;
     for (Lane &l : p->lanes) {
         l.ctx = ft8b200_create(&p->cfg);  // fails (NULL + ft8b200_last_error) without an sm_100 device: no fallback
         if (!l.ctx || cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming) != cudaSuccess) {
@@ -309,13 +308,13 @@ static void partition_release(ft8b200_pipe_t *p) {
     p->part = Partition();   // the green contexts stay in g_parts (see CachedPartition)
 }
 
-// Which SMs the back partition gets.  cuDevSmResourceSplitByCount hands the SMs out in groups of the architecture's granularity
-// (8 on sm_100); asked for ONE group of back_sms it returns the first back_sms SMs of the driver's enumeration and the rest as the
-// remainder -- on a two-die GPU with eight GPCs that takes whole GPCs away from the front end, and an HBM-bound kernel then loses
-// those GPCs' paths into the L2 fabric, not just their SMs.  layout > 0 (encoded by the caller as back_sms + 1000 * layout) asks
-// the driver for groups of 8 instead and composes the back partition from groups spread over the enumeration, the front end from
-// all the others plus the remainder (cuDevResourceGenerateDesc accepts several SM resources of one split).  Which layout is best is
-// a property of the box (floor-swept SMs differ from GPU to GPU): ft8b200_pipe_autotune measures them.
+// Which SMs the back partition gets.  Asked for ONE group of back_sms SMs, cuDevSmResourceSplitByCount returns the first groups of its
+// enumeration and the rest as the remainder; layout > 0 (encoded by the caller as back_sms + 1000 * layout) asks the driver for groups
+// of 8 instead and composes the back partition from groups picked over the enumeration, the front end from all the others plus the
+// remainder (cuDevResourceGenerateDesc accepts several SM resources of one split).  Written to find out whether the partitioned
+// block-sum kernel's box-to-box spread (0.96-1.00 of the copy peak; alone it is 1.03 everywhere) comes from which SMs it is left with.
+// It does not: on a B200 a group of 8 is already one TPC from each of four GPCs (%smid 0,1,16,17,32,33,48,49 ...), the driver's own
+// 32 SMs are 8 from each of the four 16-SM GPCs, and no layout beats that outside the probe's noise (profiles/part_layout_r2u.json).
 static int pick_groups(int layout, int n_groups, int n_back, int *idx) {
     if (n_back < 1 || n_back >= n_groups) return -1;
     for (int i = 0; i < n_back; ++i) {

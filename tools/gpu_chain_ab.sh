@@ -5,7 +5,8 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q -k "pipe" 2>&1 | tail -2
 run() {  # name chain args...
   name=$1; chain=$2; shift 2
-  FT8B200_PIPE_CHAIN_BACK=$chain timeout 300 python bench.py --steps 40 --warmup 5 --no-configs --cpu-slots 4 "$@" > gpurun_out/bench_${TAG}_${name}.json 2> gpurun_out/bench_${TAG}_${name}.err
+  [ "$chain" = 1 ] && set -- --chain-back "$@"
+  timeout 300 python bench.py --steps 40 --warmup 5 --no-configs --cpu-slots 4 "$@" > gpurun_out/bench_${TAG}_${name}.json 2> gpurun_out/bench_${TAG}_${name}.err
   python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_${TAG}_${name}.json"))
