@@ -2,7 +2,13 @@
 """A/B of cic_comb_fir_kernel builds (run under gpurun).  Each library under rtlsdr-ft8d_b200/build/ab/lib_<threads>_<tiles>.so (built with
 -DFT8B200_COMB_THREADS / -DFT8B200_COMB_TILES) runs in its own process: comb+FIR launch time at 128 raw slots on the whole GPU (CUDA events
 of the stage-wise API, minimum of 8) and inside the SM-partitioned executor (32 back-end SMs, mean over 36 batches), with a digest of the
-3200 sps outputs so that every build is seen to produce the same samples.  usage: tools/perf_combfir.py [TAG]; child: --one"""
+3200 sps outputs so that every build is seen to produce the same samples.  usage: tools/perf_combfir.py [TAG]; child: --one
+Building a variant (in rtlsdr-ft8d_b200/, after `make`):
+  nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -DFT8B200_COMB_THREADS=256 \
+       -DFT8B200_COMB_TILES=1 -c csrc/decimator.cu -o build/ab/decimator_256_1.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/ab/lib_256_1.so build/ab/decimator_256_1.o \
+       $(ls build/*.o | grep -v decimator.o) -lcudart -ldl
+and `cp libft8b200.so build/ab/lib_base.so` for the build under test (FT8B200_LIB_PATH selects the library the harness loads)."""
 import glob, hashlib, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
