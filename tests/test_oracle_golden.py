@@ -78,6 +78,33 @@ def test_fir_scale_identity():
             assert np.array_equal(ref.view(np.uint32), alt.view(np.uint32)), (e, sign)
 
 
+def test_fir_tap_as_two_fmas_equals_multiply_then_add():
+    """csrc/decimator.cu spells a FIR tap as fma(w, c, +0) followed by fma(p, 1, acc) (packed over the {I, Q} pair; ptxas would
+    contract a packed multiply + add into ONE fused multiply-add, tools/f32x2_contract_probe.cu).  That is the reference's rounded
+    product and rounded sum (rtlsdr_ft8d.c:179-192) bit for bit: fma(w, c, +0) differs from w * c only where the product is -0 (it
+    becomes +0), and an accumulator that starts at +0 is never -0, so the sums agree -- emulated here in double precision, where a
+    product of two floats, and that product plus zero, are exact (so the first fma is one rounding of the exact value; the second is
+    emulated by a double-precision add, exact unless the operands are more than 29 binades apart, where the small one cannot move a
+    float sum off a tie it is not on), over 57-tap chains of random values, zeros of both signs, tiny and huge magnitudes (fixed seed)."""
+    rng = np.random.default_rng(5)
+    n, taps = 20000, 57
+    w = (rng.standard_normal((n, taps)) * 10.0 ** rng.integers(-30, 9, size=(n, taps))).astype(np.float32)
+    w[rng.random((n, taps)) < 0.15] = np.float32(0.0)
+    w[rng.random((n, taps)) < 0.10] = np.float32(-0.0)
+    w[: n // 8] = np.rint(w[: n // 8])                      # (float)int32 inputs like the filter's
+    c = (rng.standard_normal(taps) * 0.05).astype(np.float32)
+    c[::9] = np.float32(0.0); c[4::9] = np.float32(-0.0)
+    acc_ref = np.zeros(n, np.float32)
+    acc_fma = np.zeros(n, np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        for j in range(taps):
+            acc_ref = acc_ref + w[:, j] * c[j]                                                  # float multiply, float add
+            p = (w[:, j].astype(np.float64) * np.float64(c[j]) + np.float64(0.0)).astype(np.float32)   # fma(w, c, +0)
+            acc_fma = (p.astype(np.float64) * 1.0 + acc_fma.astype(np.float64)).astype(np.float32)    # fma(p, 1, acc)
+            assert not np.any(np.signbit(acc_ref) & (acc_ref == 0)), "the accumulator is never -0"
+    assert np.array_equal(acc_ref.view(np.uint32), acc_fma.view(np.uint32))
+
+
 def test_oracle_reproduces_reference_stdout_on_real_recordings(oracle):
     """tests/golden/recordings_12k.npz: three of the reference's own real-world WAVs (PCM) + the stdout of its own
     `decode_ft8` main() on them (tools/make_golden.py).  The restatement must print the same lines."""
