@@ -78,6 +78,24 @@ def test_fir_scale_identity():
             assert np.array_equal(ref.view(np.uint32), alt.view(np.uint32)), (e, sign)
 
 
+def test_division_by_375_in_three_instructions():
+    """Groundwork for the next step of cic_comb_fir_kernel (tools/div375_proof.py): with c = RN(1/375),
+    q0 = RN(x c), r = fma(-375, q0, x), q1 = fma(r, c, q0) is the correctly rounded x / 375 for every float mantissa -- proved
+    with exact integer arithmetic, the integer model itself pinned to IEEE float multiply and divide on the same inputs."""
+    from tools import div375_proof as dp
+    bad, n = dp.prove()
+    assert n == 2 ** 23 and bad == 0
+    C = int(round(2 ** 32 / 375))
+    m = np.arange(2 ** 23, 2 ** 24, dtype=np.int64)
+    q0, e0 = dp.round_to_24_bits(m * C, 32)
+    model = (q0.astype(np.float64) * np.exp2(e0.astype(np.float64))).astype(np.float32)
+    assert np.array_equal(model.view(np.uint32), (m.astype(np.float32) * np.float32(C * 2.0 ** -32)).view(np.uint32))
+    num = m << 34
+    qr, er = dp.round_to_24_bits(((num // 375) << 1) | (num % 375 != 0), 35)
+    model = (qr.astype(np.float64) * np.exp2(er.astype(np.float64))).astype(np.float32)
+    assert np.array_equal(model.view(np.uint32), (m.astype(np.float32) / np.float32(375.0)).view(np.uint32))
+
+
 def test_fir_tap_as_two_fmas_equals_multiply_then_add():
     """csrc/decimator.cu spells a FIR tap as fma(w, c, +0) followed by fma(p, 1, acc) (packed over the {I, Q} pair; ptxas would
     contract a packed multiply + add into ONE fused multiply-add, tools/f32x2_contract_probe.cu).  That is the reference's rounded
